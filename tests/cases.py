@@ -1,0 +1,299 @@
+"""Shared case definitions for the parity tests.
+
+Every case is written against an *API adaptor* so that the same definition drives
+  * the unmodified reference (tests/golden/make_golden.py, build container only),
+  * the CPU oracle (oracle/gds_oracle.py),
+  * the CUDA product (gds_b200).
+The adaptor supplies the field constructors, `couple`, the BC helpers and `evolve()`, which installs a
+fixed-step scheme (the reference needs its integrator object swapped, see make_golden.py).
+"""
+from __future__ import annotations
+
+import math
+
+import networkx as nx
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# graphs
+# ------------------------------------------------------------------------------------------------
+def g_grid(m, n, faces_off=True):
+    G = nx.grid_2d_graph(m, n)
+    if faces_off:
+        G.faces = []
+    return G
+
+
+def g_hex(m, n):
+    return nx.hexagonal_lattice_graph(m, n)
+
+
+def g_tri(m, n):
+    return nx.triangular_lattice_graph(m, n)
+
+
+def g_grid3(dims):
+    G = nx.grid_graph(dim=list(dims))
+    G.faces = []
+    return G
+
+
+def g_rgg(n, r, seed):
+    G = nx.random_geometric_graph(n, r, seed=seed)
+    G.faces = []
+    return G
+
+
+def add_weights(G, seed, lo=0.5, hi=2.0):
+    rng = np.random.default_rng(seed)
+    for (u, v) in G.edges():
+        G[u][v]['weight'] = float(rng.uniform(lo, hi))
+    return G
+
+
+def boundary_edges_hex_top_bottom(G):
+    """Sub-graph holding the top and bottom boundary edges of a hexagonal lattice (for zero_edge_bc)."""
+    ys = [p[1] for p in nx.get_node_attributes(G, 'pos').values()]
+    lo, hi = min(ys), max(ys)
+    h = math.sqrt(3) / 2
+    pos = nx.get_node_attributes(G, 'pos')
+    keep = [n for n in G.nodes() if pos[n][1] < lo + 0.6 * h or pos[n][1] > hi - 0.6 * h]
+    return G.subgraph(keep).copy()
+
+
+def tri_boundaries(G):
+    """(lid, walls): top-row edges, and left/right/bottom boundary edges of a triangular lattice."""
+    pos = nx.get_node_attributes(G, 'pos')
+    xs = [p[0] for p in pos.values()]
+    ys = [p[1] for p in pos.values()]
+    x0, x1, y0, y1 = min(xs), max(xs), min(ys), max(ys)
+    top = [n for n in G.nodes() if pos[n][1] > y1 - 1e-9]
+    bottom = [n for n in G.nodes() if pos[n][1] < y0 + 1e-9]
+    left = [n for n in G.nodes() if pos[n][0] < x0 + 0.51]
+    right = [n for n in G.nodes() if pos[n][0] > x1 - 0.51]
+    lid = G.subgraph(top).copy()
+    walls = nx.compose_all([G.subgraph(bottom).copy(), G.subgraph(left).copy(), G.subgraph(right).copy()])
+    return lid, walls
+
+
+# ------------------------------------------------------------------------------------------------
+# operator cases: graph + seeded inputs -> dict of operator outputs
+# ------------------------------------------------------------------------------------------------
+OP_GRAPHS = {
+    'grid_6x7': lambda: g_grid(6, 7),
+    'hex_3x4': lambda: g_hex(3, 4),
+    'hex_4x5_w': lambda: add_weights(g_hex(4, 5), 11),
+    'tri_4x6': lambda: g_tri(4, 6),
+    'tri_5x7_w': lambda: add_weights(g_tri(5, 7), 12),
+    'rgg_60': lambda: g_rgg(60, 0.25, 3),
+}
+
+
+def operator_outputs(api, gname):
+    """Apply every hot-path operator to seeded inputs; returns {key: ndarray} plus the index maps."""
+    G = OP_GRAPHS[gname]()
+    rng = np.random.default_rng(1234)
+    out = {}
+    nd = api.node_gds(G)
+    ed = api.edge_gds(G)
+    V, E = nd.ndim, ed.ndim
+    yv, ye = rng.standard_normal(V), rng.standard_normal(E)
+    ye[rng.integers(0, E, size=max(1, E // 10))] = 0.0  # exact zeros exercise sign()==0 branches
+    out['in_yv'], out['in_ye'] = yv, ye
+    nodes_list = list(nd.X.keys())
+    edges_list = list(ed.X.keys())
+    out['map_edges'] = np.array([[nd.X[a], nd.X[b]] for (a, b) in edges_list], dtype=np.int64).reshape(E, 2)
+    out['map_nodes_repr'] = np.array([repr(n) for n in nodes_list])
+    out['edge_weights'] = np.asarray(ed.edge_weights, dtype=float)
+    # node field: Dirichlet on a few nodes, Neumann on a few others
+    d_nodes = {nodes_list[i]: float(0.25 * i) for i in range(0, V, 7)}
+    n_nodes = {nodes_list[i]: float(-0.1 * (i % 5 + 1)) for i in range(3, V, 11) if nodes_list[i] not in d_nodes}
+    api.evolve(nd, dydt=lambda t, y: nd.laplacian(y), max_step=1e-2)
+    nd.set_constraints(dirichlet=d_nodes, neumann=n_nodes)
+    out['node_grad'] = nd.grad(yv)
+    out['node_laplacian'] = nd.laplacian(yv)
+    out['node_bilaplacian'] = nd.bilaplacian(yv)
+    out['node_advect'] = nd.advect(ye, yv)
+    out['node_lie_advect'] = nd.lie_advect(ye, yv)
+    # edge field: Dirichlet on a few edges
+    d_edges = {edges_list[i]: float(0.1 * i) for i in range(0, E, 9)}
+    api.evolve(ed, dydt=lambda t, y: ed.laplacian(y), max_step=1e-2)
+    ed.set_constraints(dirichlet=d_edges)
+    free = np.array(sorted(set(range(2, E, 13))), dtype=np.intp)
+    normal = np.array(sorted(set(range(5, E, 17))), dtype=np.intp)
+    out['edge_div'] = ed.div(ye)
+    out['edge_influx'] = np.asarray(ed.influx(ye)).ravel()
+    out['edge_outflux'] = np.asarray(ed.outflux(ye)).ravel()
+    out['edge_dd'] = ed.dd_(ye)
+    out['edge_dd_normal'] = ed.dd_(ye, normal=normal)
+    out['edge_advect'] = ed.advect(ye)
+    nF = len(ed.faces)
+    out['n_faces'] = np.array([nF])
+    if nF > 0:
+        faces_list = list(ed.faces.keys())
+        out['map_faces_ptr'] = np.cumsum([0] + [len(f) for f in faces_list]).astype(np.int64)
+        out['map_faces_nodes'] = np.array([nd.X[n] for f in faces_list for n in f], dtype=np.int64)
+        out['edge_curl'] = ed.curl(ye)
+        out['edge_d_d'] = ed.d_d(ye)
+        out['edge_laplacian'] = ed.laplacian(ye)
+        out['edge_laplacian_fn'] = ed.laplacian(ye, free=free, normal=normal)
+        out['edge_bilaplacian'] = ed.bilaplacian(ye)
+        fd = api.face_gds(G)
+        yf = rng.standard_normal(fd.ndim)
+        out['in_yf'] = yf
+        out['face_laplacian'] = fd.laplacian(yf)
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory cases
+# ------------------------------------------------------------------------------------------------
+def _snap(sysobj, observables, dt, nsteps, every):
+    """step `nsteps` times by `dt`; record each observable's y every `every` steps (and at the end)."""
+    rec = {k: [] for k in observables}
+    rec_t = []
+    for i in range(1, nsteps + 1):
+        sysobj.step(dt)
+        if i % every == 0 or i == nsteps:
+            for k, o in observables.items():
+                rec[k].append(np.array(o.y, dtype=float, copy=True))
+            rec_t.append(float(sysobj.t))
+    out = {f'y_{k}': np.array(v) for k, v in rec.items()}
+    out['t'] = np.array(rec_t)
+    return out
+
+
+def case_heat_c1(api, n=100, nsteps=1000, every=250, scheme='rk4'):
+    """BASELINE config 1: heat equation, grid n x n, RK4 h=1e-2, static + time-varying Dirichlet
+    (README.md:208-211 / examples/heat.py:56-63)."""
+    G = g_grid(n, n)
+    T = api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=1e-2, scheme=scheme)
+    c = n / 2
+    T.set_initial(y0=lambda x: math.exp(-((x[0] - c) ** 2 + (x[1] - c) ** 2) / (n / 2)))
+    T.set_constraints(dirichlet=api.combine_bcs(
+        lambda x: 0. if x[0] == n - 1 else None,
+        lambda t, x: math.sin(t + x[1] / 4) ** 2 if x[0] == 0 else None))
+    return _snap(T, {'T': T}, 1e-2, nsteps, every)
+
+
+def case_heat_mixed(api, scheme='rk4'):
+    """Dirichlet + Neumann heat equation on a weighted 12x9 grid (examples/heat.py:25-39 pattern);
+    accepted-state form `T.laplacian()` (no argument: Appendix B.3) and step(dt) spanning several max_steps."""
+    G = add_weights(g_grid(12, 9), 5)
+    T = api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: 0.7 * T.laplacian(), max_step=4e-3, scheme=scheme)
+    rng = np.random.default_rng(7)
+    y0 = rng.random(T.ndim)
+    T.set_initial(y0=lambda x: y0[T.X[x]])
+
+    def dirichlet(t, x):
+        if x[0] == 0 or x[0] == 11:
+            return 0.5
+        if x[1] == 0:
+            return 1.0 + 0.1 * t
+        return None
+
+    def neumann(t, x):
+        if x[1] == 8 and x[0] not in (0, 11):
+            return -0.1
+        return None
+    T.set_constraints(dirichlet=dirichlet, neumann=neumann)
+    return _snap(T, {'T': T}, 1e-2, 40, 10)   # dt = 2.5 max_steps -> 3 internal steps, the last one shorter
+
+
+def case_reaction_diffusion(api):
+    """stage-argument form with pointwise nonlinearity: dy/dt = 0.3*L y + y - y**3 (Allen-Cahn pattern)."""
+    G = g_tri(6, 9)
+    T = api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: 0.3 * T.laplacian(y) + y - y ** 3, max_step=5e-3)
+    rng = np.random.default_rng(21)
+    y0 = rng.uniform(-1, 1, T.ndim)
+    T.set_initial(y0=lambda x: y0[T.X[x]])
+    return _snap(T, {'T': T}, 5e-3, 60, 20)
+
+
+def case_hex_advdiff_c2(api, m=6, n=8, nsteps=50, every=25):
+    """BASELINE config 2 at small size: edge diffusion (Hodge-1 Laplacian, Dirichlet 0 on top/bottom edges)
+    coupled with node advection-diffusion (Neumann on top row), RK4 h=1e-3."""
+    G = g_hex(m, n)
+    u = api.edge_gds(G)
+    c = api.node_gds(G)
+    nu, kappa = 0.1, 0.05
+    api.evolve(u, dydt=lambda t, y: nu * u.laplacian(y), max_step=1e-3)
+    api.evolve(c, dydt=lambda t, y: -c.advect(u) + kappa * c.laplacian(y), max_step=1e-3)
+    rng0, rng1 = np.random.default_rng(0), np.random.default_rng(1)
+    u0 = 0.1 * rng0.standard_normal(u.ndim)
+    c0 = rng1.random(c.ndim)
+    u.set_initial(y0=lambda e: u0[u.X[e]])
+    c.set_initial(y0=lambda x: c0[c.X[x]])
+    u.set_constraints(dirichlet=api.zero_edge_bc(boundary_edges_hex_top_bottom(G)))
+    pos = nx.get_node_attributes(G, 'pos')
+    ytop = max(p[1] for p in pos.values())
+    c.set_constraints(neumann=lambda x: -0.1 if pos[x][1] > ytop - 1e-9 else None)
+    sysobj = api.couple({'u': u, 'c': c})
+    return _snap(sysobj, {'u': u, 'c': c}, 1e-3, nsteps, every)
+
+
+def case_ns_cavity_c3(api, m=6, n=10, nsteps=40, every=20):
+    """BASELINE config 3 at small size: Navier-Stokes velocity law (examples/fluid.py:33-34) on a triangular
+    lattice with the pressure held as a given node vector; lid const_edge_bc (time-varying form), no-slip walls
+    (examples/lid_driven_cavity.py:17-27).  Accepted-state operators (no y argument), RK4 h=1e-4."""
+    G = g_tri(m, n)
+    p = api.node_gds(G)
+    u = api.edge_gds(G)
+    rho, visc = 0.1, 200.0
+    rngp = np.random.default_rng(3)
+    p0 = 0.01 * rngp.standard_normal(p.ndim)
+    api.evolve_nil(p)
+    p.set_initial(y0=lambda x: p0[p.X[x]])
+    api.evolve(u, dydt=lambda t, y: -u.advect() - p.grad() / rho + u.laplacian() * visc / rho, max_step=1e-4)
+    rngu = np.random.default_rng(4)
+    u0 = 0.05 * rngu.standard_normal(u.ndim)
+    u.set_initial(y0=lambda e: u0[u.X[e]])
+    lid, walls = tri_boundaries(G)
+    lid_bc = api.const_edge_bc(lid, 10.0)
+    u.set_constraints(dirichlet=api.combine_bcs(api.zero_edge_bc(walls), lambda t, e: lid_bc(e)))
+    sysobj = api.couple({'u': u, 'p': p})
+    return _snap(sysobj, {'u': u}, 1e-4, nsteps, every)
+
+
+def case_wave_c5(api, dims=(6, 7, 8), nsteps=50, every=25):
+    """BASELINE config 5 at small size: wave equation on a 3-D grid, order=2, accepted-state Laplacian
+    (examples/wave.py:14), RK4 h=0.1, no Dirichlet."""
+    G = g_grid3(dims)
+    a = api.node_gds(G)
+    c2 = 1.0
+    api.evolve(a, dydt=lambda t, y: c2 * a.laplacian(), order=2, max_step=0.1)
+    ctr = [(d - 1) / 2 for d in dims[::-1]]
+    a.set_initial(y0=lambda x: math.exp(-sum((xi - ci) ** 2 for xi, ci in zip(x, ctr)) / 4.0))
+    return _snap(a, {'a': a}, 0.1, nsteps, every)
+
+
+def cml_map(eps=0.3, deg=8.0):
+    return lambda x, y: (1 - 1.7 * y ** 2) + (eps / deg) * x.laplacian(1 - 1.7 * y ** 2)
+
+
+def case_cml_c4(api, n=400, iters=30, every=10):
+    """BASELINE config 4 at small size: coupled map lattice on a random geometric graph, map mode."""
+    r = math.sqrt(8 / (math.pi * n))
+    G = g_rgg(n, r, 42)
+    x = api.node_gds(G)
+    f = cml_map()
+    api.evolve_map(x, map_fun=lambda t, y: f(x, y), dt=1.0)
+    y0 = np.random.default_rng(2).uniform(-1, 1, x.ndim)
+    x.set_initial(y0=lambda v: y0[x.X[v]])
+    return _snap(x, {'x': x}, 1.0, iters, every)
+
+
+TRAJ_CASES = {
+    'heat_c1': case_heat_c1,
+    'heat_c1_euler_small': lambda api: case_heat_c1(api, n=20, nsteps=100, every=50, scheme='euler'),
+    'heat_mixed': case_heat_mixed,
+    'reaction_diffusion': case_reaction_diffusion,
+    'hex_advdiff_c2': case_hex_advdiff_c2,
+    'ns_cavity_c3': case_ns_cavity_c3,
+    'wave_c5': case_wave_c5,
+    'cml_c4': case_cml_c4,
+}

@@ -1,0 +1,43 @@
+"""The CPU oracle (oracle/gds_oracle.py) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  Index maps must be bit-exact; float64 results within 1e-12 relative L2
+(north_star bar for the product is 1e-10)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from adaptors import oracle_api, rel_l2
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = 1e-12
+INT_KEYS = ('map_edges', 'map_faces_ptr', 'map_faces_nodes', 'n_faces')
+
+
+@pytest.mark.parametrize('gname', list(cases.OP_GRAPHS))
+def test_operators_match_reference(gname):
+    gold = np.load(os.path.join(GOLD, f'ops_{gname}.npz'))
+    out = cases.operator_outputs(oracle_api(), gname)
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        if k in INT_KEYS or k == 'map_nodes_repr':
+            assert np.array_equal(out[k], gold[k]), k      # index maps: bit-exact
+        elif k.startswith('in_') or k == 'edge_weights':
+            assert np.array_equal(out[k], gold[k]), k      # same seeded inputs
+        else:
+            assert rel_l2(out[k], gold[k]) <= TOL, (k, rel_l2(out[k], gold[k]))
+
+
+@pytest.mark.parametrize('cname', list(cases.TRAJ_CASES))
+def test_trajectories_match_reference(cname):
+    gold = np.load(os.path.join(GOLD, f'traj_{cname}.npz'))
+    out = cases.TRAJ_CASES[cname](oracle_api())
+    assert set(out) == set(gold.files)
+    assert np.allclose(out['t'], gold['t'], rtol=0, atol=1e-12)
+    for k in gold.files:
+        if k == 't':
+            continue
+        assert np.all(np.isfinite(gold[k]))
+        for i in range(gold[k].shape[0]):
+            err = rel_l2(out[k][i], gold[k][i])
+            assert err <= TOL, (cname, k, i, err)
