@@ -1,0 +1,737 @@
+// C-ABI implementation: contexts, device vectors, graph upload, pass resolution, systems and CUDA-graph stepping.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+static thread_local std::string g_last_error;
+void gds_set_error(const std::string& msg) { g_last_error = msg; }
+
+extern "C" const char* gds_last_error(void) { return g_last_error.c_str(); }
+extern "C" int gds_abi_version(void) { return GDS_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_ctx_create(int device, gds_ctx** out) {
+  if (!out) GDS_FAIL("null out");
+  int ndev = 0;
+  GDS_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) GDS_FAIL("no such CUDA device");
+  GDS_CUDA(cudaSetDevice(device));
+  gds_ctx* c = new gds_ctx();
+  c->device = device;
+  GDS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  GDS_CUDA(cudaEventCreate(&c->ev0));
+  GDS_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return 0;
+}
+
+extern "C" int gds_ctx_destroy(gds_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int gds_ctx_set_stream(gds_ctx* c, void* s) {
+  if (!c) GDS_FAIL("null ctx");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return 0;
+}
+
+extern "C" int gds_ctx_sync(gds_ctx* c) {
+  if (!c) GDS_FAIL("null ctx");
+  GDS_CUDA(cudaSetDevice(c->device));
+  GDS_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gds_ctx_timer_start(gds_ctx* c) {
+  GDS_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+
+extern "C" int gds_ctx_timer_stop(gds_ctx* c, double* ms_out) {
+  GDS_CUDA(cudaEventRecord(c->ev1, c->stream));
+  GDS_CUDA(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  GDS_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (ms_out) *ms_out = (double)ms;
+  return 0;
+}
+
+extern "C" int gds_ctx_counters(gds_ctx* c, int64_t* kl, int64_t* gr) {
+  if (kl) *kl = c->kernel_launches;
+  if (gr) *gr = c->graph_replays;
+  return 0;
+}
+
+extern "C" int gds_ctx_flush_l2(gds_ctx* c, int64_t bytes) {
+  GDS_CUDA(cudaSetDevice(c->device));
+  if (bytes > c->flush_bytes) {
+    if (c->flush_buf) GDS_CUDA(cudaFree(c->flush_buf));
+    c->flush_buf = nullptr;
+    GDS_CUDA(cudaMalloc(&c->flush_buf, (size_t)bytes));
+    c->flush_bytes = bytes;
+  }
+  GDS_CUDA(cudaMemsetAsync(c->flush_buf, 0, (size_t)bytes, c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device vectors and masks
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_buf_create(gds_ctx* c, int64_t n, gds_buf** out) {
+  if (!c || !out || n < 0) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(c->device));
+  gds_buf* b = new gds_buf();
+  b->ctx = c;
+  b->n = n;
+  // +4 doubles: double4 stores of the aggregate pass never run past the allocation
+  GDS_CUDA(cudaMalloc((void**)&b->d, (size_t)(n + 4) * sizeof(double)));
+  GDS_CUDA(cudaMemsetAsync(b->d, 0, (size_t)(n + 4) * sizeof(double), c->stream));
+  *out = b;
+  return 0;
+}
+
+extern "C" int gds_buf_destroy(gds_buf* b) {
+  if (!b) return 0;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  cudaFree(b->d);
+  delete b;
+  return 0;
+}
+
+extern "C" int gds_buf_upload(gds_buf* b, int64_t off, const double* host, int64_t n) {
+  if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  GDS_CUDA(cudaSetDevice(b->ctx->device));
+  GDS_CUDA(cudaMemcpyAsync(b->d + off, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  return 0;
+}
+
+extern "C" int gds_buf_download(gds_buf* b, int64_t off, double* host, int64_t n) {
+  if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  GDS_CUDA(cudaSetDevice(b->ctx->device));
+  GDS_CUDA(cudaMemcpyAsync(host, b->d + off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(b->ctx->stream));
+  return 0;
+}
+
+extern "C" int gds_buf_fill(gds_buf* b, int64_t off, int64_t n, double v) {
+  if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  GDS_CUDA(cudaSetDevice(b->ctx->device));
+  return launch_fill(b->ctx, b->d + off, n, v);
+}
+
+extern "C" int gds_buf_devptr(gds_buf* b, void** dev_out, int64_t* n_out) {
+  if (!b) GDS_FAIL("null buffer");
+  if (dev_out) *dev_out = b->d;
+  if (n_out) *n_out = b->n;
+  return 0;
+}
+
+extern "C" int gds_mask_create(gds_ctx* c, int64_t n_rows, const int64_t* rows, int64_t n, gds_mask** out) {
+  if (!c || !out || n_rows < 0 || n < 0) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(c->device));
+  int64_t words = (n_rows + 31) / 32 + 1;
+  std::vector<uint32_t> bits((size_t)words, 0u);
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t r = rows[i];
+    if (r < 0 || r >= n_rows) GDS_FAIL("mask row out of range");
+    bits[(size_t)(r >> 5)] |= (1u << (r & 31));
+  }
+  gds_mask* m = new gds_mask();
+  m->ctx = c; m->n_rows = n_rows; m->n_set = n;
+  GDS_CUDA(cudaMalloc((void**)&m->d, (size_t)words * 4));
+  GDS_CUDA(cudaMemcpyAsync(m->d, bits.data(), (size_t)words * 4, cudaMemcpyHostToDevice, c->stream));
+  GDS_CUDA(cudaStreamSynchronize(c->stream));
+  *out = m;
+  return 0;
+}
+
+extern "C" int gds_mask_destroy(gds_mask* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->d);
+  delete m;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// graph upload
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(gds_graph* g, const std::vector<T>& h, const T** dev) {
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  void* d = nullptr;
+  GDS_CUDA(cudaMalloc(&d, bytes));
+  if (!h.empty()) GDS_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  g->allocs.push_back(d);
+  g->device_bytes += (int64_t)bytes;
+  *dev = (const T*)d;
+  return 0;
+}
+
+// CSR rows -> sliced-ELL offsets; slot(row, j) = soff[row/32]*32 + j*32 + row%32
+static void sell_offsets(int64_t n_rows, const std::vector<int64_t>& ptr, std::vector<uint32_t>& soff) {
+  int64_t n_slices = (n_rows + GDS_SLICE - 1) / GDS_SLICE;
+  soff.assign((size_t)n_slices + 2, 0u);
+  for (int64_t s = 0; s < n_slices; ++s) {
+    int64_t wmax = 0;
+    int64_t r1 = std::min(n_rows, (s + 1) * GDS_SLICE);
+    for (int64_t r = s * GDS_SLICE; r < r1; ++r) wmax = std::max(wmax, ptr[r + 1] - ptr[r]);
+    soff[s + 1] = soff[s] + (uint32_t)wmax;
+  }
+  soff[n_slices + 1] = soff[n_slices];
+}
+
+extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t* eu, const int32_t* ev,
+                                const double* w, int64_t F, const int64_t* face_ptr, const int32_t* face_nodes,
+                                gds_graph** out) {
+  if (!c || !out) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(c->device));
+  gds_graph* g = new gds_graph();
+  g->ctx = c;
+  int rc = lower_graph_host(V, E, eu, ev, w, F, face_ptr, face_nodes, g->h);
+  if (rc) { delete g; return rc; }
+  HostGraph& h = g->h;
+  GraphDev& d = g->d;
+  memset(&d, 0, sizeof(d));
+  d.V = V; d.E = E; d.F = F;
+  // node incidence
+  {
+    std::vector<uint32_t> soff;
+    sell_offsets(V, h.n_ptr, soff);
+    int64_t slots = (int64_t)soff[soff.size() - 1] * GDS_SLICE;
+    std::vector<int32_t> nbr((size_t)slots), edge((size_t)slots, -1);
+    std::vector<double> wv((size_t)slots, 0.0);
+    for (int64_t x = 0; x < V; ++x) {
+      int64_t base = (int64_t)soff[x >> 5] * GDS_SLICE + (x & 31);
+      int64_t width = soff[(x >> 5) + 1] - soff[x >> 5];
+      int64_t deg = h.n_ptr[x + 1] - h.n_ptr[x];
+      for (int64_t j = 0; j < width; ++j) {
+        int64_t slot = base + j * GDS_SLICE;
+        if (j < deg) {
+          int64_t a = h.n_ptr[x] + j;
+          nbr[slot] = h.n_nbr[a];
+          edge[slot] = (h.n_edge[a] << 1) | (h.n_sign[a] > 0 ? 1 : 0);
+          wv[slot] = h.w[h.n_edge[a]];
+        } else {
+          nbr[slot] = (int32_t)x;
+        }
+      }
+    }
+    // lanes of a partial last slice that are not rows: keep gathers in range
+    for (int64_t x = V; x < ((V + 31) / 32) * 32; ++x) {
+      int64_t base = (int64_t)soff[x >> 5] * GDS_SLICE + (x & 31);
+      int64_t width = soff[(x >> 5) + 1] - soff[x >> 5];
+      for (int64_t j = 0; j < width; ++j) nbr[base + j * GDS_SLICE] = 0;
+    }
+    GDS_TRY(upload(g, soff, &d.n_soff));
+    GDS_TRY(upload(g, nbr, &d.n_nbr));
+    GDS_TRY(upload(g, edge, &d.n_edge));
+    GDS_TRY(upload(g, wv, &d.n_w));
+    GDS_TRY(upload(g, h.n_dinv, &d.n_dinv));
+  }
+  GDS_TRY(upload(g, h.eu, &d.e_u));
+  GDS_TRY(upload(g, h.ev, &d.e_v));
+  GDS_TRY(upload(g, h.omega, &d.e_omega));
+  GDS_TRY(upload(g, h.w, &d.e_w));
+  // edge -> faces and face -> edges
+  auto pack = [](int64_t n_rows, const std::vector<int64_t>& ptr, const std::vector<int32_t>& idx,
+                 const std::vector<int8_t>& sign, std::vector<uint32_t>& soff, std::vector<int32_t>& packed) {
+    sell_offsets(n_rows, ptr, soff);
+    int64_t slots = (int64_t)soff[soff.size() - 1] * GDS_SLICE;
+    packed.assign((size_t)slots, -1);
+    for (int64_t r = 0; r < n_rows; ++r) {
+      int64_t base = (int64_t)soff[r >> 5] * GDS_SLICE + (r & 31);
+      for (int64_t a = ptr[r]; a < ptr[r + 1]; ++a)
+        packed[base + (a - ptr[r]) * GDS_SLICE] = (idx[a] << 1) | (sign[a] < 0 ? 1 : 0);
+    }
+  };
+  {
+    std::vector<uint32_t> soff;
+    std::vector<int32_t> packed;
+    pack(E, h.ef_ptr, h.ef_face, h.ef_sign, soff, packed);
+    GDS_TRY(upload(g, soff, &d.ef_soff));
+    GDS_TRY(upload(g, packed, &d.ef_face));
+    pack(F, h.f_ptr, h.f_edge, h.f_sign, soff, packed);
+    GDS_TRY(upload(g, soff, &d.fe_soff));
+    GDS_TRY(upload(g, packed, &d.fe_edge));
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int gds_graph_destroy(gds_graph* g) {
+  if (!g) return 0;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+  return 0;
+}
+
+extern "C" int gds_graph_sizes(gds_graph* g, int64_t* V, int64_t* E, int64_t* F) {
+  if (!g) GDS_FAIL("null graph");
+  if (V) *V = g->h.V;
+  if (E) *E = g->h.E;
+  if (F) *F = g->h.F;
+  return 0;
+}
+
+extern "C" int gds_graph_device_bytes(gds_graph* g, int64_t* bytes) {
+  if (!g) GDS_FAIL("null graph");
+  if (bytes) *bytes = g->device_bytes;
+  return 0;
+}
+
+extern "C" int gds_graph_export_csr(gds_graph* g, int32_t kind, int64_t* n_rows, int64_t* nnz, int64_t* ptr,
+                                    int32_t* idx, int32_t* sign) {
+  if (!g) GDS_FAIL("null graph");
+  const HostGraph& h = g->h;
+  const std::vector<int64_t>* p;
+  const std::vector<int32_t>* i;
+  const std::vector<int8_t>* s;
+  int64_t rows;
+  if (kind == 0) { p = &h.n_ptr; i = &h.n_edge; s = &h.n_sign; rows = h.V; }
+  else if (kind == 1) { p = &h.f_ptr; i = &h.f_edge; s = &h.f_sign; rows = h.F; }
+  else if (kind == 2) { p = &h.ef_ptr; i = &h.ef_face; s = &h.ef_sign; rows = h.E; }
+  else GDS_FAIL("unknown kind");
+  if (n_rows) *n_rows = rows;
+  if (nnz) *nnz = (int64_t)i->size();
+  if (ptr) std::copy(p->begin(), p->end(), ptr);
+  if (idx) std::copy(i->begin(), i->end(), idx);
+  if (sign) for (size_t a = 0; a < s->size(); ++a) sign[a] = (*s)[a];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass resolution
+// ---------------------------------------------------------------------------------------------------
+static int64_t domain_rows(const gds_graph* g, int32_t domain) {
+  if (domain == GDS_NODES) return g->h.V;
+  if (domain == GDS_EDGES) return g->h.E;
+  if (domain == GDS_FACES) return g->h.F;
+  return -1;
+}
+
+static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
+  if (!p) GDS_FAIL("null pass");
+  if (p->n_code < 0 || p->n_code > GDS_MAX_CODE) GDS_FAIL("row program too long");
+  if (p->n_imm < 0 || p->n_imm > GDS_MAX_IMM) GDS_FAIL("too many immediates");
+  if (p->n_vec < 0 || p->n_vec > GDS_MAX_VEC) GDS_FAIL("too many vector operands");
+  if (p->n_mask < 0 || p->n_mask > GDS_MAX_MASK) GDS_FAIL("too many masks");
+  if (p->n_out < 0 || p->n_out > GDS_MAX_OUT) GDS_FAIL("too many outputs");
+  ph.domain = p->domain; ph.when = p->when;
+  ph.code.assign(p->code, p->code + p->n_code);
+  ph.imm.assign(p->imm, p->imm + p->n_imm);
+  ph.vec.assign(p->vec, p->vec + p->n_vec);
+  ph.mask.assign(p->mask, p->mask + p->n_mask);
+  ph.out.assign(p->out, p->out + p->n_out);
+  ph.out_offset.assign(p->n_out, 0);
+  if (p->out_offset) ph.out_offset.assign(p->out_offset, p->out_offset + p->n_out);
+  ph.epilogue = p->epilogue;
+  ph.state_offset = p->state_offset;
+  ph.dirichlet = p->dirichlet;
+  // static validation of the row program: opcodes, operand indices, stack depth
+  int depth = 0, maxdepth = 0;
+  for (uint32_t ins : ph.code) {
+    uint32_t op = ins & 0xff, a = (ins >> 8) & 0xff, b = (ins >> 16) & 0xff;
+    int push = 0, pop = 0;
+    switch (op) {
+      case GDS_OP_END: break;
+      case GDS_OP_PUSH_VEC: if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range"); push = 1; break;
+      case GDS_OP_PUSH_IMM: if ((int)a >= p->n_imm) GDS_FAIL("immediate index out of range"); push = 1; break;
+      case GDS_OP_PUSH_T: case GDS_OP_PUSH_H: push = 1; break;
+      case GDS_OP_DUP: pop = 1; push = 2; break;
+      case GDS_OP_SWAP: pop = 2; push = 2; break;
+      case GDS_OP_POP: pop = 1; break;
+      case GDS_OP_SETL: if (a >= 4) GDS_FAIL("local index out of range"); pop = 1; push = 1; break;
+      case GDS_OP_GETL: if (a >= 4) GDS_FAIL("local index out of range"); push = 1; break;
+      case GDS_OP_STORE: if ((int)a >= p->n_out) GDS_FAIL("output index out of range"); pop = 1; push = 1; break;
+      case GDS_OP_MASK_ZERO: if ((int)a >= p->n_mask) GDS_FAIL("mask index out of range"); pop = 1; push = 1; break;
+      case GDS_OP_ADD: case GDS_OP_SUB: case GDS_OP_MUL: case GDS_OP_DIV: case GDS_OP_POW: case GDS_OP_MAX:
+      case GDS_OP_MIN: case GDS_OP_ATAN2: pop = 2; push = 1; break;
+      case GDS_OP_NEG: case GDS_OP_ABS: case GDS_OP_SIGN: case GDS_OP_SQRT: case GDS_OP_EXP: case GDS_OP_LOG:
+      case GDS_OP_SIN: case GDS_OP_COS: case GDS_OP_TAN: case GDS_OP_TANH: case GDS_OP_SINH: case GDS_OP_COSH:
+      case GDS_OP_ATAN: case GDS_OP_SQUARE: case GDS_OP_RECIP: case GDS_OP_POWI: pop = 1; push = 1; break;
+      case GDS_OP_N_LAP: case GDS_OP_N_BDOT: case GDS_OP_N_INFLUX: case GDS_OP_N_OUTFLUX:
+        if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
+        if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        push = 1; break;
+      case GDS_OP_N_ADVECT: case GDS_OP_N_LIE:
+        if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
+        if ((int)a >= p->n_vec || (int)b >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        push = 1; break;
+      case GDS_OP_N_EAGG:
+        if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
+        if ((int)a >= p->n_vec || (int)b >= p->n_out) GDS_FAIL("operand index out of range");
+        break;
+      case GDS_OP_E_GRADT: case GDS_OP_E_CURLT:
+        if (p->domain != GDS_EDGES) GDS_FAIL("edge gather in a non-edge pass");
+        if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        push = 1; break;
+      case GDS_OP_E_ADVFIN:
+        if (p->domain != GDS_EDGES) GDS_FAIL("edge gather in a non-edge pass");
+        if ((int)a >= p->n_vec || (int)b >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        push = 1; break;
+      case GDS_OP_F_CURL:
+        if (p->domain != GDS_FACES) GDS_FAIL("face gather in a non-face pass");
+        if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        push = 1; break;
+      default: GDS_FAIL("unknown opcode " + std::to_string(op));
+    }
+    if (depth < pop) GDS_FAIL("row program pops an empty stack");
+    depth += push - pop;
+    maxdepth = std::max(maxdepth, depth);
+  }
+  if (maxdepth > 6) GDS_FAIL("row program needs a stack deeper than 6");
+  if (ph.epilogue == GDS_EPI_RHS && depth < 1) GDS_FAIL("RHS pass leaves nothing on the stack");
+  return 0;
+}
+
+// Resolve a host pass into launch parameters.  `state`/`stage` may be null for eager passes.
+static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* state, const double* stage,
+                        PassParams& pp) {
+  memset(&pp, 0, sizeof(pp));
+  pp.g = g->d;
+  pp.n_rows = domain_rows(g, ph.domain);
+  if (pp.n_rows < 0) GDS_FAIL("unknown domain");
+  pp.n_code = (int32_t)ph.code.size();
+  for (size_t i = 0; i < ph.code.size(); ++i) pp.code[i] = ph.code[i];
+  for (size_t i = 0; i < ph.imm.size(); ++i) pp.imm[i] = ph.imm[i];
+  for (size_t i = 0; i < ph.vec.size(); ++i) {
+    const gds_vecref& v = ph.vec[i];
+    if (v.kind == GDS_VEC_BUF) {
+      if (!v.buf) GDS_FAIL("null buffer operand");
+      if (v.offset < 0 || v.offset > v.buf->n) GDS_FAIL("operand offset outside buffer");
+      pp.vec[i] = v.buf->d + v.offset;
+    } else if (v.kind == GDS_VEC_STATE) {
+      if (!state) GDS_FAIL("state operand outside a system");
+      pp.vec[i] = state + v.offset;
+    } else if (v.kind == GDS_VEC_STAGE) {
+      if (!stage) GDS_FAIL("stage operand outside a system");
+      pp.vec[i] = stage + v.offset;
+    } else {
+      GDS_FAIL("unknown operand kind");
+    }
+  }
+  for (size_t i = 0; i < ph.mask.size(); ++i) {
+    if (!ph.mask[i]) GDS_FAIL("null mask");
+    if (ph.mask[i]->n_rows < pp.n_rows) GDS_FAIL("mask shorter than the pass domain");
+    pp.mask[i] = ph.mask[i]->d;
+  }
+  for (size_t i = 0; i < ph.out.size(); ++i) {
+    if (!ph.out[i]) GDS_FAIL("null output buffer");
+    pp.out[i] = ph.out[i]->d + ph.out_offset[i];
+  }
+  pp.epilogue = ph.epilogue;
+  return 0;
+}
+
+extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass, double t) {
+  if (!c || !g) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(c->device));
+  PassHost ph;
+  GDS_TRY(copy_pass(pass, ph));
+  if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("eager passes take GDS_EPI_NONE");
+  PassParams pp;
+  GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
+  pp.t_fixed = t;
+  return launch_pass(c, pp, ph.domain);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// systems
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int32_t scheme, gds_system** out) {
+  if (!c || !g || !out || n_state <= 0) GDS_FAIL("bad argument");
+  if (scheme != GDS_SCHEME_EULER && scheme != GDS_SCHEME_RK4 && scheme != GDS_SCHEME_MAP) GDS_FAIL("unknown scheme");
+  GDS_CUDA(cudaSetDevice(c->device));
+  gds_system* s = new gds_system();
+  s->ctx = c; s->g = g; s->n_state = n_state; s->scheme = scheme;
+  size_t bytes = (size_t)(n_state + 4) * sizeof(double);
+  for (int i = 0; i < 2; ++i) {
+    GDS_CUDA(cudaMalloc((void**)&s->Y[i], bytes));
+    GDS_CUDA(cudaMemsetAsync(s->Y[i], 0, bytes, c->stream));
+    s->device_bytes += (int64_t)bytes;
+  }
+  if (scheme == GDS_SCHEME_RK4) {
+    for (int i = 0; i < 2; ++i) {
+      GDS_CUDA(cudaMalloc((void**)&s->XS[i], bytes));
+      GDS_CUDA(cudaMemsetAsync(s->XS[i], 0, bytes, c->stream));
+      s->device_bytes += (int64_t)bytes;
+    }
+    GDS_CUDA(cudaMalloc((void**)&s->ACC, bytes));
+    GDS_CUDA(cudaMemsetAsync(s->ACC, 0, bytes, c->stream));
+    s->device_bytes += (int64_t)bytes;
+  }
+  GDS_CUDA(cudaMalloc((void**)&s->d_counter, sizeof(int64_t)));
+  GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  *out = s;
+  return 0;
+}
+
+extern "C" int gds_system_destroy(gds_system* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (s->exec[i]) cudaGraphExecDestroy(s->exec[i]);
+    if (s->graph[i]) cudaGraphDestroy(s->graph[i]);
+    cudaFree(s->Y[i]);
+    cudaFree(s->XS[i]);
+  }
+  cudaFree(s->ACC);
+  cudaFree(s->d_dir_idx_static); cudaFree(s->d_dir_val_static); cudaFree(s->d_dir_idx_dyn);
+  cudaFree(s->d_bc_tab); cudaFree(s->d_steptab); cudaFree(s->d_counter);
+  delete s;
+  return 0;
+}
+
+extern "C" int gds_system_add_pass(gds_system* s, const gds_pass_desc* pass) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("system already finalized");
+  PassHost ph;
+  GDS_TRY(copy_pass(pass, ph));
+  if (ph.when != GDS_WHEN_STAGE && ph.when != GDS_WHEN_STEP) GDS_FAIL("unknown `when`");
+  int64_t rows = domain_rows(s->g, ph.domain);
+  if (rows < 0) GDS_FAIL("unknown domain");
+  if (ph.epilogue == GDS_EPI_RHS) {
+    if (ph.when != GDS_WHEN_STAGE) GDS_FAIL("an RHS pass runs every stage");
+    if (ph.state_offset < 0 || ph.state_offset + rows > s->n_state) GDS_FAIL("RHS rows outside the state vector");
+    if (ph.dirichlet && ph.dirichlet->n_rows < rows) GDS_FAIL("Dirichlet mask shorter than the pass domain");
+  } else if (ph.epilogue != GDS_EPI_NONE) {
+    GDS_FAIL("unknown epilogue");
+  }
+  for (auto& v : ph.vec) {
+    if (ph.when == GDS_WHEN_STEP && v.kind == GDS_VEC_STAGE) GDS_FAIL("a per-step pass cannot read the stage state");
+    if ((v.kind == GDS_VEC_STATE || v.kind == GDS_VEC_STAGE) && (v.offset < 0 || v.offset > s->n_state))
+      GDS_FAIL("operand offset outside the state vector");
+  }
+  s->passes.push_back(ph);
+  return 0;
+}
+
+static int add_special(gds_system* s, int32_t special, int64_t dst, int64_t src, int64_t n) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("system already finalized");
+  if (n < 0 || dst < 0 || dst + n > s->n_state || src < 0 || src + n > s->n_state) GDS_FAIL("rows outside the state vector");
+  PassHost ph;
+  ph.domain = GDS_NODES; ph.when = GDS_WHEN_STAGE;
+  ph.epilogue = GDS_EPI_RHS; ph.state_offset = dst; ph.dirichlet = nullptr;
+  ph.special = special; ph.sp_dst = dst; ph.sp_src = src; ph.sp_n = n;
+  if (special == 1) {
+    ph.code = {GDS_OP_PUSH_VEC};
+    gds_vecref v; v.kind = GDS_VEC_STAGE; v.buf = nullptr; v.offset = src;
+    ph.vec = {v};
+  } else {
+    ph.code = {GDS_OP_PUSH_IMM};
+    ph.imm = {0.0};
+  }
+  s->passes.push_back(ph);
+  return 0;
+}
+
+extern "C" int gds_system_add_shift(gds_system* s, int64_t dst, int64_t src, int64_t n) { return add_special(s, 1, dst, src, n); }
+extern "C" int gds_system_add_hold(gds_system* s, int64_t off, int64_t n) { return add_special(s, 2, off, off, n); }
+
+extern "C" int gds_system_set_dirichlet(gds_system* s, const int64_t* idx, const double* values, int64_t n, int32_t dynamic) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("system already finalized");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  for (int64_t i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= s->n_state) GDS_FAIL("Dirichlet index outside the state vector");
+  if (n == 0) return 0;
+  if (dynamic) {
+    if (s->d_dir_idx_dyn) GDS_FAIL("dynamic Dirichlet set twice");
+    GDS_CUDA(cudaMalloc((void**)&s->d_dir_idx_dyn, (size_t)n * 8));
+    GDS_CUDA(cudaMemcpy(s->d_dir_idx_dyn, idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+    s->n_dir_dyn = n;
+  } else {
+    if (s->d_dir_idx_static) GDS_FAIL("static Dirichlet set twice");
+    if (!values) GDS_FAIL("static Dirichlet needs values");
+    GDS_CUDA(cudaMalloc((void**)&s->d_dir_idx_static, (size_t)n * 8));
+    GDS_CUDA(cudaMalloc((void**)&s->d_dir_val_static, (size_t)n * 8));
+    GDS_CUDA(cudaMemcpy(s->d_dir_idx_static, idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+    GDS_CUDA(cudaMemcpy(s->d_dir_val_static, values, (size_t)n * 8, cudaMemcpyHostToDevice));
+    s->n_dir_static = n;
+  }
+  return 0;
+}
+
+static int ensure_step_capacity(gds_system* s, int64_t n_steps) {
+  if (n_steps <= s->cap_steps) return 0;
+  if (s->finalized) GDS_FAIL("internal: step tables cannot grow after capture");
+  return 0;
+}
+
+// enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
+static int enqueue_step(gds_system* s, int cur) {
+  gds_ctx* c = s->ctx;
+  const double* yn = s->Y[cur];
+  double* ynew = s->Y[cur ^ 1];
+  int n_stages = (s->scheme == GDS_SCHEME_RK4) ? 4 : 1;
+  static const double a_next[4] = {0.5, 0.5, 1.0, 0.0};
+  static const double c_stage[4] = {0.0, 0.5, 0.5, 1.0};
+  static const double acc_w[4] = {1.0, 2.0, 2.0, 1.0};
+  // per-step passes (sub-expressions of the accepted state only)
+  for (const PassHost& ph : s->passes) {
+    if (ph.when != GDS_WHEN_STEP) continue;
+    PassParams pp;
+    GDS_TRY(resolve_pass(s->g, ph, yn, nullptr, pp));
+    pp.steptab = s->d_steptab; pp.step_counter = s->d_counter; pp.c_stage = 0.0;
+    GDS_TRY(launch_pass(c, pp, ph.domain));
+  }
+  for (int st = 0; st < n_stages; ++st) {
+    const double* stage = (st == 0) ? yn : s->XS[(st - 1) & 1];
+    double* xnext = (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : nullptr;
+    for (const PassHost& ph : s->passes) {
+      if (ph.when != GDS_WHEN_STAGE) continue;
+      PassParams pp;
+      GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
+      if (ph.special) pp.n_rows = ph.sp_n;
+      pp.steptab = s->d_steptab; pp.step_counter = s->d_counter;
+      pp.c_stage = (s->scheme == GDS_SCHEME_RK4) ? c_stage[st] : 0.0;
+      if (ph.epilogue == GDS_EPI_RHS) {
+        int64_t off = ph.state_offset;
+        pp.dmask = ph.dirichlet ? ph.dirichlet->d : nullptr;
+        pp.yn = yn + off;
+        pp.ynew = ynew + off;
+        if (s->scheme == GDS_SCHEME_RK4) {
+          pp.acc_in = s->ACC + off; pp.acc_out = s->ACC + off;
+          pp.xnext = xnext ? xnext + off : nullptr;
+          pp.acc_w = acc_w[st]; pp.a_next = a_next[st]; pp.fin = 1.0 / 6.0;
+          pp.stage_mode = (st == 0) ? 0 : (st == 3 ? 2 : 1);
+        } else if (s->scheme == GDS_SCHEME_EULER) {
+          pp.stage_mode = 3;
+        } else {
+          pp.stage_mode = 4;
+        }
+      }
+      GDS_TRY(launch_pass(c, pp, ph.domain));
+    }
+  }
+  // Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter
+  GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, nullptr, s->n_dir_static, 0, s->d_counter));
+  GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_dyn, nullptr, s->d_bc_tab, s->n_dir_dyn, s->n_dir_dyn, s->d_counter));
+  GDS_TRY(launch_advance_counter(c, s->d_counter));
+  return 0;
+}
+
+#define GDS_STEP_CAPACITY 4096  // steps per table upload; longer runs are chunked
+
+extern "C" int gds_system_finalize(gds_system* s) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) return 0;
+  gds_ctx* c = s->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  // every state row must be advanced by exactly one RHS pass
+  {
+    std::vector<std::pair<int64_t, int64_t>> cover;
+    for (const PassHost& ph : s->passes)
+      if (ph.epilogue == GDS_EPI_RHS)
+        cover.emplace_back(ph.state_offset, ph.special ? ph.sp_n : domain_rows(s->g, ph.domain));
+    std::sort(cover.begin(), cover.end());
+    int64_t at = 0;
+    for (auto& iv : cover) {
+      if (iv.first != at) GDS_FAIL("RHS passes do not tile the state vector (gap or overlap at " + std::to_string(at) + ")");
+      at += iv.second;
+    }
+    if (at != s->n_state) GDS_FAIL("RHS passes do not cover the state vector");
+  }
+  s->cap_steps = GDS_STEP_CAPACITY;
+  GDS_CUDA(cudaMalloc((void**)&s->d_steptab, (size_t)s->cap_steps * sizeof(StepRec)));
+  GDS_CUDA(cudaMemset(s->d_steptab, 0, (size_t)s->cap_steps * sizeof(StepRec)));
+  if (s->n_dir_dyn > 0) GDS_CUDA(cudaMalloc((void**)&s->d_bc_tab, (size_t)s->cap_steps * s->n_dir_dyn * 8));
+  if (c->stream != c->own_stream) GDS_FAIL("finalize on the context's own stream (an external stream cannot be captured here)");
+  for (int cur = 0; cur < 2; ++cur) {
+    int64_t before = c->kernel_launches;
+    GDS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(s, cur);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &s->graph[cur]);
+    if (rc) return rc;
+    if (e != cudaSuccess) GDS_FAIL(std::string("stream capture failed: ") + cudaGetErrorString(e));
+    GDS_CUDA(cudaGraphInstantiate(&s->exec[cur], s->graph[cur], 0));
+    s->kernels_per_step = c->kernel_launches - before;
+    c->kernel_launches = before;  // captured, not launched
+  }
+  s->finalized = true;
+  (void)ensure_step_capacity;
+  return 0;
+}
+
+extern "C" int gds_system_set_state(gds_system* s, const double* host, int64_t off, int64_t n) {
+  if (!s || off < 0 || n < 0 || off + n > s->n_state) GDS_FAIL("range outside the state vector");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  GDS_CUDA(cudaMemcpyAsync(s->Y[s->cur] + off, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return 0;
+}
+
+extern "C" int gds_system_get_state(gds_system* s, double* host, int64_t off, int64_t n) {
+  if (!s || off < 0 || n < 0 || off + n > s->n_state) GDS_FAIL("range outside the state vector");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  GDS_CUDA(cudaMemcpyAsync(host, s->Y[s->cur] + off, (size_t)n * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return 0;
+}
+
+extern "C" int gds_system_state_devptr(gds_system* s, void** dev_out) {
+  if (!s || !dev_out) GDS_FAIL("bad argument");
+  *dev_out = s->Y[s->cur];
+  return 0;
+}
+
+extern "C" int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (n_steps < 0) GDS_FAIL("negative step count");
+  if (s->n_dir_dyn > 0 && !bc) GDS_FAIL("dynamic Dirichlet values missing");
+  gds_ctx* c = s->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  std::vector<StepRec> tab;
+  int64_t done = 0;
+  while (done < n_steps) {
+    int64_t m = std::min<int64_t>(n_steps - done, s->cap_steps);
+    tab.resize((size_t)m);
+    for (int64_t i = 0; i < m; ++i) { tab[i].t = t[done + i]; tab[i].h = h[done + i]; }
+    // pageable source: the copy is staged before the call returns, so `tab` may be reused
+    GDS_CUDA(cudaMemcpyAsync(s->d_steptab, tab.data(), (size_t)m * sizeof(StepRec), cudaMemcpyHostToDevice, c->stream));
+    if (s->n_dir_dyn > 0)
+      GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc + done * s->n_dir_dyn, (size_t)m * s->n_dir_dyn * 8,
+                               cudaMemcpyHostToDevice, c->stream));
+    GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+    for (int64_t i = 0; i < m; ++i) {
+      GDS_CUDA(cudaGraphLaunch(s->exec[s->cur], c->stream));
+      s->cur ^= 1;
+      c->graph_replays++;
+      c->kernel_launches += s->kernels_per_step;
+    }
+    done += m;
+  }
+  return 0;
+}
+
+extern "C" int gds_system_info(gds_system* s, int64_t* kps, int64_t* bytes) {
+  if (!s) GDS_FAIL("null system");
+  if (kps) *kps = s->kernels_per_step;
+  if (bytes) *bytes = s->device_bytes;
+  return 0;
+}

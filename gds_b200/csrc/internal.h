@@ -1,0 +1,208 @@
+// Internal structures of the gds_b200 stepping core (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "gds_b200.h"
+
+#define GDS_SLICE 32  // rows per sliced-ELL slice = one warp
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+void gds_set_error(const std::string& msg);
+#define GDS_FAIL(msg)                                                                        \
+  do {                                                                                       \
+    gds_set_error(std::string(__func__) + ": " + (msg));                                     \
+    return 1;                                                                                \
+  } while (0)
+#define GDS_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      gds_set_error(std::string(__func__) + ": " #call " -> " + cudaGetErrorString(e__));    \
+      return 2;                                                                              \
+    }                                                                                        \
+  } while (0)
+#define GDS_TRY(call)                                                                        \
+  do {                                                                                       \
+    int r__ = (call);                                                                        \
+    if (r__) return r__;                                                                     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// sliced-ELL (slice = 32 rows = one warp; column-major inside a slice so that entry j of the 32 rows of a
+// slice is one contiguous 128-byte (int32) / 256-byte (double) line).  soff[s] = first entry of slice s in
+// units of 32 entries; width of slice s = soff[s+1]-soff[s].  Padding entries hold -1.
+// ---------------------------------------------------------------------------------------------------
+struct HostSell {
+  int64_t n_rows = 0;
+  std::vector<uint32_t> soff;  // n_slices + 1
+  int64_t n_slots = 0;         // = soff.back() * 32
+};
+
+// Host-side lowered graph (index maps kept for export / parity checks)
+struct HostGraph {
+  int64_t V = 0, E = 0, F = 0;
+  std::vector<int32_t> eu, ev;
+  std::vector<double> w, omega;
+  bool unit_weights = true;
+  // B1 rows: node -> incident (edge, sign), sorted by edge id
+  std::vector<int64_t> n_ptr;
+  std::vector<int32_t> n_edge, n_nbr;
+  std::vector<int8_t> n_sign;
+  std::vector<double> n_dinv;  // 1/(weighted degree - 1), inf -> 0 (gds.py:253-257)
+  // B2 rows: face -> (edge, sign) sorted by edge id ; B2 cols: edge -> (face, sign)
+  std::vector<int64_t> f_ptr;
+  std::vector<int32_t> f_edge;
+  std::vector<int8_t> f_sign;
+  std::vector<int64_t> ef_ptr;
+  std::vector<int32_t> ef_face;
+  std::vector<int8_t> ef_sign;
+};
+
+int lower_graph_host(int64_t V, int64_t E, const int32_t* eu, const int32_t* ev, const double* w, int64_t F,
+                     const int64_t* face_ptr, const int32_t* face_nodes, HostGraph& out);
+
+// Device view handed to kernels (by value inside PassParams)
+struct GraphDev {
+  int64_t V, E, F;
+  // node incidence, sliced-ELL over nodes
+  const uint32_t* n_soff;
+  const int32_t* n_nbr;   // neighbour node, padding = own row
+  const int32_t* n_edge;  // (edge << 1) | (1 if this node is the head v of the edge), padding = -1
+  const double* n_w;      // w_e, padding = 0
+  const double* n_dinv;   // [V]
+  // edges
+  const int32_t* e_u;
+  const int32_t* e_v;
+  const double* e_omega;  // sqrt(w)
+  const double* e_w;
+  // edge -> faces, sliced-ELL over edges: (face << 1) | (1 if B2[f,e] < 0), padding = -1
+  const uint32_t* ef_soff;
+  const int32_t* ef_face;
+  // face -> edges, sliced-ELL over faces: (edge << 1) | (1 if B2[f,e] < 0), padding = -1
+  const uint32_t* fe_soff;
+  const int32_t* fe_edge;
+};
+
+struct StepRec {  // one row of the per-step table
+  double t;       // step start time
+  double h;       // step size
+};
+
+// Parameters of one pass launch (passed by value: lives in the constant bank, warp-uniform reads)
+struct PassParams {
+  GraphDev g;
+  int64_t n_rows;
+  int32_t n_code;
+  uint32_t code[GDS_MAX_CODE];
+  double imm[GDS_MAX_IMM];
+  const double* vec[GDS_MAX_VEC];
+  const uint32_t* mask[GDS_MAX_MASK];
+  double* out[GDS_MAX_OUT];
+  // epilogue
+  int32_t epilogue;   // GDS_EPI_*
+  int32_t stage_mode; // 0 first, 1 middle, 2 last (with acc), 3 last (no acc: Euler), 4 map
+  const uint32_t* dmask;
+  const double* yn;
+  const double* acc_in;
+  double* acc_out;
+  double* xnext;
+  double* ynew;
+  double acc_w;    // weight of k in acc
+  double a_next;   // xnext = yn + a_next*h*k
+  double fin;      // ynew = yn + fin*h*(acc + k)
+  double c_stage;  // stage time = t + c_stage*h
+  const StepRec* steptab;
+  const int64_t* step_counter;
+  double t_fixed;  // used when steptab == nullptr (eager application)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// objects behind the opaque handles
+// ---------------------------------------------------------------------------------------------------
+struct gds_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t kernel_launches = 0;
+  int64_t graph_replays = 0;
+  void* flush_buf = nullptr;
+  int64_t flush_bytes = 0;
+};
+
+struct gds_buf {
+  gds_ctx* ctx;
+  double* d = nullptr;
+  int64_t n = 0;
+};
+
+struct gds_mask {
+  gds_ctx* ctx;
+  uint32_t* d = nullptr;
+  int64_t n_rows = 0;
+  int64_t n_set = 0;
+};
+
+struct gds_graph {
+  gds_ctx* ctx;
+  HostGraph h;
+  GraphDev d;
+  std::vector<void*> allocs;
+  int64_t device_bytes = 0;
+};
+
+struct PassHost {  // a pass as given by the host, operands still symbolic
+  int32_t domain, when;
+  std::vector<uint32_t> code;
+  std::vector<double> imm;
+  std::vector<gds_vecref> vec;
+  std::vector<gds_mask*> mask;
+  std::vector<gds_buf*> out;
+  std::vector<int64_t> out_offset;
+  int32_t epilogue;
+  int64_t state_offset;
+  gds_mask* dirichlet;
+  // shift / hold pseudo-passes
+  int32_t special = 0;  // 0 normal, 1 shift, 2 hold
+  int64_t sp_dst = 0, sp_src = 0, sp_n = 0;
+};
+
+struct gds_system {
+  gds_ctx* ctx;
+  gds_graph* g;
+  int64_t n_state = 0;
+  int32_t scheme = GDS_SCHEME_RK4;
+  double* Y[2] = {nullptr, nullptr};  // accepted state ping-pong
+  double* XS[2] = {nullptr, nullptr}; // stage state ping-pong
+  double* ACC = nullptr;
+  int cur = 0;                        // Y[cur] is the accepted state
+  std::vector<PassHost> passes;
+  // Dirichlet overwrite
+  int64_t n_dir_static = 0, n_dir_dyn = 0;
+  int64_t* d_dir_idx_static = nullptr;
+  double* d_dir_val_static = nullptr;
+  int64_t* d_dir_idx_dyn = nullptr;
+  double* d_bc_tab = nullptr;   // [cap_steps x n_dir_dyn]
+  StepRec* d_steptab = nullptr; // [cap_steps]
+  int64_t cap_steps = 0;
+  int64_t* d_counter = nullptr;
+  bool finalized = false;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};  // one per parity of `cur`
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  int64_t kernels_per_step = 0;
+  int64_t device_bytes = 0;
+};
+
+// kernels.cu
+int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain);
+int launch_shift(gds_ctx* ctx, const PassParams& p, const double* src);
+int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* val_static, const double* bc_tab,
+                     int64_t n, int64_t n_dyn_stride, const int64_t* counter);
+int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
+int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);

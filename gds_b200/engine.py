@@ -1,0 +1,231 @@
+"""Device stepping engine: one concatenated state vector, one CUDA-graph-captured step.
+
+Replaces the Python stepping loop of the reference -- fds.step_dydt / dydt / step_map / update_constraints /
+apply_constraints (gds/fds.py:284-305,332-369) and coupled_fds.step_continuous / dydt (gds/fds.py:477-507) -- and
+the solver object behind it (protocol of gds/ode/midpoint.py:10-32).  Host work per `advance()` is only: the step
+table (t_i, h_i), the user's time-varying Dirichlet callables evaluated at the step-end times (exactly the values
+the reference consumes, fds.py:289-290), and one C call that replays the captured step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check, ptr
+from .device import Buffer, Context, Mask
+from .trace import Lowering, Stage, State, Time, TraceError, as_expr, pass_desc, trace_scope
+from .types import Integrators, IterationMode
+
+STEP_MERGE_RTOL = 1e-9  # a remainder within (1+rtol)*max_step is taken as one step ending exactly at t_bound
+
+
+def step_table(t, t_bound, max_step):
+    """(t_i, h_i) of the fixed steps from t to t_bound: h = min(max_step, t_bound - t), the last step lands exactly
+    on t_bound (solver protocol gds/ode/midpoint.py:20-32 with scipy's clamping of the final step)."""
+    ts, hs = [], []
+    while t < t_bound:
+        rem = t_bound - t
+        if rem <= max_step * (1.0 + STEP_MERGE_RTOL):
+            h, t_new = rem, t_bound
+        else:
+            h, t_new = max_step, t + max_step
+        ts.append(t)
+        hs.append(h)
+        t = t_new
+    return np.asarray(ts, dtype=np.float64), np.asarray(hs, dtype=np.float64), t
+
+
+class StepEngine:
+    """Compiled system of one or more fields advanced together."""
+
+    def __init__(self, fields, scheme, max_step, t0=0.0, ctx: Context = None):
+        assert len(fields) >= 1
+        self.fields = list(fields)
+        self.scheme = scheme
+        self.max_step = float(max_step)
+        self.t = float(t0)
+        self.low = self.fields[0]._low
+        for f in self.fields:
+            if f._low.dev is not self.low.dev:
+                raise ValueError('fields advanced together must live on the same graph object')
+        self.ctx = ctx or self.low.ctx
+        self.h = None
+        self.offsets = {}
+        off = 0
+        for f in self.fields:
+            self.offsets[id(f)] = off
+            off += f.ndim * f._order()
+        self.n_state = off
+        self.externals = {}      # id(field) -> [field, Buffer, version]
+        self._keep = []
+        self._read_cache = {}
+        self.version = 0
+        self.steps_taken = 0
+        self._build()
+
+    # ---- compilation -------------------------------------------------------------------------------------
+    def _resolve_leaf(self, e):
+        f = e.field
+        if id(f) in self.offsets:
+            off = self.offsets[id(f)]
+            if isinstance(e, Stage):
+                return (L.VEC_STAGE, None, off + f.ndim * (f._order() - 1))   # fds.py:300: last block is handed to dydt
+            return (L.VEC_STATE, None, off)                                   # fds.py:378: y = integrator.y[:ndim]
+        if isinstance(e, Stage):
+            raise TraceError('stage state of a field outside this system')
+        if id(f) not in self.externals:
+            self.externals[id(f)] = [f, Buffer(self.ctx, f.ndim), None]
+        return (L.VEC_BUF, self.externals[id(f)][1], 0)
+
+    def _build(self):
+        scheme_code = {Integrators.rk4: L.SCHEME_RK4, Integrators.euler: L.SCHEME_EULER, 'map': L.SCHEME_MAP}[self.scheme]
+        h = L.c_vp()
+        check(lib.gds_system_create(self.ctx.h, self.low.dev.h, self.n_state, scheme_code, C.byref(h)))
+        self.h = h
+        import weakref
+        self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
+        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True)
+        self.lowering = lowering
+        stat_idx, stat_val, dyn_idx = [], [], []
+        self.dyn_fields = []
+        for f in self.fields:
+            off, n, order = self.offsets[id(f)], f.ndim, f._order()
+            with trace_scope():
+                if self.scheme == 'map':
+                    root = f.map_fun(Time(), Stage(f))
+                else:
+                    root = f.dydt_fun(Time(), Stage(f))
+            root = as_expr(root, f._domain_code, f._low)
+            if root.domain is not None and root.domain != f._domain_code:
+                raise ValueError('evolution law returns a vector over the wrong domain')
+            dmask = None
+            if self.scheme != 'map' and f.dirichlet_indices.size:
+                dmask = Mask(self.ctx, n, f.dirichlet_indices)          # fds.py:303
+                self._keep.append(dmask)
+            lowering.rhs_pass(root, f._domain_code, f._low, off + n * (order - 1), dmask)
+            for p in lowering.passes:
+                d, keep = pass_desc(p)
+                check(lib.gds_system_add_pass(self.h, C.byref(d)))
+            lowering.passes_done = getattr(lowering, 'passes_done', []) + lowering.passes
+            lowering.passes = []
+            for i in range(order - 1):                                   # fds.py:297-298
+                check(lib.gds_system_add_shift(self.h, off + n * i, off + n * (i + 1), n))
+            # Dirichlet overwrite after every step: fds.py:362 addresses `dirichlet_indices - ndim`, i.e. the LAST
+            # order block
+            if f.dirichlet_indices.size:
+                idx = off + n * (order - 1) + f.dirichlet_indices.astype(np.int64)
+                if f.dynamic_dirichlet:
+                    dyn_idx.append(idx)
+                    self.dyn_fields.append(f)
+                else:
+                    stat_idx.append(idx)
+                    stat_val.append(np.asarray(f.dirichlet_values, dtype=np.float64))
+        if stat_idx:
+            i, v = L.as_i64(np.concatenate(stat_idx)), L.as_f64(np.concatenate(stat_val))
+            check(lib.gds_system_set_dirichlet(self.h, ptr(i), ptr(v), i.size, 0))
+        self.n_dyn = 0
+        if dyn_idx:
+            i = L.as_i64(np.concatenate(dyn_idx))
+            self.n_dyn = i.size
+            check(lib.gds_system_set_dirichlet(self.h, ptr(i), None, i.size, 1))
+        check(lib.gds_system_finalize(self.h))
+        kps, nbytes = L.c_i64(), L.c_i64()
+        check(lib.gds_system_info(self.h, C.byref(kps), C.byref(nbytes)))
+        self.kernels_per_step = kps.value
+        self.device_bytes = nbytes.value + lowering.temp_bytes
+        self.push_state()
+
+    # ---- state movement ------------------------------------------------------------------------------------
+    def push_state(self):
+        """upload every field's host state (what `integrator.y` holds in the reference)"""
+        for f in self.fields:
+            a = L.as_f64(f._host_state)
+            check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)], a.size))
+            f._state_on_device = True
+        self.version += 1
+        self._read_cache.clear()
+
+    def pull_state(self):
+        for f in self.fields:
+            a = np.empty(f.ndim * f._order(), dtype=np.float64)
+            check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], a.size))
+            f._host_state = a
+
+    def read(self, f, full=False):
+        """current state slice of field f as a host array (cached until the next step)"""
+        key = (id(f), full)
+        if key not in self._read_cache:
+            n = f.ndim * (f._order() if full else 1)
+            a = np.empty(n, dtype=np.float64)
+            check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], n))
+            self._read_cache[key] = a
+        return self._read_cache[key]
+
+    def write(self, f, values, offset=0):
+        a = L.as_f64(values)
+        check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)] + offset, a.size))
+        self._read_cache.clear()
+        self.version += 1
+
+    def _refresh_externals(self):
+        for rec in self.externals.values():
+            f, buf, ver = rec
+            v = f._state_version()
+            if ver != v:
+                buf.upload(f.y)
+                rec[2] = v
+
+    # ---- stepping ---------------------------------------------------------------------------------------------
+    def _bc_table(self, t_end):
+        """values of the time-varying Dirichlet conditions at the step-end times (fds.py:350-353,289-290)"""
+        if self.n_dyn == 0:
+            return None
+        tab = np.empty((t_end.size, self.n_dyn), dtype=np.float64)
+        col = 0
+        for f in self.dyn_fields:
+            k = len(f.X_dirichlet)
+            for i, t in enumerate(t_end):
+                tab[i, col:col + k] = [f.dirichlet_fun(t, x) for x in f.X_dirichlet]
+            f.dirichlet_values = tab[-1, col:col + k].copy()
+            col += k
+        return tab
+
+    def _launch(self, ts, hs, t_after):
+        bc = self._bc_table(t_after)
+        check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+        self.steps_taken += int(ts.size)
+        self.version += 1
+        self._read_cache.clear()
+
+    def advance(self, dt):
+        """drive the system to t + dt in fixed steps of at most max_step (fds.py:284-290)"""
+        self._refresh_externals()
+        ts, hs, t_new = step_table(self.t, self.t + dt, self.max_step)
+        if ts.size == 0:
+            return
+        t_after = np.append(ts[1:], t_new)
+        projecting = [f for f in self.fields if not f._identity_projection()]
+        if not projecting:
+            self._launch(ts, hs, t_after)
+        else:
+            # a user projection is arbitrary host code (fds.py:363): one device step, then a host round trip
+            for i in range(ts.size):
+                self._launch(ts[i:i + 1], hs[i:i + 1], t_after[i:i + 1])
+                for f in projecting:
+                    full = self.read(f, full=True)
+                    self.write(f, np.asarray(f.project_fun(full.copy()), dtype=np.float64))
+        self.t = t_new
+        for f in self.fields:
+            f._dt = float(hs[-1])
+
+    def apply_map(self, t_new):
+        """one application of the recurrence map at time t_new (fds.py:332-339)"""
+        self._refresh_externals()
+        ts, hs = np.asarray([t_new], dtype=np.float64), np.asarray([0.0], dtype=np.float64)
+        self._launch(ts, hs, ts)
+        self.t = t_new
+
+    def sync(self):
+        self.ctx.sync()

@@ -1,0 +1,266 @@
+"""Operator assembly: nx.Graph (or a native lattice) -> index maps + device incidence arrays.
+
+Replaces GraphObservable.__init__ / gds.__init__ / the node_gds and edge_gds constructors
+(gds/gds.py:16-55,105-109,136-145,194-271).  The index maps follow the reference bit-exactly
+(SURVEY.md Appendix C): node index = position in G.nodes(), edge index and stored orientation = position and
+(u, v) order in G.edges(), face index = discovery order of the reference's planar face walk with the outer face
+removed (gds/utils/graph/generators.py:444-511).  One lowering is shared by every field built on the same graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import networkx as nx
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check, ptr
+from .device import Context, DeviceGraph
+from .utils import bidict
+
+
+class HostGraph:
+    """handle to a native host graph (gds_hostgraph)"""
+
+    def __init__(self, h):
+        import weakref
+        self.h = h
+        self._fin = weakref.finalize(self, lib.gds_hostgraph_destroy, h)
+        v, e, f, nnz, ld, hp = L.c_i64(), L.c_i64(), L.c_i64(), L.c_i64(), L.c_i32(), L.c_i32()
+        check(lib.gds_hostgraph_sizes(h, C.byref(v), C.byref(e), C.byref(f), C.byref(nnz), C.byref(ld), C.byref(hp)))
+        self.V, self.E, self.F, self.face_nnz, self.label_dim, self.has_pos = \
+            v.value, e.value, f.value, nnz.value, ld.value, bool(hp.value)
+
+    def edges(self):
+        eu, ev = np.empty(self.E, dtype=np.int32), np.empty(self.E, dtype=np.int32)
+        check(lib.gds_hostgraph_copy(self.h, None, None, ptr(eu), ptr(ev), None, None))
+        return eu, ev
+
+    def labels(self):
+        lab = np.empty((self.V, max(1, self.label_dim)), dtype=np.int32)
+        if self.label_dim == 0:
+            lab[:, 0] = np.arange(self.V)
+            return lab
+        check(lib.gds_hostgraph_copy(self.h, ptr(lab), None, None, None, None, None))
+        return lab
+
+    def pos(self):
+        if not self.has_pos:
+            return None
+        p = np.empty((self.V, 2), dtype=np.float64)
+        check(lib.gds_hostgraph_copy(self.h, None, ptr(p), None, None, None, None))
+        return p
+
+    def faces(self):
+        fp, fn = np.empty(self.F + 1, dtype=np.int64), np.empty(self.face_nnz, dtype=np.int32)
+        check(lib.gds_hostgraph_copy(self.h, None, None, None, None, ptr(fp), ptr(fn)))
+        return fp, fn
+
+
+def native_faces(n_nodes, edge_u, edge_v, adj_ptr, adj_nbr, pos):
+    """planar face walk on the host (C++), faces as CSR of node indices"""
+    h = L.c_vp()
+    eu, ev = L.as_i32(edge_u), L.as_i32(edge_v)
+    ap, an, p = L.as_i64(adj_ptr), L.as_i32(adj_nbr), L.as_f64(pos)
+    check(lib.gds_hostgraph_from_graph(int(n_nodes), eu.size, ptr(eu), ptr(ev), ptr(ap), ptr(an), ptr(p), C.byref(h)))
+    return HostGraph(h).faces()
+
+
+class LoweredGraph:
+    """Index maps + device operators of one graph.  Use `LoweredGraph.of(G)`."""
+
+    def __init__(self, G, need_faces: bool, ctx: Context = None):
+        self.ctx = ctx or Context.default()
+        self.G = G
+        self.native = isinstance(G, NativeGraph)
+        if self.native:
+            self._init_native(G, need_faces)
+        else:
+            self._init_nx(G, need_faces)
+        self.has_faces = need_faces or self.F > 0
+
+    # -- from networkx ---------------------------------------------------------------------------------
+    def _init_nx(self, G, need_faces):
+        self.nodes = {v: i for i, v in enumerate(G.nodes())}                       # gds.py:21
+        self.edges = bidict({e: i for i, e in enumerate(G.edges())})               # gds.py:23
+        V, E = len(self.nodes), len(self.edges)
+        self.V, self.E = V, E
+        nodes = self.nodes
+        self.edge_u = np.fromiter((nodes[e[0]] for e in self.edges), dtype=np.int32, count=E)
+        self.edge_v = np.fromiter((nodes[e[1]] for e in self.edges), dtype=np.int32, count=E)
+        # gds.py:39-40, generators.py:600-607: attribute 'weight', default 1.0
+        self.weights = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=E)
+        face_ptr = face_nodes = None
+        self.outer_face = None
+        if hasattr(G, 'faces'):                                                      # gds.py:31-32
+            faces = [tuple(f) for f in G.faces]
+        elif need_faces:
+            faces = self._walk_faces(G)                                              # gds.py:34
+        else:
+            faces = []
+        self.faces = {f: i for i, f in enumerate(faces)}                            # gds.py:35
+        self.F = len(self.faces)
+        if self.F:
+            face_ptr = np.cumsum([0] + [len(f) for f in faces]).astype(np.int64)
+            face_nodes = np.fromiter((nodes[n] for f in faces for n in f), dtype=np.int32, count=int(face_ptr[-1]))
+        unit = bool(np.all(self.weights == 1.0))
+        self.dev = DeviceGraph(self.ctx, V, self.edge_u, self.edge_v, None if unit else self.weights, face_ptr, face_nodes)
+
+    def _walk_faces(self, G):
+        pos = nx.get_node_attributes(G, 'pos')
+        if pos == {}:
+            is_planar, _ = nx.check_planarity(G)
+            if not is_planar:
+                import warnings
+                warnings.warn('no faces for non-planar graphs')                     # generators.py:531-534
+                return []
+            # generators.py:513-518: fixed-seed spring layout, stored on the graph like the reference does
+            pos = nx.spring_layout(G, scale=0.9, center=(0, 0), iterations=500, seed=1, dim=2)
+            nx.set_node_attributes(G, pos, 'pos')
+        nodes = self.nodes
+        V = len(nodes)
+        P = np.empty((V, 2), dtype=np.float64)
+        for v, i in nodes.items():
+            P[i, 0], P[i, 1] = pos[v][0], pos[v][1]
+        adj_ptr = np.zeros(V + 1, dtype=np.int64)
+        adj = []
+        for v, i in nodes.items():
+            nb = [nodes[u] for u in G.neighbors(v)]
+            adj_ptr[i + 1] = adj_ptr[i] + len(nb)
+            adj.extend(nb)
+        fp, fn = native_faces(V, self.edge_u, self.edge_v, adj_ptr, np.asarray(adj, dtype=np.int32), P)
+        inv = list(nodes.keys())
+        return [tuple(inv[j] for j in fn[fp[f]:fp[f + 1]]) for f in range(fp.size - 1)]
+
+    # -- from a native lattice ---------------------------------------------------------------------------
+    def _init_native(self, G, need_faces):
+        hg = G.hostgraph(with_faces=need_faces)
+        self.V, self.E, self.F = hg.V, hg.E, hg.F
+        self.edge_u, self.edge_v = hg.edges()
+        self.weights = np.ones(self.E) if G.weights is None else L.as_f64(G.weights)
+        self.nodes = LazyNodeMap(hg)
+        self.edges = LazyEdgeMap(self)
+        self.faces = LazyFaceMap(hg, self.nodes)
+        self.outer_face = None
+        self.dev = DeviceGraph(self.ctx, self.V, None, None, G.weights, hostgraph=hg.h)
+
+    def rows(self, domain):
+        return {L.NODES: self.V, L.EDGES: self.E, L.FACES: self.F}[domain]
+
+    @staticmethod
+    def of(G, need_faces: bool) -> 'LoweredGraph':
+        cache = G.__dict__.setdefault('_gds_b200_lowered', {})
+        low = cache.get(True) or (cache.get(False) if not need_faces else None)
+        if low is None:
+            low = LoweredGraph(G, need_faces)
+            cache[need_faces] = low
+        return low
+
+
+# ------------------------------------------------------------------------------------------------
+# native lattices (10^8 .. 10^9 edges: an nx.Graph of that size does not fit in memory)
+# ------------------------------------------------------------------------------------------------
+class NativeGraph:
+    """A graph generated natively with networkx-identical node / edge / face order.  Stands in for nx.Graph in the
+    field constructors.  kind: 'grid_2d' (m, n), 'grid' (d0, d1, d2), 'triangular' (m, n), 'hexagonal' (m, n),
+    'random_geometric' (n, radius, seed)."""
+    KINDS = {'grid_2d': 0, 'grid': 1, 'triangular': 2, 'hexagonal': 3, 'random_geometric': 4}
+
+    def __init__(self, kind, *dims, weights=None):
+        self.kind, self.dims, self.weights = kind, tuple(dims), weights
+        self._hg = {}
+
+    def hostgraph(self, with_faces=False) -> HostGraph:
+        with_faces = bool(with_faces) and self.kind in ('triangular', 'hexagonal')
+        hg = self._hg.get(True) or (self._hg.get(False) if not with_faces else None)
+        if hg is None:
+            h = L.c_vp()
+            k = self.KINDS[self.kind]
+            if self.kind == 'random_geometric':
+                n, r, seed = self.dims
+                check(lib.gds_hostgraph_lattice(k, int(n), int(seed), 0, float(r), 0, C.byref(h)))
+            else:
+                d = list(self.dims) + [0, 0]
+                check(lib.gds_hostgraph_lattice(k, int(d[0]), int(d[1]), int(d[2]), 0.0, int(with_faces), C.byref(h)))
+            hg = HostGraph(h)
+            self._hg[with_faces] = hg
+        return hg
+
+    def number_of_nodes(self):
+        return self.hostgraph().V
+
+    def number_of_edges(self):
+        return self.hostgraph().E
+
+
+class LazyNodeMap:
+    """label -> index map of a native graph; materialised only on demand."""
+
+    def __init__(self, hg: HostGraph):
+        self._hg = hg
+        self._labels = None
+        self._dict = None
+
+    def labels(self):
+        if self._labels is None:
+            self._labels = self._hg.labels()
+        return self._labels
+
+    def _key(self, row):
+        return int(row[0]) if self._hg.label_dim == 0 else tuple(int(x) for x in row)
+
+    def _d(self):
+        if self._dict is None:
+            self._dict = {self._key(r): i for i, r in enumerate(self.labels())}
+        return self._dict
+
+    def __len__(self): return self._hg.V
+    def __getitem__(self, k): return self._d()[k]
+    def __contains__(self, k): return k in self._d()
+    def __iter__(self): return iter(self._d())
+    def keys(self): return self._d().keys()
+    def items(self): return self._d().items()
+    def values(self): return self._d().values()
+
+
+class LazyEdgeMap:
+    def __init__(self, low):
+        self._low = low
+        self._dict = None
+
+    def _d(self):
+        if self._dict is None:
+            lab = self._low.nodes.labels()
+            key = self._low.nodes._key
+            self._dict = bidict({(key(lab[u]), key(lab[v])): i
+                                 for i, (u, v) in enumerate(zip(self._low.edge_u, self._low.edge_v))})
+        return self._dict
+
+    def __len__(self): return self._low.E
+    def __getitem__(self, k): return self._d()[k]
+    def __contains__(self, k): return k in self._d()
+    def __iter__(self): return iter(self._d())
+    def keys(self): return self._d().keys()
+    def items(self): return self._d().items()
+    def values(self): return self._d().values()
+
+
+class LazyFaceMap:
+    def __init__(self, hg, nodes):
+        self._hg, self._nodes, self._dict = hg, nodes, None
+
+    def _d(self):
+        if self._dict is None:
+            fp, fn = self._hg.faces()
+            lab = self._nodes.labels()
+            key = self._nodes._key
+            self._dict = {tuple(key(lab[j]) for j in fn[fp[f]:fp[f + 1]]): f for f in range(fp.size - 1)}
+        return self._dict
+
+    def __len__(self): return self._hg.F
+    def __getitem__(self, k): return self._d()[k]
+    def __contains__(self, k): return k in self._d()
+    def __iter__(self): return iter(self._d())
+    def keys(self): return self._d().keys()
+    def items(self): return self._d().items()
+    def values(self): return self._d().values()

@@ -1,0 +1,207 @@
+/*
+ * gds_b200 -- C-ABI of the B200-native stepping core for asrvsn/gds' hot path.
+ *
+ * The reference (pure Python) has no FFI of its own; its boundary for this path is the Python-level
+ * field / evolution / integrator API.  This header is the C-ABI a host binds in its
+ * place; each entry point cites the reference code it replaces (paths relative to the reference root).
+ * The Python host in gds_b200/ binds it with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, with the message
+ * available from gds_last_error() (thread-local).  The caller owns host buffers; the library owns
+ * device buffers.  One host thread drives a context; all work is ordered on the context's stream.
+ * All field values are float64, all indices int32 (rows per device < 2^31, edges < 2^30).
+ */
+#ifndef GDS_B200_H
+#define GDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDS_ABI_VERSION 1
+
+typedef struct gds_ctx gds_ctx;
+typedef struct gds_graph gds_graph;
+typedef struct gds_buf gds_buf;
+typedef struct gds_mask gds_mask;
+typedef struct gds_system gds_system;
+
+/* domains of a field (gds/types.py:23-27, GraphDomain) */
+enum { GDS_NODES = 0, GDS_EDGES = 1, GDS_FACES = 3 };
+
+/* fixed-step schemes (new members beside gds/types.py:47-51 Integrators; protocol gds/ode/midpoint.py:10-32) */
+enum { GDS_SCHEME_EULER = 0, GDS_SCHEME_RK4 = 1, GDS_SCHEME_MAP = 2 };
+
+/* when a pass of the traced evolution law runs */
+enum { GDS_WHEN_STAGE = 0, /* every RHS evaluation (fds.dydt, gds/fds.py:292-305)               */
+       GDS_WHEN_STEP = 1   /* once per step, before stage 1: sub-expressions of accepted state only */ };
+
+/* what a pass does with the value its row program leaves on the stack */
+enum { GDS_EPI_NONE = 0,  /* nothing (the program used STORE)                                       */
+       GDS_EPI_RHS = 1    /* it is dy/dt of this row: Dirichlet zeroing (fds.py:303) + stage combine  */ };
+
+/* kinds of vector operand of a pass */
+enum { GDS_VEC_BUF = 0,    /* a gds_buf                                                  */
+       GDS_VEC_STATE = 1,  /* accepted state y_n of the system (`obs.y`, fds.py:373-378)  */
+       GDS_VEC_STAGE = 2   /* stage state handed to dydt (`y` argument, fds.py:300-302)   */ };
+
+/* ---- row-program opcodes: one 32-bit word  op | a<<8 | b<<16 | c<<24  -------------------------------- */
+enum {
+  GDS_OP_END = 0,
+  /* stack sources */
+  GDS_OP_PUSH_VEC = 1,   /* push vec[a][row]                      */
+  GDS_OP_PUSH_IMM = 2,   /* push imm[a]                           */
+  GDS_OP_PUSH_T = 3,     /* push stage time t_n + c_s h           */
+  GDS_OP_PUSH_H = 4,     /* push step size h                      */
+  GDS_OP_DUP = 5, GDS_OP_SWAP = 6, GDS_OP_POP = 7,
+  GDS_OP_SETL = 8,       /* local[a] = top (a < 4), keeps top     */
+  GDS_OP_GETL = 9,       /* push local[a]                         */
+  GDS_OP_STORE = 10,     /* out[a][row] = top, keeps top          */
+  GDS_OP_MASK_ZERO = 11, /* top = 0 where bit `row` of mask[a]    */
+  /* binary (second-from-top OP top) */
+  GDS_OP_ADD = 16, GDS_OP_SUB = 17, GDS_OP_MUL = 18, GDS_OP_DIV = 19, GDS_OP_POW = 20,
+  GDS_OP_MAX = 21, GDS_OP_MIN = 22, GDS_OP_ATAN2 = 23,
+  /* unary */
+  GDS_OP_NEG = 32, GDS_OP_ABS = 33, GDS_OP_SIGN = 34, GDS_OP_SQRT = 35, GDS_OP_EXP = 36, GDS_OP_LOG = 37,
+  GDS_OP_SIN = 38, GDS_OP_COS = 39, GDS_OP_TAN = 40, GDS_OP_TANH = 41, GDS_OP_SINH = 42, GDS_OP_COSH = 43,
+  GDS_OP_ATAN = 44, GDS_OP_SQUARE = 45, GDS_OP_RECIP = 46, GDS_OP_POWI = 47 /* top ** (int8)a */,
+  /* gathers over the lowered incidence structure (push the row's result) */
+  GDS_OP_N_LAP = 64,      /* nodes: sum_e w_e (v[nbr]-v[row])         L0 row, gds.py:140,159            */
+  GDS_OP_N_BDOT = 65,     /* nodes: (B1 v)[row], v on edges           gds.py:280 (div = -B1 y)          */
+  GDS_OP_N_INFLUX = 66,   /* nodes: sum relu(+B1 .* v)                gds.py:282-285                    */
+  GDS_OP_N_OUTFLUX = 67,  /* nodes: sum relu(-B1 .* v)                gds.py:287-290                    */
+  GDS_OP_N_ADVECT = 68,   /* nodes: scalar advect(v=vec a, y=vec b)   gds.py:166-177                    */
+  GDS_OP_N_LIE = 69,      /* nodes: lie_advect(v=vec a, y=vec b)      gds.py:179-189                    */
+  GDS_OP_N_EAGG = 70,     /* nodes: 4 upwind aggregates of edge vec a -> out[b] as double4 (no push)    */
+  GDS_OP_E_GRADT = 80,    /* edges: (B1^T v)[row], v on nodes         gds.py:154                        */
+  GDS_OP_E_CURLT = 81,    /* edges: (B2^T v)[row], v on faces         gds.py:305                        */
+  GDS_OP_E_ADVFIN = 82,   /* edges: self-advection from y=vec a, aggregates vec b   gds.py:326-345      */
+  GDS_OP_F_CURL = 96      /* faces: (B2 v)[row], v on edges           gds.py:294                        */
+};
+
+#define GDS_MAX_CODE 96
+#define GDS_MAX_IMM 24
+#define GDS_MAX_VEC 16
+#define GDS_MAX_MASK 6
+#define GDS_MAX_OUT 4
+
+typedef struct {
+  int32_t kind;      /* GDS_VEC_*                                                       */
+  gds_buf* buf;      /* for GDS_VEC_BUF                                                 */
+  int64_t offset;    /* element offset of the operand's row 0 (field slice / order block) */
+} gds_vecref;
+
+typedef struct {
+  int32_t domain;                 /* rows of this pass: GDS_NODES / GDS_EDGES / GDS_FACES             */
+  int32_t when;                   /* GDS_WHEN_*                                                       */
+  int32_t n_code;  const uint32_t* code;
+  int32_t n_imm;   const double* imm;
+  int32_t n_vec;   const gds_vecref* vec;
+  int32_t n_mask;  gds_mask* const* mask;
+  int32_t n_out;   gds_buf* const* out;  const int64_t* out_offset;  /* STORE / N_EAGG targets          */
+  int32_t epilogue;               /* GDS_EPI_*                                                        */
+  int64_t state_offset;           /* GDS_EPI_RHS: first state-vector element these rows advance       */
+  gds_mask* dirichlet;            /* GDS_EPI_RHS: rows whose derivative is forced to 0 (may be NULL)  */
+} gds_pass_desc;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char* gds_last_error(void);
+int gds_abi_version(void);
+
+int gds_ctx_create(int device, gds_ctx** out);
+int gds_ctx_destroy(gds_ctx* ctx);
+int gds_ctx_set_stream(gds_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
+int gds_ctx_sync(gds_ctx* ctx);
+/* device-side timing of everything enqueued between the two calls (CUDA events on the context stream) */
+int gds_ctx_timer_start(gds_ctx* ctx);
+int gds_ctx_timer_stop(gds_ctx* ctx, double* ms_out);
+/* counters since context creation: kernels launched by this library, CUDA-graph replays */
+int gds_ctx_counters(gds_ctx* ctx, int64_t* kernel_launches, int64_t* graph_replays);
+/* write `bytes` of device scratch (used to flush L2 between timed iterations) */
+int gds_ctx_flush_l2(gds_ctx* ctx, int64_t bytes);
+
+/* ---- device vectors ------------------------------------------------------------------------------------ */
+int gds_buf_create(gds_ctx* ctx, int64_t n, gds_buf** out);
+int gds_buf_destroy(gds_buf* b);
+int gds_buf_upload(gds_buf* b, int64_t offset, const double* host, int64_t n);
+int gds_buf_download(gds_buf* b, int64_t offset, double* host, int64_t n);
+int gds_buf_fill(gds_buf* b, int64_t offset, int64_t n, double value);
+int gds_buf_devptr(gds_buf* b, void** dev_out, int64_t* n_out);
+
+/* row sets as bitmaps (Dirichlet rows fds.py:303, `free` / `normal` arguments gds.py:296-317) */
+int gds_mask_create(gds_ctx* ctx, int64_t n_rows, const int64_t* rows, int64_t n, gds_mask** out);
+int gds_mask_destroy(gds_mask* m);
+
+/* ---- operator assembly: replaces GraphObservable.__init__ / gds.__init__ / node_gds / edge_gds ctors
+ *      (gds/gds.py:16-55,105-109,136-145,194-271).  Edges are given in G.edges() order with the stored
+ *      orientation (u -> v); weights NULL = all 1.0; faces as a CSR list of node indices in traversal order
+ *      (n_faces = 0: no faces).  Lowers once to device sliced-ELL incidence arrays. ------------------------ */
+int gds_graph_create(gds_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* edge_u, const int32_t* edge_v,
+                     const double* weight, int64_t n_faces, const int64_t* face_ptr, const int32_t* face_nodes,
+                     gds_graph** out);
+int gds_graph_destroy(gds_graph* g);
+int gds_graph_sizes(gds_graph* g, int64_t* n_nodes, int64_t* n_edges, int64_t* n_faces);
+/* Bit-exact index-map export for parity checks.  kind 0: B1 rows   (node -> incident edges, sign = +1 head / -1 tail),
+ *                                                 kind 1: B2 rows   (face -> edges, sign as gds.py:227-236),
+ *                                                 kind 2: B2 cols   (edge -> faces).
+ * Call with ptr/idx/sign NULL to get sizes (n_rows, nnz); ptr has n_rows+1 entries. */
+int gds_graph_export_csr(gds_graph* g, int32_t kind, int64_t* n_rows, int64_t* nnz,
+                         int64_t* ptr, int32_t* idx, int32_t* sign);
+/* bytes of device memory held by the lowered operators */
+int gds_graph_device_bytes(gds_graph* g, int64_t* bytes);
+
+/* ---- eager operator application: `op(y)` on host arrays (gds.py:152-345, the `y is not None` path).
+ *      Runs ONE pass (epilogue must be GDS_EPI_NONE) at time t. -------------------------------------------- */
+int gds_pass_run(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* pass, double t);
+
+/* ---- the stepping core: replaces fds.step / step_dydt / dydt / step_map / apply_constraints and
+ *      coupled_fds.step_continuous / dydt (gds/fds.py:264-305,332-369,471-507) plus the solver object
+ *      (gds/ode/midpoint.py:10-32).  One system = one concatenated state vector (fds.py:439,456-460). -------- */
+int gds_system_create(gds_ctx* ctx, gds_graph* g, int64_t n_state, int32_t scheme, gds_system** out);
+int gds_system_destroy(gds_system* s);
+int gds_system_add_pass(gds_system* s, const gds_pass_desc* pass);
+/* rows advanced with dy/dt = stage[src_offset + i] (order>1 block shift, fds.py:297-298) */
+int gds_system_add_shift(gds_system* s, int64_t dst_offset, int64_t src_offset, int64_t n);
+/* rows that are not advanced at all (nil systems / padding): y_{n+1} = y_n */
+int gds_system_add_hold(gds_system* s, int64_t offset, int64_t n);
+/* Dirichlet overwrite after every step (fds.py:289-290,362): state[idx[i]] = value[i]; dynamic = values come
+ * from the table passed to gds_system_step */
+int gds_system_set_dirichlet(gds_system* s, const int64_t* state_idx, const double* values, int64_t n, int32_t dynamic);
+/* capture the whole step (all passes of all stages + BC overwrite) into a CUDA graph */
+int gds_system_finalize(gds_system* s);
+int gds_system_set_state(gds_system* s, const double* host, int64_t offset, int64_t n);
+int gds_system_get_state(gds_system* s, double* host, int64_t offset, int64_t n);
+int gds_system_state_devptr(gds_system* s, void** dev_out);
+/* advance n_steps: step i goes from t[i] with size h[i]; bc_values is [n_steps x n_dynamic_dirichlet]
+ * (the host evaluates the user's g(t_{i+1}, x) -- fds.py:350-357 -- and only the end-of-step row is ever
+ * consumed, fds.py:289-290).  Replays the captured graph n_steps times; returns without synchronising. */
+int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values);
+/* algorithmic facts for the roofline: kernels per step and device bytes held */
+int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
+
+/* ---- native host graphs for sizes where an nx.Graph is impossible: generators that reproduce
+ *      networkx's node order, G.edges() order/orientation and adjacency order bit-exactly, plus the planar face walk
+ *      of gds/utils/graph/generators.py:444-511.
+ *      kind: 0 grid_2d_graph(a,b)   1 grid_graph(dim=[a,b,c])   2 triangular_lattice_graph(a,b)
+ *            3 hexagonal_lattice_graph(a,b)   4 random_geometric_graph(n=a, radius=r, seed=b) ---------------------- */
+typedef struct gds_hostgraph gds_hostgraph;
+int gds_hostgraph_lattice(int32_t kind, int64_t a, int64_t b, int64_t c, double r, int32_t with_faces, gds_hostgraph** out);
+/* any positioned plane graph: edges in G.edges() order, adjacency in G.neighbors() order; runs the face walk */
+int gds_hostgraph_from_graph(int64_t n_nodes, int64_t n_edges, const int32_t* edge_u, const int32_t* edge_v,
+                             const int64_t* adj_ptr, const int32_t* adj_nbr, const double* pos /* [n x 2] */,
+                             gds_hostgraph** out);
+int gds_hostgraph_sizes(gds_hostgraph* g, int64_t* n_nodes, int64_t* n_edges, int64_t* n_faces, int64_t* face_nnz,
+                        int32_t* label_dim, int32_t* has_pos);
+/* copy out what is wanted (NULL = skip): labels [n x label_dim], pos [n x 2], edges, faces as CSR of node indices */
+int gds_hostgraph_copy(gds_hostgraph* g, int32_t* labels, double* pos, int32_t* edge_u, int32_t* edge_v,
+                       int64_t* face_ptr, int32_t* face_nodes);
+int gds_hostgraph_destroy(gds_hostgraph* g);
+/* lower a native host graph straight to the device (weights NULL = all 1.0) */
+int gds_graph_create_from_host(gds_ctx* ctx, gds_hostgraph* g, const double* weight, gds_graph** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDS_B200_H */
