@@ -101,6 +101,7 @@ _sig('gds_system_set_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_get_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_state_devptr', c_vp, P(c_vp))
 _sig('gds_system_step', c_vp, c_i64, c_vp, c_vp, c_vp)
+_sig('gds_system_step_timed', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp)
 _sig('gds_system_info', c_vp, P(c_i64), P(c_i64))
 _sig('gds_hostgraph_lattice', c_i32, c_i64, c_i64, c_i64, c_f64, c_i32, P(c_vp))
 _sig('gds_hostgraph_from_graph', c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp))
@@ -116,7 +117,7 @@ EXPORTED = [
     'gds_mask_destroy', 'gds_graph_create', 'gds_graph_destroy', 'gds_graph_sizes', 'gds_graph_export_csr',
     'gds_graph_device_bytes', 'gds_pass_run', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
     'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_finalize',
-    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_info',
+    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_timed', 'gds_system_info',
     'gds_hostgraph_lattice', 'gds_hostgraph_from_graph', 'gds_hostgraph_sizes', 'gds_hostgraph_copy',
     'gds_hostgraph_destroy', 'gds_graph_create_from_host',
 ]

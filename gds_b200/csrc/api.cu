@@ -582,8 +582,25 @@ static int ensure_step_capacity(gds_system* s, int64_t n_steps) {
   return 0;
 }
 
+// per-launch CUDA-event timing for gds_system_step_timed (eager enqueue, not the captured graph)
+struct LaunchTimer {
+  struct Rec { cudaEvent_t a, b; int cls; };
+  std::vector<Rec> recs;
+  cudaStream_t stream;
+  int begin(int cls) {
+    Rec r; r.cls = cls;
+    GDS_CUDA(cudaEventCreate(&r.a));
+    GDS_CUDA(cudaEventCreate(&r.b));
+    GDS_CUDA(cudaEventRecord(r.a, stream));
+    recs.push_back(r);
+    return 0;
+  }
+  int end() { GDS_CUDA(cudaEventRecord(recs.back().b, stream)); return 0; }
+};
+static int domain_class(int32_t domain) { return domain == GDS_NODES ? 0 : (domain == GDS_EDGES ? 1 : 2); }
+
 // enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
-static int enqueue_step(gds_system* s, int cur) {
+static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
   gds_ctx* c = s->ctx;
   const double* yn = s->Y[cur];
   double* ynew = s->Y[cur ^ 1];
@@ -597,7 +614,9 @@ static int enqueue_step(gds_system* s, int cur) {
     PassParams pp;
     GDS_TRY(resolve_pass(s->g, ph, yn, nullptr, pp));
     pp.steptab = s->d_steptab; pp.step_counter = s->d_counter; pp.c_stage = 0.0;
+    if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
     GDS_TRY(launch_pass(c, pp, ph.domain));
+    if (lt) GDS_TRY(lt->end());
   }
   for (int st = 0; st < n_stages; ++st) {
     const double* stage = (st == 0) ? yn : s->XS[(st - 1) & 1];
@@ -625,13 +644,17 @@ static int enqueue_step(gds_system* s, int cur) {
           pp.stage_mode = 4;
         }
       }
+      if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
       GDS_TRY(launch_pass(c, pp, ph.domain));
+      if (lt) GDS_TRY(lt->end());
     }
   }
+  if (lt) GDS_TRY(lt->begin(3));
   // Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, nullptr, s->n_dir_static, 0, s->d_counter));
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_dyn, nullptr, s->d_bc_tab, s->n_dir_dyn, s->n_dir_dyn, s->d_counter));
   GDS_TRY(launch_advance_counter(c, s->d_counter));
+  if (lt) GDS_TRY(lt->end());
   return 0;
 }
 
@@ -726,6 +749,47 @@ extern "C" int gds_system_step(gds_system* s, int64_t n_steps, const double* t, 
     }
     done += m;
   }
+  return 0;
+}
+
+// Same work as gds_system_step, enqueued kernel by kernel with a CUDA-event pair around every launch (no graph
+// replay), so that the per-kernel device time is measured live.  class 0/1/2: passes over nodes/edges/faces,
+// class 3: the per-step tail (Dirichlet overwrite + step counter).  Synchronises.
+extern "C" int gds_system_step_timed(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc,
+                                     double* class_ms, int64_t* class_launches) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (n_steps < 0 || n_steps > 256) GDS_FAIL("timed stepping takes at most 256 steps per call");
+  if (n_steps > s->cap_steps) GDS_FAIL("too many steps");
+  if (s->n_dir_dyn > 0 && !bc) GDS_FAIL("dynamic Dirichlet values missing");
+  gds_ctx* c = s->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  std::vector<StepRec> tab((size_t)n_steps);
+  for (int64_t i = 0; i < n_steps; ++i) { tab[i].t = t[i]; tab[i].h = h[i]; }
+  GDS_CUDA(cudaMemcpyAsync(s->d_steptab, tab.data(), (size_t)n_steps * sizeof(StepRec), cudaMemcpyHostToDevice, c->stream));
+  if (s->n_dir_dyn > 0)
+    GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc, (size_t)n_steps * s->n_dir_dyn * 8, cudaMemcpyHostToDevice, c->stream));
+  GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  LaunchTimer lt;
+  lt.stream = c->stream;
+  int rc = 0;
+  for (int64_t i = 0; i < n_steps && !rc; ++i) {
+    rc = enqueue_step(s, s->cur, &lt);
+    s->cur ^= 1;
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < 4; ++k) { if (class_ms) class_ms[k] = 0.0; if (class_launches) class_launches[k] = 0; }
+  for (auto& r : lt.recs) {
+    float ms = 0.f;
+    if (!rc && e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (class_ms) class_ms[r.cls] += (double)ms;
+      if (class_launches) class_launches[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (rc) return rc;
+  if (e != cudaSuccess) GDS_FAIL(std::string("stream sync failed: ") + cudaGetErrorString(e));
   return 0;
 }
 

@@ -163,6 +163,12 @@ class StepEngine:
             self._read_cache[key] = a
         return self._read_cache[key]
 
+    def read_into(self, f, out):
+        """copy the value block of field f into a caller-owned (ideally pinned) host array"""
+        assert out.dtype == np.float64 and out.flags['C_CONTIGUOUS'] and out.size == f.ndim
+        check(lib.gds_system_get_state(self.h, ptr(out), self.offsets[id(f)], out.size))
+        return out
+
     def write(self, f, values, offset=0):
         a = L.as_f64(values)
         check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)] + offset, a.size))
@@ -185,9 +191,9 @@ class StepEngine:
         tab = np.empty((t_end.size, self.n_dyn), dtype=np.float64)
         col = 0
         for f in self.dyn_fields:
-            k = len(f.X_dirichlet)
+            k = f.dirichlet_indices.size
             for i, t in enumerate(t_end):
-                tab[i, col:col + k] = [f.dirichlet_fun(t, x) for x in f.X_dirichlet]
+                tab[i, col:col + k] = f._dirichlet_at(t)
             f.dirichlet_values = tab[-1, col:col + k].copy()
             col += k
         return tab
@@ -199,26 +205,64 @@ class StepEngine:
         self.version += 1
         self._read_cache.clear()
 
-    def advance(self, dt):
-        """drive the system to t + dt in fixed steps of at most max_step (fds.py:284-290)"""
-        self._refresh_externals()
+    def plan(self, dt):
+        """host part of an advance: step table and time-varying Dirichlet values (user callables run here)"""
         ts, hs, t_new = step_table(self.t, self.t + dt, self.max_step)
+        t_after = np.append(ts[1:], t_new)
+        return ts, hs, t_after, t_new, self._bc_table(t_after) if ts.size else None
+
+    def plan_steps(self, k, h):
+        """exactly k steps of size h from the current time"""
+        ts = self.t + h * np.arange(k, dtype=np.float64)
+        hs = np.full(k, h, dtype=np.float64)
+        t_after = ts + h
+        return ts, hs, t_after, float(t_after[-1]), self._bc_table(t_after)
+
+    def run(self, plan):
+        """device part of an advance: replay the captured step once per table row (asynchronous)"""
+        ts, hs, t_after, t_new, bc = plan
         if ts.size == 0:
             return
-        t_after = np.append(ts[1:], t_new)
-        projecting = [f for f in self.fields if not f._identity_projection()]
-        if not projecting:
-            self._launch(ts, hs, t_after)
-        else:
-            # a user projection is arbitrary host code (fds.py:363): one device step, then a host round trip
-            for i in range(ts.size):
-                self._launch(ts[i:i + 1], hs[i:i + 1], t_after[i:i + 1])
-                for f in projecting:
-                    full = self.read(f, full=True)
-                    self.write(f, np.asarray(f.project_fun(full.copy()), dtype=np.float64))
+        check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+        self.steps_taken += int(ts.size)
+        self.version += 1
+        self._read_cache.clear()
         self.t = t_new
         for f in self.fields:
             f._dt = float(hs[-1])
+
+    def run_timed(self, plan):
+        """like run(), but kernel by kernel with CUDA events around every launch: returns (ms, launches) per class
+        [node passes, edge passes, face passes, per-step tail] (measurement aid, synchronises)"""
+        ts, hs, t_after, t_new, bc = plan
+        ms, cnt = np.zeros(4, dtype=np.float64), np.zeros(4, dtype=np.int64)
+        check(lib.gds_system_step_timed(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None,
+                                        ptr(ms), ptr(cnt)))
+        self.steps_taken += int(ts.size)
+        self.version += 1
+        self._read_cache.clear()
+        self.t = t_new
+        return ms, cnt
+
+    def advance(self, dt):
+        """drive the system to t + dt in fixed steps of at most max_step (fds.py:284-290)"""
+        self._refresh_externals()
+        projecting = [f for f in self.fields if not f._identity_projection()]
+        if not projecting:
+            self.run(self.plan(dt))
+            return
+        # a user projection is arbitrary host code (fds.py:363): one device step, then a host round trip
+        ts, hs, t_new = step_table(self.t, self.t + dt, self.max_step)
+        t_after = np.append(ts[1:], t_new)
+        for i in range(ts.size):
+            self._launch(ts[i:i + 1], hs[i:i + 1], t_after[i:i + 1])
+            for f in projecting:
+                full = self.read(f, full=True)
+                self.write(f, np.asarray(f.project_fun(full.copy()), dtype=np.float64))
+            self.t = float(t_after[i])
+        for f in self.fields:
+            if ts.size:
+                f._dt = float(hs[-1])
 
     def apply_map(self, t_new):
         """one application of the recurrence map at time t_new (fds.py:332-339)"""

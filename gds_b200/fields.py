@@ -1,0 +1,601 @@
+"""Field / evolution / coupling API of the reference, routed to the device stepping core.
+
+Mirrors, for the fixed-step hot path only:
+  * gds/fds.py        -- fds.set_evolution / set_initial / set_constraints / step / y / t / dt, coupled_fds, couple()
+  * gds/gds.py        -- GraphObservable, gds, node_gds, edge_gds, simplex_gds, face_gds and their operators
+  * gds/system.py     -- System.step / solve
+Same names, argument meaning and error behaviour; the arithmetic runs in libgds_b200.so (CUDA, sm_100a) and nowhere
+else -- there is no CPU fallback.  Operators called with host arrays run eagerly on the device and return fresh
+numpy arrays (the `y is not None` path of gds.py:152-345); called while an evolution law is being traced they
+return symbolic expressions that are lowered into the captured step (gds_b200/trace.py, engine.py).
+
+Out of scope (raise NotImplementedError): `lhs=` / `cost=` (CVXPY programme, fds.py:97-113), `traj_t=` playback
+(fds.py:124-129), the adaptive scipy integrators and the dense implicit midpoint (fds.py:84-95).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check
+from .device import Buffer, Context
+from .engine import StepEngine
+from .graph import LoweredGraph, NativeGraph
+from .trace import (Const, EdgeAgg, Expr, Gather, Lowering, MaskZero, State, TraceError, as_expr, pass_desc,
+                    tracing, unary)
+from .types import GraphDomain, Integrators, IterationMode, Observable, Steppable
+from .utils import dict_fun, fun_ary
+
+_DOMAIN_CODE = {GraphDomain.nodes: L.NODES, GraphDomain.edges: L.EDGES, GraphDomain.faces: L.FACES}
+
+
+def _identity(x):
+    return x
+
+
+class BoundarySpec:
+    """Vectorised boundary condition for graphs too large for a per-point Python callable (extension; the
+    reference only takes dicts / callables, fds.py:208-243).  `indices` are rows of the field's domain,
+    `values` a constant array, or `fun(t) -> ndarray` for time-varying values."""
+
+    def __init__(self, indices, values=None, fun=None):
+        self.indices = np.asarray(indices, dtype=np.intp).ravel()
+        assert (values is None) != (fun is None), 'give exactly one of values / fun'
+        self.values = None if values is None else np.broadcast_to(np.asarray(values, dtype=float), self.indices.shape).copy()
+        self.fun = fun
+
+
+# ------------------------------------------------------------------------------------------------
+# fds (gds/fds.py:14-400)
+# ------------------------------------------------------------------------------------------------
+class fds(Observable, Steppable):
+    def __init__(self, X):
+        Observable.__init__(self, X)
+        Steppable.__init__(self, IterationMode.none)
+        self._set_bcs()
+        self.t0 = 0.
+        self.y0_fun = lambda _: 0.
+        self._engine = None        # StepEngine advancing this field (shared when coupled)
+        self._coupled = None       # coupled_fds owning this field
+        self._version = 0          # bumped whenever the host-visible state changes
+
+    # ---- evolution law (fds.py:30-135) ---------------------------------------------------------------------
+    def set_evolution(self, dydt=None, order=1, max_step=1e-3, integrator=Integrators.rk4, solver_args={},
+                      lhs=None, rhs=None, cost=None, map_fun=None, dt=1.0, traj_t=None, traj_y=None, nil=False):
+        given = [dydt is not None, lhs is not None, cost is not None, map_fun is not None,
+                 traj_t is not None, bool(nil)]
+        assert sum(given) == 1, 'Exactly one evolution law must be specified'       # fds.py:72
+        if lhs is not None or cost is not None:
+            raise NotImplementedError('cvx evolution (lhs= / cost=, gds/fds.py:97-113) is outside the device stepping path')
+        if traj_t is not None:
+            raise NotImplementedError('trajectory playback (traj_t=, gds/fds.py:124-129) is outside the device stepping path')
+        self._drop_engine()
+        if dydt is not None:
+            if integrator not in (Integrators.rk4, Integrators.euler):
+                # the reference's adaptive scipy solvers / implicit midpoint (fds.py:84-95) are not part of this path
+                raise ValueError('Unsupported integrator type')
+            self.iter_mode = IterationMode.dydt
+            self.dydt_fun = dydt
+            self.max_step = max_step
+            self._dt = max_step
+            self.order = order
+            self.solver_args = solver_args
+            self.integrator_type = integrator
+            self.y0 = np.zeros(self.ndim * order)
+        elif map_fun is not None:
+            self.iter_mode = IterationMode.map
+            self.map_fun = map_fun            # documented signature (t, y): fds.py:33, README.md:158
+            self.order = 1
+            self.y0 = np.zeros(self.ndim)
+            self._dt = dt
+            self._n = self.t0
+        else:
+            self.iter_mode = IterationMode.nil
+            self.order = 1
+            self.y0 = np.zeros(self.ndim)
+        self._t = self.t0
+        # like the reference (midpoint.py:13, fds.py:157-171) the solver state aliases y0 until the first step
+        self._host_state = self.y0
+        self._bump()
+
+    # ---- initial conditions (fds.py:137-173) -----------------------------------------------------------------
+    def set_initial(self, t0=0., y0=lambda _: 0.):
+        assert self.iter_mode != IterationMode.none, 'Use set_evolution() before setting initial conditions'
+        self._drop_engine()
+        self.t0 = t0
+        self._t = t0
+        if self.iter_mode is IterationMode.map:
+            self._n = int(t0)
+        if isinstance(y0, np.ndarray):            # the reference recurses here (fds.py:151-152); arrays are accepted
+            arr = np.asarray(y0, dtype=float).ravel()
+            assert arr.size == self.ndim, 'initial array has the wrong length'
+            self.y0_fun = lambda x: arr[self.X[x]]
+            keep = np.ones(self.ndim, dtype=bool)
+            keep[self.dirichlet_indices] = False
+            self._host_state[:self.ndim][keep] = arr[keep]
+        else:
+            self.y0_fun = y0
+            constrained = set(self.X_dirichlet)
+            st = self._host_state
+            for x, i in self.X.items():
+                if x not in constrained:
+                    st[i] = y0(x)
+        self._bump()
+
+    # ---- boundary conditions (fds.py:175-243) ------------------------------------------------------------------
+    def set_constraints(self, dirichlet={}, neumann={}, project=_identity):
+        assert self.iter_mode != IterationMode.none, 'Use set_evolution() before setting boundary conditions'
+        self._drop_engine()
+        self._set_bcs(dirichlet, neumann, project)
+        st = self._host_state
+        if self.iter_mode is IterationMode.dydt:
+            if st is self.y0:
+                st[self.dirichlet_indices] = self.dirichlet_values                  # fds.py:193 (y0 aliases integrator.y)
+                if project is not _identity:
+                    self.y0 = self._host_state = np.asarray(project(st), dtype=float)
+                    st = self._host_state
+            else:
+                self.y0[self.dirichlet_indices] = self.dirichlet_values
+            # fds.py:196: negative offsets -- for order>1 this addresses the LAST block
+            st[self.dirichlet_indices - self.ndim] = self.dirichlet_values
+        elif self.iter_mode is IterationMode.map:
+            st[self.dirichlet_indices] = self.dirichlet_values
+            if project is not _identity:
+                self.y0 = self._host_state = np.asarray(project(st), dtype=float)
+        else:
+            raise Exception('Unsupported iteration mode for set_constraints()')     # fds.py:205
+        self._bump()
+
+    def _set_bcs(self, dirichlet={}, neumann={}, project=_identity):
+        self.project_fun = project
+
+        def classify(bc):
+            if isinstance(bc, BoundarySpec):
+                dyn = bc.fun is not None
+                vals = np.asarray(bc.fun(0.), dtype=float).reshape(bc.indices.size) if dyn else bc.values
+                fun = (lambda t, x: None) if dyn else (lambda x: None)
+                return fun, dyn, None, bc.indices, vals, bc
+            if isinstance(bc, dict):
+                if not bc:
+                    return dict_fun(bc), False, [], np.zeros(0, dtype=np.intp), np.zeros(0), None
+                bc = dict_fun(bc)
+            dyn = fun_ary(bc) > 1                                                    # fds.py:222-223
+            call = (lambda x: bc(0., x)) if dyn else bc
+            domain, idx, vals = [], [], []
+            for x, i in self.X.items():                                              # fds.py:225-239
+                v = call(x)
+                if v is not None:
+                    domain.append(x); idx.append(i); vals.append(v)
+            return bc, dyn, domain, np.asarray(idx, dtype=np.intp), np.asarray(vals, dtype=float).reshape(len(idx)), None
+
+        (self.dirichlet_fun, self.dynamic_dirichlet, self._X_dirichlet, self.dirichlet_indices,
+         self.dirichlet_values, self._dirichlet_spec) = classify(dirichlet)
+        (self.neumann_fun, self.dynamic_neumann, self._X_neumann, self.neumann_indices,
+         self.neumann_values, self._neumann_spec) = classify(neumann)
+        both = np.intersect1d(self.dirichlet_indices, self.neumann_indices)
+        assert both.size == 0, f'Dirichlet and Neumann conditions overlap on {both}'  # fds.py:242-243
+
+    @property
+    def X_dirichlet(self):
+        if self._X_dirichlet is None:
+            self._X_dirichlet = [self.iX[int(i)] for i in self.dirichlet_indices]
+        return self._X_dirichlet
+
+    @property
+    def X_neumann(self):
+        if self._X_neumann is None:
+            self._X_neumann = [self.iX[int(i)] for i in self.neumann_indices]
+        return self._X_neumann
+
+    def _dirichlet_at(self, t):
+        """values of a time-varying Dirichlet condition at time t (fds.py:350-353)"""
+        if self._dirichlet_spec is not None:
+            return np.asarray(self._dirichlet_spec.fun(t), dtype=float).reshape(self.dirichlet_indices.size)
+        f = self.dirichlet_fun
+        return np.fromiter((f(t, x) for x in self.X_dirichlet), dtype=float, count=len(self.X_dirichlet))
+
+    # ---- stepping (fds.py:264-290,332-339) ------------------------------------------------------------------------
+    def step(self, dt: float):
+        if self._coupled is not None:
+            raise Exception('this field is advanced by its coupled system; step that instead')
+        if self.iter_mode is IterationMode.none:
+            raise Exception('Evolution law not specified')
+        elif self.iter_mode is IterationMode.dydt:
+            self._ensure_engine().advance(dt)
+        elif self.iter_mode is IterationMode.map:
+            self._t += dt
+            if (self._t - self._n) >= self._dt:
+                self._n = self._t
+                self._ensure_engine().apply_map(self._t)
+        elif self.iter_mode is IterationMode.nil:
+            self._t += dt
+        self._version += 1
+
+    def reset(self):
+        """back to the initial conditions (fds.py:248-262)"""
+        self._drop_engine(pull=False)
+        law = {IterationMode.dydt: lambda: dict(dydt=self.dydt_fun, order=self.order, max_step=self.max_step,
+                                                integrator=self.integrator_type, solver_args=self.solver_args),
+               IterationMode.map: lambda: dict(map_fun=self.map_fun, dt=self._dt),
+               IterationMode.nil: lambda: dict(nil=True)}[self.iter_mode]()
+        d, n, p = self._dirichlet_spec or self.dirichlet_fun, self._neumann_spec or self.neumann_fun, self.project_fun
+        t0, y0 = self.t0, self.y0_fun
+        self.t0 = 0.
+        self.set_evolution(**law)
+        self.set_initial(t0=t0, y0=y0)
+        if self.iter_mode is not IterationMode.nil:
+            self.set_constraints(dirichlet=d, neumann=n, project=p)
+
+    def _order(self):
+        return self.order
+
+    def _identity_projection(self):
+        return self.project_fun is _identity
+
+    def _state_version(self):
+        return (self._version, self._engine.version if self._engine is not None else -1)
+
+    def _bump(self):
+        self._version += 1
+
+    def _ensure_engine(self) -> StepEngine:
+        if self._engine is None:
+            scheme = 'map' if self.iter_mode is IterationMode.map else self.integrator_type
+            max_step = self.max_step if self.iter_mode is IterationMode.dydt else self._dt
+            self._engine = StepEngine([self], scheme, max_step, t0=self._t)
+        return self._engine
+
+    def _drop_engine(self, pull=True):
+        """host-side mutation of the set-up: bring the state back and rebuild the captured step lazily"""
+        if self._coupled is not None:
+            return  # as in the reference, changes after couple() do not reach the coupled integrator (fds.py:171,196)
+        if self._engine is not None:
+            if pull:
+                self._engine.pull_state()
+                self._t = self._engine.t
+            self._engine = None
+
+    # ---- state (fds.py:373-400) -------------------------------------------------------------------------------------
+    @property
+    def y(self):
+        if tracing():
+            return State(self)
+        if self.iter_mode is IterationMode.none:
+            return np.zeros(self.ndim)
+        if self._engine is not None:
+            return self._engine.read(self)
+        return self._host_state[:self.ndim]
+
+    @property
+    def t(self):
+        if self._coupled is not None:
+            return self._coupled.t
+        if self.iter_mode is IterationMode.dydt and self._engine is not None:
+            return self._engine.t
+        return self._t if self.iter_mode is not IterationMode.none else self.t0
+
+    @property
+    def dt(self):
+        return self._dt if self.iter_mode in (IterationMode.dydt, IterationMode.map) else 1e-3
+
+    def system(self, name: str) -> 'System':
+        return System(self, {name: self})
+
+
+# ------------------------------------------------------------------------------------------------
+# fields on graph domains (gds/gds.py)
+# ------------------------------------------------------------------------------------------------
+class GraphObservable(Observable):
+    """index maps of a graph domain (gds.py:16-55); the maps come from the shared lowering of G"""
+
+    def __init__(self, G, Gd: GraphDomain):
+        self.G, self.Gd = G, Gd
+        self._low = LoweredGraph.of(G, need_faces=(Gd is not GraphDomain.nodes) and not hasattr(G, 'faces'))
+        low = self._low
+        self.nodes, self.edges, self.faces = low.nodes, low.edges, low.faces
+        self.triangles = {}
+        self.edge_weights = low.weights
+        self.outer_face = low.outer_face
+        self._domain_code = _DOMAIN_CODE.get(Gd)
+        X = {GraphDomain.nodes: self.nodes, GraphDomain.edges: self.edges, GraphDomain.triangles: self.triangles,
+             GraphDomain.faces: self.faces}[Gd]
+        Observable.__init__(self, X)
+
+    nodes_i = property(lambda self: {i: v for v, i in self.nodes.items()})
+    edges_i = property(lambda self: {i: e for e, i in self.edges.items()})
+    faces_i = property(lambda self: {i: f for f, i in self.faces.items()})
+
+    @property
+    def edge_orientation(self):   # gds.py:43
+        return {**{e: 1 for e in self.edges}, **{(e[1], e[0]): -1 for e in self.edges}}
+
+
+class gds(fds, GraphObservable):
+    def __init__(self, G, Gd: GraphDomain):
+        GraphObservable.__init__(self, G, Gd)
+        fds.__init__(self, self.X)
+
+    # ---- operator plumbing ------------------------------------------------------------------------------------
+    def _arg(self, y, domain):
+        """operand of an operator: None -> current state (gds.py:153,158,...); host arrays become captured vectors"""
+        if y is None:
+            y = self.y
+        if isinstance(y, gds):
+            assert y._low.dev is self._low.dev, 'Incompatible domains'             # gds.py:168,184
+            y = y.y
+        return y
+
+    def _apply(self, build, *operands, domains):
+        """evaluate `build(*exprs)`: symbolically while tracing (or when handed expressions), eagerly otherwise"""
+        if tracing() or any(isinstance(o, Expr) for o in operands):
+            return build(*[as_expr(o, d, self._low) for o, d in zip(operands, domains)])
+        arrs = [np.asarray(o, dtype=float) for o in operands]
+        if any(a.ndim == 2 for a in arrs):
+            # matrix right-hand side (e.g. laplacian(np.eye(n)), examples/fluid.py:350): column by column
+            ncol = next(a.shape[1] for a in arrs if a.ndim == 2)
+            cols = [self._apply(build, *[a[:, j] if a.ndim == 2 else a for a in arrs], domains=domains) for j in range(ncol)]
+            return np.stack(cols, axis=1)
+        for a, d in zip(arrs, domains):
+            if a.shape != (self._low.rows(d),):
+                raise ValueError(f'operand of shape {a.shape} where a vector of length {self._low.rows(d)} is expected')
+        return _run_eager(self._low, build(*[Const(a, d, self._low) for a, d in zip(arrs, domains)]))
+
+
+def _run_eager(low, expr):
+    """lower one expression to passes, run them on the device, download the result"""
+    ctx = low.ctx
+    n = low.rows(expr.domain)
+    if n == 0:
+        return np.zeros(0)
+
+    def no_leaf(e):
+        raise TraceError('field state used outside an evolution law')
+    lowering = Lowering(ctx, no_leaf, hoist=False)
+    out = Buffer(ctx, n)
+    lowering.store_pass(expr, out)
+    import ctypes as C
+    for p in lowering.passes:
+        d, keep = pass_desc(p)
+        check(lib.gds_pass_run(ctx.h, low.dev.h, C.byref(d), 0.0))
+    return out.download()
+
+
+class node_gds(gds):
+    """dynamical system on the nodes of a graph (gds.py:133-189)"""
+
+    def __init__(self, G):
+        gds.__init__(self, G, GraphDomain.nodes)
+        self.neumann_correction = np.zeros(self.ndim)                               # gds.py:142
+
+    def set_constraints(self, *args, **kwargs):
+        fds.set_constraints(self, *args, **kwargs)
+        # gds.py:116-120: Dirichlet rows of L0 are zeroed (a row mask here); Neumann values become a constant
+        # source that is written once -- time-varying Neumann stays frozen at t=0 like the reference (Appendix B.5)
+        self.neumann_correction[self.neumann_indices] = self.neumann_values
+
+    def _lap(self, y):
+        out = MaskZero(Gather('N_LAP', self._low, y), self.dirichlet_indices)
+        if np.any(self.neumann_correction != 0.):
+            out = out + Const(self.neumann_correction, L.NODES, self._low)
+        return out
+
+    def partial(self, e, y=None):   # gds.py:149-150
+        u, v = e
+        w = np.sqrt(self.edge_weights[self.edges[e]])
+        if y is None:
+            y = self.y
+        return w * (y[self.X[v]] - y[self.X[u]])
+
+    def grad(self, y=None):         # gds.py:152-154
+        return self._apply(lambda a: Gather('E_GRADT', self._low, a), self._arg(y, L.NODES), domains=(L.NODES,))
+
+    def laplacian(self, y=None):    # gds.py:156-159
+        return self._apply(self._lap, self._arg(y, L.NODES), domains=(L.NODES,))
+
+    def bilaplacian(self, y=None):  # gds.py:161-164
+        return self._apply(lambda a: MaskZero(Gather('N_LAP', self._low, self._lap(a)), self.dirichlet_indices),
+                           self._arg(y, L.NODES), domains=(L.NODES,))
+
+    def advect(self, v_field, y=None):      # gds.py:166-177
+        return self._apply(lambda v, a: Gather('N_ADVECT', self._low, v, a), self._arg(v_field, L.EDGES),
+                           self._arg(y, L.NODES), domains=(L.EDGES, L.NODES))
+
+    def lie_advect(self, v_field, y=None):  # gds.py:179-189
+        return self._apply(lambda v, a: Gather('N_LIE', self._low, v, a), self._arg(v_field, L.EDGES),
+                           self._arg(y, L.NODES), domains=(L.EDGES, L.NODES))
+
+
+class edge_gds(gds):
+    """dynamical system on the edges of a graph (gds.py:192-443)"""
+
+    def __init__(self, G, v_free=None):
+        gds.__init__(self, G, GraphDomain.edges)
+        self.neumann_correction = np.zeros(self.ndim)
+
+    def __call__(self, x):          # gds.py:273-274: oriented read, -1 when x is the reverse of the stored edge
+        i = self.X[x]
+        stored = self.nodes[x[0]] == self._low.edge_u[i] and self.nodes[x[1]] == self._low.edge_v[i]
+        return (1 if stored else -1) * self.y[i]
+
+    def _mask(self, expr, *row_sets):
+        rows = [np.asarray(r, dtype=np.int64).ravel() for r in row_sets if r is not None]
+        rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+        return MaskZero(expr, rows) if rows.size else expr
+
+    def _dd(self, y, normal=None):
+        g = self._low
+        return self._mask(unary('NEG', Gather('E_GRADT', g, Gather('N_BDOT', g, y))), self.dirichlet_indices, normal)
+
+    def _d_d(self, y):
+        g = self._low
+        return self._mask(unary('NEG', Gather('E_CURLT', g, Gather('F_CURL', g, y))), self.dirichlet_indices)
+
+    def _lap(self, y, free=None, normal=None):
+        return self._mask(self._dd(y, normal) + self._d_d(y), free)
+
+    def div(self, y=None):          # gds.py:278-280
+        return self._apply(lambda a: unary('NEG', Gather('N_BDOT', self._low, a)), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def influx(self, y=None):       # gds.py:282-285
+        return self._apply(lambda a: Gather('N_INFLUX', self._low, a), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def outflux(self, y=None):      # gds.py:287-290
+        return self._apply(lambda a: Gather('N_OUTFLUX', self._low, a), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def curl(self, y=None):         # gds.py:292-294
+        if self._low.F == 0 and not tracing():
+            return np.zeros(1)      # the reference keeps a 1 x E zero matrix when there are no faces (gds.py:239)
+        return self._apply(lambda a: Gather('F_CURL', self._low, a), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def dd_(self, y=None, normal=None):   # gds.py:296-301
+        return self._apply(lambda a: self._dd(a, normal), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def d_d(self, y=None):          # gds.py:303-307
+        return self._apply(self._d_d, self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def laplacian(self, y=None, free=None, normal=None):   # gds.py:309-317
+        return self._apply(lambda a: self._lap(a, free, normal), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def bilaplacian(self, y=None):  # gds.py:319-324
+        return self._apply(lambda a: self._lap(self._lap(a)), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+    def advect(self, y=None, stiff=False, weighted=True):  # gds.py:326-345 (stiff is unused there as well)
+        if not weighted:
+            raise NotImplementedError('edge_gds.advect(weighted=False) is not part of the device path')
+        g = self._low
+        return self._apply(lambda a: Gather('E_ADVFIN', g, a, EdgeAgg(g, a)), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+
+class simplex_gds(gds):
+    """dynamical system on k-simplices of a graph -- an empty class in the reference as well (gds.py:446-448)"""
+    pass
+
+
+class face_gds(gds):
+    """dynamical system on the faces of a graph (gds.py:450-479)"""
+
+    def __init__(self, G):
+        gds.__init__(self, G, GraphDomain.faces)
+
+    def laplacian(self, y=None):    # gds.py:473-479: -B2 B2^T y
+        g = self._low
+        return self._apply(lambda a: unary('NEG', Gather('F_CURL', g, Gather('E_CURLT', g, a))), self._arg(y, L.FACES),
+                           domains=(L.FACES,))
+
+
+# ------------------------------------------------------------------------------------------------
+# coupling (gds/fds.py:408-546) and System (gds/system.py:16-57)
+# ------------------------------------------------------------------------------------------------
+class coupled_fds(Steppable):
+    """several fields advanced on ONE concatenated state by one integrator (fds.py:408-507); every field's stage
+    of every RK stage runs in the same captured step"""
+
+    def __init__(self, *systems):
+        assert len(systems) >= 1, 'Pass one or more systems to couple'
+        assert all(s.t == 0. for s in systems), 'All systems must be at zero-time initial conditions.'
+        assert all(s.iter_mode != IterationMode.none for s in systems), 'All systems must have evolution laws.'
+        Steppable.__init__(self, IterationMode.dydt)
+        self.t0 = 0.
+        self.cont = [s for s in systems if s.iter_mode is IterationMode.dydt]
+        self.maps = [s for s in systems if s.iter_mode is IterationMode.map]
+        self.nils = [s for s in systems if s.iter_mode is IterationMode.nil]
+        if self.cont and self.maps:
+            raise NotImplementedError('coupling recurrence maps with continuous fields (fds.py:491-503) is not on the device path yet')
+        self.has_integrator = len(self.cont) > 0
+        self._engine = None
+        self._t = 0.
+        members = self.cont or self.maps
+        if self.has_integrator:
+            kind = self.cont[0].integrator_type
+            assert all(s.integrator_type is kind for s in self.cont), 'All continuous dynamics must use the same integrator.'
+            self.dydt_max_step = min(s.max_step for s in self.cont)                  # fds.py:437
+            self._scheme = kind
+        else:
+            self._scheme = 'map'
+            self.dydt_max_step = min((s._dt for s in self.maps), default=1.0)
+        for s in members:
+            s._drop_engine()
+            s._host_state = np.array(s.y0, dtype=float, copy=True)                  # fds.py:439: state taken at couple() time
+            s._coupled = self
+        self._members = members
+
+    def _ensure_engine(self):
+        if self._engine is None and self._members:
+            self._engine = StepEngine(self._members, self._scheme, self.dydt_max_step, t0=self._t)
+            for s in self._members:
+                s._engine = self._engine
+        return self._engine
+
+    def step(self, dt: float):
+        if self.has_integrator:
+            self._ensure_engine().advance(dt)
+            self._t = self._engine.t
+        else:
+            self._t += dt
+            for s in self.maps:
+                s._t = self._t
+            if self.maps:
+                s0 = self.maps[0]
+                if (self._t - s0._n) >= s0._dt:
+                    for s in self.maps:
+                        s._n = self._t
+                    self._ensure_engine().apply_map(self._t)
+        for s in self.nils:
+            s._t += dt
+        for s in self._members:
+            s._version += 1
+
+    def reset(self):
+        raise NotImplementedError
+
+    def observables(self):
+        return self.cont + self.maps + self.nils
+
+    @property
+    def t(self):
+        return self._engine.t if (self.has_integrator and self._engine is not None) else self._t
+
+
+class System:
+    def __init__(self, stepper: Steppable, observables):
+        self._stepper, self._observables = stepper, observables
+
+    @property
+    def stepper(self):
+        return self._stepper
+
+    @property
+    def observables(self):
+        return self._observables
+
+    def step(self, dt: float):
+        self._stepper.step(dt)
+
+    def reset(self):
+        self._stepper.reset()
+
+    @property
+    def t(self):
+        return self._stepper.t
+
+    def solve(self, T: float, dt: float, every: int = 1):
+        """system.py:38-57; every observable comes back as an ndarray (the reference returns from inside its
+        conversion loop, Appendix B.8).  `every` > 1 keeps one snapshot per `every` steps (each snapshot is a
+        device-to-host copy)."""
+        obs = self._observables
+        data = {k: [np.array(v.y, copy=True)] for k, v in obs.items()}
+        time, t, i = [0.], 0., 0
+        while t < T:
+            self._stepper.step(dt)
+            t += dt
+            i += 1
+            if i % every == 0 or not (t < T):
+                for k, v in obs.items():
+                    data[k].append(np.array(v.y, copy=True))
+                time.append(t)
+        return np.array(time), {k: np.array(v) for k, v in data.items()}
+
+
+def couple(observables) -> System:   # fds.py:542-546
+    steppables = [o for o in observables.values() if isinstance(o, Steppable)]
+    return System(coupled_fds(*steppables), observables)

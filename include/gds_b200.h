@@ -178,6 +178,11 @@ int gds_system_state_devptr(gds_system* s, void** dev_out);
  * (the host evaluates the user's g(t_{i+1}, x) -- fds.py:350-357 -- and only the end-of-step row is ever
  * consumed, fds.py:289-290).  Replays the captured graph n_steps times; returns without synchronising. */
 int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values);
+/* the same steps enqueued kernel by kernel with a CUDA-event pair around every launch (measurement aid for the
+ * roofline: per-kernel device time).  class 0/1/2 = passes over nodes/edges/faces, 3 = per-step tail; arrays of 4.
+ * At most 256 steps per call; synchronises. */
+int gds_system_step_timed(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values,
+                          double* class_ms, int64_t* class_launches);
 /* algorithmic facts for the roofline: kernels per step and device bytes held */
 int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
 
