@@ -48,7 +48,7 @@ class StepEngine:
         self.t = float(t0)
         self.low = self.fields[0]._low
         for f in self.fields:
-            if f._low.dev is not self.low.dev:
+            if f._low is not self.low:
                 raise ValueError('fields advanced together must live on the same graph object')
         self.ctx = ctx or self.low.ctx
         self.h = None
@@ -81,8 +81,19 @@ class StepEngine:
 
     def _build(self):
         scheme_code = {Integrators.rk4: L.SCHEME_RK4, Integrators.euler: L.SCHEME_EULER, 'map': L.SCHEME_MAP}[self.scheme]
+        # run every law once with symbolic arguments (this may discover faces, which re-lowers the graph) ...
+        roots = []
+        for f in self.fields:
+            with trace_scope():
+                root = f.map_fun(Time(), Stage(f)) if self.scheme == 'map' else f.dydt_fun(Time(), Stage(f))
+            root = as_expr(root, f._domain_code, f._low)
+            if root.domain is not None and root.domain != f._domain_code:
+                raise ValueError('evolution law returns a vector over the wrong domain')
+            roots.append(root)
+        # ... then bind to the lowered operators; the engine keeps them alive for as long as the captured step runs
+        self.dev = self.low.dev
         h = L.c_vp()
-        check(lib.gds_system_create(self.ctx.h, self.low.dev.h, self.n_state, scheme_code, C.byref(h)))
+        check(lib.gds_system_create(self.ctx.h, self.dev.h, self.n_state, scheme_code, C.byref(h)))
         self.h = h
         import weakref
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
@@ -90,16 +101,8 @@ class StepEngine:
         self.lowering = lowering
         stat_idx, stat_val, dyn_idx = [], [], []
         self.dyn_fields = []
-        for f in self.fields:
+        for f, root in zip(self.fields, roots):
             off, n, order = self.offsets[id(f)], f.ndim, f._order()
-            with trace_scope():
-                if self.scheme == 'map':
-                    root = f.map_fun(Time(), Stage(f))
-                else:
-                    root = f.dydt_fun(Time(), Stage(f))
-            root = as_expr(root, f._domain_code, f._low)
-            if root.domain is not None and root.domain != f._domain_code:
-                raise ValueError('evolution law returns a vector over the wrong domain')
             dmask = None
             if self.scheme != 'map' and f.dirichlet_indices.size:
                 dmask = Mask(self.ctx, n, f.dirichlet_indices)          # fds.py:303

@@ -290,17 +290,20 @@ class GraphObservable(Observable):
 
     def __init__(self, G, Gd: GraphDomain):
         self.G, self.Gd = G, Gd
-        self._low = LoweredGraph.of(G, need_faces=(Gd is not GraphDomain.nodes) and not hasattr(G, 'faces'))
+        self._low = LoweredGraph.of(G, need_faces=(Gd is not GraphDomain.nodes))
         low = self._low
-        self.nodes, self.edges, self.faces = low.nodes, low.edges, low.faces
         self.triangles = {}
         self.edge_weights = low.weights
-        self.outer_face = low.outer_face
         self._domain_code = _DOMAIN_CODE.get(Gd)
         X = {GraphDomain.nodes: self.nodes, GraphDomain.edges: self.edges, GraphDomain.triangles: self.triangles,
              GraphDomain.faces: self.faces}[Gd]
         Observable.__init__(self, X)
 
+    # index maps live in the shared lowering; `faces` walks the embedding on first use (gds.py:21-36)
+    nodes = property(lambda self: self._low.nodes)
+    edges = property(lambda self: self._low.edges)
+    faces = property(lambda self: self._low.faces)
+    outer_face = property(lambda self: self._low.outer_face)
     nodes_i = property(lambda self: {i: v for v, i in self.nodes.items()})
     edges_i = property(lambda self: {i: e for e, i in self.edges.items()})
     faces_i = property(lambda self: {i: f for f, i in self.faces.items()})
@@ -321,7 +324,7 @@ class gds(fds, GraphObservable):
         if y is None:
             y = self.y
         if isinstance(y, gds):
-            assert y._low.dev is self._low.dev, 'Incompatible domains'             # gds.py:168,184
+            assert y._low is self._low, 'Incompatible domains'             # gds.py:168,184
             y = y.y
         return y
 
@@ -354,9 +357,10 @@ def _run_eager(low, expr):
     out = Buffer(ctx, n)
     lowering.store_pass(expr, out)
     import ctypes as C
+    dev = low.dev
     for p in lowering.passes:
         d, keep = pass_desc(p)
-        check(lib.gds_pass_run(ctx.h, low.dev.h, C.byref(d), 0.0))
+        check(lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0))
     return out.download()
 
 

@@ -67,44 +67,70 @@ def native_faces(n_nodes, edge_u, edge_v, adj_ptr, adj_nbr, pos):
 
 
 class LoweredGraph:
-    """Index maps + device operators of one graph.  Use `LoweredGraph.of(G)`."""
+    """Index maps + device operators of one graph, shared by every field built on it.  Use `LoweredGraph.of(G)`.
 
-    def __init__(self, G, need_faces: bool, ctx: Context = None):
+    Faces are found on first use (the reference walks them eagerly for every field, gds.py:31-36, which is what
+    makes node fields on non-planar graphs need the `G.faces = []` hook); the device arrays are lowered when first
+    needed and re-lowered once if faces arrive later."""
+
+    def __init__(self, G, ctx: Context = None):
         self.ctx = ctx or Context.default()
         self.G = G
         self.native = isinstance(G, NativeGraph)
-        if self.native:
-            self._init_native(G, need_faces)
-        else:
-            self._init_nx(G, need_faces)
-        self.has_faces = need_faces or self.F > 0
-
-    # -- from networkx ---------------------------------------------------------------------------------
-    def _init_nx(self, G, need_faces):
-        self.nodes = {v: i for i, v in enumerate(G.nodes())}                       # gds.py:21
-        self.edges = bidict({e: i for i, e in enumerate(G.edges())})               # gds.py:23
-        V, E = len(self.nodes), len(self.edges)
-        self.V, self.E = V, E
-        nodes = self.nodes
-        self.edge_u = np.fromiter((nodes[e[0]] for e in self.edges), dtype=np.int32, count=E)
-        self.edge_v = np.fromiter((nodes[e[1]] for e in self.edges), dtype=np.int32, count=E)
-        # gds.py:39-40, generators.py:600-607: attribute 'weight', default 1.0
-        self.weights = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=E)
-        face_ptr = face_nodes = None
+        self._dev = None
+        self._faces_done = False
         self.outer_face = None
-        if hasattr(G, 'faces'):                                                      # gds.py:31-32
-            faces = [tuple(f) for f in G.faces]
-        elif need_faces:
-            faces = self._walk_faces(G)                                              # gds.py:34
+        self.F = 0
+        if self.native:
+            hg = G.hostgraph(with_faces=False)
+            self._hg = hg
+            self.V, self.E = hg.V, hg.E
+            self.edge_u, self.edge_v = hg.edges()
+            self.weights = np.ones(self.E) if G.weights is None else L.as_f64(G.weights)
+            self.nodes = LazyNodeMap(hg)
+            self.edges = LazyEdgeMap(self)
+            self._faces = LazyFaceMap(hg, self.nodes)
+            if G.kind not in ('triangular', 'hexagonal'):
+                self._faces_done = True          # no embedded faces for grids / 3-D grids / geometric graphs
         else:
-            faces = []
-        self.faces = {f: i for i, f in enumerate(faces)}                            # gds.py:35
-        self.F = len(self.faces)
-        if self.F:
-            face_ptr = np.cumsum([0] + [len(f) for f in faces]).astype(np.int64)
-            face_nodes = np.fromiter((nodes[n] for f in faces for n in f), dtype=np.int32, count=int(face_ptr[-1]))
-        unit = bool(np.all(self.weights == 1.0))
-        self.dev = DeviceGraph(self.ctx, V, self.edge_u, self.edge_v, None if unit else self.weights, face_ptr, face_nodes)
+            self.nodes = {v: i for i, v in enumerate(G.nodes())}                       # gds.py:21
+            self.edges = bidict({e: i for i, e in enumerate(G.edges())})               # gds.py:23
+            V, E = len(self.nodes), len(self.edges)
+            self.V, self.E = V, E
+            nodes = self.nodes
+            self.edge_u = np.fromiter((nodes[e[0]] for e in self.edges), dtype=np.int32, count=E)
+            self.edge_v = np.fromiter((nodes[e[1]] for e in self.edges), dtype=np.int32, count=E)
+            # gds.py:39-40, generators.py:600-607: attribute 'weight', default 1.0
+            self.weights = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=E)
+            self._faces = {}
+            if hasattr(G, 'faces'):                                                      # gds.py:31-32
+                self._set_faces([tuple(f) for f in G.faces])
+
+    # -- faces -------------------------------------------------------------------------------------------
+    def _set_faces(self, faces):
+        self._faces = {f: i for i, f in enumerate(faces)}                               # gds.py:35
+        self.F = len(self._faces)
+        self._face_list = faces
+        self._faces_done = True
+        self._dev = None                       # lowered again, with B2, on next use
+
+    def ensure_faces(self):
+        if self._faces_done:
+            return
+        if self.native:
+            hg = self.G.hostgraph(with_faces=True)
+            self._hg = hg
+            self._faces = LazyFaceMap(hg, self.nodes)
+            self.F = hg.F
+            self._faces_done = True
+            self._dev = None
+        else:
+            self._set_faces(self._walk_faces(self.G))                                   # gds.py:34
+
+    @property
+    def faces(self):
+        self.ensure_faces()
+        return self._faces
 
     def _walk_faces(self, G):
         pos = nx.get_node_attributes(G, 'pos')
@@ -132,28 +158,36 @@ class LoweredGraph:
         inv = list(nodes.keys())
         return [tuple(inv[j] for j in fn[fp[f]:fp[f + 1]]) for f in range(fp.size - 1)]
 
-    # -- from a native lattice ---------------------------------------------------------------------------
-    def _init_native(self, G, need_faces):
-        hg = G.hostgraph(with_faces=need_faces)
-        self.V, self.E, self.F = hg.V, hg.E, hg.F
-        self.edge_u, self.edge_v = hg.edges()
-        self.weights = np.ones(self.E) if G.weights is None else L.as_f64(G.weights)
-        self.nodes = LazyNodeMap(hg)
-        self.edges = LazyEdgeMap(self)
-        self.faces = LazyFaceMap(hg, self.nodes)
-        self.outer_face = None
-        self.dev = DeviceGraph(self.ctx, self.V, None, None, G.weights, hostgraph=hg.h)
+    # -- device arrays -------------------------------------------------------------------------------------
+    @property
+    def dev(self) -> DeviceGraph:
+        if self._dev is None:
+            if self.native:
+                self._dev = DeviceGraph(self.ctx, self.V, None, None, self.G.weights, hostgraph=self._hg.h)
+            else:
+                face_ptr = face_nodes = None
+                if self.F:
+                    faces, nodes = self._face_list, self.nodes
+                    face_ptr = np.cumsum([0] + [len(f) for f in faces]).astype(np.int64)
+                    face_nodes = np.fromiter((nodes[n] for f in faces for n in f), dtype=np.int32, count=int(face_ptr[-1]))
+                unit = bool(np.all(self.weights == 1.0))
+                self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights,
+                                        face_ptr, face_nodes)
+        return self._dev
 
     def rows(self, domain):
+        if domain == L.FACES:
+            self.ensure_faces()
         return {L.NODES: self.V, L.EDGES: self.E, L.FACES: self.F}[domain]
 
     @staticmethod
-    def of(G, need_faces: bool) -> 'LoweredGraph':
-        cache = G.__dict__.setdefault('_gds_b200_lowered', {})
-        low = cache.get(True) or (cache.get(False) if not need_faces else None)
+    def of(G, need_faces: bool = False) -> 'LoweredGraph':
+        low = G.__dict__.get('_gds_b200_lowered')
         if low is None:
-            low = LoweredGraph(G, need_faces)
-            cache[need_faces] = low
+            low = LoweredGraph(G)
+            G.__dict__['_gds_b200_lowered'] = low
+        if need_faces:
+            low.ensure_faces()
         return low
 
 
