@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -405,6 +407,81 @@ static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
   if (ph.epilogue == GDS_EPI_RHS && depth < 1) GDS_FAIL("RHS pass leaves nothing on the stack");
   return 0;
 }
+static void match_lap_form(const PassHost& ph, LapForm& out);
+
+// Recognise  value = alpha * Z_mask(L0 v) + beta * b + gamma  by running the row program on symbolic affine forms.
+// Anything outside that family (time, other gathers, nonlinear pointwise ops, several Laplacians) is left to the
+// interpreter.
+static void match_lap_form(const PassHost& ph, LapForm& out) {
+  out = LapForm();
+  if (ph.domain != GDS_NODES) return;
+  struct Sym { double alpha = 0, beta = 0, gamma = 0; int v = -1, mask = -1, b = -1; };
+  std::vector<Sym> st;
+  int store = -1;
+  auto scalar = [](const Sym& x) { return x.alpha == 0.0 && x.b < 0; };
+  for (size_t pc = 0; pc < ph.code.size(); ++pc) {
+    uint32_t ins = ph.code[pc], op = ins & 0xff, a = (ins >> 8) & 0xff;
+    switch (op) {
+      case GDS_OP_END: break;
+      case GDS_OP_PUSH_IMM: { Sym x; x.gamma = ph.imm[a]; st.push_back(x); } break;
+      case GDS_OP_PUSH_VEC: { Sym x; x.beta = 1.0; x.b = (int)a; st.push_back(x); } break;
+      case GDS_OP_N_LAP: { Sym x; x.alpha = 1.0; x.v = (int)a; st.push_back(x); } break;
+      case GDS_OP_MASK_ZERO: {
+        if (st.empty()) return;
+        Sym& x = st.back();
+        if (x.alpha == 0.0 || x.b >= 0 || x.gamma != 0.0 || x.mask >= 0) return;
+        x.mask = (int)a;
+      } break;
+      case GDS_OP_NEG: {
+        if (st.empty()) return;
+        Sym& x = st.back();
+        x.alpha = -x.alpha; x.beta = -x.beta; x.gamma = -x.gamma;
+      } break;
+      case GDS_OP_ADD: case GDS_OP_SUB: {
+        if (st.size() < 2) return;
+        Sym y = st.back(); st.pop_back();
+        Sym& x = st.back();
+        double sg = (op == GDS_OP_SUB) ? -1.0 : 1.0;
+        if (y.alpha != 0.0) {
+          if (x.alpha != 0.0) { if (x.v != y.v || x.mask != y.mask) return; x.alpha += sg * y.alpha; }
+          else { x.alpha = sg * y.alpha; x.v = y.v; x.mask = y.mask; }
+        }
+        if (y.b >= 0) {
+          if (x.b >= 0) { if (x.b != y.b) return; x.beta += sg * y.beta; }
+          else { x.b = y.b; x.beta = sg * y.beta; }
+        }
+        x.gamma += sg * y.gamma;
+      } break;
+      case GDS_OP_MUL: {
+        if (st.size() < 2) return;
+        Sym y = st.back(); st.pop_back();
+        Sym& x = st.back();
+        if (scalar(y)) { x.alpha *= y.gamma; x.beta *= y.gamma; x.gamma *= y.gamma; }
+        else if (scalar(x)) { double c = x.gamma; x = y; x.alpha *= c; x.beta *= c; x.gamma *= c; }
+        else return;
+      } break;
+      case GDS_OP_DIV: {
+        if (st.size() < 2) return;
+        Sym y = st.back(); st.pop_back();
+        Sym& x = st.back();
+        if (!scalar(y)) return;
+        x.alpha /= y.gamma; x.beta /= y.gamma; x.gamma /= y.gamma;
+      } break;
+      case GDS_OP_STORE:
+        if (pc + 1 != ph.code.size() || store >= 0) return;   // only as the last instruction
+        store = (int)a;
+        break;
+      default: return;
+    }
+  }
+  if (st.size() != 1) return;
+  const Sym& r = st.back();
+  if (r.alpha == 0.0 || r.v < 0) return;
+  if (!std::isfinite(r.alpha) || !std::isfinite(r.beta) || !std::isfinite(r.gamma)) return;
+  out.ok = true;
+  out.v = r.v; out.mask = r.mask; out.b = (r.b >= 0 && r.beta != 0.0) ? r.b : -1;
+  out.alpha = r.alpha; out.beta = r.beta; out.gamma = r.gamma; out.store = store;
+}
 
 // Resolve a host pass into launch parameters.  `state`/`stage` may be null for eager passes.
 static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* state, const double* stage,
@@ -442,6 +519,14 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
     pp.out[i] = ph.out[i]->d + ph.out_offset[i];
   }
   pp.epilogue = ph.epilogue;
+  pp.unit_weights = g->h.unit_weights ? 1 : 0;
+  if (ph.lap.ok && !ph.special) {
+    pp.lap_v = pp.vec[ph.lap.v];
+    pp.lap_mask = ph.lap.mask >= 0 ? pp.mask[ph.lap.mask] : nullptr;
+    pp.lap_b = ph.lap.b >= 0 ? pp.vec[ph.lap.b] : nullptr;
+    pp.lap_store = ph.lap.store >= 0 ? pp.out[ph.lap.store] : nullptr;
+    pp.lap_alpha = ph.lap.alpha; pp.lap_beta = ph.lap.beta; pp.lap_gamma = ph.lap.gamma;
+  }
   return 0;
 }
 
@@ -450,6 +535,7 @@ extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass,
   GDS_CUDA(cudaSetDevice(c->device));
   PassHost ph;
   GDS_TRY(copy_pass(pass, ph));
+  match_lap_form(ph, ph.lap);
   if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("eager passes take GDS_EPI_NONE");
   PassParams pp;
   GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
@@ -510,6 +596,7 @@ extern "C" int gds_system_add_pass(gds_system* s, const gds_pass_desc* pass) {
   if (s->finalized) GDS_FAIL("system already finalized");
   PassHost ph;
   GDS_TRY(copy_pass(pass, ph));
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_lap_form(ph, ph.lap);
   if (ph.when != GDS_WHEN_STAGE && ph.when != GDS_WHEN_STEP) GDS_FAIL("unknown `when`");
   int64_t rows = domain_rows(s->g, ph.domain);
   if (rows < 0) GDS_FAIL("unknown domain");

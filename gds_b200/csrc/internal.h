@@ -89,6 +89,15 @@ struct GraphDev {
   const int32_t* fe_edge;
 };
 
+// A row program recognised as  value = alpha * Z_mask(L0 v)[row] + beta * b[row] + gamma  (the node-Laplacian laws:
+// heat, wave, coupled-map lattices, diffusion terms) runs in the specialised 4-rows-per-thread kernel instead of the
+// row-program interpreter.
+struct LapForm {
+  bool ok = false;
+  int v = -1, mask = -1, b = -1, store = -1;  // operand slots of the pass (-1: absent)
+  double alpha = 1.0, beta = 0.0, gamma = 0.0;
+};
+
 struct StepRec {  // one row of the per-step table
   double t;       // step start time
   double h;       // step size
@@ -120,6 +129,13 @@ struct PassParams {
   const StepRec* steptab;
   const int64_t* step_counter;
   double t_fixed;  // used when steptab == nullptr (eager application)
+  // specialised Laplacian form (LapForm resolved to pointers); lap_v == nullptr: run the interpreter
+  const double* lap_v;
+  const uint32_t* lap_mask;
+  const double* lap_b;
+  double* lap_store;
+  double lap_alpha, lap_beta, lap_gamma;
+  int32_t unit_weights;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -168,6 +184,7 @@ struct PassHost {  // a pass as given by the host, operands still symbolic
   int32_t epilogue;
   int64_t state_offset;
   gds_mask* dirichlet;
+  LapForm lap;
   // shift / hold pseudo-passes
   int32_t special = 0;  // 0 normal, 1 shift, 2 hold
   int64_t sp_dst = 0, sp_src = 0, sp_n = 0;

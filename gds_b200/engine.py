@@ -53,10 +53,13 @@ class StepEngine:
         self.ctx = ctx or self.low.ctx
         self.h = None
         self.offsets = {}
-        off = 0
+        off, self._gaps = 0, []
         for f in self.fields:
-            self.offsets[id(f)] = off
-            off += f.ndim * f._order()
+            start = (off + 3) // 4 * 4          # every field starts on a 32-byte boundary (128-bit loads / stores)
+            if start > off:
+                self._gaps.append((off, start - off))
+            self.offsets[id(f)] = start
+            off = start + f.ndim * f._order()
         self.n_state = off
         self.externals = {}      # id(field) -> [field, Buffer, version]
         self._keep = []
@@ -125,6 +128,8 @@ class StepEngine:
                 else:
                     stat_idx.append(idx)
                     stat_val.append(np.asarray(f.dirichlet_values, dtype=np.float64))
+        for (o, k) in self._gaps:
+            check(lib.gds_system_add_hold(self.h, o, k))
         if stat_idx:
             i, v = L.as_i64(np.concatenate(stat_idx)), L.as_f64(np.concatenate(stat_val))
             check(lib.gds_system_set_dirichlet(self.h, ptr(i), ptr(v), i.size, 0))
