@@ -14,7 +14,8 @@ from .types import (GraphDomain, IterationMode, Integrators, Steppable, Observab
                     VectorObservable)
 from .utils import bidict, fun_ary, dict_fun, combine_bcs, const_edge_bc, zero_edge_bc  # noqa: F401
 from .device import Context, Buffer, Mask, DeviceGraph  # noqa: F401
-from .graph import LoweredGraph, NativeGraph  # noqa: F401
+from .graph import LoweredGraph, NativeGraph, distribute  # noqa: F401
+from .partition import Partition, HaloExchange, split_bounds  # noqa: F401
 from .engine import StepEngine, step_table  # noqa: F401
 from .fields import (fds, gds, GraphObservable, node_gds, edge_gds, simplex_gds, face_gds, coupled_fds, couple,  # noqa: F401
                      System, BoundarySpec)

@@ -102,6 +102,14 @@ _sig('gds_system_get_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_state_devptr', c_vp, P(c_vp))
 _sig('gds_system_step', c_vp, c_i64, c_vp, c_vp, c_vp)
 _sig('gds_system_step_timed', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp)
+_sig('gds_system_begin_steps', c_vp, c_i64, c_vp, c_vp, c_vp)
+_sig('gds_system_run_stage', c_vp, c_i32, c_i64, c_i64)
+_sig('gds_system_stage_output', c_vp, c_i32, P(c_vp))
+_sig('gds_system_end_step', c_vp)
+_sig('gds_halo_create', c_vp, c_vp, c_i64, P(c_vp))
+_sig('gds_halo_destroy', c_vp)
+_sig('gds_halo_pack', c_vp, c_vp, c_vp)
+_sig('gds_halo_unpack', c_vp, c_vp, c_vp)
 _sig('gds_system_info', c_vp, P(c_i64), P(c_i64))
 _sig('gds_hostgraph_lattice', c_i32, c_i64, c_i64, c_i64, c_f64, c_i32, P(c_vp))
 _sig('gds_hostgraph_from_graph', c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp))
@@ -118,6 +126,8 @@ EXPORTED = [
     'gds_graph_device_bytes', 'gds_pass_run', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
     'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_finalize',
     'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_timed', 'gds_system_info',
+    'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',
+    'gds_halo_create', 'gds_halo_destroy', 'gds_halo_pack', 'gds_halo_unpack',
     'gds_hostgraph_lattice', 'gds_hostgraph_from_graph', 'gds_hostgraph_sizes', 'gds_hostgraph_copy',
     'gds_hostgraph_destroy', 'gds_graph_create_from_host',
 ]

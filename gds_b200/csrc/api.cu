@@ -21,6 +21,14 @@ extern "C" int gds_abi_version(void) { return GDS_ABI_VERSION; }
 // ---------------------------------------------------------------------------------------------------
 extern "C" int gds_ctx_create(int device, gds_ctx** out) {
   if (!out) GDS_FAIL("null out");
+  if (device == -1) {
+    // host-only context: operator assembly and row-program validation without a GPU (index-map parity checks,
+    // dry runs of the tracer).  It never computes: every call that would touch the device fails.
+    gds_ctx* c = new gds_ctx();
+    c->device = -1;
+    *out = c;
+    return 0;
+  }
   int ndev = 0;
   GDS_CUDA(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) GDS_FAIL("no such CUDA device");
@@ -35,8 +43,14 @@ extern "C" int gds_ctx_create(int device, gds_ctx** out) {
   return 0;
 }
 
+#define GDS_NEED_DEVICE(c)                                                                  \
+  do {                                                                                      \
+    if ((c)->device < 0) GDS_FAIL("host-only context: no CUDA device behind this call");    \
+  } while (0)
+
 extern "C" int gds_ctx_destroy(gds_ctx* c) {
   if (!c) return 0;
+  if (c->device < 0) { delete c; return 0; }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -55,17 +69,20 @@ extern "C" int gds_ctx_set_stream(gds_ctx* c, void* s) {
 
 extern "C" int gds_ctx_sync(gds_ctx* c) {
   if (!c) GDS_FAIL("null ctx");
+  GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaSetDevice(c->device));
   GDS_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
 extern "C" int gds_ctx_timer_start(gds_ctx* c) {
+  GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaEventRecord(c->ev0, c->stream));
   return 0;
 }
 
 extern "C" int gds_ctx_timer_stop(gds_ctx* c, double* ms_out) {
+  GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaEventRecord(c->ev1, c->stream));
   GDS_CUDA(cudaEventSynchronize(c->ev1));
   float ms = 0;
@@ -81,6 +98,7 @@ extern "C" int gds_ctx_counters(gds_ctx* c, int64_t* kl, int64_t* gr) {
 }
 
 extern "C" int gds_ctx_flush_l2(gds_ctx* c, int64_t bytes) {
+  GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaSetDevice(c->device));
   if (bytes > c->flush_bytes) {
     if (c->flush_buf) GDS_CUDA(cudaFree(c->flush_buf));
@@ -97,6 +115,12 @@ extern "C" int gds_ctx_flush_l2(gds_ctx* c, int64_t bytes) {
 // ---------------------------------------------------------------------------------------------------
 extern "C" int gds_buf_create(gds_ctx* c, int64_t n, gds_buf** out) {
   if (!c || !out || n < 0) GDS_FAIL("bad argument");
+  if (c->device < 0) {  // shape only
+    gds_buf* b = new gds_buf();
+    b->ctx = c; b->n = n;
+    *out = b;
+    return 0;
+  }
   GDS_CUDA(cudaSetDevice(c->device));
   gds_buf* b = new gds_buf();
   b->ctx = c;
@@ -110,6 +134,7 @@ extern "C" int gds_buf_create(gds_ctx* c, int64_t n, gds_buf** out) {
 
 extern "C" int gds_buf_destroy(gds_buf* b) {
   if (!b) return 0;
+  if (b->ctx->device < 0) { delete b; return 0; }
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d);
@@ -119,6 +144,7 @@ extern "C" int gds_buf_destroy(gds_buf* b) {
 
 extern "C" int gds_buf_upload(gds_buf* b, int64_t off, const double* host, int64_t n) {
   if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  if (b->ctx->device < 0) return 0;  // host-only dry run: nothing to hold the data
   GDS_CUDA(cudaSetDevice(b->ctx->device));
   GDS_CUDA(cudaMemcpyAsync(b->d + off, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, b->ctx->stream));
   GDS_CUDA(cudaStreamSynchronize(b->ctx->stream));
@@ -127,6 +153,7 @@ extern "C" int gds_buf_upload(gds_buf* b, int64_t off, const double* host, int64
 
 extern "C" int gds_buf_download(gds_buf* b, int64_t off, double* host, int64_t n) {
   if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  GDS_NEED_DEVICE(b->ctx);
   GDS_CUDA(cudaSetDevice(b->ctx->device));
   GDS_CUDA(cudaMemcpyAsync(host, b->d + off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, b->ctx->stream));
   GDS_CUDA(cudaStreamSynchronize(b->ctx->stream));
@@ -135,6 +162,7 @@ extern "C" int gds_buf_download(gds_buf* b, int64_t off, double* host, int64_t n
 
 extern "C" int gds_buf_fill(gds_buf* b, int64_t off, int64_t n, double v) {
   if (!b || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  GDS_NEED_DEVICE(b->ctx);
   GDS_CUDA(cudaSetDevice(b->ctx->device));
   return launch_fill(b->ctx, b->d + off, n, v);
 }
@@ -148,7 +176,7 @@ extern "C" int gds_buf_devptr(gds_buf* b, void** dev_out, int64_t* n_out) {
 
 extern "C" int gds_mask_create(gds_ctx* c, int64_t n_rows, const int64_t* rows, int64_t n, gds_mask** out) {
   if (!c || !out || n_rows < 0 || n < 0) GDS_FAIL("bad argument");
-  GDS_CUDA(cudaSetDevice(c->device));
+  if (c->device >= 0) GDS_CUDA(cudaSetDevice(c->device));
   int64_t words = (n_rows + 31) / 32 + 1;
   std::vector<uint32_t> bits((size_t)words, 0u);
   for (int64_t i = 0; i < n; ++i) {
@@ -158,6 +186,7 @@ extern "C" int gds_mask_create(gds_ctx* c, int64_t n_rows, const int64_t* rows, 
   }
   gds_mask* m = new gds_mask();
   m->ctx = c; m->n_rows = n_rows; m->n_set = n;
+  if (c->device < 0) { *out = m; return 0; }
   GDS_CUDA(cudaMalloc((void**)&m->d, (size_t)words * 4));
   GDS_CUDA(cudaMemcpyAsync(m->d, bits.data(), (size_t)words * 4, cudaMemcpyHostToDevice, c->stream));
   GDS_CUDA(cudaStreamSynchronize(c->stream));
@@ -167,6 +196,7 @@ extern "C" int gds_mask_create(gds_ctx* c, int64_t n_rows, const int64_t* rows, 
 
 extern "C" int gds_mask_destroy(gds_mask* m) {
   if (!m) return 0;
+  if (m->ctx->device < 0) { delete m; return 0; }
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   cudaFree(m->d);
@@ -206,11 +236,17 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
                                 const double* w, int64_t F, const int64_t* face_ptr, const int32_t* face_nodes,
                                 gds_graph** out) {
   if (!c || !out) GDS_FAIL("bad argument");
-  GDS_CUDA(cudaSetDevice(c->device));
+  if (c->device >= 0) GDS_CUDA(cudaSetDevice(c->device));
   gds_graph* g = new gds_graph();
   g->ctx = c;
   int rc = lower_graph_host(V, E, eu, ev, w, F, face_ptr, face_nodes, g->h);
   if (rc) { delete g; return rc; }
+  if (c->device < 0) {  // host-only: index maps for export, no device arrays
+    memset(&g->d, 0, sizeof(g->d));
+    g->d.V = V; g->d.E = E; g->d.F = F;
+    *out = g;
+    return 0;
+  }
   HostGraph& h = g->h;
   GraphDev& d = g->d;
   memset(&d, 0, sizeof(d));
@@ -220,8 +256,9 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
     std::vector<uint32_t> soff;
     sell_offsets(V, h.n_ptr, soff);
     int64_t slots = (int64_t)soff[soff.size() - 1] * GDS_SLICE;
+    const bool unitw = h.unit_weights;  // unit-weight kernels never read a weight: nothing to build or upload
     std::vector<int32_t> nbr((size_t)slots), edge((size_t)slots, -1);
-    std::vector<double> wv((size_t)slots, 0.0);
+    std::vector<double> wv(unitw ? 0 : (size_t)slots, 0.0);
     for (int64_t x = 0; x < V; ++x) {
       int64_t base = (int64_t)soff[x >> 5] * GDS_SLICE + (x & 31);
       int64_t width = soff[(x >> 5) + 1] - soff[x >> 5];
@@ -232,7 +269,7 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
           int64_t a = h.n_ptr[x] + j;
           nbr[slot] = h.n_nbr[a];
           edge[slot] = (h.n_edge[a] << 1) | (h.n_sign[a] > 0 ? 1 : 0);
-          wv[slot] = h.w[h.n_edge[a]];
+          if (!unitw) wv[slot] = h.w[h.n_edge[a]];
         } else {
           nbr[slot] = (int32_t)x;
         }
@@ -247,13 +284,15 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
     GDS_TRY(upload(g, soff, &d.n_soff));
     GDS_TRY(upload(g, nbr, &d.n_nbr));
     GDS_TRY(upload(g, edge, &d.n_edge));
-    GDS_TRY(upload(g, wv, &d.n_w));
+    if (!unitw) GDS_TRY(upload(g, wv, &d.n_w));
     GDS_TRY(upload(g, h.n_dinv, &d.n_dinv));
   }
   GDS_TRY(upload(g, h.eu, &d.e_u));
   GDS_TRY(upload(g, h.ev, &d.e_v));
-  GDS_TRY(upload(g, h.omega, &d.e_omega));
-  GDS_TRY(upload(g, h.w, &d.e_w));
+  if (!h.unit_weights) {
+    GDS_TRY(upload(g, h.omega, &d.e_omega));
+    GDS_TRY(upload(g, h.w, &d.e_w));
+  }
   // edge -> faces and face -> edges
   auto pack = [](int64_t n_rows, const std::vector<int64_t>& ptr, const std::vector<int32_t>& idx,
                  const std::vector<int8_t>& sign, std::vector<uint32_t>& soff, std::vector<int32_t>& packed) {
@@ -282,6 +321,7 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
 
 extern "C" int gds_graph_destroy(gds_graph* g) {
   if (!g) return 0;
+  if (g->ctx->device < 0) { delete g; return 0; }
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   for (void* p : g->allocs) cudaFree(p);
@@ -532,9 +572,10 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
 
 extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass, double t) {
   if (!c || !g) GDS_FAIL("bad argument");
-  GDS_CUDA(cudaSetDevice(c->device));
   PassHost ph;
-  GDS_TRY(copy_pass(pass, ph));
+  GDS_TRY(copy_pass(pass, ph));   // validation works on a host-only context too
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
   match_lap_form(ph, ph.lap);
   if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("eager passes take GDS_EPI_NONE");
   PassParams pp;
@@ -549,6 +590,7 @@ extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass,
 extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int32_t scheme, gds_system** out) {
   if (!c || !g || !out || n_state <= 0) GDS_FAIL("bad argument");
   if (scheme != GDS_SCHEME_EULER && scheme != GDS_SCHEME_RK4 && scheme != GDS_SCHEME_MAP) GDS_FAIL("unknown scheme");
+  GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaSetDevice(c->device));
   gds_system* s = new gds_system();
   s->ctx = c; s->g = g; s->n_state = n_state; s->scheme = scheme;
@@ -686,16 +728,12 @@ struct LaunchTimer {
 };
 static int domain_class(int32_t domain) { return domain == GDS_NODES ? 0 : (domain == GDS_EDGES ? 1 : 2); }
 
-// enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
-static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
+static int n_stages_of(const gds_system* s) { return (s->scheme == GDS_SCHEME_RK4) ? 4 : 1; }
+
+// per-step passes: sub-expressions of the accepted state only, evaluated once before stage 1
+static int enqueue_prestep(gds_system* s, int cur, LaunchTimer* lt) {
   gds_ctx* c = s->ctx;
   const double* yn = s->Y[cur];
-  double* ynew = s->Y[cur ^ 1];
-  int n_stages = (s->scheme == GDS_SCHEME_RK4) ? 4 : 1;
-  static const double a_next[4] = {0.5, 0.5, 1.0, 0.0};
-  static const double c_stage[4] = {0.0, 0.5, 0.5, 1.0};
-  static const double acc_w[4] = {1.0, 2.0, 2.0, 1.0};
-  // per-step passes (sub-expressions of the accepted state only)
   for (const PassHost& ph : s->passes) {
     if (ph.when != GDS_WHEN_STEP) continue;
     PassParams pp;
@@ -705,44 +743,73 @@ static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
     GDS_TRY(launch_pass(c, pp, ph.domain));
     if (lt) GDS_TRY(lt->end());
   }
-  for (int st = 0; st < n_stages; ++st) {
-    const double* stage = (st == 0) ? yn : s->XS[(st - 1) & 1];
-    double* xnext = (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : nullptr;
-    for (const PassHost& ph : s->passes) {
-      if (ph.when != GDS_WHEN_STAGE) continue;
-      PassParams pp;
-      GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
-      if (ph.special) pp.n_rows = ph.sp_n;
-      pp.steptab = s->d_steptab; pp.step_counter = s->d_counter;
-      pp.c_stage = (s->scheme == GDS_SCHEME_RK4) ? c_stage[st] : 0.0;
-      if (ph.epilogue == GDS_EPI_RHS) {
-        int64_t off = ph.state_offset;
-        pp.dmask = ph.dirichlet ? ph.dirichlet->d : nullptr;
-        pp.yn = yn + off;
-        pp.ynew = ynew + off;
-        if (s->scheme == GDS_SCHEME_RK4) {
-          pp.acc_in = s->ACC + off; pp.acc_out = s->ACC + off;
-          pp.xnext = xnext ? xnext + off : nullptr;
-          pp.acc_w = acc_w[st]; pp.a_next = a_next[st]; pp.fin = 1.0 / 6.0;
-          pp.stage_mode = (st == 0) ? 0 : (st == 3 ? 2 : 1);
-        } else if (s->scheme == GDS_SCHEME_EULER) {
-          pp.stage_mode = 3;
-        } else {
-          pp.stage_mode = 4;
-        }
+  return 0;
+}
+
+// vector a stage writes: the next stage state, or the new accepted state after the last stage
+static double* stage_output(gds_system* s, int cur, int st) {
+  return (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : s->Y[cur ^ 1];
+}
+
+// every pass of stage `st` over rows [row0, row1) of each pass's domain (row1 < 0: all rows)
+static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_t row0 = 0, int64_t row1 = -1) {
+  gds_ctx* c = s->ctx;
+  const double* yn = s->Y[cur];
+  double* ynew = s->Y[cur ^ 1];
+  static const double a_next[4] = {0.5, 0.5, 1.0, 0.0};
+  static const double c_stage[4] = {0.0, 0.5, 0.5, 1.0};
+  static const double acc_w[4] = {1.0, 2.0, 2.0, 1.0};
+  const double* stage = (st == 0) ? yn : s->XS[(st - 1) & 1];
+  double* xnext = (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : nullptr;
+  for (const PassHost& ph : s->passes) {
+    if (ph.when != GDS_WHEN_STAGE) continue;
+    PassParams pp;
+    GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
+    if (ph.special) pp.n_rows = ph.sp_n;
+    pp.row0 = std::min<int64_t>(row0, pp.n_rows);
+    if (row1 >= 0) pp.n_rows = std::min<int64_t>(row1, pp.n_rows);
+    pp.steptab = s->d_steptab; pp.step_counter = s->d_counter;
+    pp.c_stage = (s->scheme == GDS_SCHEME_RK4) ? c_stage[st] : 0.0;
+    if (ph.epilogue == GDS_EPI_RHS) {
+      int64_t off = ph.state_offset;
+      pp.dmask = ph.dirichlet ? ph.dirichlet->d : nullptr;
+      pp.yn = yn + off;
+      pp.ynew = ynew + off;
+      if (s->scheme == GDS_SCHEME_RK4) {
+        pp.acc_in = s->ACC + off; pp.acc_out = s->ACC + off;
+        pp.xnext = xnext ? xnext + off : nullptr;
+        pp.acc_w = acc_w[st]; pp.a_next = a_next[st]; pp.fin = 1.0 / 6.0;
+        pp.stage_mode = (st == 0) ? 0 : (st == 3 ? 2 : 1);
+      } else if (s->scheme == GDS_SCHEME_EULER) {
+        pp.stage_mode = 3;
+      } else {
+        pp.stage_mode = 4;
       }
-      if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
-      GDS_TRY(launch_pass(c, pp, ph.domain));
-      if (lt) GDS_TRY(lt->end());
     }
+    if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
+    GDS_TRY(launch_pass(c, pp, ph.domain));
+    if (lt) GDS_TRY(lt->end());
   }
+  return 0;
+}
+
+// Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter
+static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
+  gds_ctx* c = s->ctx;
+  double* ynew = s->Y[cur ^ 1];
   if (lt) GDS_TRY(lt->begin(3));
-  // Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, nullptr, s->n_dir_static, 0, s->d_counter));
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_dyn, nullptr, s->d_bc_tab, s->n_dir_dyn, s->n_dir_dyn, s->d_counter));
   GDS_TRY(launch_advance_counter(c, s->d_counter));
   if (lt) GDS_TRY(lt->end());
   return 0;
+}
+
+// enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
+static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
+  GDS_TRY(enqueue_prestep(s, cur, lt));
+  for (int st = 0; st < n_stages_of(s); ++st) GDS_TRY(enqueue_stage(s, cur, st, lt));
+  return enqueue_tail(s, cur, lt);
 }
 
 #define GDS_STEP_CAPACITY 4096  // steps per table upload; longer runs are chunked
@@ -878,6 +945,92 @@ extern "C" int gds_system_step_timed(gds_system* s, int64_t n_steps, const doubl
   if (rc) return rc;
   if (e != cudaSuccess) GDS_FAIL(std::string("stream sync failed: ") + cudaGetErrorString(e));
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage-granular stepping (one rank of a partitioned system: the halo exchange sits between the stages)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_system_begin_steps(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (n_steps < 0 || n_steps > s->cap_steps) GDS_FAIL("step count outside the table capacity (4096)");
+  if (s->n_dir_dyn > 0 && !bc) GDS_FAIL("dynamic Dirichlet values missing");
+  gds_ctx* c = s->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  std::vector<StepRec> tab((size_t)n_steps);
+  for (int64_t i = 0; i < n_steps; ++i) { tab[i].t = t[i]; tab[i].h = h[i]; }
+  GDS_CUDA(cudaMemcpyAsync(s->d_steptab, tab.data(), (size_t)n_steps * sizeof(StepRec), cudaMemcpyHostToDevice, c->stream));
+  if (s->n_dir_dyn > 0)
+    GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc, (size_t)n_steps * s->n_dir_dyn * 8, cudaMemcpyHostToDevice, c->stream));
+  GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaStreamSynchronize(c->stream));  // the tables come from pageable memory the caller may reuse
+  return 0;
+}
+
+extern "C" int gds_system_run_stage(gds_system* s, int32_t stage, int64_t row_begin, int64_t row_end) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (stage < 0 || stage >= n_stages_of(s)) GDS_FAIL("no such stage");
+  if (row_begin < 0 || (row_begin & 31)) GDS_FAIL("row_begin must be a non-negative multiple of 32");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  if (stage == 0 && row_begin == 0) GDS_TRY(enqueue_prestep(s, s->cur, nullptr));
+  return enqueue_stage(s, s->cur, stage, nullptr, row_begin, row_end);
+}
+
+extern "C" int gds_system_stage_output(gds_system* s, int32_t stage, void** dev_out) {
+  if (!s || !dev_out) GDS_FAIL("bad argument");
+  if (stage < 0 || stage >= n_stages_of(s)) GDS_FAIL("no such stage");
+  *dev_out = stage_output(s, s->cur, stage);
+  return 0;
+}
+
+extern "C" int gds_system_end_step(gds_system* s) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  GDS_TRY(enqueue_tail(s, s->cur, nullptr));
+  s->cur ^= 1;
+  return 0;
+}
+
+// halo lists: a set of state-vector positions packed into / scattered from a contiguous exchange buffer
+struct gds_halo {
+  gds_ctx* ctx;
+  int64_t* d_idx = nullptr;
+  int64_t n = 0;
+};
+
+extern "C" int gds_halo_create(gds_ctx* c, const int64_t* state_idx, int64_t n, gds_halo** out) {
+  if (!c || !out || n < 0 || (n > 0 && !state_idx)) GDS_FAIL("bad argument");
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  gds_halo* hl = new gds_halo();
+  hl->ctx = c; hl->n = n;
+  GDS_CUDA(cudaMalloc((void**)&hl->d_idx, (size_t)std::max<int64_t>(n, 1) * 8));
+  if (n) GDS_CUDA(cudaMemcpy(hl->d_idx, state_idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+  *out = hl;
+  return 0;
+}
+
+extern "C" int gds_halo_destroy(gds_halo* hl) {
+  if (!hl) return 0;
+  cudaSetDevice(hl->ctx->device);
+  cudaStreamSynchronize(hl->ctx->stream);
+  cudaFree(hl->d_idx);
+  delete hl;
+  return 0;
+}
+
+extern "C" int gds_halo_pack(gds_halo* hl, const void* vec_dev, void* buf_dev) {
+  if (!hl || !vec_dev || !buf_dev) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(hl->ctx->device));
+  return launch_halo(hl->ctx, (double*)vec_dev, (double*)buf_dev, hl->d_idx, hl->n, 0);
+}
+
+extern "C" int gds_halo_unpack(gds_halo* hl, const void* buf_dev, void* vec_dev) {
+  if (!hl || !vec_dev || !buf_dev) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(hl->ctx->device));
+  return launch_halo(hl->ctx, (double*)vec_dev, (double*)buf_dev, hl->d_idx, hl->n, 1);
 }
 
 extern "C" int gds_system_info(gds_system* s, int64_t* kps, int64_t* bytes) {

@@ -106,7 +106,8 @@ struct StepRec {  // one row of the per-step table
 // Parameters of one pass launch (passed by value: lives in the constant bank, warp-uniform reads)
 struct PassParams {
   GraphDev g;
-  int64_t n_rows;
+  int64_t row0;    // first row of this launch (multiple of 32)
+  int64_t n_rows;  // one past the last row
   int32_t n_code;
   uint32_t code[GDS_MAX_CODE];
   double imm[GDS_MAX_IMM];
@@ -223,3 +224,4 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
                      int64_t n, int64_t n_dyn_stride, const int64_t* counter);
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
+int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int64_t n, int scatter);

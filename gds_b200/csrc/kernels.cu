@@ -236,7 +236,7 @@ __device__ __forceinline__ double powi(double x, int n) {
 
 template <int DOMAIN, bool UNITW>
 __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ PassParams p) {
-  const int64_t row = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (row >= p.n_rows) return;
   const int lane = threadIdx.x & 31;
   const GraphDev& g = p.g;
@@ -396,7 +396,7 @@ __device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, b
 
 template <bool UNITW>
 __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant__ PassParams p) {
-  const int64_t r0 = ((int64_t)blockIdx.x * LAP4_BLOCK + threadIdx.x) * 4;
+  const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAP4_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
   const bool full = r0 + 3 < p.n_rows;
   const GraphDev& g = p.g;
@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
-  if (p.n_rows <= 0) return 0;
+  const int64_t rows = p.n_rows - p.row0;
+  if (rows <= 0) return 0;
   const bool unitw = p.unit_weights != 0;
   if (p.lap_v && domain == GDS_NODES) {
     // 128-bit accesses need every row-0 pointer on a 16-byte boundary (the engine lays fields out that way)
@@ -507,7 +508,7 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     if (p.epilogue == GDS_EPI_RHS)
       ok = ok && aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
     if (ok) {
-      int64_t quads = (p.n_rows + 3) / 4;
+      int64_t quads = (rows + 3) / 4;
       int64_t blocks = (quads + LAP4_BLOCK - 1) / LAP4_BLOCK;
       if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
       if (unitw) lap4_kernel<true><<<(unsigned)blocks, LAP4_BLOCK, 0, ctx->stream>>>(p);
@@ -517,7 +518,7 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       return 0;
     }
   }
-  int64_t blocks = (p.n_rows + BLOCK - 1) / BLOCK;
+  int64_t blocks = (rows + BLOCK - 1) / BLOCK;
   if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
   dim3 grid((unsigned)blocks), block(BLOCK);
   if (domain == GDS_NODES) {
@@ -580,6 +581,25 @@ int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v) {
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   fill_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p, n, v);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+// halo pack (buf[i] = vec[idx[i]]) / unpack (vec[idx[i]] = buf[i]): boundary values of a partitioned state vector
+__global__ void halo_kernel(double* __restrict__ vec, double* __restrict__ buf, const int64_t* __restrict__ idx, int64_t n,
+                            int scatter) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t k = idx[i];
+  if (scatter) vec[k] = buf[i];
+  else buf[i] = vec[k];
+}
+
+int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int64_t n, int scatter) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  halo_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(vec, buf, idx, n, scatter);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;

@@ -51,6 +51,7 @@ class StepEngine:
             if f._low is not self.low:
                 raise ValueError('fields advanced together must live on the same graph object')
         self.ctx = ctx or self.low.ctx
+        self.part = self.low.part          # this rank's part of a distributed graph (None: the whole graph is here)
         self.h = None
         self.offsets = {}
         off, self._gaps = 0, []
@@ -100,7 +101,7 @@ class StepEngine:
         self.h = h
         import weakref
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
-        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True)
+        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True, single_hop=self.part is not None)
         self.lowering = lowering
         stat_idx, stat_val, dyn_idx = [], [], []
         self.dyn_fields = []
@@ -138,12 +139,16 @@ class StepEngine:
             i = L.as_i64(np.concatenate(dyn_idx))
             self.n_dyn = i.size
             check(lib.gds_system_set_dirichlet(self.h, ptr(i), None, i.size, 1))
+        if self.part is not None:
+            check(lib.gds_ctx_set_stream(self.ctx.h, None))     # the step is captured on the context's own stream
         check(lib.gds_system_finalize(self.h))
         kps, nbytes = L.c_i64(), L.c_i64()
         check(lib.gds_system_info(self.h, C.byref(kps), C.byref(nbytes)))
         self.kernels_per_step = kps.value
         self.device_bytes = nbytes.value + lowering.temp_bytes
         self.push_state()
+        if self.part is not None:
+            self._setup_partitioned()
 
     # ---- state movement ------------------------------------------------------------------------------------
     def push_state(self):
@@ -231,13 +236,77 @@ class StepEngine:
         ts, hs, t_after, t_new, bc = plan
         if ts.size == 0:
             return
-        check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+        if self.part is not None:
+            self._run_partitioned(ts, hs, bc)
+        else:
+            check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
         self.steps_taken += int(ts.size)
         self.version += 1
         self._read_cache.clear()
         self.t = t_new
         for f in self.fields:
             f._dt = float(hs[-1])
+
+    # ---- one rank of a partitioned system ------------------------------------------------------
+    def _setup_partitioned(self):
+        """halo lists over every state block, exchange buffers, and the transport stream"""
+        import torch
+        from .partition import HaloExchange
+        part = self.part
+        for f in self.fields:
+            if f._domain_code != L.NODES:
+                raise NotImplementedError('distributed graphs carry node fields only')
+        blocks = [self.offsets[id(f)] + f.ndim * i for f in self.fields for i in range(f._order())]
+        self.hx = HaloExchange(part, nblocks=len(blocks))
+        self._halo = []
+        for which in ('send', 'recv'):
+            idx = L.as_i64(self.hx.state_indices(blocks, which))
+            h = L.c_vp()
+            check(lib.gds_halo_create(self.ctx.h, ptr(idx), idx.size, C.byref(h)))
+            self._halo.append(h)
+            import weakref
+            weakref.finalize(self, lib.gds_halo_destroy, h)
+        dev = torch.device('cuda', self.ctx.device)
+        self._send = torch.empty(max(1, self.hx.n_send), dtype=torch.float64, device=dev)
+        self._recv = torch.empty(max(1, self.hx.n_recv), dtype=torch.float64, device=dev)
+        # kernels and the NCCL transfers are ordered through torch's current stream
+        self._stream = torch.cuda.current_stream(dev)
+        check(lib.gds_ctx_set_stream(self.ctx.h, self._stream.cuda_stream))
+        self.n_stages = 4 if self.scheme == Integrators.rk4 else 1
+        self.exchanges = 0
+        self._exchange(self._state_ptr())
+
+    def _state_ptr(self):
+        p = L.c_vp()
+        check(lib.gds_system_state_devptr(self.h, C.byref(p)))
+        return p
+
+    def _exchange(self, vec_ptr):
+        """refresh the ghost rows of one state-shaped device vector from their owners"""
+        if not self.part.peers:
+            return
+        check(lib.gds_halo_pack(self._halo[0], vec_ptr, self._send.data_ptr()))
+        for r in self.hx.exchange(self._send, self._recv):
+            r.wait()
+        check(lib.gds_halo_unpack(self._halo[1], self._recv.data_ptr(), vec_ptr))
+        self.exchanges += 1
+
+    def _run_partitioned(self, ts, hs, bc):
+        done = 0
+        while done < ts.size:
+            m = min(ts.size - done, 4096)
+            check(lib.gds_system_begin_steps(self.h, m, ptr(ts[done:done + m]), ptr(hs[done:done + m]),
+                                             ptr(bc[done:done + m]) if bc is not None else None))
+            out = L.c_vp()
+            for _ in range(m):
+                for st in range(self.n_stages):
+                    check(lib.gds_system_run_stage(self.h, st, 0, -1))
+                    if st < self.n_stages - 1:
+                        check(lib.gds_system_stage_output(self.h, st, C.byref(out)))
+                        self._exchange(out)
+                check(lib.gds_system_end_step(self.h))
+                self._exchange(self._state_ptr())
+            done += m
 
     def run_timed(self, plan):
         """like run(), but kernel by kernel with CUDA events around every launch: returns (ms, launches) per class

@@ -44,6 +44,14 @@ class BoundarySpec:
         self.values = None if values is None else np.broadcast_to(np.asarray(values, dtype=float), self.indices.shape).copy()
         self.fun = fun
 
+    def localised(self, part) -> 'BoundarySpec':
+        """the rows of this rank (owned and ghost) of a condition given on GLOBAL node ids"""
+        sel, loc = part.localise(self.indices)
+        if self.fun is None:
+            return BoundarySpec(loc, values=self.values[sel])
+        fun = self.fun
+        return BoundarySpec(loc, fun=lambda t: np.asarray(fun(t), dtype=float)[sel])
+
 
 # ------------------------------------------------------------------------------------------------
 # fds (gds/fds.py:14-400)
@@ -108,6 +116,9 @@ class fds(Observable, Steppable):
             self._n = int(t0)
         if isinstance(y0, np.ndarray):            # the reference recurses here (fds.py:151-152); arrays are accepted
             arr = np.asarray(y0, dtype=float).ravel()
+            part = getattr(getattr(self, '_low', None), 'part', None)
+            if part is not None and arr.size == part.V_global:
+                arr = arr[part.global_ids]            # a global vector: keep this rank's rows
             assert arr.size == self.ndim, 'initial array has the wrong length'
             self.y0_fun = lambda x: arr[self.X[x]]
             keep = np.ones(self.ndim, dtype=bool)
@@ -151,6 +162,9 @@ class fds(Observable, Steppable):
 
         def classify(bc):
             if isinstance(bc, BoundarySpec):
+                part = getattr(getattr(self, '_low', None), 'part', None)
+                if part is not None:
+                    bc = bc.localised(part)           # indices are global node ids: keep this rank's rows
                 dyn = bc.fun is not None
                 vals = np.asarray(bc.fun(0.), dtype=float).reshape(bc.indices.size) if dyn else bc.values
                 fun = (lambda t, x: None) if dyn else (lambda x: None)
@@ -316,7 +330,26 @@ class GraphObservable(Observable):
 class gds(fds, GraphObservable):
     def __init__(self, G, Gd: GraphDomain):
         GraphObservable.__init__(self, G, Gd)
+        if self._low.part is not None and Gd is not GraphDomain.nodes:
+            raise NotImplementedError('distributed graphs carry node fields only')
         fds.__init__(self, self.X)
+
+    # ---- distributed graphs: this rank holds rows [owned | ghosts] -----------------------------------------------
+    @property
+    def partition(self):
+        return self._low.part
+
+    @property
+    def global_ids(self):
+        """global node id of every row of this field (identity on an undistributed graph)"""
+        part = self._low.part
+        return np.arange(self.ndim, dtype=np.int64) if part is None else part.global_ids
+
+    @property
+    def y_owned(self):
+        """values of the rows this rank owns (all rows on an undistributed graph)"""
+        part = self._low.part
+        return self.y if part is None else self.y[:part.n_own]
 
     # ---- operator plumbing ------------------------------------------------------------------------------------
     def _arg(self, y, domain):

@@ -81,7 +81,11 @@ class LoweredGraph:
         self._faces_done = False
         self.outer_face = None
         self.F = 0
-        if self.native:
+        self.part = None                     # Partition when the graph is distributed over several ranks
+        dist_spec = G.__dict__.get('_gds_b200_distribute')
+        if dist_spec is not None and dist_spec[1] > 1:
+            self._init_distributed(G, *dist_spec)
+        elif self.native:
             hg = G.hostgraph(with_faces=False)
             self._hg = hg
             self.V, self.E = hg.V, hg.E
@@ -105,6 +109,47 @@ class LoweredGraph:
             self._faces = {}
             if hasattr(G, 'faces'):                                                      # gds.py:31-32
                 self._set_faces([tuple(f) for f in G.faces])
+
+    # -- one rank's part of a distributed graph -------------------------------------------------------------
+    def _init_distributed(self, G, rank, world, align):
+        from .partition import Partition
+        if self.native and G.kind in ('grid_2d', 'grid') and G.weights is None:
+            A, B, C = (G.dims[0], G.dims[1], 1) if G.kind == 'grid_2d' else (G.dims[2], G.dims[1], G.dims[0])
+            part = Partition.grid_slab(rank, world, A, B, C)      # closed form: only this slab is ever generated
+            gids = part.global_ids
+            if G.kind == 'grid_2d':
+                lab = np.stack([gids // B, gids % B], axis=1)
+            else:
+                lab = np.stack([gids // (B * C), (gids // C) % B, gids % C], axis=1)
+            self.nodes = LazyNodeMap(_LabelSource(lab.astype(np.int64), lab.shape[1]))
+        elif self.native:
+            hg = G.hostgraph(with_faces=False)
+            eu, ev = hg.edges()
+            part = Partition.from_global(rank, world, hg.V, eu, ev, G.weights, align)
+            lab = hg.labels()[part.global_ids]
+            self.nodes = LazyNodeMap(_LabelSource(lab.astype(np.int64), hg.label_dim))
+        else:
+            gnodes = list(G.nodes())
+            gidx = {v: i for i, v in enumerate(gnodes)}
+            E = G.number_of_edges()
+            eu = np.fromiter((gidx[e[0]] for e in G.edges()), dtype=np.int64, count=E)
+            ev = np.fromiter((gidx[e[1]] for e in G.edges()), dtype=np.int64, count=E)
+            w = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=E)
+            part = Partition.from_global(rank, world, len(gnodes), eu, ev, w, align)
+            self.nodes = {gnodes[int(g)]: i for i, g in enumerate(part.global_ids)}
+        self.part = part
+        self.V, self.E = part.n_loc, part.E_loc
+        self.edge_u, self.edge_v = part.edge_u, part.edge_v
+        self.weights = np.ones(self.E) if part.weights is None else part.weights
+        self.edges = LazyEdgeMap(self) if self.native else bidict(
+            {(a, b): i for i, (a, b) in enumerate(self._local_edge_labels())})
+        self._faces = {}
+        self._faces_done = True               # node fields only on distributed graphs
+        self.native_local = True
+
+    def _local_edge_labels(self):
+        inv = list(self.nodes.keys())
+        return [(inv[u], inv[v]) for u, v in zip(self.edge_u, self.edge_v)]
 
     # -- faces -------------------------------------------------------------------------------------------
     def _set_faces(self, faces):
@@ -162,7 +207,10 @@ class LoweredGraph:
     @property
     def dev(self) -> DeviceGraph:
         if self._dev is None:
-            if self.native:
+            if self.part is not None:
+                unit = bool(np.all(self.weights == 1.0))
+                self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights)
+            elif self.native:
                 self._dev = DeviceGraph(self.ctx, self.V, None, None, self.G.weights, hostgraph=self._hg.h)
             else:
                 face_ptr = face_nodes = None
@@ -225,6 +273,28 @@ class NativeGraph:
 
     def number_of_edges(self):
         return self.hostgraph().E
+
+
+class _LabelSource:
+    """label array standing in for a host graph (rows of a distributed graph)"""
+
+    def __init__(self, labels, label_dim):
+        self._labels, self.V, self.label_dim = labels, int(labels.shape[0]), int(label_dim)
+
+    def labels(self):
+        return self._labels
+
+
+def distribute(G, rank=None, world=None, align=1):
+    """Mark graph G (nx.Graph or NativeGraph) as partitioned over `world` ranks; fields built on it afterwards hold
+    this rank's rows (owned nodes, then one-hop ghosts) and exchange boundary values every stage.  Defaults come from
+    the torch.distributed / torchrun environment.  Node fields only."""
+    import os
+    rank = int(os.environ.get('RANK', '0')) if rank is None else int(rank)
+    world = int(os.environ.get('WORLD_SIZE', '1')) if world is None else int(world)
+    G.__dict__['_gds_b200_distribute'] = (rank, world, int(align))
+    G.__dict__.pop('_gds_b200_lowered', None)
+    return G
 
 
 class LazyNodeMap:

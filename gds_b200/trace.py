@@ -331,8 +331,9 @@ class Lowering:
     """Lower expression DAGs to passes.  `resolve_leaf(expr)` maps Stage/State leaves to operand references
     (kind, Buffer|None, offset); the caller owns that policy (system layout)."""
 
-    def __init__(self, ctx, resolve_leaf, hoist=True):
+    def __init__(self, ctx, resolve_leaf, hoist=True, single_hop=False):
         from .device import Buffer, Mask
+        self.single_hop = single_hop   # partitioned graphs: ghost rows of a gathered vector are not valid gather inputs
         self._Buffer, self._Mask = Buffer, Mask
         self.ctx = ctx
         self.resolve_leaf = resolve_leaf
@@ -378,8 +379,11 @@ class Lowering:
         return self._need[k]
 
     # -- operands ----------------------------------------------------------------------------------
-    def operand(self, p, e):
+    def operand(self, p, e, for_gather=False):
         """vector slot in pass p for a vector-valued expression that must live in memory"""
+        if for_gather and self.single_hop and self.has_gather(e):
+            raise TraceError('two-hop operators (a gather of a gathered vector: bilaplacian, Hodge Laplacian, ...) are '
+                             'not available on a distributed graph yet: only one halo layer is exchanged per stage')
         if isinstance(e, (Stage, State)):
             ref = self.resolve_leaf(e)
             if ref[0] == L.VEC_STAGE and p.when == L.WHEN_STEP:
@@ -405,7 +409,7 @@ class Lowering:
         if isinstance(e, EdgeAgg):
             buf = self._Buffer(self.ctx, 4 * rows)
             p = Pass(L.NODES, when, e.graph)
-            ys = self.operand(p, e.args[0])
+            ys = self.operand(p, e.args[0], for_gather=True)
             p.out.append((buf, 0))
             p.emit('N_EAGG', ys, 0)
         else:
@@ -471,7 +475,7 @@ class Lowering:
                     self._masks[key] = self._Mask(self.ctx, e.graph.rows(e.domain), e.rows)
                 p.emit('MASK_ZERO', p.mask_slot(key, self._masks[key]), push=1, pop=1)
         elif isinstance(e, Gather):
-            slots = [self.operand(p, a) for a in e.args]
+            slots = [self.operand(p, a, for_gather=True) for a in e.args]
             if e.kind == 'E_ADVFIN':
                 p.emit('E_ADVFIN', slots[0], slots[1], push=1)
             elif len(slots) == 2:

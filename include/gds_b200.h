@@ -110,6 +110,8 @@ typedef struct {
 const char* gds_last_error(void);
 int gds_abi_version(void);
 
+/* device >= 0: a CUDA device.  device == -1: host-only context -- operator assembly (index maps for
+ * gds_graph_export_csr) and row-program validation work, every call that would touch a GPU fails; it never computes. */
 int gds_ctx_create(int device, gds_ctx** out);
 int gds_ctx_destroy(gds_ctx* ctx);
 int gds_ctx_set_stream(gds_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
@@ -183,6 +185,23 @@ int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const doubl
  * At most 256 steps per call; synchronises. */
 int gds_system_step_timed(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values,
                           double* class_ms, int64_t* class_launches);
+/* ---- stage-granular stepping, for one rank of a system partitioned over several GPUs: the host runs the halo
+ *      exchange between the stages, so the step is enqueued stage by stage instead of replayed as one graph.
+ *      begin_steps uploads the per-step tables; then per step: run_stage(0..n_stages-1) [exchange the vector returned by
+ *      stage_output after each], end_step (Dirichlet overwrite, step counter, accepted-state flip) [exchange the state].
+ *      Rows [row_begin, row_end) restrict every pass of the stage (row_end < 0: to the end; row_begin % 32 == 0), so
+ *      boundary rows can be computed and sent while the interior is still running. ---------------------------------- */
+int gds_system_begin_steps(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values);
+int gds_system_run_stage(gds_system* s, int32_t stage, int64_t row_begin, int64_t row_end);
+int gds_system_stage_output(gds_system* s, int32_t stage, void** dev_out);
+int gds_system_end_step(gds_system* s);
+/* halo lists: positions of a state vector gathered into (pack) / scattered from (unpack) a contiguous device buffer
+ * that the host hands to its transport (NCCL send/recv over NVLink) */
+typedef struct gds_halo gds_halo;
+int gds_halo_create(gds_ctx* ctx, const int64_t* state_idx, int64_t n, gds_halo** out);
+int gds_halo_destroy(gds_halo* h);
+int gds_halo_pack(gds_halo* h, const void* vec_dev, void* buf_dev);
+int gds_halo_unpack(gds_halo* h, const void* buf_dev, void* vec_dev);
 /* algorithmic facts for the roofline: kernels per step and device bytes held */
 int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
 

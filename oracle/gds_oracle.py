@@ -211,8 +211,7 @@ def embedded_faces(G):
     half-edge (tail, head) starts a walk that always turns to the most counter-clockwise neighbour
     (largest turn angle, first maximum wins, never straight back to the tail); the face is the visited node
     tuple starting at `head`.  The reference then removes the first face whose polygon touches every node
-    (shapely test, generators.py:498-506); on a connected plane graph that is the unbounded face, which is
-    the only one traversed clockwise -- we pick it by its negative shoelace area (checked against the
+    (shapely test, generators.py:498-506); on the lattices that is the unbounded face (checked against the
     reference on square/triangular/hexagonal lattices in tests/golden).
     """
     pos = nx.get_node_attributes(G, 'pos')
@@ -250,13 +249,42 @@ def embedded_faces(G):
                 seen.add((path[-1], path[0]))
                 for i in range(1, len(path)):
                     seen.add((path[i - 1], path[i]))
+    # generators.py:498-506: the FIRST face whose closed polygon touches every node is taken as the outer face
+    # (shapely Polygon.intersects(Point): orientation-agnostic, boundary counts).  A face whose bounding box does not
+    # cover all nodes cannot qualify, which keeps the test cheap on lattices.
+    xs = [pos[n][0] for n in G.nodes()]
+    ys = [pos[n][1] for n in G.nodes()]
+    bx0, bx1, by0, by1 = min(xs), max(xs), min(ys), max(ys)
     outer = None
     for i, f in enumerate(faces):
-        if len(f) >= 3 and shoelace_area(pos, f) < 0:
+        fx = [pos[n][0] for n in f]
+        fy = [pos[n][1] for n in f]
+        if min(fx) > bx0 or max(fx) < bx1 or min(fy) > by0 or max(fy) < by1:
+            continue
+        poly = [(float(pos[n][0]), float(pos[n][1])) for n in f]
+        if all(_closed_polygon_touches(poly, x, y) for x, y in zip(xs, ys)):
             outer = f
             del faces[i]
             break
     return faces, outer
+
+
+def _closed_polygon_touches(pts, x, y):
+    """point in or on a closed polygon (what shapely's Polygon.intersects(Point) answers)"""
+    n = len(pts)
+    inside = False
+    for i in range(n):
+        x1, y1 = pts[i]
+        x2, y2 = pts[(i + 1) % n]
+        cross = (x2 - x1) * (y - y1) - (y2 - y1) * (x - x1)
+        if abs(cross) <= 1e-12 * max(1.0, abs(x2 - x1) + abs(y2 - y1)):
+            if min(x1, x2) - 1e-12 <= x <= max(x1, x2) + 1e-12 and min(y1, y2) - 1e-12 <= y <= max(y1, y2) + 1e-12:
+                return True
+        if (y1 > y) != (y2 > y):
+            xin = x1 + (y - y1) * (x2 - x1) / (y2 - y1)
+            if xin > x:
+                inside = not inside
+    return inside
 
 
 # --------------------------------------------------------------------------------------------

@@ -18,11 +18,18 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------
 # graphs
 # ------------------------------------------------------------------------------------------------
+GRAPH_HOOK = None   # the multi-rank tests set this to mark every generated graph as distributed
+
+
+def _hook(G):
+    return GRAPH_HOOK(G) if GRAPH_HOOK is not None else G
+
+
 def g_grid(m, n, faces_off=True):
     G = nx.grid_2d_graph(m, n)
     if faces_off:
         G.faces = []
-    return G
+    return _hook(G)
 
 
 def g_hex(m, n):
@@ -36,13 +43,13 @@ def g_tri(m, n):
 def g_grid3(dims):
     G = nx.grid_graph(dim=list(dims))
     G.faces = []
-    return G
+    return _hook(G)
 
 
 def g_rgg(n, r, seed):
     G = nx.random_geometric_graph(n, r, seed=seed)
     G.faces = []
-    return G
+    return _hook(G)
 
 
 def add_weights(G, seed, lo=0.5, hi=2.0):
@@ -161,6 +168,11 @@ def _snap(sysobj, observables, dt, nsteps, every):
             rec_t.append(float(sysobj.t))
     out = {f'y_{k}': np.array(v) for k, v in rec.items()}
     out['t'] = np.array(rec_t)
+    for k, o in observables.items():
+        part = getattr(o, 'partition', None)
+        if part is not None:                      # one rank of a distributed field: rows are [owned | ghosts]
+            out[f'gid_{k}'] = np.asarray(o.global_ids)
+            out[f'nown_{k}'] = np.array([part.n_own])
     return out
 
 

@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: fixed-step tables, BC helpers, and the tracer / lowering of evolution laws to
+row programs (on a host-only context, which validates programs but never computes)."""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+import gds_b200
+from gds_b200 import _lib as L
+from gds_b200.engine import step_table
+from gds_b200.trace import Lowering, Stage, Time, as_expr, trace_scope, TraceError
+from oracle import gds_oracle
+
+OPN = {v: k for k, v in L.OP.items()}
+
+
+@pytest.fixture(autouse=True)
+def host_only(monkeypatch):
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    yield
+    gds_b200.Context._default.clear()
+
+
+@pytest.mark.parametrize('t0,dt,h', [(0., 0.1, 1e-2), (0., 1e-2, 4e-3), (0.3, 1e-2, 1e-2), (0., 0.05, 0.02),
+                                      (1.0, 1e-3, 1e-2), (0., 1.0, 0.1)])
+def test_step_table_matches_solver_protocol(t0, dt, h):
+    """same (t_i, h_i) sequence as the oracle's fixed-step solver object (protocol of gds/ode/midpoint.py:10-32)"""
+    used = []
+
+    class Rec(gds_oracle.Euler):
+        def _advance(self, t, y, hh):
+            used.append((t, hh))
+            return y
+    sol = Rec(lambda t, y: np.zeros_like(y), t0, np.zeros(1), np.inf, max_step=h)
+    t = t0
+    for _ in range(5):                       # several step(dt) calls in a row, like fds.step
+        sol.t_bound = sol.t + dt
+        sol.status = 'running'
+        ts, hs, t_new = step_table(t, t + dt, h)
+        used.clear()
+        while sol.status != 'finished':
+            sol.step()
+        assert np.array_equal(ts, [g[0] for g in used])
+        assert np.array_equal(hs, [g[1] for g in used])
+        assert t_new == sol.t
+        t = t_new
+
+
+def test_bc_helpers_follow_the_reference():
+    import networkx as nx
+    f = gds_b200.combine_bcs({(0, 0): 1.0}, lambda x: 2.0 if x == (1, 1) else None,
+                             lambda t, x: t if x in ((0, 0), (2, 2)) else None)
+    assert gds_b200.fun_ary(f) == 2
+    assert f(5.0, (0, 0)) == 1.0          # static conditions win (boundary.py:21-41)
+    assert f(5.0, (1, 1)) == 2.0
+    assert f(5.0, (2, 2)) == 5.0
+    assert f(5.0, (3, 3)) is None
+    g = gds_b200.combine_bcs({(0, 0): 1.0}, lambda x: None)
+    assert gds_b200.fun_ary(g) == 1 and g((0, 0)) == 1.0 and g((9, 9)) is None
+    dG = nx.Graph([((0, 0), (0, 1))])
+    bc = gds_b200.const_edge_bc(dG, 10.)
+    assert bc(((0, 0), (0, 1))) == 10. and bc(((0, 1), (0, 0))) == 10. and bc(((5, 5), (5, 6))) is None
+    assert gds_b200.zero_edge_bc(dG)(((0, 1), (0, 0))) == 0.
+    b = gds_b200.bidict({('a', 'b'): 3})
+    assert b[('b', 'a')] == 3 and ('b', 'a') in b and ('a', 'c') not in b
+
+
+def lower(field, law, scheme='rk4'):
+    """trace a law and lower it; returns the list of passes (code as opcode names)"""
+    ctx = field._low.ctx
+    lw = Lowering(ctx, lambda e: (L.VEC_STAGE if isinstance(e, Stage) else L.VEC_STATE, None, 0), hoist=True)
+    with trace_scope():
+        root = law(Time(), Stage(field))
+    lw.rhs_pass(as_expr(root, field._domain_code, field._low), field._domain_code, field._low, 0, None)
+    return [(p.domain, p.when, [OPN[c & 0xff] for c in p.code]) for p in lw.passes]
+
+
+def test_heat_law_is_one_fused_pass():
+    T = gds_b200.node_gds(cases.g_grid(6, 6))
+    T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2)
+    T.set_constraints(dirichlet={(0, 0): 1.0})
+    passes = lower(T, T.dydt_fun)
+    assert passes == [(L.NODES, L.WHEN_STAGE, ['N_LAP', 'MASK_ZERO'])]
+
+
+def test_accepted_state_subexpressions_are_hoisted_out_of_the_stages():
+    T = gds_b200.node_gds(cases.g_grid(6, 6))
+    T.set_evolution(dydt=lambda t, y: 0.7 * T.laplacian() + y, max_step=1e-2)     # T.laplacian(): accepted state (App. B.3)
+    passes = lower(T, T.dydt_fun)
+    assert [p[1] for p in passes] == [L.WHEN_STEP, L.WHEN_STAGE]
+    assert 'N_LAP' in passes[0][2] and 'N_LAP' not in passes[1][2]
+
+
+def test_hodge_laplacian_and_advection_pass_structure():
+    G = cases.g_hex(3, 4)
+    u = gds_b200.edge_gds(G)
+    u.set_evolution(dydt=lambda t, y: 0.1 * u.laplacian(y) - u.advect(y), max_step=1e-3)
+    passes = lower(u, u.dydt_fun)
+    doms = [p[0] for p in passes]
+    # node pass (B1 y), face pass (B2 y), node aggregate pass, then ONE fused edge pass
+    assert sorted(doms[:-1]) == sorted([L.NODES, L.FACES, L.NODES]) and doms[-1] == L.EDGES
+    last = passes[-1][2]
+    assert 'E_GRADT' in last and 'E_CURLT' in last and 'E_ADVFIN' in last
+
+
+def test_data_dependent_control_flow_is_rejected():
+    T = gds_b200.node_gds(cases.g_grid(4, 4))
+    T.set_evolution(dydt=lambda t, y: y if y else -y, max_step=1e-2)
+    with pytest.raises(TraceError):
+        lower(T, T.dydt_fun)
+
+
+def test_domain_mismatch_is_rejected():
+    G = cases.g_hex(2, 2)
+    u, c = gds_b200.edge_gds(G), gds_b200.node_gds(G)
+    u.set_evolution(dydt=lambda t, y: y + c.y, max_step=1e-2)
+    c.set_evolution(nil=True)
+    with pytest.raises(ValueError):
+        lower(u, u.dydt_fun)
+
+
+def test_row_program_validation_in_the_library():
+    """gds_pass_run validates programs before touching the device: bad programs fail with a message"""
+    import ctypes as C
+    T = gds_b200.node_gds(cases.g_grid(4, 4))
+    ctx, dev = T._low.ctx, T._low.dev
+    d = L.PassDesc()
+    code = (C.c_uint32 * 2)(L.OP['ADD'], 0)        # pops an empty stack
+    d.domain, d.when, d.n_code, d.code = L.NODES, L.WHEN_STAGE, 1, code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'empty stack' in L.lib.gds_last_error()
+    code = (C.c_uint32 * 2)(L.OP['E_GRADT'], 0)    # edge gather in a node pass
+    d.code = code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'non-edge pass' in L.lib.gds_last_error()

@@ -1,0 +1,147 @@
+"""Partitioning for multi-GPU stepping (gds_b200/partition.py): closed-form slabs against the generic path, halo-list
+symmetry, partition-independent summation order of the lowered rows, and a 2-rank halo exchange over gloo."""
+import os
+
+import networkx as nx
+import numpy as np
+import pytest
+
+import gds_b200
+from gds_b200.graph import NativeGraph
+from gds_b200.partition import HaloExchange, Partition, split_bounds
+
+
+def global_edges(kind, *dims):
+    hg = NativeGraph(kind, *dims).hostgraph()
+    eu, ev = hg.edges()
+    return hg.V, eu.astype(np.int64), ev.astype(np.int64)
+
+
+@pytest.mark.parametrize('kind,dims,abc', [('grid_2d', (9, 5), (9, 5, 1)), ('grid_2d', (4, 7), (4, 7, 1)),
+                                           ('grid', (3, 4, 6), (6, 4, 3)), ('grid', (5, 2, 8), (8, 2, 5))])
+@pytest.mark.parametrize('world', [1, 2, 3, 4])
+def test_grid_slab_equals_generic_partition(kind, dims, abc, world):
+    V, eu, ev = global_edges(kind, *dims)
+    A, B, C = abc
+    for rank in range(world):
+        a = Partition.grid_slab(rank, world, A, B, C)
+        b = Partition.from_global(rank, world, V, eu, ev, None, bounds=split_bounds(V, world, align=B * C))
+        assert (a.lo, a.hi) == (b.lo, b.hi)
+        assert np.array_equal(a.ghosts, b.ghosts)
+        assert np.array_equal(a.edge_u, b.edge_u) and np.array_equal(a.edge_v, b.edge_v)
+        for q in range(world):
+            assert np.array_equal(a.send_rows[q], b.send_rows[q])
+        assert np.array_equal(a.recv_counts, b.recv_counts)
+
+
+@pytest.mark.parametrize('world', [2, 3, 5])
+def test_halo_lists_are_symmetric(world):
+    G = nx.random_geometric_graph(300, 0.12, seed=5)
+    V = G.number_of_nodes()
+    eu = np.array([e[0] for e in G.edges()], dtype=np.int64)
+    ev = np.array([e[1] for e in G.edges()], dtype=np.int64)
+    parts = [Partition.from_global(r, world, V, eu, ev) for r in range(world)]
+    assert sum(p.n_own for p in parts) == V
+    for r, p in enumerate(parts):
+        for q in range(world):
+            if q == r:
+                continue
+            # what r sends to q (global ids) is exactly the part of q's ghost segment owned by r, in the same order
+            sent = p.send_rows[q] + p.lo
+            o, c = parts[q].recv_offsets[r], parts[q].recv_counts[r]
+            assert np.array_equal(sent, parts[q].ghosts[o:o + c])
+        # every local edge has an owned endpoint; every cut edge appears on both sides
+        assert np.all((p.edge_u < p.n_own) | (p.edge_v < p.n_own))
+    total_local = sum(p.E_loc for p in parts)
+    cut = sum(int(np.sum((p.edge_u >= p.n_own) | (p.edge_v >= p.n_own))) for p in parts) // 2
+    assert total_local == eu.size + cut
+
+
+def test_owned_rows_keep_the_global_summation_order(monkeypatch):
+    """the lowered B1 row of an owned node lists the same neighbours in the same order as the undistributed graph"""
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    try:
+        G = nx.grid_2d_graph(7, 6)
+        full = gds_b200.LoweredGraph.of(nx.grid_2d_graph(7, 6))
+        p0, i0, s0 = full.dev.export_csr(0)
+        eu0, ev0 = full.edge_u, full.edge_v
+        for rank in range(3):
+            Gd = gds_b200.distribute(nx.grid_2d_graph(7, 6), rank, 3, align=6)
+            low = gds_b200.LoweredGraph.of(Gd)
+            part = low.part
+            gid = part.global_ids
+            p, i, s = low.dev.export_csr(0)
+            for r in range(part.n_own):
+                g = part.lo + r
+                other_g = [eu0[e] if ev0[e] == g else ev0[e] for e in i0[p0[g]:p0[g + 1]]]
+                other_l = [gid[low.edge_u[e]] if low.edge_v[e] == r else gid[low.edge_v[e]] for e in i[p[r]:p[r + 1]]]
+                assert other_g == other_l
+                assert np.array_equal(s0[p0[g]:p0[g + 1]], s[p[r]:p[r + 1]])
+            # node labels of the local rows
+            assert list(low.nodes.keys()) == [list(G.nodes())[int(k)] for k in gid]
+    finally:
+        gds_b200.Context._default.clear()
+
+
+def test_boundary_spec_localisation():
+    part = Partition.grid_slab(1, 3, 9, 4, 1)       # owns rows 3..5 of a 9 x 4 grid: ids 12..23, ghosts 8..11 and 24..27
+    spec = gds_b200.BoundarySpec(np.array([0, 9, 13, 22, 26, 35]), fun=lambda t: t + np.arange(6.0))
+    loc = spec.localised(part)
+    assert np.array_equal(loc.indices, [12 + 1, 1, 10, 12 + 4 + 2])      # ghost 9, owned 13 and 22, ghost 26
+    assert np.array_equal(loc.fun(1.0), [2.0, 3.0, 4.0, 5.0])
+
+
+# ------------------------------------------------------------------------------------------------
+# two ranks over gloo: halo exchange + partitioned explicit stepping against the undistributed result
+# ------------------------------------------------------------------------------------------------
+def _worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        A, B, C = 6, 5, 4
+        part = Partition.grid_slab(rank, world, A, B, C)
+        V = A * B * C
+        rng = np.random.default_rng(0)
+        x_global = rng.standard_normal(V)
+        hx = HaloExchange(part, nblocks=1)
+        send_idx, recv_idx = hx.state_indices([0], 'send'), hx.state_indices([0], 'recv')
+        x = np.zeros(part.n_loc)
+        x[:part.n_own] = x_global[part.lo:part.hi]
+        lap = lambda y: (np.bincount(part.edge_u, weights=y[part.edge_v] - y[part.edge_u], minlength=part.n_loc) +
+                         np.bincount(part.edge_v, weights=y[part.edge_u] - y[part.edge_v], minlength=part.n_loc))
+        for step in range(4):
+            send = torch.from_numpy(x[send_idx].copy())
+            recv = torch.empty(hx.n_recv, dtype=torch.float64)
+            for r in hx.exchange(send, recv):
+                r.wait()
+            x[recv_idx] = recv.numpy()
+            if step == 0:
+                assert np.array_equal(x, x_global[part.global_ids])
+            x[:part.n_own] = (x + 0.05 * lap(x))[:part.n_own]
+        ret[rank] = (part.lo, part.hi, x[:part.n_own].copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_halo_exchange_gloo():
+    import torch.multiprocessing as mp
+    world, port = 2, 29000 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    # undistributed reference of the same 3 explicit steps
+    A, B, C = 6, 5, 4
+    V, eu, ev = global_edges('grid', C, B, A)
+    x = np.random.default_rng(0).standard_normal(V)
+    for _ in range(4):
+        d = (np.bincount(eu, weights=x[ev] - x[eu], minlength=V) + np.bincount(ev, weights=x[eu] - x[ev], minlength=V))
+        x = x + 0.05 * d
+    got = np.empty(V)
+    for r in range(world):
+        lo, hi, vals = ret[r]
+        got[lo:hi] = vals
+    assert np.allclose(got, x, rtol=0, atol=1e-14)
