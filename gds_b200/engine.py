@@ -213,7 +213,10 @@ class StepEngine:
 
     def _launch(self, ts, hs, t_after):
         bc = self._bc_table(t_after)
-        check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+        if self.part is not None:
+            self._run_partitioned(ts, hs, bc)
+        else:
+            check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
         self.steps_taken += int(ts.size)
         self.version += 1
         self._read_cache.clear()
@@ -269,8 +272,10 @@ class StepEngine:
         dev = torch.device('cuda', self.ctx.device)
         self._send = torch.empty(max(1, self.hx.n_send), dtype=torch.float64, device=dev)
         self._recv = torch.empty(max(1, self.hx.n_recv), dtype=torch.float64, device=dev)
-        # kernels and the NCCL transfers are ordered through torch's current stream
-        self._stream = torch.cuda.current_stream(dev)
+        # kernels and the transfers are ordered through one torch-visible stream (made current around every exchange;
+        # not the legacy default stream, whose handle 0 means "the context's own stream" to gds_ctx_set_stream)
+        self._torch = torch
+        self._stream = torch.cuda.Stream(dev)
         check(lib.gds_ctx_set_stream(self.ctx.h, self._stream.cuda_stream))
         self.n_stages = 4 if self.scheme == Integrators.rk4 else 1
         self.exchanges = 0
@@ -286,8 +291,9 @@ class StepEngine:
         if not self.part.peers:
             return
         check(lib.gds_halo_pack(self._halo[0], vec_ptr, self._send.data_ptr()))
-        for r in self.hx.exchange(self._send, self._recv):
-            r.wait()
+        with self._torch.cuda.stream(self._stream):
+            for r in self.hx.exchange(self._send, self._recv):
+                r.wait()
         check(lib.gds_halo_unpack(self._halo[1], self._recv.data_ptr(), vec_ptr))
         self.exchanges += 1
 

@@ -197,8 +197,8 @@ def case_heat_mixed(api, scheme='rk4'):
     T = api.node_gds(G)
     api.evolve(T, dydt=lambda t, y: 0.7 * T.laplacian(), max_step=4e-3, scheme=scheme)
     rng = np.random.default_rng(7)
-    y0 = rng.random(T.ndim)
-    T.set_initial(y0=lambda x: y0[T.X[x]])
+    y0 = rng.random(12 * 9)
+    T.set_initial(y0=lambda x: y0[x[0] * 9 + x[1]])     # = y0[T.X[x]] on the undistributed graph
 
     def dirichlet(t, x):
         if x[0] == 0 or x[0] == 11:
@@ -294,8 +294,8 @@ def case_cml_c4(api, n=400, iters=30, every=10):
     x = api.node_gds(G)
     f = cml_map()
     api.evolve_map(x, map_fun=lambda t, y: f(x, y), dt=1.0)
-    y0 = np.random.default_rng(2).uniform(-1, 1, x.ndim)
-    x.set_initial(y0=lambda v: y0[x.X[v]])
+    y0 = np.random.default_rng(2).uniform(-1, 1, n)
+    x.set_initial(y0=lambda v: y0[v])                    # nodes are 0..n-1: = y0[x.X[v]] on the undistributed graph
     return _snap(x, {'x': x}, 1.0, iters, every)
 
 
