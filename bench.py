@@ -34,21 +34,28 @@ UNIT = 'DOF-updates/s'
 # ------------------------------------------------------------------------------------------------
 # workloads: the same definition drives the CUDA product and the CPU oracle
 # ------------------------------------------------------------------------------------------------
-def heat2d_problem(api, n, native):
-    """BASELINE config 1 law on an n x n grid (README.md:208-211 / examples/heat.py:56-63), RK4 h = 1e-2"""
+def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
+    """BASELINE config 1 law on a grid (README.md:208-211 / examples/heat.py:56-63), RK4 h = 1e-2.  With `world` ranks
+    the grid is (n*world) x n, cut into `world` slabs of n x n nodes (weak scaling: fixed work per GPU)."""
     h = 1e-2
+    m = n * world
     if native:
         import gds_b200
-        G = gds_b200.NativeGraph('grid_2d', n, n)
+        wts = None
+        if weighted:   # same lattice with random edge weights: the general (weighted) operator layout
+            wts = np.random.default_rng(5).uniform(0.5, 2.0, 2 * n * (n - 1) if world == 1 else 0)
+        G = gds_b200.NativeGraph('grid_2d', m, n, weights=wts)
+        if world > 1:
+            gds_b200.distribute(G, rank, world)
         T = api.node_gds(G)
         api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=h)
-        i, j = np.divmod(np.arange(n * n), n)
-        c = n / 2
-        T.set_initial(y0=np.exp(-((i - c) ** 2 + (j - c) ** 2) / (n / 2)))
+        i, j = np.divmod(T.global_ids, n)
+        T.set_initial(y0=np.exp(-((i - m / 2) ** 2 + (j - n / 2) ** 2) / (n / 2)))
         jj = np.arange(n)
-        idx = np.concatenate([jj, (n - 1) * n + jj])           # x[0] == 0 (time-varying), x[0] == n-1 (zero)
+        idx = np.concatenate([jj, (m - 1) * n + jj])           # x[0] == 0 (time-varying), x[0] == m-1 (zero)
         T.set_constraints(dirichlet=gds_b200.BoundarySpec(
             idx, fun=lambda t: np.concatenate([np.sin(t + jj / 4) ** 2, np.zeros(n)])))
+        n_own = T.ndim if T.partition is None else T.partition.n_own
     else:
         import cases
         G = cases.g_grid(n, n)
@@ -59,16 +66,24 @@ def heat2d_problem(api, n, native):
         T.set_constraints(dirichlet=api.combine_bcs(
             lambda x: 0. if x[0] == n - 1 else None,
             lambda t, x: math.sin(t + x[1] / 4) ** 2 if x[0] == 0 else None))
-    V, E = n * n, 2 * n * (n - 1)
+        n_own = n * n
+    V, E = n_own, 2 * n_own                                     # per rank; E ~ 2V on the 2-D grid
+    if world == 1:
+        E = 2 * n * (n - 1)
     m_op = 12 * (V + 2 * E) + 4 * (V + 1)                       # L0 as CSR (fp64 values, int32 indices)
-    return dict(stepper=T, fields=[T], h=h, n_state=V, V=V, E=E, F=0,
-                bytes_per_step=4 * m_op + 136 * V,              # RK4 with fused stage combine
-                bytes_per_launch=(4 * m_op + 136 * V) / 4.0,    # dominant kernel = node pass, 4 launches per step
-                dominant_class=0, launches_per_step_dominant=4,
-                name=f'heat RK4 h=1e-2 on grid_2d_graph({n},{n}) (V={V}, E={E}), Dirichlet static+time-varying')
+    # bytes the kernel's own layout moves per step: 4 ELL columns of int32 indices (+ fp64 weights if weighted) per
+    # stage, plus the RK4 vector traffic (x / y_n / acc reads, acc / x_next / y_new writes; stage 1 reads x = y_n once)
+    k_op = (16 + (32 if weighted else 0)) * V
+    return dict(stepper=T, fields=[T], h=h, n_state=n_own, V=V, E=E, F=0,
+                bytes_per_step=4 * m_op + 136 * V, bytes_per_launch=(4 * m_op + 136 * V) / 4.0,
+                kernel_bytes_per_launch=(4 * k_op + 136 * V) / 4.0,
+                dominant_class=0, kernel='lap4_kernel<unit weights>' if not weighted else 'lap4_kernel<weighted>',
+                name=f'heat RK4 h=1e-2 on grid_2d_graph({m},{n}) (V={m * n}, E={2 * m * n - m - n}), Dirichlet static+time-varying'
+                     + (', random edge weights' if weighted else '')
+                     + (f', {world} slabs of {n}x{n} with per-stage halo exchange' if world > 1 else ''))
 
 
-WORKLOADS = {'heat2d': (heat2d_problem, 7072, 1024)}   # name -> (builder, default GPU size, CPU sample size)
+WORKLOADS = {'heat2d': (heat2d_problem, 7072, 1024)}   # name -> (builder, default GPU size per rank, CPU sample size)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,6 +204,42 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def time_steps(eng, ctx, plan, barrier, device, world, dist, torch):
+    """K steps with the state resident in HBM: CUDA events on the library's stream, max over ranks"""
+    launches0, _ = ctx.counters()
+    barrier()
+    with ClockSampler(device) as clk:
+        ctx.timer_start()
+        eng.run(plan)
+        ms = ctx.timer_stop()
+    barrier()
+    launches1, _ = ctx.counters()
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms, int(launches1 - launches0), clk.summary()
+
+
+def roofline_of(prob, eng, K, h, ms_step):
+    """per-launch time of the dominant kernel: a CUDA-event pair around every launch, eager replay of the same steps"""
+    cls_ms, cls_n = eng.run_timed(eng.plan_steps(min(K, 64), h))
+    dom = prob['dominant_class']
+    launch_ms = cls_ms[dom] / max(1, cls_n[dom])
+    peak, peak_src = measured_peak()
+    achieved = prob['bytes_per_launch'] / (launch_ms * 1e-3) / 1e9
+    kern = prob['kernel_bytes_per_launch'] / (launch_ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': None, 'peak_source': peak_src, 'kernel': prob['kernel'],
+            'algorithmic_bytes_per_launch': prob['bytes_per_launch'], 'launch_ms': launch_ms,
+            'kernel_bytes_per_launch': prob['kernel_bytes_per_launch'], 'achieved_kernel_bytes': kern,
+            'frac_kernel_bytes': kern / peak, 'kernel_share_of_step': float(cls_ms[dom] / cls_ms.sum()),
+            'timing': 'CUDA-event pair around every launch, eager replay of the same steps',
+            'step_level_gbs': prob['bytes_per_step'] / (ms_step * 1e-3) / 1e9,
+            'note': 'achieved/frac use the ALGORITHMIC bytes of SURVEY.md 8d (general weighted CSR); on a unit-weight '
+                    'graph the kernel stores no weights and moves kernel_bytes_per_launch, see frac_kernel_bytes'}
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -201,12 +252,13 @@ def gpu_arm(args):
     os.environ['GDS_B200_DEVICE'] = str(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    import gds_b200
+    import gds_b200  # noqa: F401
     from adaptors import product_api
     builder, size_default, cpu_size = WORKLOADS[args.workload]
     size = args.size or size_default
     t_build = time.perf_counter()
-    prob = builder(product_api(), size, native=True)
+    prob = builder(product_api(), size, native=True, world=world, rank=rank)
+    WORKLOAD_NAME[0] = prob['name']
     st, h, K, W = prob['stepper'], prob['h'], args.steps, args.warmup
     eng = st._ensure_engine()
     ctx = eng.ctx
@@ -220,30 +272,15 @@ def gpu_arm(args):
 
     # ---- kernel-resident throughput: K steps, state in HBM ----------------------------------------------------
     eng.run(eng.plan_steps(W, h))
-    plan = eng.plan_steps(K, h)
-    launches0, _ = ctx.counters()
-    barrier()
-    with ClockSampler(local) as clk:
-        ctx.timer_start()
-        eng.run(plan)
-        ms = ctx.timer_stop()
-    barrier()
-    launches1, _ = ctx.counters()
-    if world > 1:
-        tt = torch.tensor([ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms, launches, clocks = time_steps(eng, ctx, eng.plan_steps(K, h), barrier, local, world, dist, torch)
     n_total = prob['n_state'] * world
     value = n_total * K / (ms * 1e-3)
-
-    # ---- per-launch time of the dominant kernel (CUDA events around every launch, same K steps again) ----------
-    plan2 = eng.plan_steps(min(K, 64), h)
-    cls_ms, cls_n = eng.run_timed(plan2)
-    dom = prob['dominant_class']
-    launch_ms = cls_ms[dom] / max(1, cls_n[dom])
-    peak, peak_src = measured_peak()
-    achieved = prob['bytes_per_launch'] / (launch_ms * 1e-3) / 1e9
-    share = float(cls_ms[dom] / cls_ms.sum())
+    roof = roofline_of(prob, eng, K, h, ms / K)
+    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            roof['traffic'] = json.load(fh).get(args.workload, {}).get(str(size))
+    except Exception:
+        pass
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     n = prob['n_state']
@@ -270,6 +307,22 @@ def gpu_arm(args):
     e2e = {'value': n_total * Ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n, 'd2h_bytes_per_step': 8 * n,
            'steps': Ke, 'note': 'per step: pinned-host state upload, one public step() call, state read-back; wall clock'}
 
+    # ---- the same lattice with random edge weights: kernel bytes == algorithmic bytes (N=1 only) --------------------
+    weighted = None
+    if world == 1 and not args.no_weighted:
+        del eng, st, f
+        prob.clear()
+        pw = builder(product_api(), size, native=True, weighted=True)
+        ew = pw['stepper']._ensure_engine()
+        ew.run(ew.plan_steps(W, h))
+        msw, _, _ = time_steps(ew, ctx, ew.plan_steps(K, h), barrier, local, world, dist, torch)
+        rw = roofline_of(pw, ew, K, h, msw / K)
+        weighted = {'workload': pw['name'], 'value': pw['n_state'] * K / (msw * 1e-3), 'ms_per_step': msw / K,
+                    'achieved': rw['achieved'], 'frac': rw['frac'], 'launch_ms': rw['launch_ms'],
+                    'kernel_bytes_per_launch': rw['kernel_bytes_per_launch'], 'frac_kernel_bytes': rw['frac_kernel_bytes']}
+        prob = pw
+    roof['weighted_variant'] = weighted
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline(args.workload, args.cpu_size or cpu_size)
@@ -279,20 +332,19 @@ def gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': prob['name'], 'scheme': 'rk4', 'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
-                       'parallelism': f'{world} independent partitions' if world > 1 else 'single GPU',
+            'config': {'workload': roof.pop('workload_name', None) or WORKLOAD_NAME[0], 'scheme': 'rk4',
+                       'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
+                       'parallelism': (f'{world} graph partitions (contiguous slabs), halo exchange of boundary node '
+                                       f'values after every RK stage over NCCL send/recv') if world > 1 else 'single GPU',
                        'dof_stage_evals_per_sec': 4 * value, 'build_seconds': t_build},
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'kernel': 'pass_kernel<nodes>',
-                         'algorithmic_bytes_per_launch': prob['bytes_per_launch'], 'launch_ms': launch_ms,
-                         'kernel_share_of_step': share,
-                         'timing': 'CUDA-event pair around every launch, eager replay of the same steps',
-                         'step_level_gbs': prob['bytes_per_step'] * K / (ms * 1e-3) / 1e9},
-            'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': int(launches1 - launches0), 'clocks': clk.summary(),
+            'roofline': roof, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+WORKLOAD_NAME = [None]
 
 
 def main():
@@ -305,6 +357,7 @@ def main():
     ap.add_argument('--size', type=int, default=0)
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-weighted', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -110,6 +110,32 @@ extern "C" int gds_ctx_flush_l2(gds_ctx* c, int64_t bytes) {
   return 0;
 }
 
+// Measurement aid: device time of `reps` launches of a gather-free kernel that reads n_read and writes n_write
+// float64 vectors of n elements (the stream mix of one RK stage); returns the achieved GB/s.
+extern "C" int gds_ctx_bandwidth_probe(gds_ctx* c, int32_t n_read, int32_t n_write, int64_t n, int32_t reps, double* gbs_out) {
+  if (!c || n_read < 0 || n_read > 8 || n_write < 0 || n_write > 4 || n < 2 || reps < 1) GDS_FAIL("bad argument");
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  std::vector<double*> bufs((size_t)(n_read + n_write), nullptr);
+  int rc = 0;
+  for (auto& b : bufs) {
+    if (cudaMalloc((void**)&b, (size_t)n * 8) != cudaSuccess) { rc = 1; break; }
+    cudaMemsetAsync(b, 0, (size_t)n * 8, c->stream);
+  }
+  float ms = 0.f;
+  if (!rc) {
+    for (int i = 0; i < 2 && !rc; ++i) rc = launch_probe(c, bufs.data(), n_read, n_write, n);
+    cudaEventRecord(c->ev0, c->stream);
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_probe(c, bufs.data(), n_read, n_write, n);
+    cudaEventRecord(c->ev1, c->stream);
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) rc = 1;
+  }
+  for (auto& b : bufs) cudaFree(b);
+  if (rc) GDS_FAIL("probe failed (out of memory?)");
+  if (gbs_out) *gbs_out = (double)(n_read + n_write) * (double)n * 8.0 * reps / (ms * 1e-3) / 1e9;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // device vectors and masks
 // ---------------------------------------------------------------------------------------------------

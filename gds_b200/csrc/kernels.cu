@@ -1,10 +1,11 @@
 // sm_100a kernels of the gds stepping core.
 //
-// Two kernels.
-//  * `lap4_kernel<UNITW>`: the node-Laplacian laws (value = alpha*Z(L0 v) + beta*b + gamma: heat, wave, coupled-map
-//    lattices, diffusion terms).  One thread owns FOUR consecutive rows of a sliced-ELL slice, so every index load is
-//    one 128-bit ld.global.nc.v4.s32 and every weight / state / accumulator access a 128-bit v2.f64; the four rows
-//    give each thread 4x the loads in flight of a thread-per-row kernel, which is what a latency-bound gather needs.
+// Kernels.
+//  * `lapT_kernel<UNITW, MODE>`: the node-Laplacian laws (value = alpha*Z(L0 v) + beta*b + gamma: heat, wave,
+//    coupled-map lattices, diffusion terms) with the stage epilogue fused.  A warp owns 128 rows = 4 sliced-ELL slices,
+//    each lane one row per slice, so every warp access (indices, weights, state, accumulator, and the gather of a lattice
+//    neighbour) is a contiguous run of full sectors and each thread keeps 4 independent rows of loads in flight.
+//    `lap4_kernel<UNITW, 1>` is its generic one-row-per-thread form, used for the < 128 rows that do not fill a group.
 //  * `pass_kernel<DOMAIN, UNITW>`: everything else.  Thread-per-row over the nodes / edges / faces of the lowered
 //    graph.  Every thread runs the pass's row program -- a short, warp-uniform stack code kept in the kernel
 // parameter (constant) bank -- whose gather opcodes walk the sliced-ELL incidence arrays (one slice = one
@@ -14,6 +15,8 @@
 // fixed summation order => bitwise run-to-run reproducibility).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "internal.h"
 
@@ -360,163 +363,232 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the specialised node-Laplacian kernel: 4 consecutive rows per thread, 128-bit loads and stores
+// the specialised node-Laplacian kernel: 4 rows per thread, one per slice of a 4-slice group, so that every warp
+// access -- indices, weights, state, accumulator, and the gather of a lattice neighbour -- is one contiguous run
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int4 ld_stream_v4i32(const int32_t* p) {
-  int4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double2 ld_stream_v2f64(const double* p) {
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double2 ld_plain_v2f64(const double* p) {
-  double2 v;
-  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_v2f64(double* p, double a, double b) {
-  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-}
-// store 4 values of a quad; `full` = all four rows exist
-__device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, bool full, const double (&x)[4]) {
-  if (full) {
-    st_v2f64(p + r0, x[0], x[1]);
-    st_v2f64(p + r0 + 2, x[2], x[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (r0 + i < n_rows) p[r0 + i] = x[i];
-  }
-}
-
 #define LAP4_BLOCK 128
-
-template <bool UNITW>
+template <bool UNITW, int LAP4_ROWS>  // rows per thread: lane + 32*i of the warp's (32*ROWS)-row group
 __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant__ PassParams p) {
-  const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAP4_BLOCK + threadIdx.x) * 4;
-  if (r0 >= p.n_rows) return;
-  const bool full = r0 + 3 < p.n_rows;
+  const int lane = threadIdx.x & 31;
+  const int64_t group = p.row0 + ((int64_t)blockIdx.x * (LAP4_BLOCK / 32) + (threadIdx.x >> 5)) * (32 * LAP4_ROWS);
+  if (group >= p.n_rows) return;
   const GraphDev& g = p.g;
   const double* __restrict__ v = p.lap_v;
-  // the four rows sit in one slice (32 % 4 == 0): entry j of rows r0..r0+3 is 16 contiguous bytes of indices
-  const uint32_t o0 = __ldg(g.n_soff + (r0 >> 5)), o1 = __ldg(g.n_soff + (r0 >> 5) + 1);
-  const int64_t base = (int64_t)o0 * GDS_SLICE + (r0 & 31);
-  const uint32_t width = o1 - o0;
-  // everything that does not depend on the gather is requested first (all buffers carry >= 4 doubles of slack, so
-  // the 128-bit loads of a partial last quad stay inside their allocations)
-  double yn[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0};
-  uint32_t dbits = 0u, mbits = 0u;
   const int mode = p.stage_mode;
-  if (p.epilogue == GDS_EPI_RHS) {
-    if (mode != 4) {
-      double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
-      yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
-    }
-    if (mode == 1 || mode == 2) {
-      double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
-      ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
-    }
-    if (p.dmask) dbits = __ldg(p.dmask + (r0 >> 5)) >> (r0 & 31);
-  }
-  if (p.lap_mask) mbits = __ldg(p.lap_mask + (r0 >> 5)) >> (r0 & 31);
-  if (p.lap_b) {
-    double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
-    bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
-  }
-  double c[4];
-  {
-    double2 a = __ldg(reinterpret_cast<const double2*>(v + r0)), b = __ldg(reinterpret_cast<const double2*>(v + r0 + 2));
-    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
-  }
-  double s[4] = {0, 0, 0, 0};
-  const int32_t* nb = g.n_nbr + base;
-  const double* w = g.n_w + base;
-#pragma unroll 2
-  for (uint32_t j = 0; j < width; ++j) {
-    const int4 k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
-    if (UNITW) {
-      s[0] += ld_gather(v + k.x) - c[0];
-      s[1] += ld_gather(v + k.y) - c[1];
-      s[2] += ld_gather(v + k.z) - c[2];
-      s[3] += ld_gather(v + k.w) - c[3];
-    } else {
-      const double2 w01 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE), w23 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE + 2);
-      s[0] += w01.x * (ld_gather(v + k.x) - c[0]);
-      s[1] += w01.y * (ld_gather(v + k.y) - c[1]);
-      s[2] += w23.x * (ld_gather(v + k.z) - c[2]);
-      s[3] += w23.y * (ld_gather(v + k.w) - c[3]);
-    }
-  }
-  double k4[4];
+  const bool rhs = p.epilogue == GDS_EPI_RHS;
+  int64_t row[LAP4_ROWS], base[LAP4_ROWS];
+  uint32_t width[LAP4_ROWS], wmax = 0;
+  bool valid[LAP4_ROWS];
+  const int64_t s0 = group >> 5;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double l = ((mbits >> i) & 1u) ? 0.0 : s[i];        // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
-    double val = p.lap_alpha * l;
+  for (int i = 0; i < LAP4_ROWS; ++i) {
+    row[i] = group + 32 * i + lane;
+    valid[i] = row[i] < p.n_rows;
+    // a slice whose first row exists has offsets; lanes past the last row of a partial slice have padded slots
+    const bool slice_ok = group + 32 * i < p.n_rows;
+    const uint32_t o0 = slice_ok ? __ldg(g.n_soff + s0 + i) : 0u, o1 = slice_ok ? __ldg(g.n_soff + s0 + i + 1) : 0u;
+    base[i] = (int64_t)o0 * GDS_SLICE + lane;
+    width[i] = o1 - o0;
+    wmax = max(wmax, width[i]);
+    if (!valid[i]) row[i] = p.n_rows - 1;  // loads stay in range; nothing is stored for this lane
+  }
+  // everything that does not depend on the gather is requested first
+  double yn[LAP4_ROWS], ac[LAP4_ROWS], bb[LAP4_ROWS], c[LAP4_ROWS], s[LAP4_ROWS];
+  uint32_t dbit[LAP4_ROWS], mbit[LAP4_ROWS];
+#pragma unroll
+  for (int i = 0; i < LAP4_ROWS; ++i) {
+    yn[i] = (rhs && mode != 4) ? ld_stream_f64(p.yn + row[i]) : 0.0;
+    ac[i] = (rhs && (mode == 1 || mode == 2)) ? ld_plain_f64(p.acc_in + row[i]) : 0.0;
+    dbit[i] = (rhs && p.dmask) ? ((__ldg(p.dmask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
+    mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
+    bb[i] = p.lap_b ? ld_stream_f64(p.lap_b + row[i]) : 0.0;
+    c[i] = ld_gather(v + row[i]);
+    s[i] = 0.0;
+  }
+#pragma unroll 2
+  for (uint32_t j = 0; j < wmax; ++j) {
+    int32_t k[LAP4_ROWS];
+    double w[LAP4_ROWS];
+#pragma unroll
+    for (int i = 0; i < LAP4_ROWS; ++i) {
+      const bool on = j < width[i];  // warp-uniform
+      k[i] = on ? ld_stream_i32(g.n_nbr + base[i] + (int64_t)j * GDS_SLICE) : (int32_t)row[i];
+      if (!UNITW) w[i] = on ? ld_stream_f64(g.n_w + base[i] + (int64_t)j * GDS_SLICE) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < LAP4_ROWS; ++i) {
+      const double d = ld_gather(v + k[i]) - c[i];
+      s[i] += UNITW ? d : w[i] * d;
+    }
+  }
+  double h = 0.0;
+  if (rhs && p.steptab) h = p.steptab[*p.step_counter].h;
+#pragma unroll
+  for (int i = 0; i < LAP4_ROWS; ++i) {
+    if (!valid[i]) continue;
+    const int64_t r = row[i];
+    double val = p.lap_alpha * (mbit[i] ? 0.0 : s[i]);      // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
     if (p.lap_b) val += p.lap_beta * bb[i];
     val += p.lap_gamma;
-    k4[i] = val;
-  }
-  if (p.lap_store) st_quad(p.lap_store, r0, p.n_rows, full, k4);
-  if (p.epilogue != GDS_EPI_RHS) return;
-  double h = 0.0;
-  if (p.steptab) h = p.steptab[*p.step_counter].h;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if ((dbits >> i) & 1u) k4[i] = 0.0;                 // fds.py:303
-  double o1v[4], o2v[4];
-  switch (mode) {
-    case 0:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { o1v[i] = k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
-      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
-      st_quad(p.xnext, r0, p.n_rows, full, o2v);
-      break;
-    case 1:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { o1v[i] = ac[i] + p.acc_w * k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
-      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
-      st_quad(p.xnext, r0, p.n_rows, full, o2v);
-      break;
-    case 2:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + (p.fin * h) * (ac[i] + k4[i]);
-      st_quad(p.ynew, r0, p.n_rows, full, o1v);
-      break;
-    case 3:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
-      st_quad(p.ynew, r0, p.n_rows, full, o1v);
-      break;
-    default:
-      st_quad(p.ynew, r0, p.n_rows, full, k4);
-      break;
+    if (p.lap_store) p.lap_store[r] = val;
+    if (!rhs) continue;
+    const double k1 = dbit[i] ? 0.0 : val;                  // fds.py:303
+    switch (mode) {
+      case 0:
+        p.acc_out[r] = k1;
+        p.xnext[r] = yn[i] + (p.a_next * h) * k1;
+        break;
+      case 1:
+        p.acc_out[r] = ac[i] + p.acc_w * k1;
+        p.xnext[r] = yn[i] + (p.a_next * h) * k1;
+        break;
+      case 2: p.ynew[r] = yn[i] + (p.fin * h) * (ac[i] + k1); break;
+      case 3: p.ynew[r] = yn[i] + h * k1; break;
+      default: p.ynew[r] = k1; break;
+    }
   }
 }
 
-static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+// ---------------------------------------------------------------------------------------------------
+// lapT: the production form of the node-Laplacian stage.  A warp owns a GROUP of 128 rows = 4 consecutive slices and
+// each lane one row per slice (lane + 32 i), so every warp access is a contiguous run of full sectors; the stage mode
+// is a template parameter and only FULL groups are handled (the launcher sends the < 128 remaining rows to the generic
+// kernel), which keeps the instruction count per row at about a third of the generic kernel's -- with thousands of
+// resident threads the gather is otherwise bound by instruction issue, not by HBM.
+// MODE 0/1/2: first / middle / last RK4 stage, 3: Euler, 4: map, 5: no stage epilogue (STORE only).
+// ---------------------------------------------------------------------------------------------------
+#define LAPT_BLOCK 128  // measured best on B200 (128 > 256 threads; register caps and deeper unrolling lose occupancy)
+#define LAPT_GROUP 128
+
+template <bool UNITW, int MODE>
+__global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant__ PassParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t group = p.row0 + ((int64_t)blockIdx.x * (LAPT_BLOCK / 32) + (threadIdx.x >> 5)) * LAPT_GROUP;
+  if (group + LAPT_GROUP > p.n_rows) return;
+  const GraphDev& g = p.g;
+  const double* __restrict__ v = p.lap_v;
+  const int64_t r = group + lane;  // this lane's row in slice i is r + 32 i
+  constexpr bool RHS = MODE != 5;
+  // slice offsets of the 4 slices: 16-byte aligned (group/32 is a multiple of 4)
+  const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(g.n_soff + (group >> 5)));
+  const uint32_t o5 = __ldg(g.n_soff + (group >> 5) + 4);
+  const uint32_t off[5] = {o4.x, o4.y, o4.z, o4.w, o5};
+  double yn[4], ac[4], bb[4], c[4], s[4];
+  uint32_t dbit[4], mbit[4], width[4];
+  const int32_t* nb[4];
+  const double* wp[4];
+  uint32_t wmax = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (RHS && MODE != 4) yn[i] = ld_stream_f64(p.yn + r + 32 * i);
+    if (MODE == 1 || MODE == 2) ac[i] = ld_plain_f64(p.acc_in + r + 32 * i);
+    c[i] = ld_gather(v + r + 32 * i);
+    s[i] = 0.0;
+    width[i] = off[i + 1] - off[i];
+    wmax = max(wmax, width[i]);
+    nb[i] = g.n_nbr + (int64_t)off[i] * GDS_SLICE + lane;
+    if (!UNITW) wp[i] = g.n_w + (int64_t)off[i] * GDS_SLICE + lane;
+  }
+  if (p.lap_b) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    dbit[i] = (RHS && p.dmask) ? ((__ldg(p.dmask + (group >> 5) + i) >> lane) & 1u) : 0u;
+    mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (group >> 5) + i) >> lane) & 1u) : 0u;
+  }
+  // all index loads of a chunk of CH columns are issued before the first gather that depends on them: the chain is
+  // slice offsets -> indices -> gathers, once per chunk (the 2-D lattices have 4 columns: one chunk)
+  constexpr int CH = 2;
+  for (uint32_t j0 = 0; j0 < wmax; j0 += CH) {
+    int32_t k[CH][4];
+    double w[CH][4];
+#pragma unroll
+    for (int jj = 0; jj < CH; ++jj)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool on = j0 + jj < width[i];  // warp-uniform
+        k[jj][i] = on ? ld_stream_i32(nb[i] + (j0 + jj) * GDS_SLICE) : (int32_t)(r + 32 * i);
+        if (!UNITW) w[jj][i] = on ? ld_stream_f64(wp[i] + (j0 + jj) * GDS_SLICE) : 0.0;
+      }
+#pragma unroll
+    for (int jj = 0; jj < CH; ++jj)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double d = ld_gather(v + k[jj][i]) - c[i];
+        s[i] += UNITW ? d : w[jj][i] * d;
+      }
+  }
+  double h = 0.0;
+  if (MODE <= 3 && p.steptab) h = p.steptab[*p.step_counter].h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t ri = r + 32 * i;
+    double val = p.lap_alpha * (mbit[i] ? 0.0 : s[i]);      // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
+    if (p.lap_b) val += p.lap_beta * bb[i];
+    val += p.lap_gamma;
+    if (p.lap_store) p.lap_store[ri] = val;
+    if (!RHS) continue;
+    const double k1 = dbit[i] ? 0.0 : val;                  // fds.py:303
+    if (MODE == 0) {
+      p.acc_out[ri] = k1;
+      p.xnext[ri] = yn[i] + (p.a_next * h) * k1;
+    } else if (MODE == 1) {
+      p.acc_out[ri] = ac[i] + p.acc_w * k1;
+      p.xnext[ri] = yn[i] + (p.a_next * h) * k1;
+    } else if (MODE == 2) {
+      p.ynew[ri] = yn[i] + (p.fin * h) * (ac[i] + k1);
+    } else if (MODE == 3) {
+      p.ynew[ri] = yn[i] + h * k1;
+    } else {
+      p.ynew[ri] = k1;
+    }
+  }
+}
+
+template <bool UNITW>
+static void launch_lapT(const PassParams& p, int64_t groups, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((groups + LAPT_BLOCK / 32 - 1) / (LAPT_BLOCK / 32));
+  const int mode = (p.epilogue == GDS_EPI_RHS) ? p.stage_mode : 5;
+  switch (mode) {
+    case 0: lapT_kernel<UNITW, 0><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 1: lapT_kernel<UNITW, 1><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 2: lapT_kernel<UNITW, 2><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 3: lapT_kernel<UNITW, 3><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 4: lapT_kernel<UNITW, 4><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    default: lapT_kernel<UNITW, 5><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+  }
+}
+
+template <bool UNITW, int ROWS>
+static void launch_lap(const PassParams& p, int64_t rows, cudaStream_t st) {
+  int64_t groups = (rows + 32 * ROWS - 1) / (32 * ROWS);
+  int64_t blocks = (groups + LAP4_BLOCK / 32 - 1) / (LAP4_BLOCK / 32);
+  lap4_kernel<UNITW, ROWS><<<(unsigned)blocks, LAP4_BLOCK, 0, st>>>(p);
+}
 
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
   const int64_t rows = p.n_rows - p.row0;
   if (rows <= 0) return 0;
   const bool unitw = p.unit_weights != 0;
   if (p.lap_v && domain == GDS_NODES) {
-    // 128-bit accesses need every row-0 pointer on a 16-byte boundary (the engine lays fields out that way)
-    bool ok = aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store);
-    if (p.epilogue == GDS_EPI_RHS)
-      ok = ok && aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
-    if (ok) {
-      int64_t quads = (rows + 3) / 4;
-      int64_t blocks = (quads + LAP4_BLOCK - 1) / LAP4_BLOCK;
-      if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
-      if (unitw) lap4_kernel<true><<<(unsigned)blocks, LAP4_BLOCK, 0, ctx->stream>>>(p);
-      else lap4_kernel<false><<<(unsigned)blocks, LAP4_BLOCK, 0, ctx->stream>>>(p);
+    // full 128-row groups in lapT, the remainder (< 128 rows) in the generic kernel
+    if (rows / 32 > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
+    PassParams q = p;
+    const int64_t groups = rows / LAPT_GROUP;
+    if (groups > 0) {
+      if (unitw) launch_lapT<true>(q, groups, ctx->stream); else launch_lapT<false>(q, groups, ctx->stream);
       GDS_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
-      return 0;
     }
+    q.row0 = p.row0 + groups * LAPT_GROUP;
+    if (q.row0 < q.n_rows) {
+      if (unitw) launch_lap<true, 1>(q, q.n_rows - q.row0, ctx->stream); else launch_lap<false, 1>(q, q.n_rows - q.row0, ctx->stream);
+      GDS_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+    }
+    return 0;
   }
   int64_t blocks = (rows + BLOCK - 1) / BLOCK;
   if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
@@ -600,6 +672,50 @@ int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int6
   if (n <= 0) return 0;
   int64_t blocks = (n + 255) / 256;
   halo_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(vec, buf, idx, n, scatter);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bandwidth probe: a gather-free kernel with the stream mix of one RK stage (n_read input vectors, n_write output
+// vectors, fully coalesced 128-bit accesses) -- the practical HBM ceiling the stage kernels are compared against
+// ---------------------------------------------------------------------------------------------------
+struct ProbeParams {
+  const double* in[8];
+  double* out[4];
+  int n_read, n_write;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(256) probe_kernel(const __grid_constant__ ProbeParams p) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (i + 1 >= p.n) return;
+  double2 acc = make_double2(0.0, 0.0);
+  double2 v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < p.n_read) {
+      asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v[k].x), "=d"(v[k].y) : "l"(p.in[k] + i));
+    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < p.n_read) { acc.x += v[k].x; acc.y += v[k].y; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < p.n_write) {
+      asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p.out[k] + i), "d"(acc.x + k), "d"(acc.y) : "memory");
+    }
+}
+
+int launch_probe(gds_ctx* ctx, double* const* bufs, int n_read, int n_write, int64_t n) {
+  ProbeParams p;
+  memset(&p, 0, sizeof(p));
+  for (int k = 0; k < n_read; ++k) p.in[k] = bufs[k];
+  for (int k = 0; k < n_write; ++k) p.out[k] = bufs[n_read + k];
+  p.n_read = n_read; p.n_write = n_write; p.n = n;
+  int64_t blocks = (n / 2 + 255) / 256;
+  probe_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;

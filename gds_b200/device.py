@@ -44,6 +44,12 @@ class Context:
         check(lib.gds_ctx_counters(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def bandwidth_probe(self, n_read, n_write, n, reps=10) -> float:
+        """GB/s of a gather-free kernel reading n_read and writing n_write float64 vectors of n elements"""
+        g = L.c_f64()
+        check(lib.gds_ctx_bandwidth_probe(self.h, int(n_read), int(n_write), int(n), int(reps), C.byref(g)))
+        return g.value
+
     def flush_l2(self, nbytes=256 << 20):
         check(lib.gds_ctx_flush_l2(self.h, int(nbytes)))
 

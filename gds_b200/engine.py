@@ -178,13 +178,15 @@ class StepEngine:
 
     def read_into(self, f, out):
         """copy the value block of field f into a caller-owned (ideally pinned) host array"""
-        assert out.dtype == np.float64 and out.flags['C_CONTIGUOUS'] and out.size == f.ndim
+        assert out.dtype == np.float64 and out.flags['C_CONTIGUOUS'] and out.size <= f.ndim
         check(lib.gds_system_get_state(self.h, ptr(out), self.offsets[id(f)], out.size))
         return out
 
     def write(self, f, values, offset=0):
         a = L.as_f64(values)
         check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)] + offset, a.size))
+        if self.part is not None and self.h is not None and hasattr(self, 'hx'):
+            self._exchange(self._state_ptr())      # ghost rows follow their owners
         self._read_cache.clear()
         self.version += 1
 

@@ -121,6 +121,9 @@ int gds_ctx_timer_start(gds_ctx* ctx);
 int gds_ctx_timer_stop(gds_ctx* ctx, double* ms_out);
 /* counters since context creation: kernels launched by this library, CUDA-graph replays */
 int gds_ctx_counters(gds_ctx* ctx, int64_t* kernel_launches, int64_t* graph_replays);
+/* measurement aid: achieved GB/s of a gather-free kernel that reads n_read and writes n_write float64 vectors of n
+ * elements (the stream mix of one RK stage) -- the practical HBM ceiling the stage kernels are compared against */
+int gds_ctx_bandwidth_probe(gds_ctx* ctx, int32_t n_read, int32_t n_write, int64_t n, int32_t reps, double* gbs_out);
 /* write `bytes` of device scratch (used to flush L2 between timed iterations) */
 int gds_ctx_flush_l2(gds_ctx* ctx, int64_t bytes);
 
