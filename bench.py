@@ -83,7 +83,120 @@ def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
                      + (f', {world} slabs of {n}x{n} with per-stage halo exchange' if world > 1 else ''))
 
 
-WORKLOADS = {'heat2d': (heat2d_problem, 7072, 1024)}   # name -> (builder, default GPU size per rank, CPU sample size)
+def _edges_inside(eu, ev, node_mask):
+    """indices of the edges whose endpoints are both in the node set (= edges of G.subgraph(nodes))"""
+    return np.nonzero(node_mask[eu] & node_mask[ev])[0]
+
+
+def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
+    """BASELINE config 2: edge diffusion (Hodge-1 Laplacian, Dirichlet 0 on top/bottom boundary edges) coupled with node
+    advection-diffusion (Neumann -0.1 on the top row) on hexagonal_lattice_graph(n, n), RK4 h = 1e-3 (tests/cases.py
+    case_hex_advdiff_c2 is the same law at small size, checked against the reference)."""
+    assert world == 1 and not weighted
+    h, nu, kappa = 1e-3, 0.1, 0.05
+    if native:
+        import gds_b200
+        G = gds_b200.NativeGraph('hexagonal', n, n)
+        u, c = api.edge_gds(G), api.node_gds(G)
+        hg = G.hostgraph(with_faces=True)
+        pos, (eu, ev) = hg.pos(), hg.edges()
+        api.evolve(u, dydt=lambda t, y: nu * u.laplacian(y), max_step=h)
+        api.evolve(c, dydt=lambda t, y: -c.advect(u) + kappa * c.laplacian(y), max_step=h)
+        u.set_initial(y0=0.1 * np.random.default_rng(0).standard_normal(u.ndim))
+        c.set_initial(y0=np.random.default_rng(1).random(c.ndim))
+        hh = math.sqrt(3) / 2
+        lo, hi = pos[:, 1].min(), pos[:, 1].max()
+        bnd = (pos[:, 1] < lo + 0.6 * hh) | (pos[:, 1] > hi - 0.6 * hh)
+        u.set_constraints(dirichlet=gds_b200.BoundarySpec(_edges_inside(eu, ev, bnd), values=0.0))
+        c.set_constraints(neumann=gds_b200.BoundarySpec(np.nonzero(pos[:, 1] > hi - 1e-9)[0], values=-0.1))
+        sysobj = api.couple({'u': u, 'c': c})
+        V, E, F = hg.V, hg.E, hg.F
+    else:
+        import cases
+        import networkx as nx
+        G = cases.g_hex(n, n)
+        u, c = api.edge_gds(G), api.node_gds(G)
+        api.evolve(u, dydt=lambda t, y: nu * u.laplacian(y), max_step=h)
+        api.evolve(c, dydt=lambda t, y: -c.advect(u) + kappa * c.laplacian(y), max_step=h)
+        u0 = 0.1 * np.random.default_rng(0).standard_normal(u.ndim)
+        c0 = np.random.default_rng(1).random(c.ndim)
+        u.set_initial(y0=lambda e: u0[u.X[e]])
+        c.set_initial(y0=lambda x: c0[c.X[x]])
+        u.set_constraints(dirichlet=api.zero_edge_bc(cases.boundary_edges_hex_top_bottom(G)))
+        pos = nx.get_node_attributes(G, 'pos')
+        ytop = max(p[1] for p in pos.values())
+        c.set_constraints(neumann=lambda x: -0.1 if pos[x][1] > ytop - 1e-9 else None)
+        sysobj = api.couple({'u': u, 'c': c})
+        V, E, F = c.ndim, u.ndim, len(u.faces)
+    # SURVEY.md 8d: edge law 64E + 20V + 44F, node law 72E + 28V per RHS; RK4 vectors 136 B per state component
+    per_step = 4 * ((64 * E + 20 * V + 44 * F) + (72 * E + 28 * V)) + 136 * (E + V)
+    return dict(stepper=sysobj.stepper, fields=[u, c], h=h, n_state=E + V, V=V, E=E, F=F, bytes_per_step=per_step,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
+                kernel='all passes of one RK stage (row-program interpreter: 2 node passes, 1 face pass, 1 edge pass)',
+                name=f'edge diffusion + node advection-diffusion, RK4 h=1e-3, hexagonal_lattice_graph({n},{n}) '
+                     f'(V={V}, E={E}, F={F}), Dirichlet edges / Neumann nodes')
+
+
+def cml_problem(api, n, native, world=1, rank=0, weighted=False):
+    """BASELINE config 4: coupled map lattice on random_geometric_graph(n, sqrt(8/(pi n)), seed=42), map mode"""
+    assert world == 1 and not weighted
+    r = math.sqrt(8 / (math.pi * n))
+    eps = 0.3
+    if native:
+        import gds_b200
+        G = gds_b200.NativeGraph('random_geometric', n, r, 42)
+    else:
+        import cases
+        G = cases.g_rgg(n, r, 42)
+    x = api.node_gds(G)
+    api.evolve_map(x, map_fun=lambda t, y: (1 - 1.7 * y ** 2) + (eps / 8.0) * x.laplacian(1 - 1.7 * y ** 2), dt=1.0)
+    y0 = np.random.default_rng(2).uniform(-1, 1, n)
+    x.set_initial(y0=y0 if native else (lambda v: y0[v]))
+    V = n
+    E = x._low.E if native else x.low.E
+    per_step = 12 * (V + 2 * E) + 4 * V + 16 * V
+    return dict(stepper=x, fields=[x], h=1.0, n_state=V, V=V, E=E, F=0, bytes_per_step=per_step,
+                bytes_per_launch=per_step, kernel_bytes_per_launch=(4 * 2 * E + 8 * 4) * 1.0 + 24 * V,
+                dominant_class=0, kernel='lapT_kernel<unit weights, map> (+ pointwise pass f(y))',
+                name=f'coupled map lattice, random_geometric_graph({n}) (E={E}), map mode')
+
+
+def wave3d_problem(api, n, native, world=1, rank=0, weighted=False):
+    """BASELINE config 5 law: wave equation, order 2, accepted-state Laplacian (examples/wave.py:14) on grid_graph([n]*3)"""
+    assert not weighted
+    h = 0.1
+    if native:
+        import gds_b200
+        G = gds_b200.NativeGraph('grid', n, n, n * world)
+        if world > 1:
+            gds_b200.distribute(G, rank, world)
+    else:
+        import cases
+        G = cases.g_grid3((n, n, n))
+    a = api.node_gds(G)
+    api.evolve(a, dydt=lambda t, y: 1.0 * a.laplacian(), order=2, max_step=h)
+    if native:
+        gid = a.global_ids
+        A, B, C = n * world, n, n
+        ia, ib, ic = gid // (B * C), (gid // C) % B, gid % C
+        a.set_initial(y0=np.exp(-((ia - (A - 1) / 2) ** 2 + (ib - (B - 1) / 2) ** 2 + (ic - (C - 1) / 2) ** 2) / 200.0))
+        n_own = a.ndim if a.partition is None else a.partition.n_own
+    else:
+        ctr = (n - 1) / 2
+        a.set_initial(y0=lambda x: math.exp(-sum((xi - ctr) ** 2 for xi in x) / 200.0))
+        n_own = a.ndim
+    V, E = n_own, 3 * n_own
+    per_step = 4 * (12 * (V + 2 * E) + 4 * V) + 136 * 2 * V        # SURVEY.md 8d: Laplacian at every stage
+    return dict(stepper=a, fields=[a], h=h, n_state=2 * n_own, V=V, E=E, F=0, bytes_per_step=per_step,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
+                kernel='step level: 1 lapT pass (accepted-state Laplacian, once per step) + 8 pointwise stage passes',
+                name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{n * world}]) (V={n ** 3 * world})'
+                     + (f', {world} slabs with halo exchange' if world > 1 else ''))
+
+
+# name -> (builder, default GPU size per rank, CPU sample size)
+WORKLOADS = {'heat2d': (heat2d_problem, 7072, 1024), 'hex_advdiff': (hex_advdiff_problem, 2000, 40),
+             'cml': (cml_problem, 10_000_000, 100_000), 'wave3d': (wave3d_problem, 400, 48)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -225,7 +338,13 @@ def roofline_of(prob, eng, K, h, ms_step):
     """per-launch time of the dominant kernel: a CUDA-event pair around every launch, eager replay of the same steps"""
     cls_ms, cls_n = eng.run_timed(eng.plan_steps(min(K, 64), h))
     dom = prob['dominant_class']
-    launch_ms = cls_ms[dom] / max(1, cls_n[dom])
+    if dom < 0:      # several kernels per stage: one "launch" = all passes of one stage
+        n_st = 4 if str(eng.scheme).endswith('rk4') else 1
+        launch_ms = float(cls_ms.sum()) / (min(K, 64) * n_st)
+        cls_ms = np.array([cls_ms.sum(), 0.0])
+        dom = 0
+    else:
+        launch_ms = cls_ms[dom] / max(1, cls_n[dom])
     peak, peak_src = measured_peak()
     achieved = prob['bytes_per_launch'] / (launch_ms * 1e-3) / 1e9
     kern = prob['kernel_bytes_per_launch'] / (launch_ms * 1e-3) / 1e9
@@ -261,6 +380,7 @@ def gpu_arm(args):
     WORKLOAD_NAME[0] = prob['name']
     st, h, K, W = prob['stepper'], prob['h'], args.steps, args.warmup
     eng = st._ensure_engine()
+    SCHEME[0] = 'map' if eng.scheme == 'map' else str(eng.scheme).split('.')[-1]
     ctx = eng.ctx
     t_build = time.perf_counter() - t_build
 
@@ -283,20 +403,27 @@ def gpu_arm(args):
         pass
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
-    n = prob['n_state']
-    host_in = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    host_out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    f = prob['fields'][0]
-    eng.read_into(f, host_in)
+    fields = prob['fields']
+    sizes = [fl.ndim if getattr(fl, 'partition', None) is None else fl.partition.n_own for fl in fields]
+    n = sum(s_ * fl._order() for s_, fl in zip(sizes, fields))
+    host_in = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
+    host_out = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
+    for fl, b in zip(fields, host_in):
+        eng.read_into(fl, b)
     Ke = max(3, min(K, 10))
+
+    def one_step(src, dst):
+        for fl, b in zip(fields, src):
+            eng.write(fl, b)           # H2D of the step's input state (pinned)
+        st.step(h)                     # public API call
+        for fl, b in zip(fields, dst):
+            eng.read_into(fl, b)       # D2H of the step's result (synchronises)
     for _ in range(2):
-        eng.write(f, host_in); st.step(h); eng.read_into(f, host_out)
+        one_step(host_in, host_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        eng.write(f, host_in)          # H2D of the step's input state (pinned)
-        st.step(h)                     # public API call
-        eng.read_into(f, host_out)     # D2H of the step's result (synchronises)
+        one_step(host_in, host_out)
         host_in, host_out = host_out, host_in
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -304,13 +431,13 @@ def gpu_arm(args):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e = {'value': n_total * Ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n, 'd2h_bytes_per_step': 8 * n,
+    e2e = {'value': n_total * Ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * sum(sizes), 'd2h_bytes_per_step': 8 * sum(sizes),
            'steps': Ke, 'note': 'per step: pinned-host state upload, one public step() call, state read-back; wall clock'}
 
     # ---- the same lattice with random edge weights: kernel bytes == algorithmic bytes (N=1 only) --------------------
     weighted = None
-    if world == 1 and not args.no_weighted:
-        del eng, st, f
+    if world == 1 and not args.no_weighted and args.workload == 'heat2d':
+        del eng, st, fields, one_step
         prob.clear()
         pw = builder(product_api(), size, native=True, weighted=True)
         ew = pw['stepper']._ensure_engine()
@@ -332,7 +459,7 @@ def gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': roof.pop('workload_name', None) or WORKLOAD_NAME[0], 'scheme': 'rk4',
+            'config': {'workload': WORKLOAD_NAME[0], 'scheme': SCHEME[0],
                        'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
                        'parallelism': (f'{world} graph partitions (contiguous slabs), halo exchange of boundary node '
                                        f'values after every RK stage over NCCL send/recv') if world > 1 else 'single GPU',
@@ -345,6 +472,7 @@ def gpu_arm(args):
 
 
 WORKLOAD_NAME = [None]
+SCHEME = ['rk4']
 
 
 def main():

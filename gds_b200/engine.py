@@ -231,6 +231,9 @@ class StepEngine:
 
     def plan_steps(self, k, h):
         """exactly k steps of size h from the current time"""
+        if self.scheme == 'map':      # k applications of the map at t + h, t + 2h, ... (fds.py:332-339)
+            ts = self.t + h * (np.arange(k, dtype=np.float64) + 1.0)
+            return ts, np.zeros(k, dtype=np.float64), ts, float(ts[-1]), self._bc_table(ts)
         ts = self.t + h * np.arange(k, dtype=np.float64)
         hs = np.full(k, h, dtype=np.float64)
         t_after = ts + h
