@@ -77,7 +77,7 @@ def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
     return dict(stepper=T, fields=[T], h=h, n_state=n_own, V=V, E=E, F=0,
                 bytes_per_step=4 * m_op + 136 * V, bytes_per_launch=(4 * m_op + 136 * V) / 4.0,
                 kernel_bytes_per_launch=(4 * k_op + 136 * V) / 4.0,
-                dominant_class=0, kernel='lap4_kernel<unit weights>' if not weighted else 'lap4_kernel<weighted>',
+                dominant_class=0, kernel='lapq_kernel<unit weights>' if not weighted else 'lapT_kernel<weighted>',
                 name=f'heat RK4 h=1e-2 on grid_2d_graph({m},{n}) (V={m * n}, E={2 * m * n - m - n}), Dirichlet static+time-varying'
                      + (', random edge weights' if weighted else '')
                      + (f', {world} slabs of {n}x{n} with per-stage halo exchange' if world > 1 else ''))

@@ -568,6 +568,144 @@ static void launch_lap(const PassParams& p, int64_t rows, cudaStream_t st) {
   lap4_kernel<UNITW, ROWS><<<(unsigned)blocks, LAP4_BLOCK, 0, st>>>(p);
 }
 
+// lapq: 4 CONSECUTIVE rows per thread, every index load one ld.global.nc.v4.s32 and every vector access a v2.f64
+// (needs 16-byte aligned operands); the faster form on unit-weight graphs, where no weight stream competes for registers
+#define LAPQ_BLOCK 128
+__device__ __forceinline__ int4 ld_stream_v4i32(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream_v2f64(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_plain_v2f64(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_v2f64(double* p, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+// store 4 values of a quad; `full` = all four rows exist
+__device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, bool full, const double (&x)[4]) {
+  if (full) {
+    st_v2f64(p + r0, x[0], x[1]);
+    st_v2f64(p + r0 + 2, x[2], x[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (r0 + i < n_rows) p[r0 + i] = x[i];
+  }
+}
+
+
+template <bool UNITW>
+__global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant__ PassParams p) {
+  const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
+  if (r0 >= p.n_rows) return;
+  const bool full = r0 + 3 < p.n_rows;
+  const GraphDev& g = p.g;
+  const double* __restrict__ v = p.lap_v;
+  // the four rows sit in one slice (32 % 4 == 0): entry j of rows r0..r0+3 is 16 contiguous bytes of indices
+  const uint32_t o0 = __ldg(g.n_soff + (r0 >> 5)), o1 = __ldg(g.n_soff + (r0 >> 5) + 1);
+  const int64_t base = (int64_t)o0 * GDS_SLICE + (r0 & 31);
+  const uint32_t width = o1 - o0;
+  // everything that does not depend on the gather is requested first (all buffers carry >= 4 doubles of slack, so
+  // the 128-bit loads of a partial last quad stay inside their allocations)
+  double yn[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0};
+  uint32_t dbits = 0u, mbits = 0u;
+  const int mode = p.stage_mode;
+  if (p.epilogue == GDS_EPI_RHS) {
+    if (mode != 4) {
+      double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
+      yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
+    }
+    if (mode == 1 || mode == 2) {
+      double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
+      ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
+    }
+    if (p.dmask) dbits = __ldg(p.dmask + (r0 >> 5)) >> (r0 & 31);
+  }
+  if (p.lap_mask) mbits = __ldg(p.lap_mask + (r0 >> 5)) >> (r0 & 31);
+  if (p.lap_b) {
+    double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
+    bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
+  }
+  double c[4];
+  {
+    double2 a = __ldg(reinterpret_cast<const double2*>(v + r0)), b = __ldg(reinterpret_cast<const double2*>(v + r0 + 2));
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
+  }
+  double s[4] = {0, 0, 0, 0};
+  const int32_t* nb = g.n_nbr + base;
+  const double* w = g.n_w + base;
+#pragma unroll 2
+  for (uint32_t j = 0; j < width; ++j) {
+    const int4 k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
+    if (UNITW) {
+      s[0] += ld_gather(v + k.x) - c[0];
+      s[1] += ld_gather(v + k.y) - c[1];
+      s[2] += ld_gather(v + k.z) - c[2];
+      s[3] += ld_gather(v + k.w) - c[3];
+    } else {
+      const double2 w01 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE), w23 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE + 2);
+      s[0] += w01.x * (ld_gather(v + k.x) - c[0]);
+      s[1] += w01.y * (ld_gather(v + k.y) - c[1]);
+      s[2] += w23.x * (ld_gather(v + k.z) - c[2]);
+      s[3] += w23.y * (ld_gather(v + k.w) - c[3]);
+    }
+  }
+  double k4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double l = ((mbits >> i) & 1u) ? 0.0 : s[i];        // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
+    double val = p.lap_alpha * l;
+    if (p.lap_b) val += p.lap_beta * bb[i];
+    val += p.lap_gamma;
+    k4[i] = val;
+  }
+  if (p.lap_store) st_quad(p.lap_store, r0, p.n_rows, full, k4);
+  if (p.epilogue != GDS_EPI_RHS) return;
+  double h = 0.0;
+  if (p.steptab) h = p.steptab[*p.step_counter].h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if ((dbits >> i) & 1u) k4[i] = 0.0;                 // fds.py:303
+  double o1v[4], o2v[4];
+  switch (mode) {
+    case 0:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o1v[i] = k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
+      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
+      st_quad(p.xnext, r0, p.n_rows, full, o2v);
+      break;
+    case 1:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o1v[i] = ac[i] + p.acc_w * k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
+      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
+      st_quad(p.xnext, r0, p.n_rows, full, o2v);
+      break;
+    case 2:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + (p.fin * h) * (ac[i] + k4[i]);
+      st_quad(p.ynew, r0, p.n_rows, full, o1v);
+      break;
+    case 3:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
+      st_quad(p.ynew, r0, p.n_rows, full, o1v);
+      break;
+    default:
+      st_quad(p.ynew, r0, p.n_rows, full, k4);
+      break;
+  }
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
   const int64_t rows = p.n_rows - p.row0;
   if (rows <= 0) return 0;
@@ -576,6 +714,21 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // full 128-row groups in lapT, the remainder (< 128 rows) in the generic kernel
     if (rows / 32 > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
     PassParams q = p;
+    // measured on B200 (same box, heat RK4 on a 7072^2 grid): unit weights 0.528 ms/launch with the 128-bit quad kernel
+    // vs 0.558 ms with lapT; weighted 0.869 ms vs 0.806 ms.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
+    static const char* force = getenv("GDS_B200_LAP_KERNEL");
+    const bool use_quad = force ? !strcmp(force, "quad") : unitw;
+    bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
+    if (quad_ok && p.epilogue == GDS_EPI_RHS)
+      quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
+    if (quad_ok) {
+      int64_t blocks = ((rows + 3) / 4 + LAPQ_BLOCK - 1) / LAPQ_BLOCK;
+      if (unitw) lapq_kernel<true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      else lapq_kernel<false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      GDS_CUDA(cudaGetLastError());
+      ctx->kernel_launches++;
+      return 0;
+    }
     const int64_t groups = rows / LAPT_GROUP;
     if (groups > 0) {
       if (unitw) launch_lapT<true>(q, groups, ctx->stream); else launch_lapT<false>(q, groups, ctx->stream);
