@@ -473,44 +473,76 @@ static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
   if (ph.epilogue == GDS_EPI_RHS && depth < 1) GDS_FAIL("RHS pass leaves nothing on the stack");
   return 0;
 }
-static void match_lap_form(const PassHost& ph, LapForm& out);
 
-// Recognise  value = alpha * Z_mask(L0 v) + beta * b + gamma  by running the row program on symbolic affine forms.
-// Anything outside that family (time, other gathers, nonlinear pointwise ops, several Laplacians) is left to the
-// interpreter.
-static void match_lap_form(const PassHost& ph, LapForm& out) {
-  out = LapForm();
-  if (ph.domain != GDS_NODES) return;
-  struct Sym { double alpha = 0, beta = 0, gamma = 0; int v = -1, mask = -1, b = -1; };
+// Recognise row programs that are a linear combination of masked one-hop operators,
+//   value = sum_k coef_k * Z(op_k(...)) + beta * b + gamma,
+// by running the program on symbolic forms.  Anything outside that family (time, nonlinear pointwise operations,
+// products of vectors) is left to the interpreter.  A single N_LAP term is the LapForm of the Laplacian kernels.
+static bool is_gather(uint32_t op) {
+  switch (op) {
+    case GDS_OP_N_LAP: case GDS_OP_N_BDOT: case GDS_OP_N_INFLUX: case GDS_OP_N_OUTFLUX: case GDS_OP_N_ADVECT:
+    case GDS_OP_N_LIE: case GDS_OP_E_GRADT: case GDS_OP_E_CURLT: case GDS_OP_E_ADVFIN: case GDS_OP_F_CURL: return true;
+    default: return false;
+  }
+}
+
+static void match_forms(PassHost& ph) {
+  ph.lap = LapForm();
+  ph.terms = TermForm();
+  struct Sym {
+    std::vector<TermSym> t;
+    double beta = 0, gamma = 0;
+    int b = -1;
+  };
   std::vector<Sym> st;
   int store = -1;
-  auto scalar = [](const Sym& x) { return x.alpha == 0.0 && x.b < 0; };
+  auto scalar = [](const Sym& x) { return x.t.empty() && x.b < 0; };
+  auto scale = [](Sym& x, double c) {
+    for (auto& t : x.t) t.coef *= c;
+    x.beta *= c; x.gamma *= c;
+  };
   for (size_t pc = 0; pc < ph.code.size(); ++pc) {
-    uint32_t ins = ph.code[pc], op = ins & 0xff, a = (ins >> 8) & 0xff;
+    uint32_t ins = ph.code[pc], op = ins & 0xff, a = (ins >> 8) & 0xff, b = (ins >> 16) & 0xff;
+    if (is_gather(op)) {
+      Sym x;
+      TermSym t;
+      t.op = (int)op; t.a = (int)a; t.coef = 1.0;
+      if (op == GDS_OP_N_ADVECT || op == GDS_OP_N_LIE || op == GDS_OP_E_ADVFIN) t.b = (int)b;
+      x.t.push_back(t);
+      st.push_back(x);
+      continue;
+    }
     switch (op) {
       case GDS_OP_END: break;
       case GDS_OP_PUSH_IMM: { Sym x; x.gamma = ph.imm[a]; st.push_back(x); } break;
       case GDS_OP_PUSH_VEC: { Sym x; x.beta = 1.0; x.b = (int)a; st.push_back(x); } break;
-      case GDS_OP_N_LAP: { Sym x; x.alpha = 1.0; x.v = (int)a; st.push_back(x); } break;
       case GDS_OP_MASK_ZERO: {
         if (st.empty()) return;
         Sym& x = st.back();
-        if (x.alpha == 0.0 || x.b >= 0 || x.gamma != 0.0 || x.mask >= 0) return;
-        x.mask = (int)a;
+        if (x.t.empty() || x.b >= 0 || x.gamma != 0.0) return;
+        for (auto& t : x.t) {
+          if (t.m0 == (int)a || t.m1 == (int)a) continue;
+          if (t.m0 < 0) t.m0 = (int)a;
+          else if (t.m1 < 0) t.m1 = (int)a;
+          else return;
+        }
       } break;
       case GDS_OP_NEG: {
         if (st.empty()) return;
-        Sym& x = st.back();
-        x.alpha = -x.alpha; x.beta = -x.beta; x.gamma = -x.gamma;
+        scale(st.back(), -1.0);
       } break;
       case GDS_OP_ADD: case GDS_OP_SUB: {
         if (st.size() < 2) return;
         Sym y = st.back(); st.pop_back();
         Sym& x = st.back();
         double sg = (op == GDS_OP_SUB) ? -1.0 : 1.0;
-        if (y.alpha != 0.0) {
-          if (x.alpha != 0.0) { if (x.v != y.v || x.mask != y.mask) return; x.alpha += sg * y.alpha; }
-          else { x.alpha = sg * y.alpha; x.v = y.v; x.mask = y.mask; }
+        for (auto& ty : y.t) {
+          bool merged = false;
+          for (auto& tx : x.t)
+            if (tx.op == ty.op && tx.a == ty.a && tx.b == ty.b && tx.m0 == ty.m0 && tx.m1 == ty.m1) {
+              tx.coef += sg * ty.coef; merged = true; break;
+            }
+          if (!merged) { TermSym t = ty; t.coef = sg * ty.coef; x.t.push_back(t); }
         }
         if (y.b >= 0) {
           if (x.b >= 0) { if (x.b != y.b) return; x.beta += sg * y.beta; }
@@ -522,16 +554,17 @@ static void match_lap_form(const PassHost& ph, LapForm& out) {
         if (st.size() < 2) return;
         Sym y = st.back(); st.pop_back();
         Sym& x = st.back();
-        if (scalar(y)) { x.alpha *= y.gamma; x.beta *= y.gamma; x.gamma *= y.gamma; }
-        else if (scalar(x)) { double c = x.gamma; x = y; x.alpha *= c; x.beta *= c; x.gamma *= c; }
+        if (scalar(y)) scale(x, y.gamma);
+        else if (scalar(x)) { double c = x.gamma; x = y; scale(x, c); }
         else return;
       } break;
       case GDS_OP_DIV: {
         if (st.size() < 2) return;
         Sym y = st.back(); st.pop_back();
-        Sym& x = st.back();
         if (!scalar(y)) return;
-        x.alpha /= y.gamma; x.beta /= y.gamma; x.gamma /= y.gamma;
+        Sym& x = st.back();
+        for (auto& t : x.t) t.coef /= y.gamma;
+        x.beta /= y.gamma; x.gamma /= y.gamma;
       } break;
       case GDS_OP_STORE:
         if (pc + 1 != ph.code.size() || store >= 0) return;   // only as the last instruction
@@ -542,11 +575,20 @@ static void match_lap_form(const PassHost& ph, LapForm& out) {
   }
   if (st.size() != 1) return;
   const Sym& r = st.back();
-  if (r.alpha == 0.0 || r.v < 0) return;
-  if (!std::isfinite(r.alpha) || !std::isfinite(r.beta) || !std::isfinite(r.gamma)) return;
-  out.ok = true;
-  out.v = r.v; out.mask = r.mask; out.b = (r.b >= 0 && r.beta != 0.0) ? r.b : -1;
-  out.alpha = r.alpha; out.beta = r.beta; out.gamma = r.gamma; out.store = store;
+  if ((int)r.t.size() > GDS_MAX_TERMS) return;   // no term at all: a pointwise pass  beta * b + gamma
+  if (!std::isfinite(r.beta) || !std::isfinite(r.gamma)) return;
+  for (auto& t : r.t) if (!std::isfinite(t.coef)) return;
+  const int bslot = (r.b >= 0 && r.beta != 0.0) ? r.b : -1;
+  if (r.t.size() == 1 && r.t[0].op == GDS_OP_N_LAP && r.t[0].m1 < 0 && r.t[0].coef != 0.0) {
+    ph.lap.ok = true;
+    ph.lap.v = r.t[0].a; ph.lap.mask = r.t[0].m0; ph.lap.b = bslot;
+    ph.lap.alpha = r.t[0].coef; ph.lap.beta = r.beta; ph.lap.gamma = r.gamma; ph.lap.store = store;
+    return;
+  }
+  ph.terms.ok = true;
+  ph.terms.n = (int)r.t.size();
+  for (size_t k = 0; k < r.t.size(); ++k) ph.terms.t[k] = r.t[k];
+  ph.terms.b = bslot; ph.terms.beta = r.beta; ph.terms.gamma = r.gamma; ph.terms.store = store;
 }
 
 // Resolve a host pass into launch parameters.  `state`/`stage` may be null for eager passes.
@@ -592,6 +634,21 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
     pp.lap_b = ph.lap.b >= 0 ? pp.vec[ph.lap.b] : nullptr;
     pp.lap_store = ph.lap.store >= 0 ? pp.out[ph.lap.store] : nullptr;
     pp.lap_alpha = ph.lap.alpha; pp.lap_beta = ph.lap.beta; pp.lap_gamma = ph.lap.gamma;
+  } else if (ph.terms.ok) {
+    pp.use_terms = 1;
+    pp.n_terms = ph.terms.n;
+    for (int k = 0; k < ph.terms.n; ++k) {
+      const TermSym& t = ph.terms.t[k];
+      pp.term[k].op = t.op;
+      pp.term[k].a = pp.vec[t.a];
+      pp.term[k].b = t.b >= 0 ? pp.vec[t.b] : nullptr;
+      pp.term[k].m0 = t.m0 >= 0 ? pp.mask[t.m0] : nullptr;
+      pp.term[k].m1 = t.m1 >= 0 ? pp.mask[t.m1] : nullptr;
+      pp.term[k].coef = t.coef;
+    }
+    pp.lap_b = ph.terms.b >= 0 ? pp.vec[ph.terms.b] : nullptr;
+    pp.lap_store = ph.terms.store >= 0 ? pp.out[ph.terms.store] : nullptr;
+    pp.lap_beta = ph.terms.beta; pp.lap_gamma = ph.terms.gamma;
   }
   return 0;
 }
@@ -602,7 +659,7 @@ extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass,
   GDS_TRY(copy_pass(pass, ph));   // validation works on a host-only context too
   GDS_NEED_DEVICE(c);
   GDS_CUDA(cudaSetDevice(c->device));
-  match_lap_form(ph, ph.lap);
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(ph);
   if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("eager passes take GDS_EPI_NONE");
   PassParams pp;
   GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
@@ -664,7 +721,7 @@ extern "C" int gds_system_add_pass(gds_system* s, const gds_pass_desc* pass) {
   if (s->finalized) GDS_FAIL("system already finalized");
   PassHost ph;
   GDS_TRY(copy_pass(pass, ph));
-  if (!getenv("GDS_B200_NO_FASTPATH")) match_lap_form(ph, ph.lap);
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(ph);
   if (ph.when != GDS_WHEN_STAGE && ph.when != GDS_WHEN_STEP) GDS_FAIL("unknown `when`");
   int64_t rows = domain_rows(s->g, ph.domain);
   if (rows < 0) GDS_FAIL("unknown domain");
@@ -700,6 +757,7 @@ static int add_special(gds_system* s, int32_t special, int64_t dst, int64_t src,
     ph.code = {GDS_OP_PUSH_IMM};
     ph.imm = {0.0};
   }
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(ph);
   s->passes.push_back(ph);
   return 0;
 }

@@ -98,6 +98,23 @@ struct LapForm {
   double alpha = 1.0, beta = 0.0, gamma = 0.0;
 };
 
+// More generally, a row program that is a LINEAR COMBINATION of masked one-hop operators,
+//   value = sum_k coef_k * Z_{m0_k} Z_{m1_k}( op_k(a_k [, b_k]) )[row] + beta * b[row] + gamma,
+// (Hodge Laplacians, advection + diffusion, Navier-Stokes edge law, div / curl intermediates) runs in `terms_kernel`,
+// which evaluates the terms one after another without the stack machine.
+#define GDS_MAX_TERMS 6
+struct TermSym {
+  int op = 0, a = -1, b = -1, m0 = -1, m1 = -1;  // opcode, operand slots, mask slots
+  double coef = 0.0;
+};
+struct TermForm {
+  bool ok = false;
+  int n = 0;
+  TermSym t[GDS_MAX_TERMS];
+  int b = -1, store = -1;
+  double beta = 0.0, gamma = 0.0;
+};
+
 struct StepRec {  // one row of the per-step table
   double t;       // step start time
   double h;       // step size
@@ -136,6 +153,18 @@ struct PassParams {
   const double* lap_b;
   double* lap_store;
   double lap_alpha, lap_beta, lap_gamma;
+  // linear combination of masked operators (TermForm resolved to pointers); n_terms == 0: not used.  The additive
+  // vector / constant / STORE target reuse lap_b, lap_beta, lap_gamma, lap_store.
+  int32_t use_terms;  // 1: run terms_kernel (n_terms may be 0: value = beta * b + gamma, a pointwise pass)
+  int32_t n_terms;
+  struct {
+    int32_t op;
+    const double* a;
+    const double* b;
+    const uint32_t* m0;
+    const uint32_t* m1;
+    double coef;
+  } term[GDS_MAX_TERMS];
   int32_t unit_weights;
 };
 
@@ -186,6 +215,7 @@ struct PassHost {  // a pass as given by the host, operands still symbolic
   int64_t state_offset;
   gds_mask* dirichlet;
   LapForm lap;
+  TermForm terms;
   // shift / hold pseudo-passes
   int32_t special = 0;  // 0 normal, 1 shift, 2 hold
   int64_t sp_dst = 0, sp_src = 0, sp_n = 0;

@@ -209,6 +209,33 @@ __device__ __forceinline__ double f_curl(const GraphDev& g, const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fused stage epilogue: Dirichlet zeroing of dy/dt (fds.py:303) + Runge-Kutta / Euler / map combine
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_epilogue(const PassParams& p, int64_t row, double k, double yn, double acc,
+                                               uint32_t dbits, double h) {
+  if ((dbits >> (row & 31)) & 1u) k = 0.0;  // fds.py:303
+  switch (p.stage_mode) {
+    case 0:  // first stage
+      p.acc_out[row] = k;
+      p.xnext[row] = yn + (p.a_next * h) * k;
+      break;
+    case 1:  // middle stage
+      p.acc_out[row] = acc + p.acc_w * k;
+      p.xnext[row] = yn + (p.a_next * h) * k;
+      break;
+    case 2:  // last stage
+      p.ynew[row] = yn + (p.fin * h) * (acc + k);
+      break;
+    case 3:  // single stage (Euler)
+      p.ynew[row] = yn + h * k;
+      break;
+    default:  // map: y <- map_fun(y)  (fds.py:337)
+      p.ynew[row] = k;
+      break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the row-program interpreter
 // ---------------------------------------------------------------------------------------------------
 #define PUSH(...)                     \
@@ -336,29 +363,62 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
         break;
     }
   }
+  if (p.epilogue == GDS_EPI_RHS) stage_epilogue(p, row, s0, e_yn, e_acc, e_dbits, h);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// linear combinations of masked one-hop operators (TermForm): the terms are evaluated one after another and
+// accumulated -- no stack machine, one warp-uniform switch per term
+// ---------------------------------------------------------------------------------------------------
+template <int DOMAIN, bool UNITW>
+__global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ PassParams p) {
+  const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (row >= p.n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const GraphDev& g = p.g;
+  double e_yn = 0.0, e_acc = 0.0;
+  uint32_t e_dbits = 0u;
   if (p.epilogue == GDS_EPI_RHS) {
-    double k = s0;
-    if ((e_dbits >> (row & 31)) & 1u) k = 0.0;  // fds.py:303
-    const double yn = e_yn;
-    switch (p.stage_mode) {
-      case 0:  // first stage
-        p.acc_out[row] = k;
-        p.xnext[row] = yn + (p.a_next * h) * k;
-        break;
-      case 1:  // middle stage
-        p.acc_out[row] = e_acc + p.acc_w * k;
-        p.xnext[row] = yn + (p.a_next * h) * k;
-        break;
-      case 2:  // last stage
-        p.ynew[row] = yn + (p.fin * h) * (e_acc + k);
-        break;
-      case 3:  // single stage (Euler)
-        p.ynew[row] = yn + h * k;
-        break;
-      default:  // map: y <- map_fun(y)  (fds.py:337)
-        p.ynew[row] = k;
-        break;
+    if (p.stage_mode != 4) e_yn = ld_stream_f64(p.yn + row);
+    if (p.stage_mode == 1 || p.stage_mode == 2) e_acc = ld_plain_f64(p.acc_in + row);
+    if (p.dmask) e_dbits = __ldg(p.dmask + (row >> 5));
+  }
+  double val = p.lap_gamma;
+  if (p.lap_b) val += p.lap_beta * ld_stream_f64(p.lap_b + row);
+#pragma unroll 1
+  for (int k = 0; k < p.n_terms; ++k) {
+    const double* a = p.term[k].a;
+    const double* b = p.term[k].b;
+    uint32_t mb = 0u;
+    if (p.term[k].m0) mb = __ldg(p.term[k].m0 + (row >> 5));
+    if (p.term[k].m1) mb |= __ldg(p.term[k].m1 + (row >> 5));
+    double gv = 0.0;
+    if (DOMAIN == GDS_NODES) {
+      switch (p.term[k].op) {
+        case GDS_OP_N_LAP: gv = n_lap<UNITW>(g, a, row, lane); break;
+        case GDS_OP_N_BDOT: gv = n_bdot<0, UNITW>(g, a, row, lane); break;
+        case GDS_OP_N_INFLUX: gv = n_bdot<1, UNITW>(g, a, row, lane); break;
+        case GDS_OP_N_OUTFLUX: gv = n_bdot<2, UNITW>(g, a, row, lane); break;
+        case GDS_OP_N_ADVECT: gv = n_advect<false, UNITW>(g, a, b, row, lane); break;
+        default: gv = n_advect<true, UNITW>(g, a, b, row, lane); break;
+      }
+    } else if (DOMAIN == GDS_EDGES) {
+      switch (p.term[k].op) {
+        case GDS_OP_E_GRADT: gv = e_gradt<UNITW>(g, a, row); break;
+        case GDS_OP_E_CURLT: gv = e_curlt<UNITW>(g, a, row, lane); break;
+        default: gv = e_advfin<UNITW>(g, a, b, row); break;
+      }
+    } else {
+      gv = f_curl<UNITW>(g, a, row, lane);
     }
+    if ((mb >> (row & 31)) & 1u) gv = 0.0;
+    val += p.term[k].coef * gv;
+  }
+  if (p.lap_store) p.lap_store[row] = val;
+  if (p.epilogue == GDS_EPI_RHS) {
+    double h = 0.0;
+    if (p.steptab) h = p.steptab[*p.step_counter].h;
+    stage_epilogue(p, row, val, e_yn, e_acc, e_dbits, h);
   }
 }
 
@@ -746,6 +806,23 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
   int64_t blocks = (rows + BLOCK - 1) / BLOCK;
   if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
   dim3 grid((unsigned)blocks), block(BLOCK);
+  if (p.use_terms) {
+    if (domain == GDS_NODES) {
+      if (unitw) terms_kernel<GDS_NODES, true><<<grid, block, 0, ctx->stream>>>(p);
+      else terms_kernel<GDS_NODES, false><<<grid, block, 0, ctx->stream>>>(p);
+    } else if (domain == GDS_EDGES) {
+      if (unitw) terms_kernel<GDS_EDGES, true><<<grid, block, 0, ctx->stream>>>(p);
+      else terms_kernel<GDS_EDGES, false><<<grid, block, 0, ctx->stream>>>(p);
+    } else if (domain == GDS_FACES) {
+      if (unitw) terms_kernel<GDS_FACES, true><<<grid, block, 0, ctx->stream>>>(p);
+      else terms_kernel<GDS_FACES, false><<<grid, block, 0, ctx->stream>>>(p);
+    } else {
+      GDS_FAIL("unknown domain");
+    }
+    GDS_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+    return 0;
+  }
   if (domain == GDS_NODES) {
     if (unitw) pass_kernel<GDS_NODES, true><<<grid, block, 0, ctx->stream>>>(p);
     else pass_kernel<GDS_NODES, false><<<grid, block, 0, ctx->stream>>>(p);
