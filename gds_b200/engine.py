@@ -109,7 +109,7 @@ class StepEngine:
             off, n, order = self.offsets[id(f)], f.ndim, f._order()
             dmask = None
             if self.scheme != 'map' and f.dirichlet_indices.size:
-                dmask = Mask(self.ctx, n, f.dirichlet_indices)          # fds.py:303
+                dmask = Mask(self.ctx, n, f._low.rows_to_dev(f._domain_code, f.dirichlet_indices))   # fds.py:303
                 self._keep.append(dmask)
             lowering.rhs_pass(root, f._domain_code, f._low, off + n * (order - 1), dmask)
             for p in lowering.passes:
@@ -122,7 +122,7 @@ class StepEngine:
             # Dirichlet overwrite after every step: fds.py:362 addresses `dirichlet_indices - ndim`, i.e. the LAST
             # order block
             if f.dirichlet_indices.size:
-                idx = off + n * (order - 1) + f.dirichlet_indices.astype(np.int64)
+                idx = off + n * (order - 1) + f._low.rows_to_dev(f._domain_code, f.dirichlet_indices)
                 if f.dynamic_dirichlet:
                     dyn_idx.append(idx)
                     self.dyn_fields.append(f)
@@ -151,10 +151,24 @@ class StepEngine:
             self._setup_partitioned()
 
     # ---- state movement ------------------------------------------------------------------------------------
+    def _blocks_to_dev(self, f, host):
+        """state of field f (order blocks of ndim rows, public row order) -> device row order"""
+        low, n = f._low, f.ndim
+        if f._domain_code != L.NODES or low.i2p is None:
+            return L.as_f64(host)
+        a = np.asarray(host, dtype=np.float64)
+        return np.ascontiguousarray(np.concatenate([a[i:i + n][low.i2p] for i in range(0, a.size, n)]))
+
+    def _blocks_from_dev(self, f, dev):
+        low, n = f._low, f.ndim
+        if f._domain_code != L.NODES or low.p2i is None:
+            return dev
+        return np.concatenate([dev[i:i + n][low.p2i] for i in range(0, dev.size, n)])
+
     def push_state(self):
         """upload every field's host state (what `integrator.y` holds in the reference)"""
         for f in self.fields:
-            a = L.as_f64(f._host_state)
+            a = self._blocks_to_dev(f, f._host_state)
             check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)], a.size))
             f._state_on_device = True
         self.version += 1
@@ -164,7 +178,7 @@ class StepEngine:
         for f in self.fields:
             a = np.empty(f.ndim * f._order(), dtype=np.float64)
             check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], a.size))
-            f._host_state = a
+            f._host_state = self._blocks_from_dev(f, a)
 
     def read(self, f, full=False):
         """current state slice of field f as a host array (cached until the next step)"""
@@ -173,17 +187,26 @@ class StepEngine:
             n = f.ndim * (f._order() if full else 1)
             a = np.empty(n, dtype=np.float64)
             check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], n))
-            self._read_cache[key] = a
+            self._read_cache[key] = self._blocks_from_dev(f, a)
         return self._read_cache[key]
 
     def read_into(self, f, out):
         """copy the value block of field f into a caller-owned (ideally pinned) host array"""
         assert out.dtype == np.float64 and out.flags['C_CONTIGUOUS'] and out.size <= f.ndim
+        if f._domain_code == L.NODES and f._low.p2i is not None:
+            assert out.size == f.ndim
+            tmp = np.empty(f.ndim, dtype=np.float64)
+            check(lib.gds_system_get_state(self.h, ptr(tmp), self.offsets[id(f)], tmp.size))
+            np.take(tmp, f._low.p2i, out=out)
+            return out
         check(lib.gds_system_get_state(self.h, ptr(out), self.offsets[id(f)], out.size))
         return out
 
     def write(self, f, values, offset=0):
         a = L.as_f64(values)
+        if f._domain_code == L.NODES and f._low.i2p is not None:
+            assert offset % f.ndim == 0 and a.size % f.ndim == 0, 'a renumbered field is written block by block'
+            a = self._blocks_to_dev(f, a)
         check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)] + offset, a.size))
         if self.part is not None and self.h is not None and hasattr(self, 'hx'):
             self._exchange(self._state_ptr())      # ghost rows follow their owners
@@ -195,7 +218,7 @@ class StepEngine:
             f, buf, ver = rec
             v = f._state_version()
             if ver != v:
-                buf.upload(f.y)
+                buf.upload(f._low.to_dev(f._domain_code, f.y))
                 rec[2] = v
 
     # ---- stepping ---------------------------------------------------------------------------------------------

@@ -394,7 +394,7 @@ def _run_eager(low, expr):
     for p in lowering.passes:
         d, keep = pass_desc(p)
         check(lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0))
-    return out.download()
+    return low.from_dev(expr.domain, out.download())
 
 
 class node_gds(gds):

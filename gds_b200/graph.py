@@ -9,6 +9,7 @@ removed (gds/utils/graph/generators.py:444-511).  One lowering is shared by ever
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import networkx as nx
 import numpy as np
@@ -66,6 +67,42 @@ def native_faces(n_nodes, edge_u, edge_v, adj_ptr, adj_nbr, pos):
     return HostGraph(h).faces()
 
 
+def morton_order(pos: np.ndarray) -> np.ndarray:
+    """ordering of points along a Z-order (Morton) curve: nearby points get nearby ranks"""
+    lo, hi = pos.min(axis=0), pos.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((pos - lo) / span * 65535.0).astype(np.uint64), 65535)
+
+    def spread(v):
+        v = (v | (v << 8)) & np.uint64(0x00FF00FF)
+        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << 2)) & np.uint64(0x33333333)
+        v = (v | (v << 1)) & np.uint64(0x55555555)
+        return v
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return np.argsort(key, kind='stable')
+
+
+def locality_permutation(V, edge_u, edge_v, pos, window=1024):
+    """Internal node numbering for graphs whose public numbering has no locality (random geometric graphs):
+    Z-order of the node positions, then -- inside windows of `window` consecutive nodes -- by decreasing degree, so that
+    the 32 rows of a sliced-ELL slice have (nearly) the same width.  Returns i2p (internal -> public) or None when the
+    public numbering is already local (lattices).  The public index maps never change; vectors are permuted on the way
+    to and from the device, and every row still sums its edges in edge-id order, so results are bit-identical."""
+    E = len(edge_u)
+    if pos is None or V < 64 or E == 0:
+        return None
+    if float(np.mean(np.abs(edge_u.astype(np.int64) - edge_v.astype(np.int64)))) <= 0.05 * V:
+        return None
+    i2p = morton_order(np.asarray(pos, dtype=np.float64))
+    deg = np.bincount(edge_u, minlength=V) + np.bincount(edge_v, minlength=V)
+    d = deg[i2p]
+    window = min(window, max(32, V // 16))
+    win = np.arange(V) // window
+    order = np.lexsort((-d, win))            # by window, then by decreasing degree (stable)
+    return i2p[order]
+
+
 class LoweredGraph:
     """Index maps + device operators of one graph, shared by every field built on it.  Use `LoweredGraph.of(G)`.
 
@@ -81,6 +118,7 @@ class LoweredGraph:
         self._faces_done = False
         self.outer_face = None
         self.F = 0
+        self.i2p = self.p2i = None           # internal <-> public node numbering (None: identical)
         self.part = None                     # Partition when the graph is distributed over several ranks
         dist_spec = G.__dict__.get('_gds_b200_distribute')
         if dist_spec is not None and dist_spec[1] > 1:
@@ -96,6 +134,8 @@ class LoweredGraph:
             self._faces = LazyFaceMap(hg, self.nodes)
             if G.kind not in ('triangular', 'hexagonal'):
                 self._faces_done = True          # no embedded faces for grids / 3-D grids / geometric graphs
+            if G.kind == 'random_geometric':
+                self._set_perm(locality_permutation(self.V, self.edge_u, self.edge_v, hg.pos()))
         else:
             self.nodes = {v: i for i, v in enumerate(G.nodes())}                       # gds.py:21
             self.edges = bidict({e: i for i, e in enumerate(G.edges())})               # gds.py:23
@@ -109,6 +149,11 @@ class LoweredGraph:
             self._faces = {}
             if hasattr(G, 'faces'):                                                      # gds.py:31-32
                 self._set_faces([tuple(f) for f in G.faces])
+            pos = nx.get_node_attributes(G, 'pos')
+            if len(pos) == V and V:
+                P = np.array([pos[v][:2] for v in self.nodes], dtype=np.float64).reshape(V, -1)
+                if P.shape[1] == 2:
+                    self._set_perm(locality_permutation(V, self.edge_u, self.edge_v, P))
 
     # -- one rank's part of a distributed graph -------------------------------------------------------------
     def _init_distributed(self, G, rank, world, align):
@@ -150,6 +195,33 @@ class LoweredGraph:
     def _local_edge_labels(self):
         inv = list(self.nodes.keys())
         return [(inv[u], inv[v]) for u, v in zip(self.edge_u, self.edge_v)]
+
+    # -- internal node numbering ---------------------------------------------------------------------------
+    def _set_perm(self, i2p):
+        if i2p is None or os.environ.get('GDS_B200_NO_RENUMBER'):
+            return
+        self.i2p = np.ascontiguousarray(i2p, dtype=np.int64)
+        self.p2i = np.empty_like(self.i2p)
+        self.p2i[self.i2p] = np.arange(self.i2p.size, dtype=np.int64)
+        self._dev = None
+
+    def to_dev(self, domain, host_vec):
+        """a host vector in public row order -> the order the device arrays use"""
+        if domain != L.NODES or self.i2p is None:
+            return host_vec
+        return np.asarray(host_vec)[self.i2p]
+
+    def from_dev(self, domain, dev_vec):
+        if domain != L.NODES or self.p2i is None:
+            return dev_vec
+        return np.asarray(dev_vec)[self.p2i]
+
+    def rows_to_dev(self, domain, rows):
+        """public row indices -> device row indices (same order)"""
+        rows = np.asarray(rows, dtype=np.int64)
+        if domain != L.NODES or self.p2i is None:
+            return rows
+        return self.p2i[rows]
 
     # -- faces -------------------------------------------------------------------------------------------
     def _set_faces(self, faces):
@@ -210,8 +282,12 @@ class LoweredGraph:
             if self.part is not None:
                 unit = bool(np.all(self.weights == 1.0))
                 self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights)
-            elif self.native:
+            elif self.native and self.p2i is None:
                 self._dev = DeviceGraph(self.ctx, self.V, None, None, self.G.weights, hostgraph=self._hg.h)
+            elif self.native:
+                fp, fn = (self._hg.faces() if self._hg.F else (None, None))
+                self._dev = DeviceGraph(self.ctx, self.V, self.p2i[self.edge_u], self.p2i[self.edge_v], self.G.weights,
+                                        fp, None if fn is None else self.p2i[fn])
             else:
                 face_ptr = face_nodes = None
                 if self.F:
@@ -219,8 +295,11 @@ class LoweredGraph:
                     face_ptr = np.cumsum([0] + [len(f) for f in faces]).astype(np.int64)
                     face_nodes = np.fromiter((nodes[n] for f in faces for n in f), dtype=np.int32, count=int(face_ptr[-1]))
                 unit = bool(np.all(self.weights == 1.0))
-                self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights,
-                                        face_ptr, face_nodes)
+                eu, ev = self.edge_u, self.edge_v
+                if self.p2i is not None:
+                    eu, ev = self.p2i[eu], self.p2i[ev]
+                    face_nodes = None if face_nodes is None else self.p2i[face_nodes]
+                self._dev = DeviceGraph(self.ctx, self.V, eu, ev, None if unit else self.weights, face_ptr, face_nodes)
         return self._dev
 
     def rows(self, domain):

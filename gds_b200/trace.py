@@ -392,7 +392,7 @@ class Lowering:
         if isinstance(e, Const):
             if id(e) not in self._consts:
                 self._keep.append(e)
-                self._consts[id(e)] = self._Buffer(self.ctx, e.arr.size, e.arr)
+                self._consts[id(e)] = self._Buffer(self.ctx, e.arr.size, e.graph.to_dev(e.domain, e.arr))
             buf = self._consts[id(e)]
             return p.vec_slot(('buf', id(buf), 0), (L.VEC_BUF, buf, 0))
         buf = self.materialize(e)
@@ -472,7 +472,7 @@ class Lowering:
             if e.rows.size:
                 key = (e.domain, id(e.graph), e.rows.tobytes())
                 if key not in self._masks:
-                    self._masks[key] = self._Mask(self.ctx, e.graph.rows(e.domain), e.rows)
+                    self._masks[key] = self._Mask(self.ctx, e.graph.rows(e.domain), e.graph.rows_to_dev(e.domain, e.rows))
                 p.emit('MASK_ZERO', p.mask_slot(key, self._masks[key]), push=1, pop=1)
         elif isinstance(e, Gather):
             slots = [self.operand(p, a, for_gather=True) for a in e.args]

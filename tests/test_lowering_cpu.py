@@ -132,3 +132,34 @@ def test_api_preconditions():
         T.set_evolution(dydt=lambda t, y: y, integrator=gds_b200.Integrators.lsoda)   # fds.py:95
     with pytest.raises(Exception):
         T.step(0.1)                             # no evolution law
+
+
+def test_internal_renumbering_keeps_public_maps_and_row_contents():
+    """graphs without index locality (random geometric graphs) are renumbered internally along a Z-order curve; the
+    public index maps do not change and every device row holds the same (edge, sign) list as its public row"""
+    import gds_b200
+    from oracle import gds_oracle
+    G = cases.g_rgg(500, 0.08, 9)
+    low = gds_b200.LoweredGraph.of(G)
+    ref = gds_oracle.Lowered(cases.g_rgg(500, 0.08, 9), need_faces=False)
+    assert low.i2p is not None and sorted(low.i2p) == list(range(500))
+    assert list(low.nodes.items()) == list(ref.nodes.items()) and list(low.edges.items()) == list(ref.edges.items())
+    p, i, s = low.dev.export_csr(0)
+    Bref = ref.B.tocsr()
+    for r_int in range(500):
+        r_pub = low.i2p[r_int]
+        cols = Bref.indices[Bref.indptr[r_pub]:Bref.indptr[r_pub + 1]]
+        sg = np.sign(Bref.data[Bref.indptr[r_pub]:Bref.indptr[r_pub + 1]])
+        order = np.argsort(cols)
+        assert np.array_equal(i[p[r_int]:p[r_int + 1]], cols[order])
+        assert np.array_equal(s[p[r_int]:p[r_int + 1]], sg[order])
+    # vectors and row sets travel through the permutation and back
+    x = np.arange(500.0)
+    assert np.array_equal(low.from_dev(gds_b200._lib.NODES, low.to_dev(gds_b200._lib.NODES, x)), x)
+    assert np.array_equal(low.i2p[low.rows_to_dev(gds_b200._lib.NODES, [3, 77, 400])], [3, 77, 400])
+    # lattices keep their numbering
+    assert gds_b200.LoweredGraph.of(cases.g_hex(6, 8)).i2p is None
+    # locality: the renumbered edge list is far more banded than the public one
+    d_pub = np.mean(np.abs(low.edge_u.astype(np.int64) - low.edge_v))
+    d_int = np.mean(np.abs(low.p2i[low.edge_u] - low.p2i[low.edge_v]))
+    assert d_int < 0.5 * d_pub
