@@ -137,6 +137,58 @@ def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
                      f'(V={V}, E={E}, F={F}), Dirichlet edges / Neumann nodes')
 
 
+def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):
+    """BASELINE config 3: Navier-Stokes velocity law (examples/fluid.py:33-34) on triangular_lattice_graph(n, n), lid
+    const_edge_bc (time-varying form), no-slip walls (examples/lid_driven_cavity.py:17-27), pressure held as a given node
+    vector; accepted-state operators as in the reference law, RK4 h = 1e-4 (tests/cases.py case_ns_cavity_c3)."""
+    assert world == 1 and not weighted
+    h, rho, visc = 1e-4, 0.1, 200.0
+    if native:
+        import gds_b200
+        G = gds_b200.NativeGraph('triangular', n, n)
+        p, u = api.node_gds(G), api.edge_gds(G)
+        hg = G.hostgraph(with_faces=True)
+        pos, (eu, ev) = hg.pos(), hg.edges()
+        api.evolve_nil(p)
+        p.set_initial(y0=0.01 * np.random.default_rng(3).standard_normal(p.ndim))
+        api.evolve(u, dydt=lambda t, y: -u.advect() - p.grad() / rho + u.laplacian() * visc / rho, max_step=h)
+        u.set_initial(y0=0.05 * np.random.default_rng(4).standard_normal(u.ndim))
+        x0, x1, y0_, y1 = pos[:, 0].min(), pos[:, 0].max(), pos[:, 1].min(), pos[:, 1].max()
+        lid = _edges_inside(eu, ev, pos[:, 1] > y1 - 1e-9)
+        walls = np.unique(np.concatenate([_edges_inside(eu, ev, pos[:, 1] < y0_ + 1e-9),
+                                          _edges_inside(eu, ev, pos[:, 0] < x0 + 0.51),
+                                          _edges_inside(eu, ev, pos[:, 0] > x1 - 0.51)]))
+        lid = np.setdiff1d(lid, walls)                     # static (wall) conditions win (boundary.py:21-41)
+        idx = np.concatenate([walls, lid])
+        vals = np.concatenate([np.zeros(walls.size), np.full(lid.size, 10.0)])
+        u.set_constraints(dirichlet=gds_b200.BoundarySpec(idx, fun=lambda t: vals))
+        sysobj = api.couple({'u': u, 'p': p})
+        V, E, F = hg.V, hg.E, hg.F
+    else:
+        import cases
+        G = cases.g_tri(n, n)
+        p, u = api.node_gds(G), api.edge_gds(G)
+        p0 = 0.01 * np.random.default_rng(3).standard_normal(p.ndim)
+        api.evolve_nil(p)
+        p.set_initial(y0=lambda x: p0[p.X[x]])
+        api.evolve(u, dydt=lambda t, y: -u.advect() - p.grad() / rho + u.laplacian() * visc / rho, max_step=h)
+        u0 = 0.05 * np.random.default_rng(4).standard_normal(u.ndim)
+        u.set_initial(y0=lambda e: u0[u.X[e]])
+        lid, walls = cases.tri_boundaries(G)
+        lid_bc = api.const_edge_bc(lid, 10.0)
+        u.set_constraints(dirichlet=api.combine_bcs(api.zero_edge_bc(walls), lambda t, e: lid_bc(e)))
+        sysobj = api.couple({'u': u, 'p': p})
+        V, E, F = p.ndim, u.ndim, len(u.faces)
+    # SURVEY.md 8d: advect 48E + 76V, grad 16E + 8V, Hodge-1 Laplacian 64E + 20V + 32F per RHS
+    per_step = 4 * (128 * E + 104 * V + 32 * F) + 136 * E
+    return dict(stepper=sysobj.stepper, fields=[u], h=h, n_state=E, V=V, E=E, F=F, bytes_per_step=per_step,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
+                kernel='step level: the law reads accepted state only, so its operators run once per step (5 passes) '
+                       'and the 4 stages are pointwise',
+                name=f'Navier-Stokes edge law (advect + grad p + Hodge-1 Laplacian), RK4 h=1e-4, '
+                     f'triangular_lattice_graph({n},{n}) (V={V}, E={E}, F={F}), lid + no-slip Dirichlet')
+
+
 def cml_problem(api, n, native, world=1, rank=0, weighted=False):
     """BASELINE config 4: coupled map lattice on random_geometric_graph(n, sqrt(8/(pi n)), seed=42), map mode"""
     assert world == 1 and not weighted
@@ -196,6 +248,7 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False):
 
 # name -> (builder, default GPU size per rank, CPU sample size)
 WORKLOADS = {'heat2d': (heat2d_problem, 7072, 1024), 'hex_advdiff': (hex_advdiff_problem, 2000, 40),
+             'ns_cavity': (ns_cavity_problem, 4000, 40),
              'cml': (cml_problem, 10_000_000, 100_000), 'wave3d': (wave3d_problem, 400, 48)}
 
 
