@@ -124,13 +124,18 @@ class fds(Observable, Steppable):
             keep = np.ones(self.ndim, dtype=bool)
             keep[self.dirichlet_indices] = False
             self._host_state[:self.ndim][keep] = arr[keep]
+            if self.y0 is not self._host_state:                 # fds.py:168-173 writes y0 and the solver state
+                self.y0[:self.ndim][keep] = arr[keep]
         else:
             self.y0_fun = y0
             constrained = set(self.X_dirichlet)
-            st = self._host_state
+            st, both = self._host_state, self.y0 is not self._host_state
             for x, i in self.X.items():
                 if x not in constrained:
-                    st[i] = y0(x)
+                    v = y0(x)
+                    st[i] = v
+                    if both:
+                        self.y0[i] = v
         self._bump()
 
     # ---- boundary conditions (fds.py:175-243) ------------------------------------------------------------------
@@ -138,21 +143,15 @@ class fds(Observable, Steppable):
         assert self.iter_mode != IterationMode.none, 'Use set_evolution() before setting boundary conditions'
         self._drop_engine()
         self._set_bcs(dirichlet, neumann, project)
-        st = self._host_state
+        # fds.py:193: y0 = project(replace(y0, ...)) -- the replacement is in place, so it also reaches the solver state
+        # while that still aliases y0; the projection only does when it works in place
+        self.y0[self.dirichlet_indices] = self.dirichlet_values
+        self.y0 = np.asarray(project(self.y0), dtype=float)
         if self.iter_mode is IterationMode.dydt:
-            if st is self.y0:
-                st[self.dirichlet_indices] = self.dirichlet_values                  # fds.py:193 (y0 aliases integrator.y)
-                if project is not _identity:
-                    self.y0 = self._host_state = np.asarray(project(st), dtype=float)
-                    st = self._host_state
-            else:
-                self.y0[self.dirichlet_indices] = self.dirichlet_values
             # fds.py:196: negative offsets -- for order>1 this addresses the LAST block
-            st[self.dirichlet_indices - self.ndim] = self.dirichlet_values
+            self._host_state[self.dirichlet_indices - self.ndim] = self.dirichlet_values
         elif self.iter_mode is IterationMode.map:
-            st[self.dirichlet_indices] = self.dirichlet_values
-            if project is not _identity:
-                self.y0 = self._host_state = np.asarray(project(st), dtype=float)
+            self._host_state = self.y0.copy()                                       # fds.py:203
         else:
             raise Exception('Unsupported iteration mode for set_constraints()')     # fds.py:205
         self._bump()

@@ -1,0 +1,116 @@
+"""The rest of the drop-in surface on the device path: reset, System.solve / system(name), derived observables
+(project), point reads, oriented edge reads, single-edge differences, vectorised boundary specs and native graphs
+driven through the same field API -- each against the CPU oracle."""
+import math
+
+import networkx as nx
+import numpy as np
+import pytest
+
+import cases
+from adaptors import oracle_api, product_api, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def heat(api, n=10):
+    G = cases.g_grid(n, n)
+    T = api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=2e-3)
+    T.set_initial(y0=lambda x: math.exp(-((x[0] - 4) ** 2 + (x[1] - 5) ** 2) / 6))
+    T.set_constraints(dirichlet=lambda t, x: math.cos(t) if x[0] == 0 else None)
+    return T
+
+
+def test_reset_returns_to_initial_conditions():
+    T = heat(product_api())
+    y0 = np.array(T.y, copy=True)
+    T.step(0.01)
+    y1 = np.array(T.y, copy=True)
+    assert T.t == pytest.approx(0.01) and not np.array_equal(y0, y1)
+    T.reset()
+    assert T.t == 0. and np.array_equal(np.asarray(T.y), y0)
+    T.step(0.01)
+    assert np.array_equal(np.asarray(T.y), y1)         # deterministic replay
+
+
+def test_system_solve_matches_oracle():
+    def run(api):
+        T = heat(api)
+        return T.system('T').solve(0.02, 0.004)
+    (ta, da), (tb, db) = run(product_api()), run(oracle_api())
+    assert np.allclose(ta, tb, rtol=0, atol=1e-12)
+    assert da['T'].shape == db['T'].shape
+    for i in range(db['T'].shape[0]):
+        assert rel_l2(da['T'][i], db['T'][i]) <= 1e-10
+
+
+def test_point_reads_projections_and_partials():
+    import gds_b200
+    G = cases.add_weights(cases.g_hex(3, 4), 2)
+    u, ref_u = gds_b200.edge_gds(G), oracle_api().edge_gds(cases.add_weights(cases.g_hex(3, 4), 2))
+    rng = np.random.default_rng(3)
+    y0 = rng.standard_normal(u.ndim)
+    for f in (u, ref_u):
+        f.set_evolution(dydt=lambda t, y, f=f: 0.1 * f.laplacian(y), max_step=1e-3)
+        f.set_initial(y0=lambda e, f=f: y0[f.X[e]])
+    u.step(3e-3); ref_u.step(3e-3)
+    e = list(u.X.keys())[5]
+    assert u(e) == pytest.approx(ref_u(e), rel=1e-10)
+    assert u((e[1], e[0])) == pytest.approx(-ref_u(e), rel=1e-10)       # oriented read (gds.py:273-274)
+    assert u[5] == pytest.approx(ref_u.y[5], rel=1e-10)
+    # derived observable (types.py:95-105): vorticity = curl of the velocity field, evaluated lazily on the device
+    vort = u.project(gds_b200.GraphObservable, lambda obs: obs.curl(), G, gds_b200.GraphDomain.faces)
+    assert vort.t == u.t and rel_l2(vort.y, ref_u.curl()) <= 1e-10
+    c, ref_c = gds_b200.node_gds(G), oracle_api().node_gds(cases.add_weights(cases.g_hex(3, 4), 2))
+    x = rng.standard_normal(c.ndim)
+    assert c.partial(e, x) == pytest.approx(ref_c.grad(x)[ref_u.X[e]], rel=1e-12)   # gds.py:149-150
+
+
+def test_native_graph_and_boundary_spec_equal_networkx_and_callables():
+    """the same heat problem through nx.Graph + per-point callables and through NativeGraph + vectorised BoundarySpec"""
+    import gds_b200
+    n = 37
+    T1 = gds_b200.node_gds(cases.g_grid(n, n))
+    T1.set_evolution(dydt=lambda t, y: T1.laplacian(y), max_step=1e-2, integrator=gds_b200.Integrators.rk4)
+    T1.set_initial(y0=lambda x: math.exp(-((x[0] - 18) ** 2 + (x[1] - 18) ** 2) / 20))
+    T1.set_constraints(dirichlet=gds_b200.combine_bcs(lambda x: 0. if x[0] == n - 1 else None,
+                                                      lambda t, x: math.sin(t + x[1] / 4) ** 2 if x[0] == 0 else None))
+    T2 = gds_b200.node_gds(gds_b200.NativeGraph('grid_2d', n, n))
+    T2.set_evolution(dydt=lambda t, y: T2.laplacian(y), max_step=1e-2, integrator=gds_b200.Integrators.rk4)
+    i, j = np.divmod(np.arange(n * n), n)
+    T2.set_initial(y0=np.exp(-((i - 18) ** 2 + (j - 18) ** 2) / 20))
+    jj = np.arange(n)
+    T2.set_constraints(dirichlet=gds_b200.BoundarySpec(
+        np.concatenate([jj, (n - 1) * n + jj]), fun=lambda t: np.concatenate([np.sin(t + jj / 4) ** 2, np.zeros(n)])))
+    for _ in range(5):
+        T1.step(3e-2); T2.step(3e-2)
+    assert T1.t == T2.t
+    assert rel_l2(T1.y, T2.y) <= 1e-13                 # math.exp / math.sin vs their numpy counterparts: last-ulp inputs
+    assert list(T2.X.keys())[:3] == [(0, 0), (0, 1), (0, 2)] and T2((1, 2)) == pytest.approx(T1((1, 2)), rel=1e-12)
+
+
+def test_user_projection_runs_on_the_host_every_step():
+    """project= is arbitrary host code (fds.py:363): supported through one host round trip per step"""
+    def run(api):
+        T = heat(api, n=8)
+        T.set_constraints(dirichlet={(0, 0): 1.0}, project=lambda y: np.clip(y, 0.0, 0.6))
+        T.step(0.01)
+        return np.array(T.y, copy=True)
+    assert rel_l2(run(product_api()), run(oracle_api())) <= 1e-10
+
+
+def test_external_field_and_several_max_steps_per_call():
+    """a law may read a field outside its system (uploaded when it changes); step(dt) spans several max_steps"""
+    def run(api):
+        G = cases.g_grid(7, 9)
+        src, T = api.node_gds(G), api.node_gds(G)
+        api.evolve_nil(src)
+        src.set_initial(y0=lambda x: 0.1 * x[0] - 0.05 * x[1])
+        api.evolve(T, dydt=lambda t, y: T.laplacian(y) + 2.0 * src.y - y * t, max_step=3e-3)
+        T.set_initial(y0=lambda x: float(x[0] == 3))
+        for _ in range(3):
+            T.step(1e-2)
+        return np.array(T.y, copy=True), T.t
+    (a, ta), (b, tb) = run(product_api()), run(oracle_api())
+    assert ta == pytest.approx(tb, abs=1e-15) and rel_l2(a, b) <= 1e-10
