@@ -668,6 +668,73 @@ extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// conjugate gradients with the operator given as a pass
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_cg_solve(gds_ctx* c, gds_graph* g, const gds_pass_desc* apply, gds_buf* x, gds_buf* b, gds_buf* r,
+                            gds_buf* p, gds_buf* ap, int64_t n, double rtol, int32_t max_iter, int32_t check_every,
+                            int32_t* iters_out, double* relres_out) {
+  if (!c || !g || !apply || !x || !b || !r || !p || !ap) GDS_FAIL("bad argument");
+  if (n < 0 || x->n < n || b->n < n || r->n < n || p->n < n || ap->n < n) GDS_FAIL("vector shorter than n");
+  if (max_iter < 0 || check_every < 1 || !(rtol >= 0.0)) GDS_FAIL("bad iteration parameters");
+  PassHost ph;
+  GDS_TRY(copy_pass(apply, ph));
+  if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("the operator pass takes GDS_EPI_NONE");
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(ph);
+  PassParams pp;
+  GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
+  double* S = nullptr;
+  double* partial = nullptr;
+  GDS_CUDA(cudaMalloc((void**)&S, 8 * sizeof(double)));
+  if (cudaMalloc((void**)&partial, 2048 * sizeof(double)) != cudaSuccess) { cudaFree(S); GDS_FAIL("out of device memory"); }
+  int rc = 0, it = 0;
+  double h[7] = {0, 0, 0, 0, 0, 0, 0};
+  auto fetch = [&]() -> int {
+    GDS_CUDA(cudaMemcpyAsync(h, S, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GDS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  // x = 0, r = b, p = b, rr = bb = b.b
+  rc = cudaMemsetAsync(x->d, 0, (size_t)n * 8, c->stream) != cudaSuccess;
+  rc = rc || cudaMemcpyAsync(r->d, b->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
+  rc = rc || cudaMemcpyAsync(p->d, b->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
+  rc = rc || cudaMemsetAsync(S, 0, 8 * sizeof(double), c->stream) != cudaSuccess;
+  if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, r->d, r->d, n, S, partial, 0);
+  if (!rc) rc = launch_cg(c, 1, nullptr, nullptr, nullptr, nullptr, n, S, partial, 2);
+  if (!rc) rc = fetch();
+  const double bb = h[4], target = rtol * rtol * bb;
+  double best = bb;
+  if (!rc) rc = cudaMemcpyAsync(S + 5, &target, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess;
+  if (!rc) rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
+  while (!rc && it < max_iter && h[0] > target && bb > 0.0 && h[6] == 0.0) {
+    int m = std::min<int>(check_every, max_iter - it);
+    for (int k = 0; k < m && !rc; ++k) {
+      rc = launch_pass(c, pp, ph.domain);                                                   // ap = A p
+      if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, p->d, ap->d, n, S, partial, 0);       // p.Ap
+      if (!rc) rc = launch_cg(c, 1, nullptr, nullptr, nullptr, nullptr, n, S, partial, 0);  // alpha
+      if (!rc) rc = launch_cg(c, 2, x->d, r->d, p->d, ap->d, n, S, partial, 0);             // x, r, partial r.r
+      if (!rc) rc = launch_cg(c, 1, nullptr, nullptr, nullptr, nullptr, n, S, partial, 1);  // beta, rr
+      if (!rc) rc = launch_cg(c, 3, nullptr, r->d, p->d, nullptr, n, S, partial, 0);        // p = r + beta p
+    }
+    it += m;
+    if (!rc) rc = fetch();
+    // a right-hand side with a component outside the range of a singular operator stalls and then diverges: stop
+    // once the residual has grown well past its best value
+    if (!rc) {
+      if (!(h[0] == h[0]) || h[0] > 1e4 * best) break;
+      best = std::min(best, h[0]);
+    }
+  }
+  cudaFree(S);
+  cudaFree(partial);
+  if (rc) { if (rc == 1) GDS_FAIL("CUDA failure inside the CG loop"); return rc; }
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = (bb > 0.0) ? std::sqrt(h[0] / bb) : 0.0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // systems
 // ---------------------------------------------------------------------------------------------------
 extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int32_t scheme, gds_system** out) {

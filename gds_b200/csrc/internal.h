@@ -254,5 +254,7 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
                      int64_t n, int64_t n_dyn_stride, const int64_t* counter);
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
+int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
+              int mode);
 int launch_probe(gds_ctx* ctx, double* const* bufs, int n_read, int n_write, int64_t n);
 int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int64_t n, int scatter);

@@ -950,3 +950,95 @@ int launch_probe(gds_ctx* ctx, double* const* bufs, int n_read, int n_write, int
   ctx->kernel_launches++;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// conjugate gradients: vector kernels with the scalars (alpha, beta, residual norms) resident on the device, so an
+// iteration needs no host round trip.  Reductions run on a fixed grid with a fixed tree: bitwise reproducible.
+// S[0] = rr, S[1] = pAp, S[2] = alpha, S[3] = beta, S[4] = bb (|b|^2), S[5] = target for rr, S[6] = finished flag
+// ---------------------------------------------------------------------------------------------------
+#define CG_BLOCKS 1184  // 148 SMs x 8
+#define CG_THREADS 256
+
+__device__ __forceinline__ void block_reduce_store(double v, double* out) {
+  __shared__ double sh[CG_THREADS];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = CG_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+__global__ void __launch_bounds__(CG_THREADS) cg_dot_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                            int64_t n, double* __restrict__ partial) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS)
+    acc += a[i] * b[i];
+  block_reduce_store(acc, partial + blockIdx.x);
+}
+
+// mode 0: S.pAp = v, S.alpha = rr / v;   mode 1: S.beta = v / rr, S.rr = v;   mode 2 (start): S.rr = S.bb = v
+__global__ void __launch_bounds__(CG_THREADS) cg_final_kernel(const double* __restrict__ partial, double* __restrict__ S,
+                                                              int mode) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < CG_BLOCKS; i += CG_THREADS) acc += partial[i];
+  __shared__ double total;
+  block_reduce_store(acc, &total);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double v = total;
+    // S[5] = convergence target for r.r, S[6] = 1 once converged or broken down: later iterations of the same batch
+    // (the host only looks every `check_every` iterations) must not touch x any more -- with r at rounding level
+    // p.Ap underflows faster than r.r and alpha would blow up
+    if (mode == 0) {
+      S[1] = v;
+      const bool live = S[6] == 0.0 && v > 0.0 && isfinite(v);
+      if (!live) S[6] = 1.0;
+      S[2] = live ? S[0] / v : 0.0;
+    } else if (mode == 1) {
+      S[3] = (S[6] == 0.0 && S[0] != 0.0) ? v / S[0] : 0.0;
+      S[0] = v;
+      if (!(v > S[5])) S[6] = 1.0;
+    } else {
+      S[0] = v; S[4] = v;
+    }
+  }
+}
+
+// x += alpha p;  r -= alpha Ap;  partial sums of the new r.r
+__global__ void __launch_bounds__(CG_THREADS) cg_update_kernel(double* __restrict__ x, double* __restrict__ r,
+                                                               const double* __restrict__ p, const double* __restrict__ ap,
+                                                               int64_t n, const double* __restrict__ S,
+                                                               double* __restrict__ partial) {
+  const double alpha = S[2];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    acc += ri * ri;
+  }
+  block_reduce_store(acc, partial + blockIdx.x);
+}
+
+// p = r + beta p
+__global__ void __launch_bounds__(CG_THREADS) cg_direction_kernel(double* __restrict__ p, const double* __restrict__ r,
+                                                                  int64_t n, const double* __restrict__ S) {
+  const double beta = S[3];
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS)
+    p[i] = r[i] + beta * p[i];
+}
+
+int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
+              int mode) {
+  switch (what) {
+    case 0: cg_dot_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, ap, n, partial); break;      // any two vectors
+    case 1: cg_final_kernel<<<1, CG_THREADS, 0, ctx->stream>>>(partial, S, mode); break;
+    case 2: cg_update_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(x, r, p, ap, n, S, partial); break;
+    default: cg_direction_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, r, n, S); break;
+  }
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}

@@ -21,7 +21,7 @@ from ._lib import lib, check
 from .device import Buffer, Context
 from .engine import StepEngine
 from .graph import LoweredGraph, NativeGraph
-from .trace import (Const, EdgeAgg, Expr, Gather, Lowering, MaskZero, State, TraceError, as_expr, pass_desc,
+from .trace import (Const, DevVec, EdgeAgg, Expr, Gather, Lowering, MaskZero, State, TraceError, as_expr, pass_desc,
                     tracing, unary)
 from .types import GraphDomain, Integrators, IterationMode, Observable, Steppable
 from .utils import dict_fun, fun_ary
@@ -396,6 +396,22 @@ def _run_eager(low, expr):
     return low.from_dev(expr.domain, out.download())
 
 
+def _lower_into(low, expr, out_buf):
+    """passes (ctypes descriptors + keep-alives) that evaluate `expr` into the device buffer `out_buf`"""
+    def no_leaf(e):
+        raise TraceError('field state used outside an evolution law')
+    lowering = Lowering(low.ctx, no_leaf, hoist=False)
+    lowering.store_pass(expr, out_buf)
+    return [pass_desc(p) for p in lowering.passes], lowering
+
+
+def _run_passes(low, descs):
+    import ctypes as C
+    dev = low.dev
+    for d, keep in descs:
+        check(lib.gds_pass_run(low.ctx.h, dev.h, C.byref(d), 0.0))
+
+
 class node_gds(gds):
     """dynamical system on the nodes of a graph (gds.py:133-189)"""
 
@@ -500,6 +516,53 @@ class edge_gds(gds):
             raise NotImplementedError('edge_gds.advect(weighted=False) is not part of the device path')
         g = self._low
         return self._apply(lambda a: Gather('E_ADVFIN', g, a, EdgeAgg(g, a)), self._arg(y, L.EDGES), domains=(L.EDGES,))
+
+
+    def leray_project(self, y=None, rtol=1e-13, max_iter=None, return_info=False):
+        """Projection onto the divergence-free edge fields, y - B1^T pinv(B1 B1^T) B1 y (gds.py:249,414-427).  The
+        reference forms the dense |E| x |E| projector with a dense pinv; here B1 B1^T phi = B1 y is solved by conjugate
+        gradients on the device (the system is singular -- constants per component -- but consistent, and CG started
+        at 0 converges to the pinv solution), then y - B1^T phi.  The reference's branch for fields with Dirichlet
+        conditions stacks a non-square system into np.linalg.solve and cannot run; it is not reproduced."""
+        import ctypes as C
+        if tracing():
+            raise TraceError('leray_project solves a linear system; apply it between steps, not inside an evolution law')
+        if self.dirichlet_indices.size:
+            raise NotImplementedError('leray_project with Dirichlet conditions (gds.py:420-427 is not runnable in the reference)')
+        y = np.asarray(self.y if y is None else y, dtype=float)
+        if y.shape != (self.ndim,):
+            raise ValueError(f'operand of shape {y.shape} where a vector of length {self.ndim} is expected')
+        low, ctx = self._low, self._low.ctx
+        V, E = low.V, low.E
+        if E == 0:
+            return y.copy()
+        yb = Buffer(ctx, E, y)
+        b, x, r, p, ap = (Buffer(ctx, V) for _ in range(5))
+        out = Buffer(ctx, E)
+        d_rhs, k1 = _lower_into(low, Gather('N_BDOT', low, DevVec(yb, L.EDGES, low)), b)            # B1 y
+        _run_passes(low, d_rhs)
+        # a right-hand side at rounding level (y already divergence-free) has no meaningful solution: the noise is not in
+        # the range of the singular operator
+        bh, ynorm = b.download(), float(np.linalg.norm(y))
+        if float(np.linalg.norm(bh)) <= 4e-13 * ynorm:
+            self.last_solve = {'iterations': 0, 'relative_residual': 0.0}
+            return (y.copy(), self.last_solve) if return_info else y.copy()
+        # B1 y sums to zero over every connected component; rounding leaves a residue outside the range of B1 B1^T that
+        # conjugate gradients cannot reduce -- remove it
+        ncomp, lab = low.component_labels()
+        bh -= (np.bincount(lab, weights=bh, minlength=ncomp) / np.bincount(lab, minlength=ncomp))[lab]
+        b.upload(bh)
+        d_op, k2 = _lower_into(low, unary('NEG', Gather('N_LAP', low, DevVec(p, L.NODES, low))), ap)  # B1 B1^T p = -L0 p
+        assert len(d_op) == 1
+        iters, relres = C.c_int32(), C.c_double()
+        max_iter = int(max_iter) if max_iter is not None else max(1000, 20 * int(np.sqrt(V)) + 200)
+        check(lib.gds_cg_solve(ctx.h, low.dev.h, C.byref(d_op[0][0]), x.h, b.h, r.h, p.h, ap.h, V, float(rtol),
+                               max_iter, 25, C.byref(iters), C.byref(relres)))
+        d_out, k3 = _lower_into(low, DevVec(yb, L.EDGES, low) - Gather('E_GRADT', low, DevVec(x, L.NODES, low)), out)
+        _run_passes(low, d_out)
+        res = out.download()
+        self.last_solve = {'iterations': iters.value, 'relative_residual': relres.value}
+        return (res, self.last_solve) if return_info else res
 
 
 class simplex_gds(gds):

@@ -302,6 +302,17 @@ class LoweredGraph:
                 self._dev = DeviceGraph(self.ctx, self.V, eu, ev, None if unit else self.weights, face_ptr, face_nodes)
         return self._dev
 
+    def component_labels(self):
+        """connected component of every node, in DEVICE row order (cached); used to keep right-hand sides of the
+        singular graph Laplacian in its range"""
+        if getattr(self, '_components', None) is None:
+            import scipy.sparse as sp
+            from scipy.sparse.csgraph import connected_components
+            A = sp.coo_matrix((np.ones(self.E, dtype=np.int8), (self.edge_u, self.edge_v)), shape=(self.V, self.V))
+            ncomp, lab = connected_components(A, directed=False)
+            self._components = (ncomp, np.ascontiguousarray(self.to_dev(L.NODES, lab)))
+        return self._components
+
     def rows(self, domain):
         if domain == L.FACES:
             self.ensure_faces()

@@ -145,6 +145,13 @@ class Const(Expr):
         self.domain, self.graph = domain, graph
 
 
+class DevVec(Expr):
+    """a vector that already lives on the device (work vectors of the solvers)"""
+
+    def __init__(self, buf, domain, graph):
+        self.buf, self.domain, self.graph = buf, domain, graph
+
+
 class Unary(Expr):
     def __init__(self, op, x):
         self.op, self.args, self.domain, self.graph = op, (x,), x.domain, x.graph
@@ -389,6 +396,8 @@ class Lowering:
             if ref[0] == L.VEC_STAGE and p.when == L.WHEN_STEP:
                 raise TraceError('internal: stage operand in a per-step pass')
             return p.vec_slot(('leaf', ref[0], id(ref[1]), ref[2]), ref)
+        if isinstance(e, DevVec):
+            return p.vec_slot(('buf', id(e.buf), 0), (L.VEC_BUF, e.buf, 0))
         if isinstance(e, Const):
             if id(e) not in self._consts:
                 self._keep.append(e)
@@ -441,14 +450,14 @@ class Lowering:
             raise ValueError(f'a vector over {_DOMAIN_NAME[e.domain]} cannot be used pointwise in a law over '
                              f'{_DOMAIN_NAME[p.domain]}')
         # hoist accepted-state-only sub-expressions that contain a gather out of the per-stage pass
-        if (self.hoist and p.when == L.WHEN_STAGE and not isinstance(e, (Stage, State, Const))
+        if (self.hoist and p.when == L.WHEN_STAGE and not isinstance(e, (Stage, State, Const, DevVec))
                 and e.domain is not None and not self.variant(e) and self.has_gather(e)):
             p.emit('PUSH_VEC', self.operand(p, e), push=1)
             return
         if id(e) in self._temps and e.domain is not None:
             p.emit('PUSH_VEC', self.operand(p, e), push=1)
             return
-        if isinstance(e, (Stage, State, Const)):
+        if isinstance(e, (Stage, State, Const, DevVec)):
             p.emit('PUSH_VEC', self.operand(p, e), push=1)
         elif isinstance(e, Unary):
             self.emit(p, e.args[0])

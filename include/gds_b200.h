@@ -161,6 +161,15 @@ int gds_graph_device_bytes(gds_graph* g, int64_t* bytes);
  *      Runs ONE pass (epilogue must be GDS_EPI_NONE) at time t. -------------------------------------------- */
 int gds_pass_run(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* pass, double t);
 
+/* ---- conjugate gradients for A x = b, A given as a pass that reads buffer `p` and STOREs A p into buffer `ap`
+ *      (x starts at 0; symmetric positive semi-definite A with b in its range, e.g. B1 B1^T = -L0).  Replaces the dense
+ *      pinv / solve of the Leray projection (gds/gds.py:249,414-427) and is the kernel of a device pressure-Poisson solve
+ *      (SURVEY.md 8f-1).  All vectors hold >= n values; scalars stay on the device, the residual is read back every
+ *      `check_every` iterations; stops at |r| <= rtol |b| or max_iter. ------------------------------------------------ */
+int gds_cg_solve(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* apply, gds_buf* x, gds_buf* b, gds_buf* r, gds_buf* p,
+                 gds_buf* ap, int64_t n, double rtol, int32_t max_iter, int32_t check_every, int32_t* iters_out,
+                 double* relres_out);
+
 /* ---- the stepping core: replaces fds.step / step_dydt / dydt / step_map / apply_constraints and
  *      coupled_fds.step_continuous / dydt (gds/fds.py:264-305,332-369,471-507) plus the solver object
  *      (gds/ode/midpoint.py:10-32).  One system = one concatenated state vector (fds.py:439,456-460). -------- */

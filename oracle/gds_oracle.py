@@ -681,6 +681,15 @@ class edge_gds(gds):
         return -(sp.csr_matrix(A) @ y)
 
 
+    def leray_project(self, y=None):  # gds.py:249,414-419 (the Dirichlet branch, gds.py:420-427, is not runnable)
+        if y is None: y = self.y
+        assert self.dirichlet_indices.size == 0
+        B = self.incidence
+        # the reference applies the dense projector I - B^T pinv(B B^T) B; same product without forming it
+        phi = np.linalg.pinv((B @ B.T).toarray(), hermitian=True) @ (B @ np.asarray(y, dtype=float))
+        return np.asarray(y, dtype=float) - B.T @ phi
+
+
 class face_gds(gds):
     def __init__(self, G, lowered=None):
         gds.__init__(self, G, GraphDomain.faces, lowered)

@@ -123,6 +123,7 @@ def operator_outputs(api, gname):
     out['node_bilaplacian'] = nd.bilaplacian(yv)
     out['node_advect'] = nd.advect(ye, yv)
     out['node_lie_advect'] = nd.lie_advect(ye, yv)
+    out['edge_leray'] = ed.leray_project(ye)      # before any Dirichlet condition (gds.py:418-419)
     # edge field: Dirichlet on a few edges
     d_edges = {edges_list[i]: float(0.1 * i) for i in range(0, E, 9)}
     api.evolve(ed, dydt=lambda t, y: ed.laplacian(y), max_step=1e-2)

@@ -114,3 +114,25 @@ def test_external_field_and_several_max_steps_per_call():
         return np.array(T.y, copy=True), T.t
     (a, ta), (b, tb) = run(product_api()), run(oracle_api())
     assert ta == pytest.approx(tb, abs=1e-15) and rel_l2(a, b) <= 1e-10
+
+
+def test_leray_projection_matches_dense_pinv_and_is_a_projection():
+    """edge_gds.leray_project (gds.py:249,414-419): device CG on B1 B1^T against the oracle's dense pinv (the golden
+    files pin the same function to the unmodified reference at small size), plus divergence-freeness and idempotence"""
+    import gds_b200
+    for make in (lambda: cases.add_weights(cases.g_tri(9, 12), 4), lambda: cases.g_hex(7, 9), lambda: cases.g_rgg(300, 0.12, 1)):
+        u, ref = gds_b200.edge_gds(make()), oracle_api().edge_gds(make())
+        y = np.random.default_rng(8).standard_normal(u.ndim)
+        z, info = u.leray_project(y, return_info=True)
+        assert info['relative_residual'] <= 1e-12
+        assert rel_l2(z, ref.leray_project(y)) <= 1e-10
+        assert np.max(np.abs(u.div(z))) <= 1e-10 * np.max(np.abs(u.div(y)))
+        assert rel_l2(u.leray_project(z), z) <= 1e-10
+        # gradients are annihilated, divergence-free fields are kept
+        c = gds_b200.node_gds(u.G)
+        g = c.grad(np.random.default_rng(9).standard_normal(c.ndim))
+        assert np.linalg.norm(u.leray_project(g)) <= 1e-10 * np.linalg.norm(g)
+    with pytest.raises(NotImplementedError):
+        u.set_evolution(dydt=lambda t, yy: u.laplacian(yy))
+        u.set_constraints(dirichlet={list(u.X.keys())[0]: 1.0})
+        u.leray_project(y)
