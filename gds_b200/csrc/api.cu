@@ -442,6 +442,16 @@ static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
       case GDS_OP_N_LAP: case GDS_OP_N_BDOT: case GDS_OP_N_INFLUX: case GDS_OP_N_OUTFLUX:
         if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
         if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range");
+        if (op == GDS_OP_N_LAP && (ins >> 24)) {   // pointwise chain on the gathered values
+          int n = (int)(ins >> 24);
+          if (n > GDS_MAX_CHAIN) GDS_FAIL("pointwise chain longer than GDS_MAX_CHAIN");
+          if ((int)b + 2 * n > p->n_imm) GDS_FAIL("pointwise chain outside the immediates");
+          for (int k = 0; k < n; ++k) {
+            double code = p->imm[b + 2 * k];
+            if (!(code >= GDS_CHAIN_SQUARE && code <= GDS_CHAIN_ABS) || code != (double)(int)code)
+              GDS_FAIL("unknown pointwise chain step");
+          }
+        }
         push = 1; break;
       case GDS_OP_N_ADVECT: case GDS_OP_N_LIE:
         if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
@@ -493,6 +503,12 @@ static void match_forms(PassHost& ph) {
     std::vector<TermSym> t;
     double beta = 0, gamma = 0;
     int b = -1;
+    Chain bchain = {};
+  };
+  auto same_chain = [](const Chain& x, const Chain& y) {
+    if (x.n != y.n) return false;
+    for (int i = 0; i < x.n; ++i) if (x.pre[i] != y.pre[i] || x.m[i] != y.m[i] || x.a[i] != y.a[i]) return false;
+    return true;
   };
   std::vector<Sym> st;
   int store = -1;
@@ -508,6 +524,10 @@ static void match_forms(PassHost& ph) {
       TermSym t;
       t.op = (int)op; t.a = (int)a; t.coef = 1.0;
       if (op == GDS_OP_N_ADVECT || op == GDS_OP_N_LIE || op == GDS_OP_E_ADVFIN) t.b = (int)b;
+      if (op == GDS_OP_N_LAP) {
+        for (int k = 0; k < (int)(ins >> 24); ++k)
+          if (!chain_push(t.chain, (int)ph.imm[b + 2 * k], ph.imm[b + 2 * k + 1])) return;
+      }
       x.t.push_back(t);
       st.push_back(x);
       continue;
@@ -531,6 +551,17 @@ static void match_forms(PassHost& ph) {
         if (st.empty()) return;
         scale(st.back(), -1.0);
       } break;
+      case GDS_OP_SWAP: {
+        if (st.size() < 2) return;
+        std::swap(st[st.size() - 1], st[st.size() - 2]);
+      } break;
+      case GDS_OP_SQUARE: case GDS_OP_ABS: {
+        // g(b[row]) for a bare vector: a pointwise chain on the additive operand (beta * g(b))
+        if (st.empty()) return;
+        Sym& x = st.back();
+        if (!x.t.empty() || x.b < 0 || x.beta != 1.0 || x.gamma != 0.0) return;
+        if (!chain_push(x.bchain, (op == GDS_OP_SQUARE) ? GDS_CHAIN_SQUARE : GDS_CHAIN_ABS, 0.0)) return;
+      } break;
       case GDS_OP_ADD: case GDS_OP_SUB: {
         if (st.size() < 2) return;
         Sym y = st.back(); st.pop_back();
@@ -539,14 +570,15 @@ static void match_forms(PassHost& ph) {
         for (auto& ty : y.t) {
           bool merged = false;
           for (auto& tx : x.t)
-            if (tx.op == ty.op && tx.a == ty.a && tx.b == ty.b && tx.m0 == ty.m0 && tx.m1 == ty.m1) {
+            if (tx.op == ty.op && tx.a == ty.a && tx.b == ty.b && tx.m0 == ty.m0 && tx.m1 == ty.m1 &&
+                same_chain(tx.chain, ty.chain)) {
               tx.coef += sg * ty.coef; merged = true; break;
             }
           if (!merged) { TermSym t = ty; t.coef = sg * ty.coef; x.t.push_back(t); }
         }
         if (y.b >= 0) {
-          if (x.b >= 0) { if (x.b != y.b) return; x.beta += sg * y.beta; }
-          else { x.b = y.b; x.beta = sg * y.beta; }
+          if (x.b >= 0) { if (x.b != y.b || !same_chain(x.bchain, y.bchain)) return; x.beta += sg * y.beta; }
+          else { x.b = y.b; x.beta = sg * y.beta; x.bchain = y.bchain; }
         }
         x.gamma += sg * y.gamma;
       } break;
@@ -583,12 +615,15 @@ static void match_forms(PassHost& ph) {
     ph.lap.ok = true;
     ph.lap.v = r.t[0].a; ph.lap.mask = r.t[0].m0; ph.lap.b = bslot;
     ph.lap.alpha = r.t[0].coef; ph.lap.beta = r.beta; ph.lap.gamma = r.gamma; ph.lap.store = store;
+    ph.lap.chain = r.t[0].chain;
+    if (bslot >= 0) ph.lap.bchain = r.bchain;
     return;
   }
   ph.terms.ok = true;
   ph.terms.n = (int)r.t.size();
   for (size_t k = 0; k < r.t.size(); ++k) ph.terms.t[k] = r.t[k];
   ph.terms.b = bslot; ph.terms.beta = r.beta; ph.terms.gamma = r.gamma; ph.terms.store = store;
+  if (bslot >= 0) ph.terms.bchain = r.bchain;
 }
 
 // Resolve a host pass into launch parameters.  `state`/`stage` may be null for eager passes.
@@ -634,6 +669,7 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
     pp.lap_b = ph.lap.b >= 0 ? pp.vec[ph.lap.b] : nullptr;
     pp.lap_store = ph.lap.store >= 0 ? pp.out[ph.lap.store] : nullptr;
     pp.lap_alpha = ph.lap.alpha; pp.lap_beta = ph.lap.beta; pp.lap_gamma = ph.lap.gamma;
+    pp.lap_chain = ph.lap.chain; pp.lap_bchain = ph.lap.bchain;
   } else if (ph.terms.ok) {
     pp.use_terms = 1;
     pp.n_terms = ph.terms.n;
@@ -645,7 +681,9 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
       pp.term[k].m0 = t.m0 >= 0 ? pp.mask[t.m0] : nullptr;
       pp.term[k].m1 = t.m1 >= 0 ? pp.mask[t.m1] : nullptr;
       pp.term[k].coef = t.coef;
+      pp.term[k].chain = t.chain;
     }
+    pp.lap_bchain = ph.terms.bchain;
     pp.lap_b = ph.terms.b >= 0 ? pp.vec[ph.terms.b] : nullptr;
     pp.lap_store = ph.terms.store >= 0 ? pp.out[ph.terms.store] : nullptr;
     pp.lap_beta = ph.terms.beta; pp.lap_gamma = ph.terms.gamma;

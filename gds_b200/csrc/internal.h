@@ -92,10 +92,38 @@ struct GraphDev {
 // A row program recognised as  value = alpha * Z_mask(L0 v)[row] + beta * b[row] + gamma  (the node-Laplacian laws:
 // heat, wave, coupled-map lattices, diffusion terms) runs in the specialised 4-rows-per-thread kernel instead of the
 // row-program interpreter.
+// a chain of <= GDS_MAX_CHAIN pointwise steps applied to a value on the fly.  Every GDS_CHAIN_* step is stored in the
+// branch-free form  x <- pre(x) * m + a  with pre = identity / square / abs: multiplying by 1 and adding 0 are exact, so
+// the result is bit-identical to the step written out (x*x, x*k, x+k, k-x = (-1)x + k, -x, |x|).
+struct Chain {  // plain data: lives inside kernel parameters
+  int32_t n;
+  int32_t pre[GDS_MAX_CHAIN];  // 0 identity, 1 square, 2 abs
+  double m[GDS_MAX_CHAIN];
+  double a[GDS_MAX_CHAIN];
+};
+inline bool chain_push(Chain& c, int code, double k) {
+  if (c.n >= GDS_MAX_CHAIN) return false;
+  int i = c.n;
+  c.pre[i] = 0; c.m[i] = 1.0; c.a[i] = 0.0;
+  switch (code) {
+    case GDS_CHAIN_SQUARE: c.pre[i] = 1; break;
+    case GDS_CHAIN_MUL: c.m[i] = k; break;
+    case GDS_CHAIN_ADD: c.a[i] = k; break;
+    case GDS_CHAIN_RSUB: c.m[i] = -1.0; c.a[i] = k; break;
+    case GDS_CHAIN_NEG: c.m[i] = -1.0; break;
+    case GDS_CHAIN_ABS: c.pre[i] = 2; break;
+    default: return false;
+  }
+  c.n++;
+  return true;
+}
+
 struct LapForm {
   bool ok = false;
   int v = -1, mask = -1, b = -1, store = -1;  // operand slots of the pass (-1: absent)
   double alpha = 1.0, beta = 0.0, gamma = 0.0;
+  Chain chain = {};   // applied to the gathered vector: L0 f(v)
+  Chain bchain = {};  // applied to the additive vector: beta * g(b)
 };
 
 // More generally, a row program that is a LINEAR COMBINATION of masked one-hop operators,
@@ -106,6 +134,7 @@ struct LapForm {
 struct TermSym {
   int op = 0, a = -1, b = -1, m0 = -1, m1 = -1;  // opcode, operand slots, mask slots
   double coef = 0.0;
+  Chain chain = {};  // N_LAP only
 };
 struct TermForm {
   bool ok = false;
@@ -113,6 +142,7 @@ struct TermForm {
   TermSym t[GDS_MAX_TERMS];
   int b = -1, store = -1;
   double beta = 0.0, gamma = 0.0;
+  Chain bchain = {};
 };
 
 struct StepRec {  // one row of the per-step table
@@ -153,6 +183,7 @@ struct PassParams {
   const double* lap_b;
   double* lap_store;
   double lap_alpha, lap_beta, lap_gamma;
+  Chain lap_chain, lap_bchain;
   // linear combination of masked operators (TermForm resolved to pointers); n_terms == 0: not used.  The additive
   // vector / constant / STORE target reuse lap_b, lap_beta, lap_gamma, lap_store.
   int32_t use_terms;  // 1: run terms_kernel (n_terms may be 0: value = beta * b + gamma, a pointwise pass)
@@ -164,6 +195,7 @@ struct PassParams {
     const uint32_t* m0;
     const uint32_t* m1;
     double coef;
+    Chain chain;
   } term[GDS_MAX_TERMS];
   int32_t unit_weights;
 };

@@ -58,10 +58,31 @@ __device__ __forceinline__ SliceRange slice_of(const uint32_t* soff, int64_t row
   return s;
 }
 
-// L0 row: sum_e w_e (v[nbr] - v[row])     (gds.py:140: L0 = -B B^T)
+// pointwise chain f(x) (GDS_CHAIN_*): the steps are warp-uniform, evaluated in the order they were traced so that the
+// result is bit-identical to a separate pointwise pass
+__device__ __forceinline__ double chain_apply(const Chain& ch, double x) {
+  for (int i = 0; i < ch.n; ++i) {
+    const double t = (ch.pre[i] == 1) ? __dmul_rn(x, x) : ((ch.pre[i] == 2) ? fabs(x) : x);
+    x = __dadd_rn(__dmul_rn(t, ch.m[i]), ch.a[i]);  // two roundings, never contracted into an FMA
+  }
+  return x;
+}
+
+// L0 row: sum_e w_e (f(v[nbr]) - f(v[row]))     (gds.py:140: L0 = -B B^T; f = identity unless a chain is given)
 template <bool UNITW>
-__device__ __forceinline__ double n_lap(const GraphDev& g, const double* __restrict__ v, int64_t row, int lane) {
+__device__ __forceinline__ double n_lap(const GraphDev& g, const double* __restrict__ v, int64_t row, int lane,
+                                        const Chain& ch) {
   SliceRange s = slice_of(g.n_soff, row, lane);
+  if (ch.n > 0) {
+    const double c = chain_apply(ch, ld_gather(v + row));
+    double acc = 0.0;
+    for (uint32_t j = 0; j < s.width; ++j) {
+      int32_t k = ld_stream_i32(g.n_nbr + s.base + (int64_t)j * GDS_SLICE);
+      double d = chain_apply(ch, ld_gather(v + k)) - c;
+      acc += UNITW ? d : ld_stream_f64(g.n_w + s.base + (int64_t)j * GDS_SLICE) * d;
+    }
+    return acc;
+  }
   const double c = ld_gather(v + row);
   double acc = 0.0;
   const int32_t* nb = g.n_nbr + s.base;
@@ -335,7 +356,18 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
       default:
         if (DOMAIN == GDS_NODES) {
           switch (op) {
-            case GDS_OP_N_LAP: PUSH(n_lap<UNITW>(g, p.vec[a], row, lane)); break;
+            case GDS_OP_N_LAP: {
+              Chain ch;
+              ch.n = (int)((ins >> 24) & 0xffu);
+              for (int i = 0; i < GDS_MAX_CHAIN; ++i) {
+                const int code = (i < ch.n) ? (int)p.imm[b + 2 * i] : 0;
+                const double k = (i < ch.n) ? p.imm[b + 2 * i + 1] : 0.0;
+                ch.pre[i] = (code == GDS_CHAIN_SQUARE) ? 1 : ((code == GDS_CHAIN_ABS) ? 2 : 0);
+                ch.m[i] = (code == GDS_CHAIN_MUL) ? k : ((code == GDS_CHAIN_RSUB || code == GDS_CHAIN_NEG) ? -1.0 : 1.0);
+                ch.a[i] = (code == GDS_CHAIN_ADD || code == GDS_CHAIN_RSUB) ? k : 0.0;
+              }
+              PUSH(n_lap<UNITW>(g, p.vec[a], row, lane, ch));
+            } break;
             case GDS_OP_N_BDOT: PUSH(n_bdot<0, UNITW>(g, p.vec[a], row, lane)); break;
             case GDS_OP_N_INFLUX: PUSH(n_bdot<1, UNITW>(g, p.vec[a], row, lane)); break;
             case GDS_OP_N_OUTFLUX: PUSH(n_bdot<2, UNITW>(g, p.vec[a], row, lane)); break;
@@ -384,7 +416,7 @@ __global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ Pa
     if (p.dmask) e_dbits = __ldg(p.dmask + (row >> 5));
   }
   double val = p.lap_gamma;
-  if (p.lap_b) val += p.lap_beta * ld_stream_f64(p.lap_b + row);
+  if (p.lap_b) val += p.lap_beta * chain_apply(p.lap_bchain, ld_stream_f64(p.lap_b + row));
 #pragma unroll 1
   for (int k = 0; k < p.n_terms; ++k) {
     const double* a = p.term[k].a;
@@ -395,7 +427,7 @@ __global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ Pa
     double gv = 0.0;
     if (DOMAIN == GDS_NODES) {
       switch (p.term[k].op) {
-        case GDS_OP_N_LAP: gv = n_lap<UNITW>(g, a, row, lane); break;
+        case GDS_OP_N_LAP: gv = n_lap<UNITW>(g, a, row, lane, p.term[k].chain); break;
         case GDS_OP_N_BDOT: gv = n_bdot<0, UNITW>(g, a, row, lane); break;
         case GDS_OP_N_INFLUX: gv = n_bdot<1, UNITW>(g, a, row, lane); break;
         case GDS_OP_N_OUTFLUX: gv = n_bdot<2, UNITW>(g, a, row, lane); break;
@@ -461,8 +493,8 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
     ac[i] = (rhs && (mode == 1 || mode == 2)) ? ld_plain_f64(p.acc_in + row[i]) : 0.0;
     dbit[i] = (rhs && p.dmask) ? ((__ldg(p.dmask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
     mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
-    bb[i] = p.lap_b ? ld_stream_f64(p.lap_b + row[i]) : 0.0;
-    c[i] = ld_gather(v + row[i]);
+    bb[i] = p.lap_b ? chain_apply(p.lap_bchain, ld_stream_f64(p.lap_b + row[i])) : 0.0;
+    c[i] = chain_apply(p.lap_chain, ld_gather(v + row[i]));
     s[i] = 0.0;
   }
 #pragma unroll 2
@@ -477,7 +509,7 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
     }
 #pragma unroll
     for (int i = 0; i < LAP4_ROWS; ++i) {
-      const double d = ld_gather(v + k[i]) - c[i];
+      const double d = chain_apply(p.lap_chain, ld_gather(v + k[i])) - c[i];
       s[i] += UNITW ? d : w[i] * d;
     }
   }
@@ -520,7 +552,7 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 #define LAPT_BLOCK 128  // measured best on B200 (128 > 256 threads; register caps and deeper unrolling lose occupancy)
 #define LAPT_GROUP 128
 
-template <bool UNITW, int MODE>
+template <bool UNITW, int MODE, bool CHAINED>
 __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant__ PassParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t group = p.row0 + ((int64_t)blockIdx.x * (LAPT_BLOCK / 32) + (threadIdx.x >> 5)) * LAPT_GROUP;
@@ -543,6 +575,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
     if (RHS && MODE != 4) yn[i] = ld_stream_f64(p.yn + r + 32 * i);
     if (MODE == 1 || MODE == 2) ac[i] = ld_plain_f64(p.acc_in + r + 32 * i);
     c[i] = ld_gather(v + r + 32 * i);
+    if (CHAINED) c[i] = chain_apply(p.lap_chain, c[i]);
     s[i] = 0.0;
     width[i] = off[i + 1] - off[i];
     wmax = max(wmax, width[i]);
@@ -551,7 +584,10 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   }
   if (p.lap_b) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
+    for (int i = 0; i < 4; ++i) {
+      bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
+      if (CHAINED) bb[i] = chain_apply(p.lap_bchain, bb[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -576,7 +612,9 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
     for (int jj = 0; jj < CH; ++jj)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double d = ld_gather(v + k[jj][i]) - c[i];
+        double gv = ld_gather(v + k[jj][i]);
+        if (CHAINED) gv = chain_apply(p.lap_chain, gv);
+        const double d = gv - c[i];
         s[i] += UNITW ? d : w[jj][i] * d;
       }
   }
@@ -607,18 +645,25 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   }
 }
 
-template <bool UNITW>
-static void launch_lapT(const PassParams& p, int64_t groups, cudaStream_t st) {
+template <bool UNITW, bool CHAINED>
+static void launch_lapT_c(const PassParams& p, int64_t groups, cudaStream_t st) {
   const unsigned blocks = (unsigned)((groups + LAPT_BLOCK / 32 - 1) / (LAPT_BLOCK / 32));
   const int mode = (p.epilogue == GDS_EPI_RHS) ? p.stage_mode : 5;
   switch (mode) {
-    case 0: lapT_kernel<UNITW, 0><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 1: lapT_kernel<UNITW, 1><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 2: lapT_kernel<UNITW, 2><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 3: lapT_kernel<UNITW, 3><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 4: lapT_kernel<UNITW, 4><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    default: lapT_kernel<UNITW, 5><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 0: lapT_kernel<UNITW, 0, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 1: lapT_kernel<UNITW, 1, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 2: lapT_kernel<UNITW, 2, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 3: lapT_kernel<UNITW, 3, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 4: lapT_kernel<UNITW, 4, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    default: lapT_kernel<UNITW, 5, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
   }
+}
+
+template <bool UNITW>
+static void launch_lapT(const PassParams& p, int64_t groups, cudaStream_t st) {
+  // the pointwise-chain instantiation (L0 f(v), beta g(b)) only when a chain is present: it costs registers
+  if (p.lap_chain.n > 0 || p.lap_bchain.n > 0) launch_lapT_c<UNITW, true>(p, groups, st);
+  else launch_lapT_c<UNITW, false>(p, groups, st);
 }
 
 template <bool UNITW, int ROWS>
@@ -777,7 +822,7 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // measured on B200 (same box, heat RK4 on a 7072^2 grid): unit weights 0.528 ms/launch with the 128-bit quad kernel
     // vs 0.558 ms with lapT; weighted 0.869 ms vs 0.806 ms.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
-    const bool use_quad = force ? !strcmp(force, "quad") : unitw;
+    const bool use_quad = (force ? !strcmp(force, "quad") : unitw) && p.lap_chain.n == 0 && p.lap_bchain.n == 0;
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);

@@ -483,6 +483,18 @@ class Lowering:
                 if key not in self._masks:
                     self._masks[key] = self._Mask(self.ctx, e.graph.rows(e.domain), e.graph.rows_to_dev(e.domain, e.rows))
                 p.emit('MASK_ZERO', p.mask_slot(key, self._masks[key]), push=1, pop=1)
+        elif isinstance(e, Gather) and e.kind == 'N_LAP' and self._chain_of(e.args[0]) is not None:
+            # L0 f(v) with f a short pointwise chain over a vector in memory: evaluated on the fly inside the gather
+            # (for the row and each neighbour) instead of through an intermediate vector
+            leaf, steps = self._chain_of(e.args[0])
+            base = len(p.imm)
+            if base + 2 * len(steps) > L.MAX_IMM:
+                raise TraceError('evolution law uses too many distinct constants in one pass')
+            for code, k in steps:
+                p.imm.extend([float(code), float(k)])
+            p.code.append(OP['N_LAP'] | (self.operand(p, leaf, for_gather=True) << 8) | (base << 16) | (len(steps) << 24))
+            p.depth += 1
+            p.max_depth = max(p.max_depth, p.depth)
         elif isinstance(e, Gather):
             slots = [self.operand(p, a, for_gather=True) for a in e.args]
             if e.kind == 'E_ADVFIN':
@@ -495,6 +507,39 @@ class Lowering:
             raise TraceError('internal: edge aggregates are only consumed by E_ADVFIN')
         else:
             raise TraceError(f'cannot lower {type(e).__name__}')
+
+    CHAIN = {'SQUARE': 1, 'MUL': 2, 'ADD': 3, 'RSUB': 4, 'NEG': 5, 'ABS': 6}   # GDS_CHAIN_*
+
+    def _chain_of(self, e):
+        """(leaf, [(code, constant), ...]) if e is a chain of at most 4 pointwise steps with constants over ONE vector
+        that lives in memory, in evaluation order; None otherwise (or for a bare leaf: nothing to fuse)"""
+        steps = []
+        while True:
+            if isinstance(e, (Stage, State, Const, DevVec)):
+                break
+            if isinstance(e, Unary) and e.op in ('SQUARE', 'NEG', 'ABS'):
+                steps.append((self.CHAIN[e.op], 0.0))
+                e = e.args[0]
+            elif isinstance(e, Binary) and e.op in ('ADD', 'SUB', 'MUL'):
+                a, b = e.args
+                if isinstance(b, Imm) and not isinstance(a, Imm):
+                    # x op k:  x + k, x - k == x + (-k) exactly, x * k
+                    code, k = {'ADD': ('ADD', b.value), 'SUB': ('ADD', -b.value), 'MUL': ('MUL', b.value)}[e.op]
+                    steps.append((self.CHAIN[code], k))
+                    e = a
+                elif isinstance(a, Imm) and e.op in ('ADD', 'SUB', 'MUL'):
+                    code = {'ADD': 'ADD', 'SUB': 'RSUB', 'MUL': 'MUL'}[e.op]       # k + x, k - x, k * x (commutative: exact)
+                    steps.append((self.CHAIN[code], a.value))
+                    e = b
+                else:
+                    return None
+            else:
+                return None
+            if len(steps) > 4:
+                return None
+        if not steps or id(e) in self._temps:
+            return None
+        return e, steps[::-1]
 
     def rhs_pass(self, e, domain, graph, state_offset, dirichlet_mask):
         """final pass of a field: value of e is dy/dt of the rows at state_offset"""

@@ -68,7 +68,10 @@ enum {
   GDS_OP_SIN = 38, GDS_OP_COS = 39, GDS_OP_TAN = 40, GDS_OP_TANH = 41, GDS_OP_SINH = 42, GDS_OP_COSH = 43,
   GDS_OP_ATAN = 44, GDS_OP_SQUARE = 45, GDS_OP_RECIP = 46, GDS_OP_POWI = 47 /* top ** (int8)a */,
   /* gathers over the lowered incidence structure (push the row's result) */
-  GDS_OP_N_LAP = 64,      /* nodes: sum_e w_e (v[nbr]-v[row])         L0 row, gds.py:140,159            */
+  GDS_OP_N_LAP = 64,      /* nodes: sum_e w_e (v[nbr]-v[row])         L0 row, gds.py:140,159
+                           * c > 0: applied to f(v) instead of v, f = a chain of c <= 4 pointwise steps evaluated on the fly
+                           * for the row and every gathered neighbour (no intermediate vector); step k is the pair
+                           * imm[b + 2k] = GDS_CHAIN_* code, imm[b + 2k + 1] = its constant                               */
   GDS_OP_N_BDOT = 65,     /* nodes: (B1 v)[row], v on edges           gds.py:280 (div = -B1 y)          */
   GDS_OP_N_INFLUX = 66,   /* nodes: sum relu(+B1 .* v)                gds.py:282-285                    */
   GDS_OP_N_OUTFLUX = 67,  /* nodes: sum relu(-B1 .* v)                gds.py:287-290                    */
@@ -80,6 +83,11 @@ enum {
   GDS_OP_E_ADVFIN = 82,   /* edges: self-advection from y=vec a, aggregates vec b   gds.py:326-345      */
   GDS_OP_F_CURL = 96      /* faces: (B2 v)[row], v on edges           gds.py:294                        */
 };
+
+/* steps of a pointwise chain (see GDS_OP_N_LAP): x -> x*x, x*k, x+k, k-x, -x, |x| */
+enum { GDS_CHAIN_SQUARE = 1, GDS_CHAIN_MUL = 2, GDS_CHAIN_ADD = 3, GDS_CHAIN_RSUB = 4, GDS_CHAIN_NEG = 5,
+       GDS_CHAIN_ABS = 6 };
+#define GDS_MAX_CHAIN 4
 
 #define GDS_MAX_CODE 96
 #define GDS_MAX_IMM 24
