@@ -501,8 +501,8 @@ static void match_forms(PassHost& ph) {
   ph.terms = TermForm();
   struct Sym {
     std::vector<TermSym> t;
-    double beta = 0, gamma = 0;
-    int b = -1;
+    double beta = 0, beta2 = 0, gamma = 0;
+    int b = -1, b2 = -1;     // up to two additive vectors; only the first may carry a pointwise chain
     Chain bchain = {};
   };
   auto same_chain = [](const Chain& x, const Chain& y) {
@@ -515,7 +515,19 @@ static void match_forms(PassHost& ph) {
   auto scalar = [](const Sym& x) { return x.t.empty() && x.b < 0; };
   auto scale = [](Sym& x, double c) {
     for (auto& t : x.t) t.coef *= c;
-    x.beta *= c; x.gamma *= c;
+    x.beta *= c; x.beta2 *= c; x.gamma *= c;
+  };
+  // x += sg * (beta * g(b))  for one additive vector of y; false if x has no room for it
+  auto add_vec = [&](Sym& x, int slot, double beta, const Chain& ch) -> bool {
+    if (slot < 0) return true;
+    if (x.b == slot && same_chain(x.bchain, ch)) { x.beta += beta; return true; }
+    if (x.b2 == slot && ch.n == 0) { x.beta2 += beta; return true; }
+    if (x.b < 0) { x.b = slot; x.beta = beta; x.bchain = ch; return true; }
+    if (x.b2 < 0 && ch.n == 0) { x.b2 = slot; x.beta2 = beta; return true; }
+    if (x.b2 < 0 && x.bchain.n == 0) {   // keep the chained vector in the first place
+      x.b2 = x.b; x.beta2 = x.beta; x.b = slot; x.beta = beta; x.bchain = ch; return true;
+    }
+    return false;
   };
   for (size_t pc = 0; pc < ph.code.size(); ++pc) {
     uint32_t ins = ph.code[pc], op = ins & 0xff, a = (ins >> 8) & 0xff, b = (ins >> 16) & 0xff;
@@ -559,7 +571,7 @@ static void match_forms(PassHost& ph) {
         // g(b[row]) for a bare vector: a pointwise chain on the additive operand (beta * g(b))
         if (st.empty()) return;
         Sym& x = st.back();
-        if (!x.t.empty() || x.b < 0 || x.beta != 1.0 || x.gamma != 0.0) return;
+        if (!x.t.empty() || x.b < 0 || x.b2 >= 0 || x.beta != 1.0 || x.gamma != 0.0) return;
         if (!chain_push(x.bchain, (op == GDS_OP_SQUARE) ? GDS_CHAIN_SQUARE : GDS_CHAIN_ABS, 0.0)) return;
       } break;
       case GDS_OP_ADD: case GDS_OP_SUB: {
@@ -576,10 +588,9 @@ static void match_forms(PassHost& ph) {
             }
           if (!merged) { TermSym t = ty; t.coef = sg * ty.coef; x.t.push_back(t); }
         }
-        if (y.b >= 0) {
-          if (x.b >= 0) { if (x.b != y.b || !same_chain(x.bchain, y.bchain)) return; x.beta += sg * y.beta; }
-          else { x.b = y.b; x.beta = sg * y.beta; x.bchain = y.bchain; }
-        }
+        if (!add_vec(x, y.b, sg * y.beta, y.bchain)) return;
+        const Chain none = {};
+        if (!add_vec(x, y.b2, sg * y.beta2, none)) return;
         x.gamma += sg * y.gamma;
       } break;
       case GDS_OP_MUL: {
@@ -596,7 +607,7 @@ static void match_forms(PassHost& ph) {
         if (!scalar(y)) return;
         Sym& x = st.back();
         for (auto& t : x.t) t.coef /= y.gamma;
-        x.beta /= y.gamma; x.gamma /= y.gamma;
+        x.beta /= y.gamma; x.beta2 /= y.gamma; x.gamma /= y.gamma;
       } break;
       case GDS_OP_STORE:
         if (pc + 1 != ph.code.size() || store >= 0) return;   // only as the last instruction
@@ -608,15 +619,17 @@ static void match_forms(PassHost& ph) {
   if (st.size() != 1) return;
   const Sym& r = st.back();
   if ((int)r.t.size() > GDS_MAX_TERMS) return;   // no term at all: a pointwise pass  beta * b + gamma
-  if (!std::isfinite(r.beta) || !std::isfinite(r.gamma)) return;
+  if (!std::isfinite(r.beta) || !std::isfinite(r.beta2) || !std::isfinite(r.gamma)) return;
   for (auto& t : r.t) if (!std::isfinite(t.coef)) return;
   const int bslot = (r.b >= 0 && r.beta != 0.0) ? r.b : -1;
+  const int b2slot = (r.b2 >= 0 && r.beta2 != 0.0) ? r.b2 : -1;
   if (r.t.size() == 1 && r.t[0].op == GDS_OP_N_LAP && r.t[0].m1 < 0 && r.t[0].coef != 0.0) {
     ph.lap.ok = true;
     ph.lap.v = r.t[0].a; ph.lap.mask = r.t[0].m0; ph.lap.b = bslot;
     ph.lap.alpha = r.t[0].coef; ph.lap.beta = r.beta; ph.lap.gamma = r.gamma; ph.lap.store = store;
     ph.lap.chain = r.t[0].chain;
     if (bslot >= 0) ph.lap.bchain = r.bchain;
+    ph.lap.b2 = b2slot; ph.lap.beta2 = r.beta2;
     return;
   }
   ph.terms.ok = true;
@@ -624,6 +637,7 @@ static void match_forms(PassHost& ph) {
   for (size_t k = 0; k < r.t.size(); ++k) ph.terms.t[k] = r.t[k];
   ph.terms.b = bslot; ph.terms.beta = r.beta; ph.terms.gamma = r.gamma; ph.terms.store = store;
   if (bslot >= 0) ph.terms.bchain = r.bchain;
+  ph.terms.b2 = b2slot; ph.terms.beta2 = r.beta2;
 }
 
 // Resolve a host pass into launch parameters.  `state`/`stage` may be null for eager passes.
@@ -670,6 +684,8 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
     pp.lap_store = ph.lap.store >= 0 ? pp.out[ph.lap.store] : nullptr;
     pp.lap_alpha = ph.lap.alpha; pp.lap_beta = ph.lap.beta; pp.lap_gamma = ph.lap.gamma;
     pp.lap_chain = ph.lap.chain; pp.lap_bchain = ph.lap.bchain;
+    pp.lap_b2 = ph.lap.b2 >= 0 ? pp.vec[ph.lap.b2] : nullptr;
+    pp.lap_beta2 = ph.lap.beta2;
   } else if (ph.terms.ok) {
     pp.use_terms = 1;
     pp.n_terms = ph.terms.n;
@@ -684,10 +700,23 @@ static int resolve_pass(const gds_graph* g, const PassHost& ph, const double* st
       pp.term[k].chain = t.chain;
     }
     pp.lap_bchain = ph.terms.bchain;
+    pp.lap_b2 = ph.terms.b2 >= 0 ? pp.vec[ph.terms.b2] : nullptr;
+    pp.lap_beta2 = ph.terms.beta2;
     pp.lap_b = ph.terms.b >= 0 ? pp.vec[ph.terms.b] : nullptr;
     pp.lap_store = ph.terms.store >= 0 ? pp.out[ph.terms.store] : nullptr;
     pp.lap_beta = ph.terms.beta; pp.lap_gamma = ph.terms.gamma;
   }
+  return 0;
+}
+
+// which kernel family a pass runs in: 0 row-program interpreter, 1 Laplacian kernels (lapq / lapT), 2 terms_kernel.
+// Pure host logic (works on a host-only context): lets the parity tests pin the dispatch of every BASELINE law.
+extern "C" int gds_pass_kernel_kind(const gds_pass_desc* pass, int32_t* kind_out) {
+  if (!kind_out) GDS_FAIL("null out");
+  PassHost ph;
+  GDS_TRY(copy_pass(pass, ph));
+  match_forms(ph);
+  *kind_out = ph.lap.ok ? 1 : (ph.terms.ok ? 2 : 0);
   return 0;
 }
 

@@ -120,8 +120,8 @@ inline bool chain_push(Chain& c, int code, double k) {
 
 struct LapForm {
   bool ok = false;
-  int v = -1, mask = -1, b = -1, store = -1;  // operand slots of the pass (-1: absent)
-  double alpha = 1.0, beta = 0.0, gamma = 0.0;
+  int v = -1, mask = -1, b = -1, b2 = -1, store = -1;  // operand slots of the pass (-1: absent)
+  double alpha = 1.0, beta = 0.0, beta2 = 0.0, gamma = 0.0;  // value = alpha Z(L0 f(v)) + beta g(b) + beta2 b2 + gamma
   Chain chain = {};   // applied to the gathered vector: L0 f(v)
   Chain bchain = {};  // applied to the additive vector: beta * g(b)
 };
@@ -140,8 +140,8 @@ struct TermForm {
   bool ok = false;
   int n = 0;
   TermSym t[GDS_MAX_TERMS];
-  int b = -1, store = -1;
-  double beta = 0.0, gamma = 0.0;
+  int b = -1, b2 = -1, store = -1;
+  double beta = 0.0, beta2 = 0.0, gamma = 0.0;
   Chain bchain = {};
 };
 
@@ -181,6 +181,8 @@ struct PassParams {
   const double* lap_v;
   const uint32_t* lap_mask;
   const double* lap_b;
+  const double* lap_b2;   // second additive vector (e.g. a Neumann source next to a hoisted term)
+  double lap_beta2;
   double* lap_store;
   double lap_alpha, lap_beta, lap_gamma;
   Chain lap_chain, lap_bchain;

@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ Pa
   }
   double val = p.lap_gamma;
   if (p.lap_b) val += p.lap_beta * chain_apply(p.lap_bchain, ld_stream_f64(p.lap_b + row));
+  if (p.lap_b2) val += p.lap_beta2 * ld_stream_f64(p.lap_b2 + row);
 #pragma unroll 1
   for (int k = 0; k < p.n_terms; ++k) {
     const double* a = p.term[k].a;
@@ -493,7 +494,8 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
     ac[i] = (rhs && (mode == 1 || mode == 2)) ? ld_plain_f64(p.acc_in + row[i]) : 0.0;
     dbit[i] = (rhs && p.dmask) ? ((__ldg(p.dmask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
     mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (row[i] >> 5)) >> (row[i] & 31)) & 1u) : 0u;
-    bb[i] = p.lap_b ? chain_apply(p.lap_bchain, ld_stream_f64(p.lap_b + row[i])) : 0.0;
+    bb[i] = p.lap_b ? p.lap_beta * chain_apply(p.lap_bchain, ld_stream_f64(p.lap_b + row[i])) : 0.0;
+    if (p.lap_b2) bb[i] += p.lap_beta2 * ld_stream_f64(p.lap_b2 + row[i]);
     c[i] = chain_apply(p.lap_chain, ld_gather(v + row[i]));
     s[i] = 0.0;
   }
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
     if (!valid[i]) continue;
     const int64_t r = row[i];
     double val = p.lap_alpha * (mbit[i] ? 0.0 : s[i]);      // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
-    if (p.lap_b) val += p.lap_beta * bb[i];
+    if (p.lap_b || p.lap_b2) val += bb[i];
     val += p.lap_gamma;
     if (p.lap_store) p.lap_store[r] = val;
     if (!rhs) continue;
@@ -587,7 +589,12 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
     for (int i = 0; i < 4; ++i) {
       bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
       if (CHAINED) bb[i] = chain_apply(p.lap_bchain, bb[i]);
+      bb[i] *= p.lap_beta;
     }
+  }
+  if (p.lap_b2) {  // second additive vector: folded into bb (beta * g(b) + beta2 * b2)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bb[i] = (p.lap_b ? bb[i] : 0.0) + p.lap_beta2 * ld_stream_f64(p.lap_b2 + r + 32 * i);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   for (int i = 0; i < 4; ++i) {
     const int64_t ri = r + 32 * i;
     double val = p.lap_alpha * (mbit[i] ? 0.0 : s[i]);      // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
-    if (p.lap_b) val += p.lap_beta * bb[i];
+    if (p.lap_b || p.lap_b2) val += bb[i];
     val += p.lap_gamma;
     if (p.lap_store) p.lap_store[ri] = val;
     if (!RHS) continue;
@@ -822,7 +829,7 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // measured on B200 (same box, heat RK4 on a 7072^2 grid): unit weights 0.528 ms/launch with the 128-bit quad kernel
     // vs 0.558 ms with lapT; weighted 0.869 ms vs 0.806 ms.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
-    const bool use_quad = (force ? !strcmp(force, "quad") : unitw) && p.lap_chain.n == 0 && p.lap_bchain.n == 0;
+    const bool use_quad = (force ? !strcmp(force, "quad") : unitw) && p.lap_chain.n == 0 && p.lap_bchain.n == 0 && !p.lap_b2;
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);

@@ -168,6 +168,9 @@ int gds_graph_device_bytes(gds_graph* g, int64_t* bytes);
 /* ---- eager operator application: `op(y)` on host arrays (gds.py:152-345, the `y is not None` path).
  *      Runs ONE pass (epilogue must be GDS_EPI_NONE) at time t. -------------------------------------------- */
 int gds_pass_run(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* pass, double t);
+/* which kernel family would run this pass: 0 row-program interpreter, 1 Laplacian kernels, 2 term-list kernel
+ * (validates the program; no device needed) */
+int gds_pass_kernel_kind(const gds_pass_desc* pass, int32_t* kind_out);
 
 /* ---- conjugate gradients for A x = b, A given as a pass that reads buffer `p` and STOREs A p into buffer `ap`
  *      (x starts at 0; symmetric positive semi-definite A with b in its range, e.g. B1 B1^T = -L0).  Replaces the dense

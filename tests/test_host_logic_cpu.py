@@ -135,3 +135,54 @@ def test_row_program_validation_in_the_library():
     d.code = code
     rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
     assert rc != 0 and b'non-edge pass' in L.lib.gds_last_error()
+
+
+def kernel_kinds(field, law, scheme='rk4'):
+    """kernel family (0 interpreter, 1 Laplacian kernels, 2 term-list kernel) of every pass a law lowers to"""
+    import ctypes as C
+    from gds_b200.trace import pass_desc
+    ctx = field._low.ctx
+    lw = Lowering(ctx, lambda e: (L.VEC_STAGE if isinstance(e, Stage) else L.VEC_STATE, None, 0), hoist=True)
+    with trace_scope():
+        root = law(Time(), Stage(field))
+    lw.rhs_pass(as_expr(root, field._domain_code, field._low), field._domain_code, field._low, 0, None)
+    kinds = []
+    for p in lw.passes:
+        d, keep = pass_desc(p)
+        k = C.c_int32()
+        assert L.lib.gds_pass_kernel_kind(C.byref(d), C.byref(k)) == 0, L.lib.gds_last_error()
+        kinds.append(k.value)
+    return kinds
+
+
+def test_kernel_dispatch_of_the_baseline_laws():
+    G = cases.g_hex(3, 4)
+    T, u = gds_b200.node_gds(G), gds_b200.edge_gds(G)
+    T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2)
+    T.set_constraints(dirichlet={list(T.X)[0]: 1.0}, neumann={list(T.X)[5]: -0.1})
+    u.set_evolution(nil=True)
+    assert kernel_kinds(T, lambda t, y: T.laplacian(y)) == [1]                               # C1 heat: Laplacian kernel
+    P = gds_b200.node_gds(cases.g_grid(4, 4))
+    P.set_evolution(dydt=lambda t, y: P.laplacian(y), max_step=1e-2)
+    P.set_constraints(dirichlet={(0, 0): 1.0})
+    assert kernel_kinds(P, lambda t, y: 0.7 * P.laplacian(y) - 2.0 * y + 0.5) == [1]         # affine tail stays fused
+    assert kernel_kinds(T, lambda t, y: 0.7 * T.laplacian(y) - 2.0 * y) == [1]               # Neumann source + y: two additive vectors
+    assert kernel_kinds(T, lambda t, y: 0.7 * T.laplacian(y) - 2.0 * y + T.y) == [0]         # three: interpreter
+    # C2 node law: the accepted-state advection term is hoisted to a per-step term-list pass, the stage pass is the
+    # Laplacian kernel with two additive vectors (hoisted term + Neumann source)
+    assert kernel_kinds(T, lambda t, y: -T.advect(u) + 0.05 * T.laplacian(y)) == [2, 1]
+    assert kernel_kinds(T, lambda t, y: -T.advect(u, y) + 0.05 * T.laplacian(y)) == [2]      # stage-form advection: one term-list pass
+    assert kernel_kinds(u, lambda t, y: 0.1 * u.laplacian(y)) == [2, 2, 2]                   # C2 edge law: div, curl, edge pass
+    assert kernel_kinds(T, lambda t, y: 0.3 * T.laplacian(y) + y - y ** 3) == [0]            # cubic reaction: interpreter
+    assert kernel_kinds(T, lambda t, y: T.laplacian(y) * t) == [0]                           # time-dependent coefficient
+    # C4 coupled map lattice: f(y) + eps/8 L f(y) in ONE Laplacian-kernel pass, f fused into the gather as a chain
+    f = cases.cml_map()
+    x = gds_b200.node_gds(cases.g_grid(5, 5))
+    x.set_evolution(map_fun=lambda t, y: f(x, y))
+    passes = lower(x, x.map_fun)
+    assert len(passes) == 1 and passes[0][2].count('N_LAP') == 1
+    assert kernel_kinds(x, x.map_fun) == [1]
+    # C5 wave: accepted-state Laplacian hoisted to a per-step Laplacian-kernel pass, the stage pass is pointwise
+    a = gds_b200.node_gds(cases.g_grid3((3, 4, 5)))
+    a.set_evolution(dydt=lambda t, y: 1.0 * a.laplacian(), order=2, max_step=0.1)
+    assert kernel_kinds(a, a.dydt_fun) == [1, 2]
