@@ -829,6 +829,10 @@ extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int3
   }
   GDS_CUDA(cudaMalloc((void**)&s->d_counter, sizeof(int64_t)));
   GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaMalloc((void**)&s->d_flags, 64 * sizeof(int64_t)));
+  GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, 64 * sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaMalloc((void**)&s->d_p2p_epoch, 2 * sizeof(int64_t)));
+  GDS_CUDA(cudaMemsetAsync(s->d_p2p_epoch, 0, 2 * sizeof(int64_t), c->stream));
   *out = s;
   return 0;
 }
@@ -846,6 +850,9 @@ extern "C" int gds_system_destroy(gds_system* s) {
   cudaFree(s->ACC);
   cudaFree(s->d_dir_idx_static); cudaFree(s->d_dir_val_static); cudaFree(s->d_dir_idx_dyn);
   cudaFree(s->d_bc_tab); cudaFree(s->d_steptab); cudaFree(s->d_counter);
+  for (auto& pr : s->peers)
+    for (void* m : pr.mapped) if (m) cudaIpcCloseMemHandle(m);
+  cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst);
   delete s;
   return 0;
 }
@@ -984,6 +991,8 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
     PassParams pp;
     GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
     if (ph.special) pp.n_rows = ph.sp_n;
+    // peer-to-peer halo: ghost rows of the state are written by their owners only
+    if (s->p2p && ph.epilogue == GDS_EPI_RHS && !ph.special) pp.n_rows = std::min<int64_t>(s->owned_rows, pp.n_rows);
     pp.row0 = std::min<int64_t>(row0, pp.n_rows);
     if (row1 >= 0) pp.n_rows = std::min<int64_t>(row1, pp.n_rows);
     pp.steptab = s->d_steptab; pp.step_counter = s->d_counter;
@@ -1023,11 +1032,41 @@ static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
   return 0;
 }
 
+// peer-to-peer halo: push this rank's boundary values of buffer `which` (0/1 = Y, 2/3 = XS) into the neighbours' ghost
+// rows, then wait for theirs
+static int enqueue_exchange(gds_system* s, int which) {
+  if (!s->p2p || s->peers.empty()) return 0;
+  const double* mine[4] = {s->Y[0], s->Y[1], s->XS[0], s->XS[1]};
+  PushParams pu;
+  WaitParams wa;
+  memset(&pu, 0, sizeof(pu));
+  memset(&wa, 0, sizeof(wa));
+  pu.n_peers = wa.n_peers = (int32_t)s->peers.size();
+  pu.src = mine[which];
+  pu.src_idx = s->d_p2p_src; pu.dst_idx = s->d_p2p_dst;
+  pu.epoch = s->d_p2p_epoch; wa.epoch = s->d_p2p_epoch; wa.err = s->d_p2p_epoch + 1;
+  for (size_t q = 0; q < s->peers.size(); ++q) {
+    const gds_system::Peer& pr = s->peers[q];
+    pu.dst[q] = (double*)pr.mapped[which];
+    pu.flag[q] = (int64_t*)pr.mapped[4] + s->my_rank;
+    pu.s0[q] = pr.send0; pu.s1[q] = pr.send1;
+    wa.flag[q] = s->d_flags + pr.rank;
+  }
+  GDS_TRY(launch_push(s->ctx, pu));
+  return launch_wait(s->ctx, wa);
+}
+
 // enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
 static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
   GDS_TRY(enqueue_prestep(s, cur, lt));
-  for (int st = 0; st < n_stages_of(s); ++st) GDS_TRY(enqueue_stage(s, cur, st, lt));
-  return enqueue_tail(s, cur, lt);
+  const int ns = n_stages_of(s);
+  for (int st = 0; st < ns; ++st) {
+    GDS_TRY(enqueue_stage(s, cur, st, lt));
+    if (st < ns - 1 && !lt) GDS_TRY(enqueue_exchange(s, 2 + (st & 1)));   // x_next of this stage
+  }
+  GDS_TRY(enqueue_tail(s, cur, lt));
+  if (!lt) GDS_TRY(enqueue_exchange(s, cur ^ 1));                          // the new accepted state
+  return 0;
 }
 
 #define GDS_STEP_CAPACITY 4096  // steps per table upload; longer runs are chunked
@@ -1208,6 +1247,73 @@ extern "C" int gds_system_end_step(gds_system* s) {
   GDS_CUDA(cudaSetDevice(s->ctx->device));
   GDS_TRY(enqueue_tail(s, s->cur, nullptr));
   s->cur ^= 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// peer-to-peer halo over NVLink
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gds_system_ipc_export(gds_system* s, uint8_t* handles) {
+  if (!s || !handles) GDS_FAIL("bad argument");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  void* bufs[5] = {s->Y[0], s->Y[1], s->XS[0], s->XS[1], s->d_flags};
+  memset(handles, 0, 5 * 64);
+  for (int i = 0; i < 5; ++i) {
+    if (!bufs[i]) continue;   // Euler / map systems have no stage buffers
+    cudaIpcMemHandle_t h;
+    GDS_CUDA(cudaIpcGetMemHandle(&h, bufs[i]));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handles + 64 * i, &h, 64);
+  }
+  return 0;
+}
+
+extern "C" int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_peers, const int32_t* peer_rank,
+                                     const uint8_t* peer_handles, const int64_t* send_ptr, const int64_t* src_idx,
+                                     const int64_t* dst_idx, int64_t owned_rows) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("attach the peers before gds_system_finalize (the exchange is part of the captured step)");
+  if (n_peers < 0 || n_peers > GDS_MAX_PEERS) GDS_FAIL("at most 8 neighbouring ranks");
+  if (my_rank < 0 || my_rank >= 64) GDS_FAIL("rank outside the flag table");
+  if (owned_rows < 0) GDS_FAIL("bad owned_rows");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  s->peers.clear();
+  void* mine[5] = {s->Y[0], s->Y[1], s->XS[0], s->XS[1], s->d_flags};
+  for (int q = 0; q < n_peers; ++q) {
+    gds_system::Peer pr;
+    pr.rank = peer_rank[q];
+    if (pr.rank < 0 || pr.rank >= 64 || pr.rank == my_rank) GDS_FAIL("bad peer rank");
+    pr.send0 = send_ptr[q]; pr.send1 = send_ptr[q + 1];
+    for (int i = 0; i < 5; ++i) {
+      if (!mine[i]) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, peer_handles + (size_t)(q * 5 + i) * 64, 64);
+      GDS_CUDA(cudaIpcOpenMemHandle(&pr.mapped[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    s->peers.push_back(pr);
+  }
+  const int64_t n = n_peers ? send_ptr[n_peers] : 0;
+  GDS_CUDA(cudaMalloc((void**)&s->d_p2p_src, (size_t)std::max<int64_t>(n, 1) * 8));
+  GDS_CUDA(cudaMalloc((void**)&s->d_p2p_dst, (size_t)std::max<int64_t>(n, 1) * 8));
+  if (n) {
+    GDS_CUDA(cudaMemcpy(s->d_p2p_src, src_idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+    GDS_CUDA(cudaMemcpy(s->d_p2p_dst, dst_idx, (size_t)n * 8, cudaMemcpyHostToDevice));
+  }
+  s->my_rank = my_rank;
+  s->owned_rows = owned_rows;
+  s->p2p = true;
+  return 0;
+}
+
+// 0 = fine; k > 0: the wait for neighbour number k-1 timed out (a peer stopped): the state is not to be trusted
+extern "C" int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t* error) {
+  if (!s) GDS_FAIL("null system");
+  int64_t h[2] = {0, 0};
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  GDS_CUDA(cudaMemcpyAsync(h, s->d_p2p_epoch, 16, cudaMemcpyDeviceToHost, s->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (exchanges) *exchanges = h[0];
+  if (error) *error = h[1];
   return 0;
 }
 

@@ -279,7 +279,41 @@ struct gds_system {
   cudaGraph_t graph[2] = {nullptr, nullptr};
   int64_t kernels_per_step = 0;
   int64_t device_bytes = 0;
+  // peer-to-peer halo (one rank of a partitioned system): see gds_system_p2p_attach
+  struct Peer {
+    int rank = -1;
+    void* mapped[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // peer's Y0 Y1 XS0 XS1 FLAGS (IPC-mapped)
+    int64_t send0 = 0, send1 = 0;                                      // range in d_p2p_src / d_p2p_dst
+  };
+  std::vector<Peer> peers;
+  bool p2p = false;
+  int my_rank = 0;
+  int64_t owned_rows = -1;        // RHS passes stop here: ghost rows are written by the peers only
+  int64_t* d_flags = nullptr;     // [64] arrival flags, slot = sender's rank (written by peers over NVLink)
+  int64_t* d_p2p_epoch = nullptr; // [2]: exchanges sent so far; error flag of the wait kernel
+  int64_t* d_p2p_src = nullptr;
+  int64_t* d_p2p_dst = nullptr;
 };
+
+#define GDS_MAX_PEERS 8
+struct PushParams {
+  int32_t n_peers;
+  const double* src;                 // my stage output
+  double* dst[GDS_MAX_PEERS];        // the same logical buffer on each peer
+  int64_t* flag[GDS_MAX_PEERS];      // peer's arrival flag for this rank
+  int64_t s0[GDS_MAX_PEERS], s1[GDS_MAX_PEERS];
+  const int64_t* src_idx;
+  const int64_t* dst_idx;
+  int64_t* epoch;
+};
+struct WaitParams {
+  int32_t n_peers;
+  const int64_t* flag[GDS_MAX_PEERS];  // my flags, one per neighbour
+  const int64_t* epoch;
+  int64_t* err;
+};
+int launch_push(gds_ctx* ctx, const PushParams& p);
+int launch_wait(gds_ctx* ctx, const WaitParams& p);
 
 // kernels.cu
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain);

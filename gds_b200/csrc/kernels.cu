@@ -1094,3 +1094,58 @@ int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* a
   ctx->kernel_launches++;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// peer-to-peer halo exchange over NVLink, inside the captured step.
+// push: one block per neighbour stores this rank's boundary values straight into the neighbour's ghost rows
+// (peer-mapped memory), fences, and publishes the exchange number in the neighbour's flag slot.
+// wait: right after the push, one thread per neighbour polls the local flag slot until the neighbour's values of the
+// same exchange have arrived; only then may the next stage gather from the ghost rows.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) push_kernel(const __grid_constant__ PushParams p) {
+  const int q = blockIdx.x;
+  const double* __restrict__ src = p.src;
+  double* dst = p.dst[q];
+  for (int64_t i = p.s0[q] + threadIdx.x; i < p.s1[q]; i += 1024) dst[p.dst_idx[i]] = src[p.src_idx[i]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t e = *p.epoch + 1;          // number of this exchange; the counter is advanced by the wait that follows
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q]), "l"(e) : "memory");
+  }
+}
+
+__global__ void wait_kernel(const __grid_constant__ WaitParams p) {
+  // exchange number being completed = exchanges completed so far + 1 (the push just before used the same number)
+  const int q = threadIdx.x;
+  const int64_t expect = *p.epoch + 1;
+  if (q < p.n_peers) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int64_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.flag[q]) : "memory");
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { *p.err = 1 + q; break; }   // 20 s: a peer died; do not hang the GPU
+    } while (seen < expect);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (q == 0) *const_cast<int64_t*>(p.epoch) = expect;
+}
+
+int launch_push(gds_ctx* ctx, const PushParams& p) {
+  if (p.n_peers <= 0) return 0;
+  push_kernel<<<p.n_peers, 1024, 0, ctx->stream>>>(p);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+int launch_wait(gds_ctx* ctx, const WaitParams& p) {
+  if (p.n_peers <= 0) return 0;
+  wait_kernel<<<1, 32, 0, ctx->stream>>>(p);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}

@@ -139,8 +139,11 @@ class StepEngine:
             i = L.as_i64(np.concatenate(dyn_idx))
             self.n_dyn = i.size
             check(lib.gds_system_set_dirichlet(self.h, ptr(i), None, i.size, 1))
+        self.p2p = False
+        self._stream = None
+        check(lib.gds_ctx_set_stream(self.ctx.h, None))         # the step is captured on the context's own stream
         if self.part is not None:
-            check(lib.gds_ctx_set_stream(self.ctx.h, None))     # the step is captured on the context's own stream
+            self._attach_peers()
         check(lib.gds_system_finalize(self.h))
         kps, nbytes = L.c_i64(), L.c_i64()
         check(lib.gds_system_info(self.h, C.byref(kps), C.byref(nbytes)))
@@ -167,6 +170,7 @@ class StepEngine:
 
     def push_state(self):
         """upload every field's host state (what `integrator.y` holds in the reference)"""
+        self._bind_stream()
         for f in self.fields:
             a = self._blocks_to_dev(f, f._host_state)
             check(lib.gds_system_set_state(self.h, ptr(a), self.offsets[id(f)], a.size))
@@ -175,6 +179,7 @@ class StepEngine:
         self._read_cache.clear()
 
     def pull_state(self):
+        self._bind_stream()
         for f in self.fields:
             a = np.empty(f.ndim * f._order(), dtype=np.float64)
             check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], a.size))
@@ -182,6 +187,7 @@ class StepEngine:
 
     def read(self, f, full=False):
         """current state slice of field f as a host array (cached until the next step)"""
+        self._bind_stream()
         key = (id(f), full)
         if key not in self._read_cache:
             n = f.ndim * (f._order() if full else 1)
@@ -192,6 +198,7 @@ class StepEngine:
 
     def read_into(self, f, out):
         """copy the value block of field f into a caller-owned (ideally pinned) host array"""
+        self._bind_stream()
         assert out.dtype == np.float64 and out.flags['C_CONTIGUOUS'] and out.size <= f.ndim
         if f._domain_code == L.NODES and f._low.p2i is not None:
             assert out.size == f.ndim
@@ -203,6 +210,7 @@ class StepEngine:
         return out
 
     def write(self, f, values, offset=0):
+        self._bind_stream()
         a = L.as_f64(values)
         if f._domain_code == L.NODES and f._low.i2p is not None:
             assert offset % f.ndim == 0 and a.size % f.ndim == 0, 'a renumbered field is written block by block'
@@ -237,8 +245,9 @@ class StepEngine:
         return tab
 
     def _launch(self, ts, hs, t_after):
+        self._bind_stream()
         bc = self._bc_table(t_after)
-        if self.part is not None:
+        if self.part is not None and not self.p2p:
             self._run_partitioned(ts, hs, bc)
         else:
             check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
@@ -262,14 +271,20 @@ class StepEngine:
         t_after = ts + h
         return ts, hs, t_after, float(t_after[-1]), self._bc_table(t_after)
 
+    def _bind_stream(self):
+        """engines of one context may use different streams (a partitioned engine shares a torch stream with its
+        transport): select this engine's before enqueueing"""
+        check(lib.gds_ctx_set_stream(self.ctx.h, self._stream.cuda_stream if self._stream is not None else None))
+
     def run(self, plan):
         """device part of an advance: replay the captured step once per table row (asynchronous)"""
         ts, hs, t_after, t_new, bc = plan
         if ts.size == 0:
             return
-        if self.part is not None:
+        self._bind_stream()
+        if self.part is not None and not self.p2p:
             self._run_partitioned(ts, hs, bc)
-        else:
+        else:   # one GPU, or peer-to-peer halo fused into the captured step
             check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
         self.steps_taken += int(ts.size)
         self.version += 1
@@ -279,15 +294,71 @@ class StepEngine:
             f._dt = float(hs[-1])
 
     # ---- one rank of a partitioned system ------------------------------------------------------
+    def _halo_blocks(self):
+        for f in self.fields:
+            if f._domain_code != L.NODES:
+                raise NotImplementedError('distributed graphs carry node fields only')
+        return [self.offsets[id(f)] + f.ndim * i for f in self.fields for i in range(f._order())]
+
+    def _attach_peers(self):
+        """Peer-to-peer halo (GDS_B200_HALO=p2p, the default on an NCCL process group): the ranks swap the CUDA-IPC
+        handles of their state buffers and the positions of their ghost rows, and the library fuses a push / wait pair
+        into the captured step after every stage -- boundary values cross NVLink by direct stores into the neighbour's
+        memory, with no host and no NCCL on the data path.  Otherwise (gloo test transport, GDS_B200_HALO=nccl) the
+        host drives pack -> send/recv -> unpack between the stages."""
+        import os
+        import torch.distributed as dist
+        from .partition import HaloExchange
+        part = self.part
+        mode = os.environ.get('GDS_B200_HALO', '')
+        if not (dist.is_available() and dist.is_initialized() and part.world > 1):
+            return
+        if not mode:
+            mode = 'p2p' if dist.get_backend() == 'nccl' else 'host'
+        if mode != 'p2p':
+            return
+        if len(part.peers) > 8:
+            return
+        blocks = self._halo_blocks()
+        hx = HaloExchange(part, nblocks=len(blocks))
+        handles = (C.c_uint8 * 320)()
+        check(lib.gds_system_ipc_export(self.h, handles))
+        recv_from = {}
+        for q in part.peers:
+            rows = part.n_own + part.recv_offsets[q] + np.arange(part.recv_counts[q], dtype=np.int64)
+            recv_from[q] = np.concatenate([off + rows for off in blocks]).astype(np.int64)
+        mine = {'handles': bytes(handles), 'recv_from': recv_from}
+        everyone = [None] * part.world
+        dist.all_gather_object(everyone, mine)
+        peers = [q for q in part.peers]
+        src, dst, ptr_, hbytes = [], [], [0], b''
+        for q in peers:
+            s_idx = np.concatenate([off + part.send_rows[q] for off in blocks]).astype(np.int64)
+            d_idx = np.asarray(everyone[q]['recv_from'][part.rank], dtype=np.int64)
+            assert s_idx.size == d_idx.size, 'halo lists of two neighbouring ranks disagree'
+            src.append(s_idx); dst.append(d_idx); ptr_.append(ptr_[-1] + s_idx.size)
+            hbytes += everyone[q]['handles']
+        src = L.as_i64(np.concatenate(src)) if src else np.zeros(0, dtype=np.int64)
+        dst = L.as_i64(np.concatenate(dst)) if dst else np.zeros(0, dtype=np.int64)
+        ptr_arr = L.as_i64(np.asarray(ptr_))
+        pr = L.as_i32(np.asarray(peers, dtype=np.int32))
+        hb = (C.c_uint8 * max(1, len(hbytes))).from_buffer_copy(hbytes or b'\0')
+        check(lib.gds_system_p2p_attach(self.h, part.rank, len(peers), ptr(pr), hb, ptr(ptr_arr), ptr(src), ptr(dst),
+                                        part.n_own))
+        self.p2p = True
+
+    def p2p_status(self):
+        """(exchanges completed, error flag) of the fused peer-to-peer halo"""
+        a, b = L.c_i64(), L.c_i64()
+        check(lib.gds_system_p2p_status(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def _setup_partitioned(self):
         """halo lists over every state block, exchange buffers, and the transport stream"""
         import torch
         from .partition import HaloExchange
         part = self.part
-        for f in self.fields:
-            if f._domain_code != L.NODES:
-                raise NotImplementedError('distributed graphs carry node fields only')
-        blocks = [self.offsets[id(f)] + f.ndim * i for f in self.fields for i in range(f._order())]
+        blocks = self._halo_blocks()
         self.hx = HaloExchange(part, nblocks=len(blocks))
         self._halo = []
         for which in ('send', 'recv'):
@@ -346,6 +417,7 @@ class StepEngine:
         """like run(), but kernel by kernel with CUDA events around every launch: returns (ms, launches) per class
         [node passes, edge passes, face passes, per-step tail] (measurement aid, synchronises)"""
         ts, hs, t_after, t_new, bc = plan
+        self._bind_stream()
         ms, cnt = np.zeros(4, dtype=np.float64), np.zeros(4, dtype=np.int64)
         check(lib.gds_system_step_timed(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None,
                                         ptr(ms), ptr(cnt)))

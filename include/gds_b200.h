@@ -225,6 +225,20 @@ int gds_halo_create(gds_ctx* ctx, const int64_t* state_idx, int64_t n, gds_halo*
 int gds_halo_destroy(gds_halo* h);
 int gds_halo_pack(gds_halo* h, const void* vec_dev, void* buf_dev);
 int gds_halo_unpack(gds_halo* h, const void* buf_dev, void* vec_dev);
+/* ---- peer-to-peer halo over NVLink, fused into the captured step (no host, no NCCL on the data path): after every
+ *      stage a push kernel stores this rank's boundary values straight into the neighbours' ghost rows (their state
+ *      buffers mapped through CUDA IPC) and publishes the exchange number in their flag table; a wait kernel polls the
+ *      local flags before the next stage may gather.  Protocol: every rank exports its 5 handles (Y0 Y1 XS0 XS1 FLAGS,
+ *      64 bytes each), the host transport distributes them, every rank attaches its neighbours BEFORE
+ *      gds_system_finalize; then gds_system_step replays the step graph as on one GPU.  src_idx: positions in this
+ *      rank's state of the values sent to neighbour q (send_ptr[q] .. send_ptr[q+1]); dst_idx: where they land in the
+ *      neighbour's state.  RHS passes are restricted to rows < owned_rows (ghost rows belong to the peers).
+ *      The wait gives up after 20 s (a dead peer) and raises the error flag read by gds_system_p2p_status. --------- */
+int gds_system_ipc_export(gds_system* s, uint8_t* handles /* 5 x 64 bytes */);
+int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_peers, const int32_t* peer_rank,
+                          const uint8_t* peer_handles /* n_peers x 5 x 64 */, const int64_t* send_ptr,
+                          const int64_t* src_idx, const int64_t* dst_idx, int64_t owned_rows);
+int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t* error);
 /* algorithmic facts for the roofline: kernels per step and device bytes held */
 int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
 
