@@ -434,6 +434,8 @@ def gpu_arm(args):
     st, h, K, W = prob['stepper'], prob['h'], args.steps, args.warmup
     eng = st._ensure_engine()
     SCHEME[0] = 'map' if eng.scheme == 'map' else str(eng.scheme).split('.')[-1]
+    HALO[0] = ('peer-to-peer stores over NVLink fused into the captured step (CUDA IPC, no NCCL on the data path)'
+               if getattr(eng, 'p2p', False) else 'pack kernel, NCCL send/recv, unpack kernel, driven by the host')
     ctx = eng.ctx
     t_build = time.perf_counter() - t_build
 
@@ -514,8 +516,8 @@ def gpu_arm(args):
             'data': 'synthetic',
             'config': {'workload': WORKLOAD_NAME[0], 'scheme': SCHEME[0],
                        'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
-                       'parallelism': (f'{world} graph partitions (contiguous slabs), halo exchange of boundary node '
-                                       f'values after every RK stage over NCCL send/recv') if world > 1 else 'single GPU',
+                       'parallelism': (f'{world} graph partitions (contiguous slabs), halo exchange of boundary node values '
+                                       f'after every RK stage: ' + HALO[0]) if world > 1 else 'single GPU',
                        'dof_stage_evals_per_sec': 4 * value, 'build_seconds': t_build},
             'roofline': roof, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
@@ -526,6 +528,7 @@ def gpu_arm(args):
 
 WORKLOAD_NAME = [None]
 SCHEME = ['rk4']
+HALO = ['']
 
 
 def main():
