@@ -309,6 +309,23 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
     }
     GDS_TRY(upload(g, soff, &d.n_soff));
     GDS_TRY(upload(g, nbr, &d.n_nbr));
+    {  // 16-bit relative neighbour indices when they all fit
+      const int64_t n_slices = (V + GDS_SLICE - 1) / GDS_SLICE;
+      std::vector<int16_t> rel((size_t)slots, 0);
+      bool fits = V > 0 && !getenv("GDS_B200_NO_IDX16");
+      for (int64_t sl = 0; sl < n_slices && fits; ++sl) {
+        const int64_t width = soff[sl + 1] - soff[sl];
+        for (int64_t j = 0; j < width && fits; ++j)
+          for (int64_t lane = 0; lane < GDS_SLICE; ++lane) {
+            const int64_t row = sl * GDS_SLICE + lane;
+            const int64_t slot = (int64_t)soff[sl] * GDS_SLICE + j * GDS_SLICE + lane;
+            const int64_t dlt = (row < V) ? (int64_t)nbr[slot] - row : 0;   // lanes past the last row point at themselves
+            if (dlt < -32767 || dlt > 32767) { fits = false; break; }
+            rel[slot] = (int16_t)dlt;
+          }
+      }
+      if (fits) GDS_TRY(upload(g, rel, &d.n_nbr16));
+    }
     GDS_TRY(upload(g, edge, &d.n_edge));
     if (!unitw) GDS_TRY(upload(g, wv, &d.n_w));
     GDS_TRY(upload(g, h.n_dinv, &d.n_dinv));

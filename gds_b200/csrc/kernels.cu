@@ -34,6 +34,16 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
   return v;
 }
 __device__ __forceinline__ double ld_gather(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int32_t ld_stream_i16(const int16_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int2 ld_stream_v2i32(const void* p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
 // coherent streaming load (the accumulator is read and rewritten in place by the same thread)
 __device__ __forceinline__ double ld_plain_f64(const double* p) {
   double v;
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 #define LAPT_BLOCK 128  // measured best on B200 (128 > 256 threads; register caps and deeper unrolling lose occupancy)
 #define LAPT_GROUP 128
 
-template <bool UNITW, int MODE, bool CHAINED>
+template <bool UNITW, int MODE, bool CHAINED, bool IDX16>
 __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant__ PassParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t group = p.row0 + ((int64_t)blockIdx.x * (LAPT_BLOCK / 32) + (threadIdx.x >> 5)) * LAPT_GROUP;
@@ -570,6 +580,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   double yn[4], ac[4], bb[4], c[4], s[4];
   uint32_t dbit[4], mbit[4], width[4];
   const int32_t* nb[4];
+  const int16_t* nb16[4];
   const double* wp[4];
   uint32_t wmax = 0;
 #pragma unroll
@@ -582,6 +593,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
     width[i] = off[i + 1] - off[i];
     wmax = max(wmax, width[i]);
     nb[i] = g.n_nbr + (int64_t)off[i] * GDS_SLICE + lane;
+    if (IDX16) nb16[i] = g.n_nbr16 + (int64_t)off[i] * GDS_SLICE + lane;
     if (!UNITW) wp[i] = g.n_w + (int64_t)off[i] * GDS_SLICE + lane;
   }
   if (p.lap_b) {
@@ -612,7 +624,8 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool on = j0 + jj < width[i];  // warp-uniform
-        k[jj][i] = on ? ld_stream_i32(nb[i] + (j0 + jj) * GDS_SLICE) : (int32_t)(r + 32 * i);
+        if (IDX16) k[jj][i] = (int32_t)(r + 32 * i) + (on ? ld_stream_i16(nb16[i] + (j0 + jj) * GDS_SLICE) : 0);
+        else k[jj][i] = on ? ld_stream_i32(nb[i] + (j0 + jj) * GDS_SLICE) : (int32_t)(r + 32 * i);
         if (!UNITW) w[jj][i] = on ? ld_stream_f64(wp[i] + (j0 + jj) * GDS_SLICE) : 0.0;
       }
 #pragma unroll
@@ -652,25 +665,27 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   }
 }
 
-template <bool UNITW, bool CHAINED>
+template <bool UNITW, bool CHAINED, bool IDX16>
 static void launch_lapT_c(const PassParams& p, int64_t groups, cudaStream_t st) {
   const unsigned blocks = (unsigned)((groups + LAPT_BLOCK / 32 - 1) / (LAPT_BLOCK / 32));
   const int mode = (p.epilogue == GDS_EPI_RHS) ? p.stage_mode : 5;
   switch (mode) {
-    case 0: lapT_kernel<UNITW, 0, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 1: lapT_kernel<UNITW, 1, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 2: lapT_kernel<UNITW, 2, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 3: lapT_kernel<UNITW, 3, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    case 4: lapT_kernel<UNITW, 4, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    default: lapT_kernel<UNITW, 5, CHAINED><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 0: lapT_kernel<UNITW, 0, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 1: lapT_kernel<UNITW, 1, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 2: lapT_kernel<UNITW, 2, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 3: lapT_kernel<UNITW, 3, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 4: lapT_kernel<UNITW, 4, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    default: lapT_kernel<UNITW, 5, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
   }
 }
 
 template <bool UNITW>
 static void launch_lapT(const PassParams& p, int64_t groups, cudaStream_t st) {
   // the pointwise-chain instantiation (L0 f(v), beta g(b)) only when a chain is present: it costs registers
-  if (p.lap_chain.n > 0 || p.lap_bchain.n > 0) launch_lapT_c<UNITW, true>(p, groups, st);
-  else launch_lapT_c<UNITW, false>(p, groups, st);
+  // 16-bit relative indices (IDX16) are measured slower here (2-byte loads per lane: 0.848 vs 0.730 ms per launch on the
+  // weighted 7072^2 heat problem) and are only used by the quad kernel (one 64-bit load per 4 rows: 0.500 vs 0.524 ms)
+  if (p.lap_chain.n > 0 || p.lap_bchain.n > 0) launch_lapT_c<UNITW, true, false>(p, groups, st);
+  else launch_lapT_c<UNITW, false, false>(p, groups, st);
 }
 
 template <bool UNITW, int ROWS>
@@ -714,7 +729,7 @@ __device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, b
 }
 
 
-template <bool UNITW>
+template <bool UNITW, bool IDX16>
 __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant__ PassParams p) {
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
@@ -756,7 +771,17 @@ __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant_
   const double* w = g.n_w + base;
 #pragma unroll 2
   for (uint32_t j = 0; j < width; ++j) {
-    const int4 k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
+    int4 k;
+    if (IDX16) {  // 4 x int16 (neighbour - row) in one 64-bit load
+      const int2 raw = ld_stream_v2i32(g.n_nbr16 + base + (int64_t)j * GDS_SLICE);
+      const int32_t rr = (int32_t)r0;
+      k.x = rr + (int32_t)(int16_t)(raw.x & 0xffff);
+      k.y = rr + 1 + (raw.x >> 16);
+      k.z = rr + 2 + (int32_t)(int16_t)(raw.y & 0xffff);
+      k.w = rr + 3 + (raw.y >> 16);
+    } else {
+      k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
+    }
     if (UNITW) {
       s[0] += ld_gather(v + k.x) - c[0];
       s[1] += ld_gather(v + k.y) - c[1];
@@ -835,8 +860,13 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
     if (quad_ok) {
       int64_t blocks = ((rows + 3) / 4 + LAPQ_BLOCK - 1) / LAPQ_BLOCK;
-      if (unitw) lapq_kernel<true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
-      else lapq_kernel<false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      if (p.g.n_nbr16) {
+        if (unitw) lapq_kernel<true, true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+        else lapq_kernel<false, true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      } else {
+        if (unitw) lapq_kernel<true, false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+        else lapq_kernel<false, false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      }
       GDS_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
       return 0;

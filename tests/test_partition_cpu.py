@@ -145,3 +145,34 @@ def test_two_rank_halo_exchange_gloo():
         lo, hi, vals = ret[r]
         got[lo:hi] = vals
     assert np.allclose(got, x, rtol=0, atol=1e-14)
+
+
+def test_peer_push_lists_fill_every_ghost_row():
+    """the peer-to-peer halo stores state[src_idx] of rank r into state[dst_idx] of rank q, where dst_idx is what q
+    publishes as the positions of its ghost rows owned by r (engine._attach_peers): emulate the push with numpy for a
+    two-block state (order 2) and check that every ghost row ends up with its owner's value"""
+    world, V = 4, 9 * 6 * 5
+    parts = [Partition.grid_slab(r, world, 9, 6, 5) for r in range(world)]
+    rng = np.random.default_rng(3)
+    xg = [rng.standard_normal(V), rng.standard_normal(V)]                     # two state blocks, global order
+    state, blocks = [], []
+    for p in parts:
+        blocks.append([0, p.n_loc])                                            # block offsets in the local state
+        st = np.full(2 * p.n_loc, np.nan)
+        for b in range(2):
+            st[blocks[-1][b]:blocks[-1][b] + p.n_own] = xg[b][p.lo:p.hi]       # owned rows only
+        state.append(st)
+    published = []
+    for r, p in enumerate(parts):
+        published.append({q: np.concatenate([off + p.n_own + p.recv_offsets[q] + np.arange(p.recv_counts[q])
+                                             for off in blocks[r]]) for q in p.peers})
+    for r, p in enumerate(parts):
+        for q in p.peers:
+            src = np.concatenate([off + p.send_rows[q] for off in blocks[r]])
+            dst = published[q][r]
+            assert src.size == dst.size
+            state[q][dst] = state[r][src]                                       # the push kernel
+    for r, p in enumerate(parts):
+        gid = p.global_ids
+        for b in range(2):
+            assert np.array_equal(state[r][blocks[r][b]:blocks[r][b] + p.n_loc], xg[b][gid])
