@@ -465,7 +465,7 @@ static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
           if ((int)b + 2 * n > p->n_imm) GDS_FAIL("pointwise chain outside the immediates");
           for (int k = 0; k < n; ++k) {
             double code = p->imm[b + 2 * k];
-            if (!(code >= GDS_CHAIN_SQUARE && code <= GDS_CHAIN_ABS) || code != (double)(int)code)
+            if (!(code >= GDS_CHAIN_SQUARE && code <= GDS_CHAIN_CUBE) || code != (double)(int)code)
               GDS_FAIL("unknown pointwise chain step");
           }
         }
@@ -583,6 +583,14 @@ static void match_forms(PassHost& ph) {
       case GDS_OP_SWAP: {
         if (st.size() < 2) return;
         std::swap(st[st.size() - 1], st[st.size() - 2]);
+      } break;
+      case GDS_OP_POWI: {
+        // b[row]**2 / **3 of a bare vector: the same pointwise chain step as SQUARE / the interpreter's powi
+        if (st.empty()) return;
+        Sym& x = st.back();
+        const int n = (int)(int8_t)a;
+        if ((n != 2 && n != 3) || !x.t.empty() || x.b < 0 || x.b2 >= 0 || x.beta != 1.0 || x.gamma != 0.0) return;
+        if (!chain_push(x.bchain, n == 2 ? GDS_CHAIN_SQUARE : GDS_CHAIN_CUBE, 0.0)) return;
       } break;
       case GDS_OP_SQUARE: case GDS_OP_ABS: {
         // g(b[row]) for a bare vector: a pointwise chain on the additive operand (beta * g(b))

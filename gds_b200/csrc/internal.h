@@ -96,10 +96,10 @@ struct GraphDev {
 // row-program interpreter.
 // a chain of <= GDS_MAX_CHAIN pointwise steps applied to a value on the fly.  Every GDS_CHAIN_* step is stored in the
 // branch-free form  x <- pre(x) * m + a  with pre = identity / square / abs: multiplying by 1 and adding 0 are exact, so
-// the result is bit-identical to the step written out (x*x, x*k, x+k, k-x = (-1)x + k, -x, |x|).
+// the result is bit-identical to the step written out (x*x, x*k, x+k, k-x = (-1)x + k, -x, |x|, (x*x)*x).
 struct Chain {  // plain data: lives inside kernel parameters
   int32_t n;
-  int32_t pre[GDS_MAX_CHAIN];  // 0 identity, 1 square, 2 abs
+  int32_t pre[GDS_MAX_CHAIN];  // 0 identity, 1 square, 2 abs, 3 cube
   double m[GDS_MAX_CHAIN];
   double a[GDS_MAX_CHAIN];
 };
@@ -114,6 +114,7 @@ inline bool chain_push(Chain& c, int code, double k) {
     case GDS_CHAIN_RSUB: c.m[i] = -1.0; c.a[i] = k; break;
     case GDS_CHAIN_NEG: c.m[i] = -1.0; break;
     case GDS_CHAIN_ABS: c.pre[i] = 2; break;
+    case GDS_CHAIN_CUBE: c.pre[i] = 3; break;
     default: return false;
   }
   c.n++;

@@ -72,7 +72,10 @@ __device__ __forceinline__ SliceRange slice_of(const uint32_t* soff, int64_t row
 // result is bit-identical to a separate pointwise pass
 __device__ __forceinline__ double chain_apply(const Chain& ch, double x) {
   for (int i = 0; i < ch.n; ++i) {
-    const double t = (ch.pre[i] == 1) ? __dmul_rn(x, x) : ((ch.pre[i] == 2) ? fabs(x) : x);
+    double t = x;
+    if (ch.pre[i] == 1) t = __dmul_rn(x, x);
+    else if (ch.pre[i] == 2) t = fabs(x);
+    else if (ch.pre[i] == 3) t = __dmul_rn(__dmul_rn(x, x), x);   // = powi(x, 3) of the interpreter: x * (x*x)
     x = __dadd_rn(__dmul_rn(t, ch.m[i]), ch.a[i]);  // two roundings, never contracted into an FMA
   }
   return x;
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
               for (int i = 0; i < GDS_MAX_CHAIN; ++i) {
                 const int code = (i < ch.n) ? (int)p.imm[b + 2 * i] : 0;
                 const double k = (i < ch.n) ? p.imm[b + 2 * i + 1] : 0.0;
-                ch.pre[i] = (code == GDS_CHAIN_SQUARE) ? 1 : ((code == GDS_CHAIN_ABS) ? 2 : 0);
+                ch.pre[i] = (code == GDS_CHAIN_SQUARE) ? 1 : ((code == GDS_CHAIN_ABS) ? 2 : ((code == GDS_CHAIN_CUBE) ? 3 : 0));
                 ch.m[i] = (code == GDS_CHAIN_MUL) ? k : ((code == GDS_CHAIN_RSUB || code == GDS_CHAIN_NEG) ? -1.0 : 1.0);
                 ch.a[i] = (code == GDS_CHAIN_ADD || code == GDS_CHAIN_RSUB) ? k : 0.0;
               }

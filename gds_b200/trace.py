@@ -508,7 +508,7 @@ class Lowering:
         else:
             raise TraceError(f'cannot lower {type(e).__name__}')
 
-    CHAIN = {'SQUARE': 1, 'MUL': 2, 'ADD': 3, 'RSUB': 4, 'NEG': 5, 'ABS': 6}   # GDS_CHAIN_*
+    CHAIN = {'SQUARE': 1, 'MUL': 2, 'ADD': 3, 'RSUB': 4, 'NEG': 5, 'ABS': 6, 'CUBE': 7}   # GDS_CHAIN_*
 
     def _chain_of(self, e):
         """(leaf, [(code, constant), ...]) if e is a chain of at most 4 pointwise steps with constants over ONE vector
@@ -519,6 +519,9 @@ class Lowering:
                 break
             if isinstance(e, Unary) and e.op in ('SQUARE', 'NEG', 'ABS'):
                 steps.append((self.CHAIN[e.op], 0.0))
+                e = e.args[0]
+            elif isinstance(e, PowI) and e.n == 3:
+                steps.append((self.CHAIN['CUBE'], 0.0))
                 e = e.args[0]
             elif isinstance(e, Binary) and e.op in ('ADD', 'SUB', 'MUL'):
                 a, b = e.args

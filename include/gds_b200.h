@@ -84,9 +84,9 @@ enum {
   GDS_OP_F_CURL = 96      /* faces: (B2 v)[row], v on edges           gds.py:294                        */
 };
 
-/* steps of a pointwise chain (see GDS_OP_N_LAP): x -> x*x, x*k, x+k, k-x, -x, |x| */
+/* steps of a pointwise chain (see GDS_OP_N_LAP): x -> x*x, x*k, x+k, k-x, -x, |x|, x*x*x */
 enum { GDS_CHAIN_SQUARE = 1, GDS_CHAIN_MUL = 2, GDS_CHAIN_ADD = 3, GDS_CHAIN_RSUB = 4, GDS_CHAIN_NEG = 5,
-       GDS_CHAIN_ABS = 6 };
+       GDS_CHAIN_ABS = 6, GDS_CHAIN_CUBE = 7 };
 #define GDS_MAX_CHAIN 4
 
 #define GDS_MAX_CODE 96

@@ -173,7 +173,9 @@ def test_kernel_dispatch_of_the_baseline_laws():
     assert kernel_kinds(T, lambda t, y: -T.advect(u) + 0.05 * T.laplacian(y)) == [2, 1]
     assert kernel_kinds(T, lambda t, y: -T.advect(u, y) + 0.05 * T.laplacian(y)) == [2]      # stage-form advection: one term-list pass
     assert kernel_kinds(u, lambda t, y: 0.1 * u.laplacian(y)) == [2, 2, 2]                   # C2 edge law: div, curl, edge pass
-    assert kernel_kinds(T, lambda t, y: 0.3 * T.laplacian(y) + y - y ** 3) == [0]            # cubic reaction: interpreter
+    assert kernel_kinds(P, lambda t, y: 0.3 * P.laplacian(y) + y - y ** 3) == [1]            # Allen-Cahn: y and y**3 ride along
+    assert kernel_kinds(P, lambda t, y: P.laplacian(y ** 3)) == [1]                          # porous medium: chain in the gather
+    assert kernel_kinds(P, lambda t, y: P.laplacian(y) + np.sin(y)) == [0]                   # transcendental: interpreter
     assert kernel_kinds(T, lambda t, y: T.laplacian(y) * t) == [0]                           # time-dependent coefficient
     # C4 coupled map lattice: f(y) + eps/8 L f(y) in ONE Laplacian-kernel pass, f fused into the gather as a chain
     f = cases.cml_map()
