@@ -104,6 +104,9 @@ _sig('gds_system_set_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_get_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_state_devptr', c_vp, P(c_vp))
 _sig('gds_system_step', c_vp, c_i64, c_vp, c_vp, c_vp)
+_sig('gds_system_enable_recording', c_vp)
+_sig('gds_system_set_trajectory', c_vp, c_vp)
+_sig('gds_system_step_record', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp)
 _sig('gds_system_step_timed', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp)
 _sig('gds_system_begin_steps', c_vp, c_i64, c_vp, c_vp, c_vp)
 _sig('gds_system_run_stage', c_vp, c_i32, c_i64, c_i64)
@@ -135,6 +138,7 @@ EXPORTED = [
     'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',
     'gds_halo_create', 'gds_halo_destroy', 'gds_halo_pack', 'gds_halo_unpack',
     'gds_system_ipc_export', 'gds_system_p2p_attach', 'gds_system_p2p_status',
+    'gds_system_enable_recording', 'gds_system_set_trajectory', 'gds_system_step_record',
     'gds_hostgraph_lattice', 'gds_hostgraph_from_graph', 'gds_hostgraph_sizes', 'gds_hostgraph_copy',
     'gds_hostgraph_destroy', 'gds_graph_create_from_host',
 ]

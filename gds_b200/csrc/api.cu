@@ -878,6 +878,7 @@ extern "C" int gds_system_destroy(gds_system* s) {
   for (auto& pr : s->peers)
     for (void* m : pr.mapped) if (m) cudaIpcCloseMemHandle(m);
   cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst);
+  cudaFree(s->d_rec); cudaFree(s->d_traj);
   delete s;
   return 0;
 }
@@ -1052,6 +1053,7 @@ static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
   if (lt) GDS_TRY(lt->begin(3));
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, nullptr, s->n_dir_static, 0, s->d_counter));
   GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_dyn, nullptr, s->d_bc_tab, s->n_dir_dyn, s->n_dir_dyn, s->d_counter));
+  if (s->recording && !lt) GDS_TRY(launch_record(c, ynew, s->d_traj, s->d_rec, s->d_counter, s->n_state));
   GDS_TRY(launch_advance_counter(c, s->d_counter));
   if (lt) GDS_TRY(lt->end());
   return 0;
@@ -1119,6 +1121,12 @@ extern "C" int gds_system_finalize(gds_system* s) {
   GDS_CUDA(cudaMalloc((void**)&s->d_steptab, (size_t)s->cap_steps * sizeof(StepRec)));
   GDS_CUDA(cudaMemset(s->d_steptab, 0, (size_t)s->cap_steps * sizeof(StepRec)));
   if (s->n_dir_dyn > 0) GDS_CUDA(cudaMalloc((void**)&s->d_bc_tab, (size_t)s->cap_steps * s->n_dir_dyn * 8));
+  if (s->recording) {
+    GDS_CUDA(cudaMalloc((void**)&s->d_rec, (size_t)s->cap_steps * 8));
+    GDS_CUDA(cudaMemset(s->d_rec, 0xff, (size_t)s->cap_steps * 8));   // -1: record nothing
+    GDS_CUDA(cudaMalloc((void**)&s->d_traj, sizeof(double*)));
+    GDS_CUDA(cudaMemset(s->d_traj, 0, sizeof(double*)));
+  }
   if (c->stream != c->own_stream) GDS_FAIL("finalize on the context's own stream (an external stream cannot be captured here)");
   for (int cur = 0; cur < 2; ++cur) {
     int64_t before = c->kernel_launches;
@@ -1158,7 +1166,43 @@ extern "C" int gds_system_state_devptr(gds_system* s, void** dev_out) {
   return 0;
 }
 
+static int system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc,
+                       const int64_t* rec_slot);
+
 extern "C" int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc) {
+  return system_step(s, n_steps, t, h, bc, nullptr);
+}
+
+// ---- trajectory recording (System.solve, gds/system.py:38-57: a host copy of every observable after every step there):
+//      snapshots are taken on the device inside the captured step and read back once
+extern "C" int gds_system_enable_recording(gds_system* s) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("enable recording before gds_system_finalize (the snapshot kernel is part of the captured step)");
+  s->recording = true;
+  return 0;
+}
+
+extern "C" int gds_system_set_trajectory(gds_system* s, gds_buf* traj) {
+  if (!s || !traj) GDS_FAIL("bad argument");
+  if (!s->recording || !s->finalized) GDS_FAIL("recording is not enabled on this system");
+  GDS_CUDA(cudaSetDevice(s->ctx->device));
+  s->traj_slots = traj->n / s->n_state;
+  GDS_CUDA(cudaMemcpyAsync(s->d_traj, &traj->d, sizeof(double*), cudaMemcpyHostToDevice, s->ctx->stream));
+  GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return 0;
+}
+
+extern "C" int gds_system_step_record(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc,
+                                      const int64_t* rec_slot) {
+  if (!s || !rec_slot) GDS_FAIL("bad argument");
+  if (!s->recording || s->traj_slots <= 0) GDS_FAIL("no trajectory buffer set");
+  for (int64_t i = 0; i < n_steps; ++i)
+    if (rec_slot[i] >= s->traj_slots) GDS_FAIL("snapshot slot outside the trajectory buffer");
+  return system_step(s, n_steps, t, h, bc, rec_slot);
+}
+
+static int system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc,
+                       const int64_t* rec_slot) {
   if (!s) GDS_FAIL("null system");
   if (!s->finalized) GDS_FAIL("system not finalized");
   if (n_steps < 0) GDS_FAIL("negative step count");
@@ -1176,6 +1220,14 @@ extern "C" int gds_system_step(gds_system* s, int64_t n_steps, const double* t, 
     if (s->n_dir_dyn > 0)
       GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc + done * s->n_dir_dyn, (size_t)m * s->n_dir_dyn * 8,
                                cudaMemcpyHostToDevice, c->stream));
+    if (s->recording) {
+      if (rec_slot) {
+        GDS_CUDA(cudaMemcpyAsync(s->d_rec, rec_slot + done, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+        GDS_CUDA(cudaStreamSynchronize(c->stream));   // pageable source owned by the caller
+      } else {
+        GDS_CUDA(cudaMemsetAsync(s->d_rec, 0xff, (size_t)m * 8, c->stream));
+      }
+    }
     GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
     for (int64_t i = 0; i < m; ++i) {
       GDS_CUDA(cudaGraphLaunch(s->exec[s->cur], c->stream));

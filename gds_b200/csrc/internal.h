@@ -282,6 +282,12 @@ struct gds_system {
   cudaGraph_t graph[2] = {nullptr, nullptr};
   int64_t kernels_per_step = 0;
   int64_t device_bytes = 0;
+  // trajectory recording (System.solve): after a step whose row of d_rec holds a slot >= 0 the new state is copied into
+  // that slot of the trajectory buffer, inside the captured step
+  bool recording = false;
+  double** d_traj = nullptr;      // device cell holding the trajectory buffer's address (set any time)
+  int64_t traj_slots = 0;
+  int64_t* d_rec = nullptr;       // [cap_steps]
   // peer-to-peer halo (one rank of a partitioned system): see gds_system_p2p_attach
   struct Peer {
     int rank = -1;
@@ -315,6 +321,7 @@ struct WaitParams {
   const int64_t* epoch;
   int64_t* err;
 };
+int launch_record(gds_ctx* ctx, const double* y, double* const* traj, const int64_t* rec, const int64_t* counter, int64_t n);
 int launch_push(gds_ctx* ctx, const PushParams& p);
 int launch_wait(gds_ctx* ctx, const WaitParams& p);
 

@@ -14,6 +14,8 @@
 // field is ONE pass over HBM.  fp64 throughout, no tensor cores (sparse gather), no atomics (pull form:
 // fixed summation order => bitwise run-to-run reproducibility).
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1178,6 +1180,26 @@ int launch_push(gds_ctx* ctx, const PushParams& p) {
 int launch_wait(gds_ctx* ctx, const WaitParams& p) {
   if (p.n_peers <= 0) return 0;
   wait_kernel<<<1, 32, 0, ctx->stream>>>(p);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trajectory recording: copy the new accepted state into slot rec[step] of the trajectory buffer (no-op for -1)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) record_kernel(const double* __restrict__ y, double* const* __restrict__ traj,
+                                                     const int64_t* __restrict__ rec, const int64_t* __restrict__ counter,
+                                                     int64_t n) {
+  const int64_t slot = rec[*counter];
+  if (slot < 0) return;
+  double* dst = *traj + slot * n;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] = y[i];
+}
+
+int launch_record(gds_ctx* ctx, const double* y, double* const* traj, const int64_t* rec, const int64_t* counter, int64_t n) {
+  int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 8);
+  record_kernel<<<(unsigned)std::max<int64_t>(blocks, 1), 256, 0, ctx->stream>>>(y, traj, rec, counter, n);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;

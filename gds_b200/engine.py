@@ -40,7 +40,8 @@ def step_table(t, t_bound, max_step):
 class StepEngine:
     """Compiled system of one or more fields advanced together."""
 
-    def __init__(self, fields, scheme, max_step, t0=0.0, ctx: Context = None):
+    def __init__(self, fields, scheme, max_step, t0=0.0, ctx: Context = None, record=False):
+        self.record = bool(record)   # snapshot kernel inside the captured step (System.solve)
         assert len(fields) >= 1
         self.fields = list(fields)
         self.scheme = scheme
@@ -141,6 +142,8 @@ class StepEngine:
             check(lib.gds_system_set_dirichlet(self.h, ptr(i), None, i.size, 1))
         self.p2p = False
         self._stream = None
+        if self.record:
+            check(lib.gds_system_enable_recording(self.h))
         check(lib.gds_ctx_set_stream(self.ctx.h, None))         # the step is captured on the context's own stream
         if self.part is not None:
             self._attach_peers()
@@ -412,6 +415,47 @@ class StepEngine:
                 check(lib.gds_system_end_step(self.h))
                 self._exchange(self._state_ptr())
             done += m
+
+    def solve_record(self, n_calls, dt, rec_calls, max_bytes=4 << 30):
+        """`n_calls` consecutive step(dt) calls with the state after the calls listed in `rec_calls` (0-based, sorted)
+        recorded ON THE DEVICE inside the captured step; returns [len(rec_calls), n_state] after one read-back per chunk
+        (System.solve, gds/system.py:38-57, copies every observable to the host after every step)"""
+        assert self.record and self.scheme != 'map' and self.part is None
+        self._bind_stream()
+        self._refresh_externals()
+        rec_set = {int(c): i for i, c in enumerate(rec_calls)}
+        out = np.empty((len(rec_calls), self.n_state), dtype=np.float64)
+        per_chunk = max(1, int(max_bytes // (8 * self.n_state)))
+        call = 0
+        while call < n_calls:
+            ts_l, hs_l, slots, t = [], [], [], self.t
+            rows, first_row = 0, len([c for c in rec_calls if c < call])
+            while call < n_calls and rows < per_chunk and len(ts_l) < 100000:
+                ts, hs, t_new = step_table(t, t + dt, self.max_step)
+                sl = np.full(ts.size, -1, dtype=np.int64)
+                if call in rec_set and ts.size:
+                    sl[-1] = rows
+                    rows += 1
+                ts_l.append(ts); hs_l.append(hs); slots.append(sl)
+                t = t_new
+                call += 1
+            ts, hs, sl = np.concatenate(ts_l), np.concatenate(hs_l), L.as_i64(np.concatenate(slots))
+            t_after = np.append(ts[1:], t)
+            bc = self._bc_table(t_after)
+            if rows:
+                traj = Buffer(self.ctx, rows * self.n_state)
+                check(lib.gds_system_set_trajectory(self.h, traj.h))
+                check(lib.gds_system_step_record(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None, ptr(sl)))
+                out[first_row:first_row + rows] = traj.download().reshape(rows, self.n_state)
+            else:
+                check(lib.gds_system_step(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+            self.steps_taken += int(ts.size)
+            self.t = t
+            for f in self.fields:
+                f._dt = float(hs[-1])
+        self.version += 1
+        self._read_cache.clear()
+        return out
 
     def run_timed(self, plan):
         """like run(), but kernel by kernel with CUDA events around every launch: returns (ms, launches) per class

@@ -251,11 +251,13 @@ class fds(Observable, Steppable):
     def _bump(self):
         self._version += 1
 
-    def _ensure_engine(self) -> StepEngine:
+    def _ensure_engine(self, record=False) -> StepEngine:
+        if self._engine is not None and record and not self._engine.record:
+            self._drop_engine()                      # rebuild with the snapshot kernel in the captured step
         if self._engine is None:
             scheme = 'map' if self.iter_mode is IterationMode.map else self.integrator_type
             max_step = self.max_step if self.iter_mode is IterationMode.dydt else self._dt
-            self._engine = StepEngine([self], scheme, max_step, t0=self._t)
+            self._engine = StepEngine([self], scheme, max_step, t0=self._t, record=record)
         return self._engine
 
     def _drop_engine(self, pull=True):
@@ -618,9 +620,13 @@ class coupled_fds(Steppable):
             s._coupled = self
         self._members = members
 
-    def _ensure_engine(self):
+    def _ensure_engine(self, record=False):
+        if self._engine is not None and record and not self._engine.record:
+            self._engine.pull_state()
+            self._t = self._engine.t
+            self._engine = None                      # rebuild with the snapshot kernel in the captured step
         if self._engine is None and self._members:
-            self._engine = StepEngine(self._members, self._scheme, self.dydt_max_step, t0=self._t)
+            self._engine = StepEngine(self._members, self._scheme, self.dydt_max_step, t0=self._t, record=record)
             for s in self._members:
                 s._engine = self._engine
         return self._engine
@@ -682,6 +688,9 @@ class System:
         conversion loop, Appendix B.8).  `every` > 1 keeps one snapshot per `every` steps (each snapshot is a
         device-to-host copy)."""
         obs = self._observables
+        fast = self._solve_on_device(T, dt, every)
+        if fast is not None:
+            return fast
         data = {k: [np.array(v.y, copy=True)] for k, v in obs.items()}
         time, t, i = [0.], 0., 0
         while t < T:
@@ -693,6 +702,40 @@ class System:
                     data[k].append(np.array(v.y, copy=True))
                 time.append(t)
         return np.array(time), {k: np.array(v) for k, v in data.items()}
+
+
+    def _solve_on_device(self, T, dt, every):
+        """snapshots taken on the device inside the captured step, one read-back at the end; None when the stepper
+        needs the host every step (recurrence maps, user projections, derived observables, distributed graphs)"""
+        st, obs = self._stepper, self._observables
+        members = [st] if isinstance(st, fds) else list(getattr(st, '_members', []))
+        if not members or not hasattr(st, '_ensure_engine'):
+            return None
+        if any(m.iter_mode is not IterationMode.dydt or not m._identity_projection() or m._low.part is not None
+               for m in members):
+            return None
+        if any(not any(v is m for m in members) for v in obs.values()):
+            return None
+        time, t, calls = [0.], 0., 0
+        while t < T:                       # the reference's loop (system.py:45-50)
+            t += dt
+            calls += 1
+            time.append(t)
+        rec = [i for i in range(calls) if (i + 1) % every == 0 or i == calls - 1]
+        data = {k: [np.array(v.y, copy=True)] for k, v in obs.items()}
+        eng = st._ensure_engine(record=True)
+        traj = eng.solve_record(calls, dt, rec)
+        if isinstance(st, coupled_fds):
+            st._t = eng.t
+        for m in members:
+            m._version += 1
+        for k, v in obs.items():
+            off, n = eng.offsets[id(v)], v.ndim
+            block = traj[:, off:off + n]
+            if v._domain_code == L.NODES and v._low.p2i is not None:
+                block = block[:, v._low.p2i]
+            data[k] = np.concatenate([data[k][0][None, :], block], axis=0)
+        return np.array([time[0]] + [time[i + 1] for i in rec]), data
 
 
 def couple(observables) -> System:   # fds.py:542-546

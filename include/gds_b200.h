@@ -208,6 +208,14 @@ int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const doubl
  * At most 256 steps per call; synchronises. */
 int gds_system_step_timed(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values,
                           double* class_ms, int64_t* class_launches);
+/* ---- trajectory recording: replaces the per-step host copies of System.solve (gds/system.py:38-57).  Enable before
+ *      finalize; then give a device buffer of k * n_state values and step with a slot per step (-1: no snapshot): the
+ *      new accepted state is copied into its slot inside the captured step; the caller downloads the buffer once. ---- */
+int gds_system_enable_recording(gds_system* s);
+int gds_system_set_trajectory(gds_system* s, gds_buf* traj);
+int gds_system_step_record(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values,
+                           const int64_t* rec_slot);
+
 /* ---- stage-granular stepping, for one rank of a system partitioned over several GPUs: the host runs the halo
  *      exchange between the stages, so the step is enqueued stage by stage instead of replayed as one graph.
  *      begin_steps uploads the per-step tables; then per step: run_stage(0..n_stages-1) [exchange the vector returned by

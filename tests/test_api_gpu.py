@@ -136,3 +136,36 @@ def test_leray_projection_matches_dense_pinv_and_is_a_projection():
         u.set_evolution(dydt=lambda t, yy: u.laplacian(yy))
         u.set_constraints(dirichlet={list(u.X.keys())[0]: 1.0})
         u.leray_project(y)
+
+
+def test_solve_records_on_the_device_and_matches_the_stepping_loop():
+    """System.solve keeps its snapshots on the device (one read-back); same numbers as stepping and copying by hand,
+    for a coupled system, a stride, and several internal steps per call"""
+    import gds_b200
+
+    def build():
+        G = cases.g_hex(4, 5)
+        u, c = gds_b200.edge_gds(G), gds_b200.node_gds(G)
+        u.set_evolution(dydt=lambda t, y: 0.1 * u.laplacian(y), max_step=1e-3, integrator=gds_b200.Integrators.rk4)
+        c.set_evolution(dydt=lambda t, y: -c.advect(u) + 0.05 * c.laplacian(y), max_step=1e-3,
+                        integrator=gds_b200.Integrators.rk4)
+        r = np.random.default_rng(11)
+        u.set_initial(y0=0.1 * r.standard_normal(u.ndim))
+        c.set_initial(y0=r.random(c.ndim))
+        c.set_constraints(dirichlet=lambda t, x: math.sin(5 * t) if x == list(c.X)[0] else None)
+        return gds_b200.couple({'u': u, 'c': c}), u, c
+    s1, u1, c1 = build()
+    time, data = s1.solve(0.0199, 2.5e-3, every=3)          # 8 calls of 3 internal steps; snapshots after calls 3, 6, 8
+    assert data['u'].shape == (4, u1.ndim) and data['c'].shape == (4, c1.ndim)
+    assert np.allclose(time, [0.0, 7.5e-3, 15e-3, 20e-3], rtol=0, atol=1e-12)
+    s2, u2, c2 = build()
+    want_u, want_c = [np.array(u2.y, copy=True)], [np.array(c2.y, copy=True)]
+    for i in range(1, 9):
+        s2.step(2.5e-3)
+        if i % 3 == 0 or i == 8:
+            want_u.append(np.array(u2.y, copy=True)); want_c.append(np.array(c2.y, copy=True))
+    assert np.array_equal(data['u'], np.array(want_u)) and np.array_equal(data['c'], np.array(want_c))
+    assert s1.t == pytest.approx(s2.t, abs=1e-15)
+    assert np.array_equal(np.asarray(u1.y), np.asarray(u2.y))          # the fields carry on from the end of solve()
+    s1.step(2.5e-3); s2.step(2.5e-3)
+    assert np.array_equal(np.asarray(c1.y), np.asarray(c2.y))
