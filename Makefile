@@ -1,4 +1,5 @@
-# Builds the C-ABI shared library (CUDA, sm_100a) and the CPU oracle helper.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+# Builds the C-ABI shared library (CUDA, sm_100a).  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+# (The oracle is numpy / scipy: nothing to compile for it; the reference is pure Python: there is no oracle/_ref.)
 # -fmad=false: no FMA contraction, so every kernel family (interpreter, term list, Laplacian kernels) rounds like the
 # numpy reference and like each other -- partitioned and one-GPU runs stay bit-identical whatever kernel a row lands in.
 NVCC ?= /usr/local/cuda/bin/nvcc

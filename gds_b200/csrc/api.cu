@@ -956,12 +956,6 @@ extern "C" int gds_system_set_dirichlet(gds_system* s, const int64_t* idx, const
   return 0;
 }
 
-static int ensure_step_capacity(gds_system* s, int64_t n_steps) {
-  if (n_steps <= s->cap_steps) return 0;
-  if (s->finalized) GDS_FAIL("internal: step tables cannot grow after capture");
-  return 0;
-}
-
 // per-launch CUDA-event timing for gds_system_step_timed (eager enqueue, not the captured graph)
 struct LaunchTimer {
   struct Rec { cudaEvent_t a, b; int cls; };
@@ -1140,7 +1134,6 @@ extern "C" int gds_system_finalize(gds_system* s) {
     c->kernel_launches = before;  // captured, not launched
   }
   s->finalized = true;
-  (void)ensure_step_capacity;
   return 0;
 }
 

@@ -327,7 +327,6 @@ int launch_wait(gds_ctx* ctx, const WaitParams& p);
 
 // kernels.cu
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain);
-int launch_shift(gds_ctx* ctx, const PassParams& p, const double* src);
 int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* val_static, const double* bc_tab,
                      int64_t n, int64_t n_dyn_stride, const int64_t* counter);
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);

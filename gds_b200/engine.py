@@ -15,8 +15,8 @@ import numpy as np
 from . import _lib as L
 from ._lib import lib, check, ptr
 from .device import Buffer, Context, Mask
-from .trace import Lowering, Stage, State, Time, TraceError, as_expr, pass_desc, trace_scope
-from .types import Integrators, IterationMode
+from .trace import Lowering, Stage, Time, TraceError, as_expr, pass_desc, trace_scope
+from .types import Integrators
 
 STEP_MERGE_RTOL = 1e-9  # a remainder within (1+rtol)*max_step is taken as one step ending exactly at t_bound
 
@@ -104,6 +104,7 @@ class StepEngine:
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
         lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True, single_hop=self.part is not None)
         self.lowering = lowering
+        self.passes = []
         stat_idx, stat_val, dyn_idx = [], [], []
         self.dyn_fields = []
         for f, root in zip(self.fields, roots):
@@ -116,7 +117,7 @@ class StepEngine:
             for p in lowering.passes:
                 d, keep = pass_desc(p)
                 check(lib.gds_system_add_pass(self.h, C.byref(d)))
-            lowering.passes_done = getattr(lowering, 'passes_done', []) + lowering.passes
+            self.passes.extend(lowering.passes)      # kept for introspection (tests, kernel-kind queries)
             lowering.passes = []
             for i in range(order - 1):                                   # fds.py:297-298
                 check(lib.gds_system_add_shift(self.h, off + n * i, off + n * (i + 1), n))

@@ -18,9 +18,9 @@ import numpy as np
 
 from . import _lib as L
 from ._lib import lib, check
-from .device import Buffer, Context
+from .device import Buffer
 from .engine import StepEngine
-from .graph import LoweredGraph, NativeGraph
+from .graph import LoweredGraph
 from .trace import (Const, DevVec, EdgeAgg, Expr, Gather, Lowering, MaskZero, State, TraceError, as_expr, pass_desc,
                     tracing, unary)
 from .types import GraphDomain, Integrators, IterationMode, Observable, Steppable
