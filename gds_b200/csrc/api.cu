@@ -158,9 +158,18 @@ extern "C" int gds_buf_create(gds_ctx* c, int64_t n, gds_buf** out) {
   return 0;
 }
 
+// a view of n values at a device address owned elsewhere (e.g. a slice of a system's state) usable as a pass operand
+extern "C" int gds_buf_view(gds_ctx* c, void* dev_ptr, int64_t n, gds_buf** out) {
+  if (!c || !out || !dev_ptr || n < 0) GDS_FAIL("bad argument");
+  gds_buf* b = new gds_buf();
+  b->ctx = c; b->d = (double*)dev_ptr; b->n = n; b->owned = false;
+  *out = b;
+  return 0;
+}
+
 extern "C" int gds_buf_destroy(gds_buf* b) {
   if (!b) return 0;
-  if (b->ctx->device < 0) { delete b; return 0; }
+  if (b->ctx->device < 0 || !b->owned) { delete b; return 0; }
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d);

@@ -223,6 +223,7 @@ struct gds_buf {
   gds_ctx* ctx;
   double* d = nullptr;
   int64_t n = 0;
+  bool owned = true;  // false: a view of memory owned elsewhere (gds_buf_view)
 };
 
 struct gds_mask {

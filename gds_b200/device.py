@@ -84,6 +84,16 @@ class Buffer:
         return p.value
 
 
+class BufferView(Buffer):
+    """non-owning view of device memory (a slice of a system's state) usable wherever a Buffer is"""
+
+    def __init__(self, ctx: Context, dev_ptr: int, n: int):
+        h = L.c_vp()
+        check(lib.gds_buf_view(ctx.h, L.c_vp(dev_ptr), int(n), C.byref(h)))
+        self.h, self.n, self.ctx = h, int(n), ctx
+        self._fin = weakref.finalize(self, lib.gds_buf_destroy, h)
+
+
 class Mask:
     """A set of rows as a device bitmap."""
 

@@ -80,6 +80,8 @@ class StepEngine:
             return (L.VEC_STATE, None, off)                                   # fds.py:378: y = integrator.y[:ndim]
         if isinstance(e, Stage):
             raise TraceError('stage state of a field outside this system')
+        if getattr(f, '_dev_y', None) is not None:
+            return (L.VEC_BUF, f._dev_y, 0)       # an `lhs=` field: its state already lives on the device
         if id(f) not in self.externals:
             self.externals[id(f)] = [f, Buffer(self.ctx, f.ndim), None]
         return (L.VEC_BUF, self.externals[id(f)][1], 0)

@@ -9,8 +9,10 @@ else -- there is no CPU fallback.  Operators called with host arrays run eagerly
 numpy arrays (the `y is not None` path of gds.py:152-345); called while an evolution law is being traced they
 return symbolic expressions that are lowered into the captured step (gds_b200/trace.py, engine.py).
 
-Out of scope (raise NotImplementedError): `lhs=` / `cost=` (CVXPY programme, fds.py:97-113), `traj_t=` playback
-(fds.py:124-129), the adaptive scipy integrators and the dense implicit midpoint (fds.py:84-95).
+`lhs=` laws that are affine in y with a Laplacian-form linear part (the pressure law of examples/fluid.py) are solved
+on the device by conjugate gradients.  Out of scope (raise NotImplementedError): general convex `cost=` programmes
+(fds.py:97-113), `traj_t=` playback (fds.py:124-129), the adaptive scipy integrators and the dense implicit midpoint
+(fds.py:84-95).
 """
 from __future__ import annotations
 
@@ -18,11 +20,11 @@ import numpy as np
 
 from . import _lib as L
 from ._lib import lib, check
-from .device import Buffer
+from .device import Buffer, BufferView
 from .engine import StepEngine
 from .graph import LoweredGraph
-from .trace import (Const, DevVec, EdgeAgg, Expr, Gather, Lowering, MaskZero, State, TraceError, as_expr, pass_desc,
-                    tracing, unary)
+from .trace import (Const, DevVec, EdgeAgg, Expr, Gather, Lowering, MaskZero, Stage, State, Time, TraceError, as_expr,
+                    pass_desc, split_affine, substitute, trace_scope, tracing, unary)
 from .types import GraphDomain, Integrators, IterationMode, Observable, Steppable
 from .utils import dict_fun, fun_ary
 
@@ -66,15 +68,17 @@ class fds(Observable, Steppable):
         self._engine = None        # StepEngine advancing this field (shared when coupled)
         self._coupled = None       # coupled_fds owning this field
         self._version = 0          # bumped whenever the host-visible state changes
+        self._dev_y = self._dev_y_cache = None   # device-resident state of an `lhs=` field
 
     # ---- evolution law (fds.py:30-135) ---------------------------------------------------------------------
     def set_evolution(self, dydt=None, order=1, max_step=1e-3, integrator=Integrators.rk4, solver_args={},
-                      lhs=None, rhs=None, cost=None, map_fun=None, dt=1.0, traj_t=None, traj_y=None, nil=False):
+                      lhs=None, rhs=None, cost=None, refresh_cvx=True, map_fun=None, dt=1.0, traj_t=None, traj_y=None,
+                      nil=False):
         given = [dydt is not None, lhs is not None, cost is not None, map_fun is not None,
                  traj_t is not None, bool(nil)]
         assert sum(given) == 1, 'Exactly one evolution law must be specified'       # fds.py:72
-        if lhs is not None or cost is not None:
-            raise NotImplementedError('cvx evolution (lhs= / cost=, gds/fds.py:97-113) is outside the device stepping path')
+        if cost is not None:
+            raise NotImplementedError('a general convex cost (cost=, gds/fds.py:97-113) is outside the device stepping path')
         if traj_t is not None:
             raise NotImplementedError('trajectory playback (traj_t=, gds/fds.py:124-129) is outside the device stepping path')
         self._drop_engine()
@@ -90,6 +94,16 @@ class fds(Observable, Steppable):
             self.solver_args = solver_args
             self.integrator_type = integrator
             self.y0 = np.zeros(self.ndim * order)
+        elif lhs is not None:
+            # `lhs(t, y) = 0` in the least-squares sense (fds.py:97-113: CVXPY there).  Here: lhs affine in y with a
+            # symmetric definite linear part (the pressure-Poisson form of examples/fluid.py:26-31), solved by
+            # conjugate gradients on the device (gds_cg_solve).  Parity against CVXPY is unpinned (not installed).
+            self.iter_mode = IterationMode.cvx
+            self.lhs_fun = lhs
+            self.order = 1
+            self.y0 = np.zeros(self.ndim)
+            self._lhs_cache = {}
+            self._dev_y = None
         elif map_fun is not None:
             self.iter_mode = IterationMode.map
             self.map_fun = map_fun            # documented signature (t, y): fds.py:33, README.md:158
@@ -150,8 +164,10 @@ class fds(Observable, Steppable):
         if self.iter_mode is IterationMode.dydt:
             # fds.py:196: negative offsets -- for order>1 this addresses the LAST block
             self._host_state[self.dirichlet_indices - self.ndim] = self.dirichlet_values
-        elif self.iter_mode is IterationMode.map:
-            self._host_state = self.y0.copy()                                       # fds.py:203
+        elif self.iter_mode in (IterationMode.map, IterationMode.cvx):
+            self._host_state = self.y0.copy()                                       # fds.py:197-203
+            if self.iter_mode is IterationMode.cvx:
+                self._dev_y, self._lhs_cache = None, {}
         else:
             raise Exception('Unsupported iteration mode for set_constraints()')     # fds.py:205
         self._bump()
@@ -220,6 +236,9 @@ class fds(Observable, Steppable):
             if (self._t - self._n) >= self._dt:
                 self._n = self._t
                 self._ensure_engine().apply_map(self._t)
+        elif self.iter_mode is IterationMode.cvx:
+            self._t += dt                     # fds.py:317-328
+            self._solve_lhs(self._t)
         elif self.iter_mode is IterationMode.nil:
             self._t += dt
         self._version += 1
@@ -230,6 +249,7 @@ class fds(Observable, Steppable):
         law = {IterationMode.dydt: lambda: dict(dydt=self.dydt_fun, order=self.order, max_step=self.max_step,
                                                 integrator=self.integrator_type, solver_args=self.solver_args),
                IterationMode.map: lambda: dict(map_fun=self.map_fun, dt=self._dt),
+               IterationMode.cvx: lambda: dict(lhs=self.lhs_fun),
                IterationMode.nil: lambda: dict(nil=True)}[self.iter_mode]()
         d, n, p = self._dirichlet_spec or self.dirichlet_fun, self._neumann_spec or self.neumann_fun, self.project_fun
         t0, y0 = self.t0, self.y0_fun
@@ -279,6 +299,10 @@ class fds(Observable, Steppable):
             return np.zeros(self.ndim)
         if self._engine is not None:
             return self._engine.read(self)
+        if self.iter_mode is IterationMode.cvx and self._dev_y is not None:
+            if self._dev_y_cache is None:
+                self._dev_y_cache = self._low.from_dev(self._domain_code, self._dev_y.download())
+            return self._dev_y_cache
         return self._host_state[:self.ndim]
 
     @property
@@ -378,6 +402,32 @@ class gds(fds, GraphObservable):
         return _run_eager(self._low, build(*[Const(a, d, self._low) for a, d in zip(arrs, domains)]))
 
 
+def _state_operand(f):
+    """a device vector holding the current state of field f, for passes that run outside f's own system"""
+    low = f._low
+    if f._engine is not None:
+        eng = f._engine
+        off = eng.offsets[id(f)]
+        return BufferView(low.ctx, eng._state_ptr().value + 8 * off, f.ndim)
+    if f._dev_y is not None:
+        return f._dev_y
+    return Buffer(low.ctx, f.ndim, low.to_dev(f._domain_code, f._host_state[:f.ndim]))
+
+
+def _bind_states(expr, memo):
+    """copy of an expression with every State leaf replaced by a device vector of that field's current state"""
+    if isinstance(expr, State):
+        if id(expr.field) not in memo:
+            memo[id(expr.field)] = DevVec(_state_operand(expr.field), expr.domain, expr.graph)
+        return memo[id(expr.field)]
+    if not expr.args:
+        return expr
+    import copy
+    c = copy.copy(expr)
+    c.args = tuple(_bind_states(a, memo) for a in expr.args)
+    return c
+
+
 def _run_eager(low, expr):
     """lower one expression to passes, run them on the device, download the result"""
     ctx = low.ctx
@@ -412,6 +462,77 @@ def _run_passes(low, descs):
     dev = low.dev
     for d, keep in descs:
         check(lib.gds_pass_run(low.ctx.h, dev.h, C.byref(d), 0.0))
+
+
+def _solve_lhs(self, t):
+    """`lhs(t, y) = 0` for an lhs affine in y (module docstring of set_evolution): trace once, split into constant and
+    linear part, then per call  b = -Z_D(const + lin(g)),  lin(p) = b by conjugate gradients,  y = p + g  (g = Dirichlet
+    values, 0 elsewhere).  Everything stays on the device; the result is this field's state."""
+    import ctypes as C
+    low, ctx, n, dom = self._low, self._low.ctx, self.ndim, self._domain_code
+    if self.dynamic_dirichlet:
+        self.dirichlet_values = self._dirichlet_at(t)                  # fds.py:350-355
+    if 'split' not in self._lhs_cache:
+        with trace_scope():
+            root = as_expr(self.lhs_fun(Time(), Stage(self)), dom, low)
+        const, lin = split_affine(root, self)
+        if lin is None:
+            raise TraceError('lhs= does not depend on y')
+        self._lhs_cache['split'] = (const, lin)
+    const, lin = self._lhs_cache['split']
+    D = self.dirichlet_indices
+    g = np.zeros(n)
+    g[D] = self.dirichlet_values
+    gvec = Const(g, dom, low)
+    work = self._lhs_cache.setdefault('work', tuple(Buffer(ctx, n) for _ in range(6)))
+    x, b, r, p, ap, out = work
+    memo = {}
+    rhs = substitute(lin, self, gvec) if const is None else const + substitute(lin, self, gvec)
+    rhs = _bind_states(MaskZero(unary('NEG', rhs), D), memo)
+    d_rhs, k1 = _lower_into(low, rhs, b)
+    _run_passes_at(low, d_rhs, t)
+    op = _bind_states(MaskZero(substitute(lin, self, DevVec(p, dom, low)), D), memo)
+    d_op, k2 = _lower_into(low, op, ap)
+    if len(d_op) != 1:
+        raise NotImplementedError('lhs=: the part linear in y must be a one-hop operator (a Laplacian form)')
+    kind = C.c_int32()
+    check(lib.gds_pass_kernel_kind(C.byref(d_op[0][0]), C.byref(kind)))
+    iters, relres = C.c_int32(), C.c_double()
+    max_iter = max(1000, 20 * int(np.sqrt(n)) + 200)
+    for attempt in range(2):
+        check(lib.gds_cg_solve(ctx.h, low.dev.h, C.byref(d_op[0][0]), x.h, b.h, r.h, p.h, ap.h, n, 1e-13, max_iter, 25,
+                               C.byref(iters), C.byref(relres)))
+        if attempt == 0 and iters.value <= 25 and relres.value > 0.5:
+            # p.Ap was not positive: the linear part is negative definite -- solve (-lin) p = -b instead
+            op = _bind_states(MaskZero(unary('NEG', substitute(lin, self, DevVec(p, dom, low))), D), memo)
+            d_op, k2 = _lower_into(low, op, ap)
+            d_neg, k3 = _lower_into(low, unary('NEG', DevVec(b, dom, low)), r)
+            _run_passes_at(low, d_neg, t)
+            d_cp, k4 = _lower_into(low, DevVec(r, dom, low) + 0.0, b)
+            _run_passes_at(low, d_cp, t)
+            continue
+        break
+    if self._dev_y is None:
+        self._dev_y = Buffer(ctx, n)
+    d_out, k5 = _lower_into(low, DevVec(x, dom, low) + gvec, self._dev_y)
+    _run_passes_at(low, d_out, t)
+    self._dev_y_cache = None
+    self.last_solve = {'iterations': iters.value, 'relative_residual': relres.value}
+    self._version += 1
+    if not self._identity_projection():
+        y = np.asarray(self.project_fun(np.array(self.y, copy=True)), dtype=float)   # fds.py:364-366
+        self._dev_y.upload(low.to_dev(dom, y))
+        self._dev_y_cache = None
+
+
+fds._solve_lhs = _solve_lhs
+
+
+def _run_passes_at(low, descs, t):
+    import ctypes as C
+    dev = low.dev
+    for d, keep in descs:
+        check(lib.gds_pass_run(low.ctx.h, dev.h, C.byref(d), float(t)))
 
 
 class node_gds(gds):
@@ -600,6 +721,9 @@ class coupled_fds(Steppable):
         self.cont = [s for s in systems if s.iter_mode is IterationMode.dydt]
         self.maps = [s for s in systems if s.iter_mode is IterationMode.map]
         self.nils = [s for s in systems if s.iter_mode is IterationMode.nil]
+        self.cvxs = [s for s in systems if s.iter_mode is IterationMode.cvx]
+        if self.cvxs and not self.cont:
+            raise NotImplementedError('lhs= fields are coupled to at least one continuous field')
         if self.cont and self.maps:
             raise NotImplementedError('coupling recurrence maps with continuous fields (fds.py:491-503) is not on the device path yet')
         self.has_integrator = len(self.cont) > 0
@@ -619,6 +743,11 @@ class coupled_fds(Steppable):
             s._host_state = np.array(s.y0, dtype=float, copy=True)                  # fds.py:439: state taken at couple() time
             s._coupled = self
         self._members = members
+        for s in self.cvxs:
+            # the state of an `lhs=` field lives on the device from the start: the continuous laws read it in place
+            s._coupled = self
+            s._dev_y = Buffer(s._low.ctx, s.ndim, s._low.to_dev(s._domain_code, s._host_state[:s.ndim]))
+            s._dev_y_cache = None
 
     def _ensure_engine(self, record=False):
         if self._engine is not None and record and not self._engine.record:
@@ -632,7 +761,18 @@ class coupled_fds(Steppable):
         return self._engine
 
     def step(self, dt: float):
-        if self.has_integrator:
+        if self.has_integrator and self.cvxs:
+            # fds.py:505-507 solves the discrete systems before every RHS evaluation; they read accepted state only, so
+            # the solves of one internal step coincide: solve once at its start, then advance that step
+            from .engine import step_table
+            eng = self._ensure_engine()
+            ts, hs, t_new = step_table(eng.t, eng.t + dt, eng.max_step)
+            for i in range(ts.size):
+                for c in self.cvxs:
+                    c._solve_lhs(float(ts[i]))
+                eng.advance(float(hs[i]) if i < ts.size - 1 else (t_new - float(ts[i])))
+            self._t = eng.t
+        elif self.has_integrator:
             self._ensure_engine().advance(dt)
             self._t = self._engine.t
         else:
@@ -654,7 +794,7 @@ class coupled_fds(Steppable):
         raise NotImplementedError
 
     def observables(self):
-        return self.cont + self.maps + self.nils
+        return self.cont + self.cvxs + self.maps + self.nils
 
     @property
     def t(self):

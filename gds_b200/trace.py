@@ -87,8 +87,15 @@ class Expr:
                          '`free=` / `normal=` arguments or multiply by a 0/1 vector')
 
     def __setitem__(self, idx, val):
-        raise TraceError('in-place assignment into a traced field expression is not supported; multiply by a 0/1 '
-                         'vector instead')
+        """`expr[rows] = 0.` (examples/fluid.py:29): the node turns, in place, into the masked form of itself"""
+        if not (isinstance(val, numbers.Real) and float(val) == 0.0) or self.domain is None:
+            raise TraceError('only `expr[rows] = 0.` can be captured; multiply by a 0/1 vector for anything else')
+        import copy
+        inner = copy.copy(self)
+        rows = np.arange(len(self))[idx]
+        self.__class__ = MaskZero
+        self.__dict__.clear()
+        MaskZero.__init__(self, inner, rows)
 
     # ---- numpy ufuncs ------------------------------------------------------------------------------
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
@@ -266,6 +273,66 @@ def _fold_binary(op, a, b):
          'POW': lambda: a ** b, 'MAX': lambda: max(a, b), 'MIN': lambda: min(a, b),
          'ATAN2': lambda: math.atan2(a, b)}[op]
     return f()
+
+
+# ------------------------------------------------------------------------------------------------
+# affine laws: value(y) = const + lin(y)   (the `lhs=` form of set_evolution)
+# ------------------------------------------------------------------------------------------------
+_LINEAR_GATHERS = ('N_LAP', 'N_BDOT', 'E_GRADT', 'E_CURLT', 'F_CURL')
+
+
+def depends_on(e, field):
+    if isinstance(e, Stage):
+        return e.field is field
+    return any(depends_on(a, field) for a in e.args)
+
+
+def substitute(e, field, replacement):
+    """copy of e with the stage vector of `field` replaced"""
+    if isinstance(e, Stage) and e.field is field:
+        return replacement
+    if not e.args or not depends_on(e, field):
+        return e
+    import copy
+    c = copy.copy(e)
+    c.args = tuple(substitute(a, field, replacement) for a in e.args)
+    return c
+
+
+def split_affine(e, field):
+    """(const, lin): e == const + lin with lin linear in the stage vector of `field` (either may be None)"""
+    if not depends_on(e, field):
+        return e, None
+    if isinstance(e, Stage):
+        return None, e
+
+    def add(a, b, op='ADD'):
+        if a is None:
+            return b if op == 'ADD' or b is None else unary('NEG', b)
+        return a if b is None else binary(op, a, b)
+    if isinstance(e, Binary) and e.op in ('ADD', 'SUB'):
+        (ca, la), (cb, lb) = split_affine(e.args[0], field), split_affine(e.args[1], field)
+        return add(ca, cb, e.op), add(la, lb, e.op)
+    if isinstance(e, Binary) and e.op == 'MUL':
+        a, b = e.args
+        if depends_on(a, field) and depends_on(b, field):
+            raise TraceError('lhs= must be affine in y (a product of two y-dependent factors was found)')
+        dep, ind = (a, b) if depends_on(a, field) else (b, a)
+        c, l = split_affine(dep, field)
+        return (None if c is None else binary('MUL', c, ind)), (None if l is None else binary('MUL', l, ind))
+    if isinstance(e, Binary) and e.op == 'DIV' and not depends_on(e.args[1], field):
+        c, l = split_affine(e.args[0], field)
+        return (None if c is None else binary('DIV', c, e.args[1])), (None if l is None else binary('DIV', l, e.args[1]))
+    if isinstance(e, Unary) and e.op == 'NEG':
+        c, l = split_affine(e.args[0], field)
+        return (None if c is None else unary('NEG', c)), (None if l is None else unary('NEG', l))
+    if isinstance(e, MaskZero):
+        c, l = split_affine(e.args[0], field)
+        return (None if c is None else MaskZero(c, e.rows)), (None if l is None else MaskZero(l, e.rows))
+    if isinstance(e, Gather) and e.kind in _LINEAR_GATHERS:
+        c, l = split_affine(e.args[0], field)
+        return (None if c is None else Gather(e.kind, e.graph, c)), (None if l is None else Gather(e.kind, e.graph, l))
+    raise TraceError(f'lhs= must be affine in y ({type(e).__name__} of y is not)')
 
 
 # ------------------------------------------------------------------------------------------------

@@ -137,6 +137,8 @@ int gds_ctx_flush_l2(gds_ctx* ctx, int64_t bytes);
 
 /* ---- device vectors ------------------------------------------------------------------------------------ */
 int gds_buf_create(gds_ctx* ctx, int64_t n, gds_buf** out);
+/* non-owning view of n values at a device address (e.g. a slice of a system's state) usable as a pass operand */
+int gds_buf_view(gds_ctx* ctx, void* dev_ptr, int64_t n, gds_buf** out);
 int gds_buf_destroy(gds_buf* b);
 int gds_buf_upload(gds_buf* b, int64_t offset, const double* host, int64_t n);
 int gds_buf_download(gds_buf* b, int64_t offset, double* host, int64_t n);

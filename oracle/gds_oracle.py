@@ -21,6 +21,9 @@ Deliberate positions on reference quirks:
   * map mode follows gds/fds.py:332-339 with the two fixes needed to make it reachable
     (`_y = y0.copy()` for fds.py:122, documented `(t, y)` signature for fds.py:337).
   * `set_initial(y0=ndarray)` is accepted (fds.py:151-152 recurses in the reference).
+  * `lhs=` (cvx mode, fds.py:97-113,309-328): the reference hands `sum_squares(lhs(t, y))` to CVXPY, which is not
+    installed here, so this mode is PARITY UNPINNED against the reference: for an `lhs` affine in y the restatement
+    takes the least-squares solution with the Dirichlet values imposed (minimum norm over the free unknowns).
 """
 from __future__ import annotations
 
@@ -363,8 +366,8 @@ class fds:
 
     # fds.py:30-135 (dydt and map branches; cvx/traj are out of scope)
     def set_evolution(self, dydt=None, order=1, max_step=1e-3, integrator=Integrators.rk4, solver_args={},
-                      map_fun=None, dt=1.0, nil=False):
-        assert sum(x is not None and x is not False for x in (dydt, map_fun, nil or None)) == 1, \
+                      map_fun=None, dt=1.0, nil=False, lhs=None, refresh_cvx=True):
+        assert sum(x is not None and x is not False for x in (dydt, map_fun, nil or None, lhs)) == 1, \
             'Exactly one evolution law must be specified'
         if dydt is not None:
             self.iter_mode = IterationMode.dydt
@@ -376,6 +379,14 @@ class fds:
             self.y0 = np.zeros(self.ndim * order)
             self.integrator_type = integrator
             self.integrator = make_integrator(integrator, self.dydt, self.t0, self.y0, max_step, solver_args)
+        elif lhs is not None:   # fds.py:97-113
+            self.iter_mode = IterationMode.cvx
+            self.lhs_fun = lhs
+            self.refresh_cvx = refresh_cvx
+            self.initialized = False
+            self.y0 = np.zeros(self.ndim)
+            self._t = self.t0
+            self._y = self.y0.copy()
         elif map_fun is not None:
             self.iter_mode = IterationMode.map
             self.map_fun = map_fun
@@ -425,7 +436,7 @@ class fds:
         if self.iter_mode is IterationMode.dydt:
             # fds.py:196 -- negative offsets: for order>1 this addresses the LAST block (Appendix B.4)
             self.integrator.y[self.dirichlet_indices - self.ndim] = self.dirichlet_values
-        elif self.iter_mode is IterationMode.map:
+        elif self.iter_mode in (IterationMode.map, IterationMode.cvx):   # fds.py:197-203
             self._y = self.y0.copy()
         else:
             raise Exception('Unsupported iteration mode for set_constraints()')
@@ -465,8 +476,31 @@ class fds:
                 self.apply_constraints()
         elif self.iter_mode is IterationMode.map:
             self.step_map(dt)
+        elif self.iter_mode is IterationMode.cvx:
+            self.step_cvx(dt)
         else:
             self._t += dt
+
+    # fds.py:317-328 -- minimise |lhs(t, y)|^2 subject to the Dirichlet values (CVXPY in the reference)
+    def step_cvx(self, dt):
+        self._t += dt
+        if (not self.initialized) or self.refresh_cvx:
+            self.update_constraints(self.t)
+            n = self.ndim
+            c = np.asarray(self.lhs_fun(self.t, np.zeros(n)), dtype=float).reshape(-1)
+            A = np.empty((c.size, n))
+            for j in range(n):          # lhs is affine in y: probe its linear part column by column
+                e = np.zeros(n); e[j] = 1.0
+                A[:, j] = np.asarray(self.lhs_fun(self.t, e), dtype=float).reshape(-1) - c
+            fixed = np.zeros(n, dtype=bool)
+            fixed[self.dirichlet_indices] = True
+            y = np.zeros(n)
+            y[self.dirichlet_indices] = self.dirichlet_values
+            rhs = -(c + A[:, fixed] @ y[fixed])
+            y[~fixed] = np.linalg.lstsq(A[:, ~fixed], rhs, rcond=None)[0]
+            self._y = y
+            self.apply_constraints()
+            self.initialized = True
 
     # fds.py:292-305
     def dydt(self, t, y):
@@ -504,6 +538,8 @@ class fds:
         if self.iter_mode is IterationMode.dydt:
             self.integrator.y[self.dirichlet_indices - self.ndim] = self.dirichlet_values
             self.integrator.y = self.project_fun(self.integrator.y)
+        elif self.iter_mode is IterationMode.cvx:
+            self._y = self.project_fun(self._y)   # boundary values are part of the solution (fds.py:364-366)
         elif self.iter_mode is IterationMode.map:
             self._y[self.dirichlet_indices] = self.dirichlet_values
             self._y = self.project_fun(self._y)
@@ -525,7 +561,7 @@ class fds:
 
     @property
     def dt(self):
-        return self._dt if self.iter_mode in (IterationMode.dydt, IterationMode.map) else 1e-3
+        return self._dt if self.iter_mode in (IterationMode.dydt, IterationMode.map) else 1e-3   # fds.py:395-400
 
     def __call__(self, x):
         return self.y[self.X[x]]
@@ -710,9 +746,10 @@ class coupled_fds:
         assert all(s.iter_mode != IterationMode.none for s in systems), 'All systems must have evolution laws.'
         self.t0 = 0.
         self.cont = [s for s in systems if s.iter_mode is IterationMode.dydt]
+        self.cvxs = [s for s in systems if s.iter_mode is IterationMode.cvx]
         self.maps = [s for s in systems if s.iter_mode is IterationMode.map]
         self.discrete_t = self.t0
-        self.discrete_y = {id(s): s.y0 for s in self.maps}
+        self.discrete_y = {id(s): s.y0 for s in self.cvxs + self.maps}
         self.has_integrator = len(self.cont) > 0
         if self.has_integrator:
             kind = self.cont[0].integrator_type
@@ -729,7 +766,7 @@ class coupled_fds:
             s.view = slice(last, last + s.y0.size)
             last += s.y0.size
             _rebind(s, y=lambda s_: self.integrator.y[s_.view], t=lambda _: self.t)
-        for s in self.maps:
+        for s in self.cvxs + self.maps:
             _rebind(s, y=lambda s_: self.discrete_y[id(s_)], t=lambda _: self.t)
 
     def step(self, dt):  # fds.py:471-489
@@ -747,9 +784,9 @@ class coupled_fds:
                 self.integrator.y[s.view] = s.project_fun(self.integrator.y[s.view])
 
     def step_discrete(self, dt):  # fds.py:491-503
-        for s in self.maps:
+        for s in self.cvxs + self.maps:
             fds.step(s, dt)
-        for s in self.maps:
+        for s in self.cvxs + self.maps:
             np.copyto(self.discrete_y[id(s)], s._y)
         self.discrete_t += dt
 
@@ -758,7 +795,7 @@ class coupled_fds:
         return np.concatenate([s.dydt(t, y[s.view]) for s in self.cont])
 
     def observables(self):
-        return self.cont + self.maps
+        return self.cont + self.cvxs + self.maps
 
     @property
     def t(self):

@@ -18,6 +18,10 @@ def _mk(mod):
             obs.set_evolution(dydt=dydt, order=order, max_step=max_step, integrator=kind)
 
         @staticmethod
+        def evolve_lhs(obs, lhs):
+            obs.set_evolution(lhs=lhs)
+
+        @staticmethod
         def evolve_nil(obs):
             obs.set_evolution(nil=True)
 

@@ -272,6 +272,37 @@ def case_ns_cavity_c3(api, m=6, n=10, nsteps=40, every=20):
     return _snap(sysobj, {'u': u}, 1e-4, nsteps, every)
 
 
+def case_ns_pressure(api, m=5, n=8, nsteps=12, every=6, rho=1.0, visc=0.05, h=1e-3):
+    """Navier-Stokes with the pressure solved every step (examples/fluid.py:14-38 `navier_stokes`): the pressure field
+    is defined by `lhs=` -- divergence of the provisional velocity minus the pressure Laplacian, set to zero -- with a
+    pressure drop between an inlet and an outlet node; the velocity law reads `pressure.grad()`.  NOT in the golden
+    set: the reference solves `lhs=` with CVXPY, which is not installed here (parity unpinned).  h equals the law's
+    min_step so that `max(min_step, velocity.dt)` does not depend on the reference's `dt` bookkeeping (App. B.7)."""
+    G = g_tri(m, n)
+    pressure, velocity = api.node_gds(G), api.edge_gds(G)
+    nodes = list(pressure.X.keys())
+    inlet, outlet = nodes[0], nodes[-1]
+    v_free = np.array([pressure.X[inlet], pressure.X[outlet]], dtype=np.intp)
+    min_step = 1e-3
+
+    def pressure_f(t, y):
+        dt = max(min_step, velocity.dt)
+        lhs = velocity.div(velocity.y / dt - velocity.advect() + velocity.laplacian() * visc / rho)
+        lhs[v_free] = 0.
+        lhs -= pressure.laplacian(y) / rho
+        return lhs
+
+    def velocity_f(t, y):
+        return -velocity.advect() - pressure.grad() / rho + velocity.laplacian() * visc / rho
+    api.evolve_lhs(pressure, pressure_f)
+    api.evolve(velocity, dydt=velocity_f, max_step=h)
+    u0 = 0.05 * np.random.default_rng(13).standard_normal(velocity.ndim)
+    velocity.set_initial(y0=lambda e: u0[velocity.X[e]])
+    pressure.set_constraints(dirichlet={inlet: 1.0, outlet: -1.0})
+    sysobj = api.couple({'velocity': velocity, 'pressure': pressure})
+    return _snap(sysobj, {'velocity': velocity, 'pressure': pressure}, h, nsteps, every)
+
+
 def case_wave_c5(api, dims=(6, 7, 8), nsteps=50, every=25):
     """BASELINE config 5 at small size: wave equation on a 3-D grid, order=2, accepted-state Laplacian
     (examples/wave.py:14), RK4 h=0.1, no Dirichlet."""

@@ -188,3 +188,39 @@ def test_kernel_dispatch_of_the_baseline_laws():
     a = gds_b200.node_gds(cases.g_grid3((3, 4, 5)))
     a.set_evolution(dydt=lambda t, y: 1.0 * a.laplacian(), order=2, max_step=0.1)
     assert kernel_kinds(a, a.dydt_fun) == [1, 2]
+
+
+def test_affine_split_of_an_lhs_law():
+    """`lhs=` laws are split into a constant part and a part linear in y (fluid.py:26-31 pressure law), including the
+    in-place `lhs[rows] = 0.` and `lhs -= ...` of the example"""
+    from gds_b200.trace import split_affine, depends_on, MaskZero, Gather, TraceError
+    G = cases.g_tri(3, 4)
+    pressure, velocity = gds_b200.node_gds(G), gds_b200.edge_gds(G)
+    velocity.set_evolution(dydt=lambda t, y: -velocity.advect(), max_step=1e-3)
+    rows = np.array([0, 3])
+
+    def pressure_f(t, y):
+        lhs = velocity.div(velocity.y / 1e-3 - velocity.advect() + velocity.laplacian() * 0.05)
+        lhs[rows] = 0.
+        lhs -= pressure.laplacian(y) / 2.0
+        return lhs
+    pressure.set_evolution(lhs=pressure_f)
+    pressure.set_constraints(dirichlet={list(pressure.X)[0]: 1.0})
+    with trace_scope():
+        root = pressure.lhs_fun(Time(), Stage(pressure))
+    const, lin = split_affine(root, pressure)
+    assert const is not None and lin is not None
+    assert not depends_on(const, pressure) and depends_on(lin, pressure)
+    # the constant part carries the row mask of `lhs[rows] = 0.`
+    assert isinstance(const, MaskZero) and np.array_equal(const.rows, rows)
+
+    def kinds(e):
+        out = [e.kind] if isinstance(e, Gather) else []
+        for a in e.args:
+            out += kinds(a)
+        return out
+    assert kinds(lin) == ['N_LAP'] and 'N_BDOT' in kinds(const)
+    with trace_scope():
+        bad = pressure.laplacian(Stage(pressure)) * Stage(pressure)
+    with pytest.raises(TraceError):
+        split_affine(bad, pressure)

@@ -138,3 +138,13 @@ def test_accepted_state_vs_stage_argument_differ_like_the_reference():
     b0, b1 = run(oracle_api(), False), run(oracle_api(), True)
     assert rel_l2(a0, b0) <= TOL and rel_l2(a1, b1) <= TOL
     assert rel_l2(a0, a1) > 1e-3
+
+
+def test_navier_stokes_with_pressure_solve_every_step():
+    """`lhs=` pressure field coupled to the velocity law (examples/fluid.py:14-38): device CG against the oracle's dense
+    least squares.  Parity against the reference itself is unpinned for this mode (CVXPY is not installed here)."""
+    a, b = cases.case_ns_pressure(product_api()), cases.case_ns_pressure(oracle_api())
+    assert np.allclose(a['t'], b['t'], rtol=0, atol=1e-12)
+    for i in range(b['y_velocity'].shape[0]):
+        assert rel_l2(a['y_velocity'][i], b['y_velocity'][i]) <= 1e-9, rel_l2(a['y_velocity'][i], b['y_velocity'][i])
+        assert rel_l2(a['y_pressure'][i], b['y_pressure'][i]) <= 1e-8, rel_l2(a['y_pressure'][i], b['y_pressure'][i])
