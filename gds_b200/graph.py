@@ -319,10 +319,23 @@ class LoweredGraph:
         return {L.NODES: self.V, L.EDGES: self.E, L.FACES: self.F}[domain]
 
     @staticmethod
+    def _signature(G):
+        """cheap fingerprint of what the lowering depends on: a graph edited after a field was built is lowered again"""
+        if isinstance(G, NativeGraph):
+            return (G.kind, G.dims, id(G.weights), G.__dict__.get('_gds_b200_distribute'))
+        wsum = sum(d.get('weight', 1.0) for (_, _, d) in G.edges(data=True))
+        nf = len(G.faces) if hasattr(G, 'faces') else -1
+        return (G.number_of_nodes(), G.number_of_edges(), wsum, nf, G.__dict__.get('_gds_b200_distribute'))
+
+    @staticmethod
     def of(G, need_faces: bool = False) -> 'LoweredGraph':
         low = G.__dict__.get('_gds_b200_lowered')
+        sig = LoweredGraph._signature(G)
+        if low is not None and low._sig != sig:
+            low = None
         if low is None:
             low = LoweredGraph(G)
+            low._sig = sig
             G.__dict__['_gds_b200_lowered'] = low
         if need_faces:
             low.ensure_faces()

@@ -163,3 +163,16 @@ def test_internal_renumbering_keeps_public_maps_and_row_contents():
     d_pub = np.mean(np.abs(low.edge_u.astype(np.int64) - low.edge_v))
     d_int = np.mean(np.abs(low.p2i[low.edge_u] - low.p2i[low.edge_v]))
     assert d_int < 0.5 * d_pub
+
+
+def test_graph_edited_after_a_field_was_built_is_lowered_again():
+    import gds_b200
+    G = cases.g_grid(4, 4)
+    a = gds_b200.node_gds(G)
+    b = gds_b200.node_gds(G)
+    assert a._low is b._low                       # one lowering per graph
+    cases.add_weights(G, 3)
+    c = gds_b200.node_gds(G)
+    assert c._low is not a._low and not np.all(c.edge_weights == 1.0)
+    G.add_edge((0, 0), (3, 3))
+    assert gds_b200.node_gds(G)._low.E == a._low.E + 1
