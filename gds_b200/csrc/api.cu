@@ -861,8 +861,8 @@ extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int3
     GDS_CUDA(cudaMemsetAsync(s->ACC, 0, bytes, c->stream));
     s->device_bytes += (int64_t)bytes;
   }
-  GDS_CUDA(cudaMalloc((void**)&s->d_counter, sizeof(int64_t)));
-  GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaMalloc((void**)&s->d_counter, 2 * sizeof(int64_t)));   // [step, block ticket of the tail kernel]
+  GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(int64_t), c->stream));
   GDS_CUDA(cudaMalloc((void**)&s->d_flags, 64 * sizeof(int64_t)));
   GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, 64 * sizeof(int64_t), c->stream));
   GDS_CUDA(cudaMalloc((void**)&s->d_p2p_epoch, 2 * sizeof(int64_t)));
@@ -1054,10 +1054,13 @@ static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
   gds_ctx* c = s->ctx;
   double* ynew = s->Y[cur ^ 1];
   if (lt) GDS_TRY(lt->begin(3));
-  GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, nullptr, s->n_dir_static, 0, s->d_counter));
-  GDS_TRY(launch_dirichlet(c, ynew, s->d_dir_idx_dyn, nullptr, s->d_bc_tab, s->n_dir_dyn, s->n_dir_dyn, s->d_counter));
-  if (s->recording && !lt) GDS_TRY(launch_record(c, ynew, s->d_traj, s->d_rec, s->d_counter, s->n_state));
-  GDS_TRY(launch_advance_counter(c, s->d_counter));
+  const bool rec = s->recording && !lt;   // the snapshot reads the step counter after the overwrite: advance it last
+  GDS_TRY(launch_tail(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, s->n_dir_static, s->d_dir_idx_dyn, s->d_bc_tab,
+                      s->n_dir_dyn, s->d_counter, rec ? 0 : 1));
+  if (rec) {
+    GDS_TRY(launch_record(c, ynew, s->d_traj, s->d_rec, s->d_counter, s->n_state));
+    GDS_TRY(launch_advance_counter(c, s->d_counter));
+  }
   if (lt) GDS_TRY(lt->end());
   return 0;
 }

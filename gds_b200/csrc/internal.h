@@ -331,6 +331,8 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain);
 int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* val_static, const double* bc_tab,
                      int64_t n, int64_t n_dyn_stride, const int64_t* counter);
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
+int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
+                const double* tab, int64_t nd, int64_t* counter, int advance);
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode);

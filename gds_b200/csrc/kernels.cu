@@ -950,6 +950,36 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
   return 0;
 }
 
+// The whole per-step tail in one launch: static and time-varying Dirichlet overwrite, and (advance != 0) the step
+// counter, bumped by the last block to finish so that every block has read the step's table row first.
+// counter[0] = step, counter[1] = block ticket.
+__global__ void __launch_bounds__(256) tail_kernel(double* __restrict__ y, const int64_t* __restrict__ sidx,
+                                                   const double* __restrict__ sval, int64_t ns,
+                                                   const int64_t* __restrict__ didx, const double* __restrict__ tab,
+                                                   int64_t nd, int64_t* counter, int advance) {
+  const int64_t step = counter[0];
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < ns) y[sidx[i]] = sval[i];
+  else if (i < ns + nd) y[didx[i - ns]] = tab[step * nd + (i - ns)];
+  if (!advance) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(counter + 1), 1ull);
+    if (t == gridDim.x - 1) { counter[1] = 0; counter[0] = step + 1; }
+  }
+}
+
+int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
+                const double* tab, int64_t nd, int64_t* counter, int advance) {
+  if (ns + nd <= 0 && !advance) return 0;
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, (ns + nd + 255) / 256);
+  tail_kernel<<<blocks, 256, 0, ctx->stream>>>(y, sidx, sval, ns, didx, tab, nd, counter, advance);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
 __global__ void advance_counter_kernel(int64_t* c) { *c += 1; }
 
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter) {
