@@ -104,7 +104,8 @@ class StepEngine:
         self.h = h
         import weakref
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
-        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True, single_hop=self.part is not None)
+        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True,
+                            single_hop=self.part is not None and not hasattr(self.part, 'gid_dom'))
         self.lowering = lowering
         self.passes = []
         stat_idx, stat_val, dyn_idx = [], [], []
@@ -301,10 +302,62 @@ class StepEngine:
 
     # ---- one rank of a partitioned system ------------------------------------------------------
     def _halo_blocks(self):
+        """(offset, domain) of every state block that has ghost rows"""
+        deep = hasattr(self.part, 'gid_dom')
         for f in self.fields:
-            if f._domain_code != L.NODES:
-                raise NotImplementedError('distributed graphs carry node fields only')
-        return [self.offsets[id(f)] + f.ndim * i for f in self.fields for i in range(f._order())]
+            if f._domain_code != L.NODES and not deep:
+                raise NotImplementedError('edge and face fields need distribute(G, hops=k) with k >= 2')
+        return [(self.offsets[id(f)] + f.ndim * i, f._domain_code) for f in self.fields for i in range(f._order())]
+
+    def _check_ghost_layers(self):
+        """Deep partitions recompute intermediates on the ghost layers instead of exchanging them: every gather eats
+        one layer (an edge <- face gather floor(k/2) of them, k = largest face).  Propagate the level up to which each
+        vector is valid through the lowered passes and make sure every law is still valid on the rows this rank owns."""
+        part, h = self.part, self.part.hops
+        kf = part.max_face // 2
+        INF = 10 ** 9
+        lv = {}
+
+        def level_of(ref):
+            kind, buf, _ = ref
+            return lv.get(id(buf), h) if kind == L.VEC_BUF else h
+        need = {L.NODES: 0, L.EDGES: 1, L.FACES: kf}
+        OPN = {v: k for k, v in L.OP.items()}
+        for p in self.passes:
+            st = []
+            for ins in p.code:
+                op, a, b = OPN[ins & 0xff], (ins >> 8) & 0xff, (ins >> 16) & 0xff
+                if op == 'PUSH_VEC':
+                    st.append(level_of(p.vec[a]))
+                elif op in ('PUSH_IMM', 'PUSH_T', 'PUSH_H'):
+                    st.append(INF)
+                elif op in ('N_LAP', 'N_BDOT', 'N_INFLUX', 'N_OUTFLUX'):
+                    st.append(min(h - 1, level_of(p.vec[a]) - 1))
+                elif op in ('N_ADVECT', 'N_LIE'):
+                    st.append(min(h - 1, level_of(p.vec[a]) - 1, level_of(p.vec[b]) - 1))
+                elif op == 'N_EAGG':
+                    lv[id(p.out[b][0])] = min(h - 1, level_of(p.vec[a]) - 1)
+                elif op in ('E_GRADT', 'F_CURL'):
+                    st.append(level_of(p.vec[a]))
+                elif op == 'E_CURLT':
+                    st.append(min(h, level_of(p.vec[a])) - kf)
+                elif op == 'E_ADVFIN':
+                    st.append(min(level_of(p.vec[a]), level_of(p.vec[b])))
+                elif op == 'STORE':
+                    lv[id(p.out[a][0])] = st[-1]
+                elif op in ('ADD', 'SUB', 'MUL', 'DIV', 'POW', 'MAX', 'MIN', 'ATAN2'):
+                    y = st.pop(); st[-1] = min(st[-1], y)
+                elif op == 'DUP':
+                    st.append(st[-1])
+                elif op == 'SWAP':
+                    st[-1], st[-2] = st[-2], st[-1]
+                elif op == 'POP':
+                    st.pop()
+                elif op == 'GETL':
+                    st.append(0)     # locals are not produced by the tracer; be conservative
+            if p.epilogue == L.EPI_RHS and st and st[-1] < need[p.domain]:
+                raise TraceError(f'this law needs more ghost layers than distribute(G, hops={h}) provides '
+                                 f'(valid up to level {st[-1]}, needed {need[p.domain]})')
 
     def _attach_peers(self):
         """Peer-to-peer halo (GDS_B200_HALO=p2p, the default on an NCCL process group): the ranks swap the CUDA-IPC
@@ -323,10 +376,9 @@ class StepEngine:
             mode = 'p2p' if dist.get_backend() == 'nccl' else 'host'
         if mode != 'p2p':
             return
-        if len(part.peers) > 8:
-            return
-        blocks = self._halo_blocks()
-        hx = HaloExchange(part, nblocks=len(blocks))
+        if len(part.peers) > 8 or hasattr(part, 'gid_dom'):
+            return      # deep partitions (edge / face fields) use the host-driven exchange for now
+        blocks = [b for b, _ in self._halo_blocks()]
         handles = (C.c_uint8 * 320)()
         check(lib.gds_system_ipc_export(self.h, handles))
         recv_from = {}
@@ -365,7 +417,9 @@ class StepEngine:
         from .partition import HaloExchange
         part = self.part
         blocks = self._halo_blocks()
-        self.hx = HaloExchange(part, nblocks=len(blocks))
+        self.hx = HaloExchange(part, blocks)
+        if hasattr(part, 'gid_dom'):
+            self._check_ghost_layers()
         self._halo = []
         for which in ('send', 'recv'):
             idx = L.as_i64(self.hx.state_indices(blocks, which))

@@ -46,9 +46,9 @@ class BoundarySpec:
         self.values = None if values is None else np.broadcast_to(np.asarray(values, dtype=float), self.indices.shape).copy()
         self.fun = fun
 
-    def localised(self, part) -> 'BoundarySpec':
-        """the rows of this rank (owned and ghost) of a condition given on GLOBAL node ids"""
-        sel, loc = part.localise(self.indices)
+    def localised(self, part, domain=0) -> 'BoundarySpec':
+        """the rows of this rank (owned and ghost) of a condition given on GLOBAL row ids"""
+        sel, loc = part.localise(self.indices, domain) if hasattr(part, 'gid_dom') else part.localise(self.indices)
         if self.fun is None:
             return BoundarySpec(loc, values=self.values[sel])
         fun = self.fun
@@ -131,8 +131,8 @@ class fds(Observable, Steppable):
         if isinstance(y0, np.ndarray):            # the reference recurses here (fds.py:151-152); arrays are accepted
             arr = np.asarray(y0, dtype=float).ravel()
             part = getattr(getattr(self, '_low', None), 'part', None)
-            if part is not None and arr.size == part.V_global:
-                arr = arr[part.global_ids]            # a global vector: keep this rank's rows
+            if part is not None and arr.size != self.ndim:
+                arr = arr[self.global_ids]            # a global vector: keep this rank's rows
             assert arr.size == self.ndim, 'initial array has the wrong length'
             self.y0_fun = lambda x: arr[self.X[x]]
             keep = np.ones(self.ndim, dtype=bool)
@@ -179,7 +179,7 @@ class fds(Observable, Steppable):
             if isinstance(bc, BoundarySpec):
                 part = getattr(getattr(self, '_low', None), 'part', None)
                 if part is not None:
-                    bc = bc.localised(part)           # indices are global node ids: keep this rank's rows
+                    bc = bc.localised(part, getattr(self, '_domain_code', 0))   # global row ids: keep this rank's rows
                 dyn = bc.fun is not None
                 vals = np.asarray(bc.fun(0.), dtype=float).reshape(bc.indices.size) if dyn else bc.values
                 fun = (lambda t, x: None) if dyn else (lambda x: None)
@@ -355,8 +355,8 @@ class GraphObservable(Observable):
 class gds(fds, GraphObservable):
     def __init__(self, G, Gd: GraphDomain):
         GraphObservable.__init__(self, G, Gd)
-        if self._low.part is not None and Gd is not GraphDomain.nodes:
-            raise NotImplementedError('distributed graphs carry node fields only')
+        if self._low.part is not None and Gd is not GraphDomain.nodes and self._low.part.hops < 2:
+            raise NotImplementedError('edge and face fields need a graph distributed with ghost layers: distribute(G, hops=k), k >= 2')
         fds.__init__(self, self.X)
 
     # ---- distributed graphs: this rank holds rows [owned | ghosts] -----------------------------------------------
@@ -368,13 +368,28 @@ class gds(fds, GraphObservable):
     def global_ids(self):
         """global node id of every row of this field (identity on an undistributed graph)"""
         part = self._low.part
-        return np.arange(self.ndim, dtype=np.int64) if part is None else part.global_ids
+        if part is None:
+            return np.arange(self.ndim, dtype=np.int64)
+        return part.gid_dom[self._domain_code] if hasattr(part, 'gid_dom') else part.global_ids
+
+    @property
+    def owned_mask(self):
+        """which rows of this field this rank owns (all of them on an undistributed graph)"""
+        part = self._low.part
+        if part is None:
+            return np.ones(self.ndim, dtype=bool)
+        if hasattr(part, 'owned_dom'):
+            return part.owned_dom[self._domain_code]
+        return np.arange(self.ndim) < part.n_own
 
     @property
     def y_owned(self):
         """values of the rows this rank owns (all rows on an undistributed graph)"""
-        part = self._low.part
-        return self.y if part is None else self.y[:part.n_own]
+        return np.asarray(self.y)[self.owned_mask]
+
+    def global_index(self, x):
+        """row of point x in the undistributed field"""
+        return int(self.global_ids[self.X[x]])
 
     # ---- operator plumbing ------------------------------------------------------------------------------------
     def _arg(self, y, domain):

@@ -156,8 +156,10 @@ class LoweredGraph:
                     self._set_perm(locality_permutation(V, self.edge_u, self.edge_v, P))
 
     # -- one rank's part of a distributed graph -------------------------------------------------------------
-    def _init_distributed(self, G, rank, world, align):
+    def _init_distributed(self, G, rank, world, align, hops=1):
         from .partition import Partition
+        if hops > 1:
+            return self._init_distributed_deep(G, rank, world, align, hops)
         if self.native and G.kind in ('grid_2d', 'grid') and G.weights is None:
             A, B, C = (G.dims[0], G.dims[1], 1) if G.kind == 'grid_2d' else (G.dims[2], G.dims[1], G.dims[0])
             part = Partition.grid_slab(rank, world, A, B, C)      # closed form: only this slab is ever generated
@@ -190,6 +192,50 @@ class LoweredGraph:
             {(a, b): i for i, (a, b) in enumerate(self._local_edge_labels())})
         self._faces = {}
         self._faces_done = True               # node fields only on distributed graphs
+        self.native_local = True
+
+    def _init_distributed_deep(self, G, rank, world, align, hops):
+        """this rank's part with `hops` ghost layers, its edges and faces (partition.DeepPartition)"""
+        from .partition import DeepPartition, split_bounds
+        if self.native:
+            hg = G.hostgraph(with_faces=G.kind in ('triangular', 'hexagonal'))
+            eu, ev = hg.edges()
+            w = G.weights
+            fp, fn = hg.faces() if hg.F else (None, None)
+            glabels = hg.labels()
+            Vg = hg.V
+        else:
+            gnodes = list(G.nodes())
+            gidx = {v: i for i, v in enumerate(gnodes)}
+            Eg = G.number_of_edges()
+            eu = np.fromiter((gidx[e[0]] for e in G.edges()), dtype=np.int64, count=Eg)
+            ev = np.fromiter((gidx[e[1]] for e in G.edges()), dtype=np.int64, count=Eg)
+            w = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=Eg)
+            # faces of the WHOLE graph, in the reference's order (gds.py:31-36), found before the cut
+            self.nodes, self.edge_u, self.edge_v = gidx, eu.astype(np.int32), ev.astype(np.int32)
+            faces = [tuple(f) for f in G.faces] if hasattr(G, 'faces') else self._walk_faces(G)
+            fp = np.cumsum([0] + [len(f) for f in faces]).astype(np.int64) if faces else None
+            fn = np.fromiter((gidx[n] for f in faces for n in f), dtype=np.int64, count=int(fp[-1])) if faces else None
+            Vg = len(gnodes)
+        part = DeepPartition(rank, world, Vg, eu, ev, w, split_bounds(Vg, world, align), hops, fp, fn)
+        if self.native:
+            lab = glabels[part.global_ids]
+            self.nodes = LazyNodeMap(_LabelSource(lab.astype(np.int64), hg.label_dim))
+        else:
+            self.nodes = {gnodes[int(g)]: i for i, g in enumerate(part.global_ids)}
+        self.part = part
+        self.V, self.E, self.F = part.n_loc, part.E_loc, part.F_loc
+        self.edge_u, self.edge_v = part.edge_u, part.edge_v
+        self.weights = np.ones(self.E) if part.weights is None else part.weights
+        if self.native:
+            self.edges = LazyEdgeMap(self)
+            self._faces = _LocalFaceMap(self, part)
+        else:
+            inv = list(self.nodes.keys())
+            self.edges = bidict({(inv[u], inv[v]): i for i, (u, v) in enumerate(zip(self.edge_u, self.edge_v))})
+            fpl, fnl = part.faces_local
+            self._faces = {tuple(inv[j] for j in fnl[fpl[f]:fpl[f + 1]]): f for f in range(part.F_loc)}
+        self._faces_done = True
         self.native_local = True
 
     def _local_edge_labels(self):
@@ -281,7 +327,8 @@ class LoweredGraph:
         if self._dev is None:
             if self.part is not None:
                 unit = bool(np.all(self.weights == 1.0))
-                self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights)
+                fpl, fnl = self.part.faces_local if self.part.faces_local is not None and self.F else (None, None)
+                self._dev = DeviceGraph(self.ctx, self.V, self.edge_u, self.edge_v, None if unit else self.weights, fpl, fnl)
             elif self.native and self.p2i is None:
                 self._dev = DeviceGraph(self.ctx, self.V, None, None, self.G.weights, hostgraph=self._hg.h)
             elif self.native:
@@ -388,16 +435,41 @@ class _LabelSource:
         return self._labels
 
 
-def distribute(G, rank=None, world=None, align=1):
+def distribute(G, rank=None, world=None, align=1, hops=1):
     """Mark graph G (nx.Graph or NativeGraph) as partitioned over `world` ranks; fields built on it afterwards hold
-    this rank's rows (owned nodes, then one-hop ghosts) and exchange boundary values every stage.  Defaults come from
-    the torch.distributed / torchrun environment.  Node fields only."""
+    this rank's rows and exchange boundary values every stage.  Defaults come from the torch.distributed / torchrun
+    environment.  hops = 1: node fields with one-hop laws (owned nodes, then one layer of ghosts).  hops > 1: `hops`
+    layers of ghost nodes with every edge and face inside them -- edge and face fields, and laws that chain gathers
+    (Hodge Laplacian, self-advection): intermediates are recomputed on the ghost layers, only the state is exchanged."""
     import os
     rank = int(os.environ.get('RANK', '0')) if rank is None else int(rank)
     world = int(os.environ.get('WORLD_SIZE', '1')) if world is None else int(world)
-    G.__dict__['_gds_b200_distribute'] = (rank, world, int(align))
+    G.__dict__['_gds_b200_distribute'] = (rank, world, int(align), int(hops))
     G.__dict__.pop('_gds_b200_lowered', None)
     return G
+
+
+class _LocalFaceMap:
+    """faces of one rank of a distributed native graph, as tuples of node labels -> local face index (lazy)"""
+
+    def __init__(self, low, part):
+        self._low, self._part, self._dict = low, part, None
+
+    def _d(self):
+        if self._dict is None:
+            fp, fn = self._part.faces_local
+            lab = self._low.nodes.labels()
+            key = self._low.nodes._key
+            self._dict = {tuple(key(lab[j]) for j in fn[fp[f]:fp[f + 1]]): f for f in range(fp.size - 1)}
+        return self._dict
+
+    def __len__(self): return self._part.F_loc
+    def __getitem__(self, k): return self._d()[k]
+    def __contains__(self, k): return k in self._d()
+    def __iter__(self): return iter(self._d())
+    def keys(self): return self._d().keys()
+    def items(self): return self._d().items()
+    def values(self): return self._d().values()
 
 
 class LazyNodeMap:

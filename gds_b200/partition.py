@@ -66,6 +66,12 @@ class Partition:
         self.send_counts = np.array([r.size for r in self.send_rows], dtype=np.int64)
         self.send_offsets = np.concatenate([[0], np.cumsum(self.send_counts)])[:-1]
         self.peers = [q for q in range(world) if q != rank and (self.send_counts[q] or self.recv_counts[q])]
+        # the same lists per domain (0 nodes, 1 edges, 3 faces): local rows sent to / filled from every rank
+        self.hops = 1
+        self.send_dom = {0: self.send_rows}
+        self.recv_dom = {0: [self.n_own + self.recv_offsets[q] + np.arange(self.recv_counts[q], dtype=np.int64)
+                             for q in range(world)]}
+        self.faces_local = None
 
     @property
     def global_ids(self) -> np.ndarray:
@@ -127,27 +133,128 @@ class Partition:
         return Partition(rank, world, V, bounds, u, v, None, ghosts=ghosts)
 
 
+def _reach(V, eu, ev, lo, hi, hops):
+    """node levels: 0 for [lo, hi), k for nodes first reached after k hops, -1 beyond `hops`"""
+    level = np.full(V, -1, dtype=np.int64)
+    level[lo:hi] = 0
+    for k in range(1, hops + 1):
+        inside = level >= 0
+        m = inside[eu] != inside[ev]
+        new = np.concatenate([eu[m & ~inside[eu]], ev[m & ~inside[ev]]])
+        level[new[level[new] < 0]] = k
+    return level
+
+
+class DeepPartition(Partition):
+    """One rank's part of a graph with `hops` layers of ghost nodes and every edge / face that lies inside them, for
+    edge and face fields and for laws that chain several gathers: the intermediate vectors (div, curl, upwind
+    aggregates) are recomputed on the ghost layers instead of exchanged, so one exchange of the STATE per stage is
+    enough.  Nodes are owned by index range, an edge by the owner of its tail node, a face by the owner
+    of its first node.  Local edges and faces keep their global relative order (rows sum in the same order as on one
+    GPU); local nodes are [owned | ghosts by global id]."""
+
+    def __init__(self, rank, world, V, eu, ev, weights, bounds, hops, face_ptr=None, face_nodes=None):
+        self.rank, self.world, self.V_global = int(rank), int(world), int(V)
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        lo, hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.lo, self.hi, self.n_own, self.hops = lo, hi, hi - lo, int(hops)
+        eu, ev = np.asarray(eu, dtype=np.int64), np.asarray(ev, dtype=np.int64)
+        F = 0 if face_ptr is None else len(face_ptr) - 1
+        fp = np.zeros(1, dtype=np.int64) if face_ptr is None else np.asarray(face_ptr, dtype=np.int64)
+        fn = np.zeros(0, dtype=np.int64) if face_nodes is None else np.asarray(face_nodes, dtype=np.int64)
+        node_owner = np.searchsorted(self.bounds, np.arange(V), side='right') - 1
+        edge_owner = node_owner[eu]
+        face_owner = node_owner[fn[fp[:-1]]] if F else np.zeros(0, dtype=np.int64)
+
+        def local_sets(r):
+            lev = _reach(V, eu, ev, int(self.bounds[r]), int(self.bounds[r + 1]), self.hops)
+            inn = lev >= 0
+            e_in = inn[eu] & inn[ev]
+            f_in = np.minimum.reduceat(inn[fn].astype(np.int8), fp[:-1]).astype(bool) if F else np.zeros(0, dtype=bool)
+            return lev, inn, e_in, f_in
+        lev, inn, e_in, f_in = local_sets(rank)
+        ghosts = np.nonzero(inn & (node_owner != rank))[0]
+        self.ghosts, self.n_ghost = ghosts, int(ghosts.size)
+        self.n_loc = self.n_own + self.n_ghost
+        g2l = np.full(V, -1, dtype=np.int64)
+        g2l[lo:hi] = np.arange(self.n_own)
+        g2l[ghosts] = self.n_own + np.arange(self.n_ghost)
+        self.edge_gid = np.nonzero(e_in)[0]
+        self.face_gid = np.nonzero(f_in)[0]
+        self.edge_u, self.edge_v = g2l[eu[self.edge_gid]].astype(np.int32), g2l[ev[self.edge_gid]].astype(np.int32)
+        self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)[self.edge_gid]
+        self.E_loc, self.F_loc = int(self.edge_gid.size), int(self.face_gid.size)
+        if F:
+            sizes = (fp[1:] - fp[:-1])[self.face_gid]
+            self.face_ptr_l = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            take = np.concatenate([np.arange(fp[f], fp[f + 1]) for f in self.face_gid]) if self.F_loc else np.zeros(0, dtype=np.int64)
+            self.face_nodes_l = g2l[fn[take]].astype(np.int32)
+            self.max_face = int((fp[1:] - fp[:-1]).max())
+        else:
+            self.face_ptr_l, self.face_nodes_l, self.max_face = np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), 0
+        self.level_node = lev[self.global_ids]
+        # rows filled from / sent to every rank, per domain, in global order inside an owner
+        gid = {0: self.global_ids, 1: self.edge_gid, 3: self.face_gid}
+        own = {0: node_owner[gid[0]], 1: edge_owner[gid[1]], 3: face_owner[gid[3]] if F else np.zeros(0, dtype=np.int64)}
+        self.gid_dom = gid
+        self.owned_dom = {d: own[d] == rank for d in gid}
+        self.recv_dom = {d: [np.nonzero(own[d] == q)[0].astype(np.int64) if q != rank else np.zeros(0, dtype=np.int64)
+                             for q in range(world)] for d in gid}
+        self.send_dom = {d: [np.zeros(0, dtype=np.int64) for _ in range(world)] for d in gid}
+        e_g2l = np.full(eu.size, -1, dtype=np.int64); e_g2l[self.edge_gid] = np.arange(self.E_loc)
+        f_g2l = np.full(F, -1, dtype=np.int64); f_g2l[self.face_gid] = np.arange(self.F_loc)
+        for q in range(world):
+            if q == rank:
+                continue
+            _, inn_q, e_q, f_q = local_sets(q)
+            self.send_dom[0][q] = g2l[np.nonzero(inn_q & (node_owner == rank))[0]]
+            self.send_dom[1][q] = e_g2l[np.nonzero(e_q & (edge_owner == rank))[0]]
+            if F:
+                self.send_dom[3][q] = f_g2l[np.nonzero(f_q & (face_owner == rank))[0]]
+        for d in gid:
+            for q in range(world):
+                assert np.all(self.send_dom[d][q] >= 0), 'a rank must hold every row it owns'
+        self.send_rows = self.send_dom[0]
+        self.peers = [q for q in range(world) if q != rank and
+                      any(self.send_dom[d][q].size or self.recv_dom[d][q].size for d in gid)]
+        self.faces_local = (self.face_ptr_l, self.face_nodes_l)
+
+    def localise(self, global_idx, domain=0):
+        g = np.asarray(global_idx, dtype=np.int64)
+        ids = self.gid_dom[domain]
+        order = np.argsort(ids, kind='stable')
+        pos = np.minimum(np.searchsorted(ids[order], g), max(ids.size - 1, 0))
+        sel = (ids[order][pos] == g) if ids.size else np.zeros(g.shape, dtype=bool)
+        return sel, order[pos][sel]
+
+
 class HaloExchange:
     """per-stage exchange of boundary values: point-to-point over torch.distributed (NCCL on GPUs -> NVLink;
-    gloo in the CPU tests).  `send` / `recv` are contiguous tensors laid out by peer (Partition.send_offsets /
-    recv_offsets), one segment of `nblocks` values per listed row."""
+    gloo in the CPU tests).  `blocks` lists the state blocks that travel, as (offset, domain) pairs (a bare offset is a
+    node block); `send` / `recv` are contiguous tensors laid out by peer and, inside a peer, by block."""
 
-    def __init__(self, part: Partition, nblocks: int = 1, group=None):
-        self.part, self.nblocks, self.group = part, int(nblocks), group
-        self.n_send = int(part.send_counts.sum()) * self.nblocks
-        self.n_recv = int(part.recv_counts.sum()) * self.nblocks
+    def __init__(self, part: Partition, blocks=None, nblocks=None, group=None):
+        if blocks is None:
+            blocks = [0] * int(nblocks if nblocks is not None else 1)
+        self.part, self.group = part, group
+        self.blocks = [(b, 0) if np.isscalar(b) else (int(b[0]), int(b[1])) for b in blocks]
+        self.nblocks = len(self.blocks)
+        w = part.world
+        self.send_sizes = np.array([sum(part.send_dom[d][q].size for _, d in self.blocks) for q in range(w)], dtype=np.int64)
+        self.recv_sizes = np.array([sum(part.recv_dom[d][q].size for _, d in self.blocks) for q in range(w)], dtype=np.int64)
+        self.send_off = np.concatenate([[0], np.cumsum(self.send_sizes)])[:-1]
+        self.recv_off = np.concatenate([[0], np.cumsum(self.recv_sizes)])[:-1]
+        self.n_send, self.n_recv = int(self.send_sizes.sum()), int(self.recv_sizes.sum())
 
     def state_indices(self, block_offsets, which):
         """positions in the state vector of the rows sent ('send') or of the ghost rows filled ('recv'), grouped by
-        peer and, inside a peer, by state block"""
+        peer and, inside a peer, by state block (`block_offsets`: offsets, or (offset, domain) pairs)"""
         p, out = self.part, []
+        blocks = [(b, 0) if np.isscalar(b) else (int(b[0]), int(b[1])) for b in block_offsets]
+        lists = p.send_dom if which == 'send' else p.recv_dom
         for q in range(p.world):
-            if which == 'send':
-                rows = p.send_rows[q]
-            else:
-                rows = p.n_own + p.recv_offsets[q] + np.arange(p.recv_counts[q], dtype=np.int64)
-            for off in block_offsets:
-                out.append(off + rows)
+            for off, d in blocks:
+                out.append(off + lists[d][q])
         return np.concatenate(out).astype(np.int64) if out else np.zeros(0, dtype=np.int64)
 
     def exchange(self, send, recv):
@@ -161,10 +268,10 @@ class HaloExchange:
                 r.wait()
             recv.copy_(recv_h)
             return []
-        p, nb, ops = self.part, self.nblocks, []
+        p, ops = self.part, []
         for q in p.peers:
-            so, sc = int(p.send_offsets[q]) * nb, int(p.send_counts[q]) * nb
-            ro, rc = int(p.recv_offsets[q]) * nb, int(p.recv_counts[q]) * nb
+            so, sc = int(self.send_off[q]), int(self.send_sizes[q])
+            ro, rc = int(self.recv_off[q]), int(self.recv_sizes[q])
             if rc:
                 ops.append(dist.P2POp(dist.irecv, recv[ro:ro + rc], q, self.group))
             if sc:

@@ -49,9 +49,8 @@ def main():
                     f = k[2:]
                     got = np.full_like(single[k], np.nan)
                     for r in range(world):
-                        n_own = int(gathered[r][mode][f'nown_{f}'][0])
-                        gid = gathered[r][mode][f'gid_{f}'][:n_own]
-                        got[:, gid] = gathered[r][mode][k][:, :n_own]
+                        own, gid = gathered[r][mode][f'own_{f}'], gathered[r][mode][f'gid_{f}']
+                        got[:, gid[own]] = gathered[r][mode][k][:, own]
                     same = np.array_equal(got, single[k])
                     ok = ok and same
                     print(f'{name:12s} {mode:5s} {k}: bit-identical to one GPU: {same}'

@@ -12,12 +12,16 @@ from adaptors import oracle_api, product_api, rel_l2
 
 pytestmark = pytest.mark.gpu
 
+# name -> (case, alignment of the cuts, ghost layers).  The last two carry edge fields and two-hop laws: they need the deep
+# partition (hex faces: 6 nodes -> 4 layers; triangles: 2).
 CASES = {
-    'heat': (lambda api: cases.case_heat_c1(api, n=24, nsteps=30, every=15), 24),
-    'heat_mixed': (cases.case_heat_mixed, 9),
-    'reaction_diffusion_grid': (lambda api: _rd_grid(api), 10),
-    'wave': (lambda api: cases.case_wave_c5(api, dims=(5, 6, 9), nsteps=20, every=10), 30),
-    'cml': (lambda api: cases.case_cml_c4(api, n=600, iters=12, every=6), 1),
+    'heat': (lambda api: cases.case_heat_c1(api, n=24, nsteps=30, every=15), 24, 1),
+    'heat_mixed': (cases.case_heat_mixed, 9, 1),
+    'reaction_diffusion_grid': (lambda api: _rd_grid(api), 10, 1),
+    'wave': (lambda api: cases.case_wave_c5(api, dims=(5, 6, 9), nsteps=20, every=10), 30, 1),
+    'cml': (lambda api: cases.case_cml_c4(api, n=600, iters=12, every=6), 1, 1),
+    'hex_advdiff': (lambda api: cases.case_hex_advdiff_c2(api, m=8, n=10, nsteps=12, every=6), 1, 4),
+    'ns_cavity': (lambda api: cases.case_ns_cavity_c3(api, m=8, n=12, nsteps=12, every=6), 1, 2),
 }
 
 
@@ -38,8 +42,8 @@ def _worker(rank, world, port, name, ret):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         import gds_b200
-        fn, align = CASES[name]
-        cases.GRAPH_HOOK = lambda G: gds_b200.distribute(G, rank, world, align=align)
+        fn, align, hops = CASES[name]
+        cases.GRAPH_HOOK = lambda G: gds_b200.distribute(G, rank, world, align=align, hops=hops)
         out = fn(product_api())
         ret[rank] = {k: np.asarray(v) for k, v in out.items()}
     finally:
@@ -54,7 +58,7 @@ def test_partitioned_matches_undistributed(name, world):
     port = 29500 + (os.getpid() + hash(name) + world) % 1500
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, name, ret), nprocs=world, join=True)
-    fn, _ = CASES[name]
+    fn = CASES[name][0]
     want = fn(oracle_api())
     single = fn(product_api())
     keys = [k for k in want if k.startswith('y_')]
@@ -62,12 +66,10 @@ def test_partitioned_matches_undistributed(name, world):
         f = k[2:]
         got = np.full_like(want[k], np.nan)
         for r in range(world):
-            n_own = int(ret[r][f'nown_{f}'][0])
-            gid = ret[r][f'gid_{f}'][:n_own]
-            got[:, gid] = ret[r][k][:, :n_own]
+            own, gid = ret[r][f'own_{f}'], ret[r][f'gid_{f}']
+            got[:, gid[own]] = ret[r][k][:, own]
             # ghost rows hold their owner's values after every step
-            ghost = ret[r][f'gid_{f}'][n_own:]
-            assert np.array_equal(ret[r][k][:, n_own:], single[k][:, ghost])
+            assert np.array_equal(ret[r][k][:, ~own], single[k][:, gid[~own]])
         assert np.all(np.isfinite(got))
         assert np.array_equal(got, single[k]), (name, k, 'partitioned result differs from the one-GPU result')
         for i in range(want[k].shape[0]):

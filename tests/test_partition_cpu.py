@@ -176,3 +176,64 @@ def test_peer_push_lists_fill_every_ghost_row():
         gid = p.global_ids
         for b in range(2):
             assert np.array_equal(state[r][blocks[r][b]:blocks[r][b] + p.n_loc], xg[b][gid])
+
+
+def _hodge1(V, eu, ev, faces, y):
+    """-B1^T B1 y - B2^T B2 y with unit weights, faces as lists of node ids (the sign rule of gds.py:227-236)"""
+    import scipy.sparse as sp
+    E = eu.size
+    ar = np.arange(E)
+    B1 = sp.csr_matrix((np.concatenate([-np.ones(E), np.ones(E)]), (np.concatenate([eu, ev]), np.concatenate([ar, ar]))),
+                       shape=(V, E))
+    eid = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(eu, ev))}
+    rows, cols, vals = [], [], []
+    for fi, f in enumerate(faces):
+        k = len(f)
+        for i in range(k):
+            a, b = int(f[i]), int(f[(i + 1) % k])
+            if (a, b) in eid:
+                rows.append(fi); cols.append(eid[(a, b)]); vals.append(1.0)
+            elif (b, a) in eid:
+                rows.append(fi); cols.append(eid[(b, a)]); vals.append(-1.0)
+    B2 = sp.csr_matrix((vals, (rows, cols)), shape=(max(len(faces), 1), E))
+    return -(B1.T @ (B1 @ y)) - (B2.T @ (B2 @ y))
+
+
+@pytest.mark.parametrize('kind,dims,hops', [('hexagonal', (5, 6), 4), ('triangular', (6, 8), 2)])
+@pytest.mark.parametrize('world', [2, 3])
+def test_deep_partition_recomputes_two_hop_operators_on_the_ghost_layers(kind, dims, hops, world):
+    """edge fields on a partitioned graph: with enough ghost layers the Hodge-1 Laplacian of the OWNED edges needs no
+    exchange of intermediates -- every rank evaluates it on its local graph after one exchange of the edge values"""
+    from gds_b200.partition import DeepPartition
+    hg = NativeGraph(kind, *dims).hostgraph(with_faces=True)
+    eu, ev = (a.astype(np.int64) for a in hg.edges())
+    fp, fn = hg.faces()
+    faces = [fn[fp[i]:fp[i + 1]] for i in range(fp.size - 1)]
+    V, E = hg.V, eu.size
+    y = np.random.default_rng(4).standard_normal(E)
+    want = _hodge1(V, eu, ev, faces, y)
+    bounds = split_bounds(V, world)
+    parts = [DeepPartition(r, world, V, eu, ev, None, bounds, hops, fp, fn) for r in range(world)]
+    # ownership partitions every domain, halo lists are symmetric
+    for d, n in ((0, V), (1, E), (3, len(faces))):
+        owned = np.concatenate([p.gid_dom[d][p.owned_dom[d]] for p in parts])
+        assert np.array_equal(np.sort(owned), np.arange(n))
+        for r, p in enumerate(parts):
+            for q in range(world):
+                if q != r:
+                    assert np.array_equal(p.gid_dom[d][p.send_dom[d][q]], parts[q].gid_dom[d][parts[q].recv_dom[d][r]])
+    # exchange the edge values, evaluate locally, compare the owned rows
+    local = []
+    for p in parts:
+        v = np.full(p.E_loc, np.nan)
+        v[p.owned_dom[1]] = y[p.edge_gid[p.owned_dom[1]]]
+        local.append(v)
+    for r, p in enumerate(parts):
+        for q in p.peers:
+            local[q][parts[q].recv_dom[1][r]] = local[r][p.send_dom[1][q]]
+    for p, v in zip(parts, local):
+        assert np.array_equal(v, y[p.edge_gid])
+        lf = [p.face_nodes_l[p.face_ptr_l[i]:p.face_ptr_l[i + 1]] for i in range(p.F_loc)]
+        got = _hodge1(p.n_loc, p.edge_u.astype(np.int64), p.edge_v.astype(np.int64), lf, v)
+        own = p.owned_dom[1]
+        assert np.allclose(got[own], want[p.edge_gid[own]], rtol=0, atol=1e-12)
