@@ -93,25 +93,30 @@ def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
     """BASELINE config 2: edge diffusion (Hodge-1 Laplacian, Dirichlet 0 on top/bottom boundary edges) coupled with node
     advection-diffusion (Neumann -0.1 on the top row) on hexagonal_lattice_graph(n, n), RK4 h = 1e-3 (tests/cases.py
     case_hex_advdiff_c2 is the same law at small size, checked against the reference)."""
-    assert world == 1 and not weighted
+    assert not weighted
     h, nu, kappa = 1e-3, 0.1, 0.05
     if native:
         import gds_b200
-        G = gds_b200.NativeGraph('hexagonal', n, n)
+        # with `world` ranks: hexagonal_lattice_graph(n, n*world) cut into node-index ranges (vertical strips), 4 ghost
+        # layers (hexagons: the edge <- face gather needs 3), edge and node state exchanged after every stage
+        G = gds_b200.NativeGraph('hexagonal', n, n * world)
+        if world > 1:
+            gds_b200.distribute(G, rank, world, hops=4)
         u, c = api.edge_gds(G), api.node_gds(G)
         hg = G.hostgraph(with_faces=True)
         pos, (eu, ev) = hg.pos(), hg.edges()
         api.evolve(u, dydt=lambda t, y: nu * u.laplacian(y), max_step=h)
         api.evolve(c, dydt=lambda t, y: -c.advect(u) + kappa * c.laplacian(y), max_step=h)
-        u.set_initial(y0=0.1 * np.random.default_rng(0).standard_normal(u.ndim))
-        c.set_initial(y0=np.random.default_rng(1).random(c.ndim))
+        u.set_initial(y0=0.1 * np.random.default_rng(0).standard_normal(hg.E))
+        c.set_initial(y0=np.random.default_rng(1).random(hg.V))
         hh = math.sqrt(3) / 2
         lo, hi = pos[:, 1].min(), pos[:, 1].max()
         bnd = (pos[:, 1] < lo + 0.6 * hh) | (pos[:, 1] > hi - 0.6 * hh)
         u.set_constraints(dirichlet=gds_b200.BoundarySpec(_edges_inside(eu, ev, bnd), values=0.0))
         c.set_constraints(neumann=gds_b200.BoundarySpec(np.nonzero(pos[:, 1] > hi - 1e-9)[0], values=-0.1))
         sysobj = api.couple({'u': u, 'c': c})
-        V, E, F = hg.V, hg.E, hg.F
+        V, E = int(c.owned_mask.sum()), int(u.owned_mask.sum())      # this rank's share
+        F = hg.F // world
     else:
         import cases
         import networkx as nx
@@ -467,7 +472,9 @@ def gpu_arm(args):
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
     fields = prob['fields']
-    sizes = [fl.ndim if getattr(fl, 'partition', None) is None else fl.partition.n_own for fl in fields]
+    # host buffers per field: the rows this rank owns (the whole local vector where owned rows are not a prefix)
+    sizes = [fl.ndim if (getattr(fl, 'partition', None) is None or hasattr(fl.partition, 'gid_dom')) else fl.partition.n_own
+             for fl in fields]
     n = sum(s_ * fl._order() for s_, fl in zip(sizes, fields))
     host_in = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
     host_out = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
@@ -524,7 +531,7 @@ def gpu_arm(args):
             'data': 'synthetic',
             'config': {'workload': WORKLOAD_NAME[0], 'scheme': SCHEME[0],
                        'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
-                       'parallelism': (f'{world} graph partitions (contiguous slabs), halo exchange of boundary node values '
+                       'parallelism': (f'{world} graph partitions (contiguous node ranges), halo exchange of boundary values '
                                        f'after every RK stage: ' + HALO[0]) if world > 1 else 'single GPU',
                        'dof_stage_evals_per_sec': 4 * value, 'build_seconds': t_build},
             'roofline': roof, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,

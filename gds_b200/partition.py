@@ -187,7 +187,9 @@ class DeepPartition(Partition):
         if F:
             sizes = (fp[1:] - fp[:-1])[self.face_gid]
             self.face_ptr_l = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-            take = np.concatenate([np.arange(fp[f], fp[f + 1]) for f in self.face_gid]) if self.F_loc else np.zeros(0, dtype=np.int64)
+            # positions of the kept faces' nodes in fn: each face's start repeated, plus the running offset inside it
+            take = (np.repeat(fp[self.face_gid] - self.face_ptr_l[:-1], sizes) + np.arange(int(self.face_ptr_l[-1]))
+                    if self.F_loc else np.zeros(0, dtype=np.int64))
             self.face_nodes_l = g2l[fn[take]].astype(np.int32)
             self.max_face = int((fp[1:] - fp[:-1]).max())
         else:
