@@ -138,9 +138,11 @@ def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
     per_step = 4 * ((64 * E + 20 * V + 44 * F) + (72 * E + 28 * V)) + 136 * (E + V)
     return dict(stepper=sysobj.stepper, fields=[u, c], h=h, n_state=E + V, V=V, E=E, F=F, bytes_per_step=per_step,
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
-                kernel='all passes of one RK stage (row-program interpreter: 2 node passes, 1 face pass, 1 edge pass)',
-                name=f'edge diffusion + node advection-diffusion, RK4 h=1e-3, hexagonal_lattice_graph({n},{n}) '
-                     f'(V={V}, E={E}, F={F}), Dirichlet edges / Neumann nodes')
+                kernel='all passes of one RK stage (terms_kernel: node divergence, face curl, edge RHS; lapT_kernel: '
+                       'node RHS)',
+                name=f'edge diffusion + node advection-diffusion, RK4 h=1e-3, hexagonal_lattice_graph({n},{n * world}) '
+                     + (f'in {world} deep partitions (4 ghost layers), per rank ' if world > 1 else '')
+                     + f'(V={V}, E={E}, F={F}), Dirichlet edges / Neumann nodes')
 
 
 def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):

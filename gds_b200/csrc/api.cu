@@ -863,8 +863,8 @@ extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int3
   }
   GDS_CUDA(cudaMalloc((void**)&s->d_counter, 2 * sizeof(int64_t)));   // [step, block ticket of the tail kernel]
   GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(int64_t), c->stream));
-  GDS_CUDA(cudaMalloc((void**)&s->d_flags, 64 * sizeof(int64_t)));
-  GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, 64 * sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaMalloc((void**)&s->d_flags, 128 * sizeof(int64_t)));
+  GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, 128 * sizeof(int64_t), c->stream));
   GDS_CUDA(cudaMalloc((void**)&s->d_p2p_epoch, 2 * sizeof(int64_t)));
   GDS_CUDA(cudaMemsetAsync(s->d_p2p_epoch, 0, 2 * sizeof(int64_t), c->stream));
   *out = s;
@@ -1021,7 +1021,8 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
     GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
     if (ph.special) pp.n_rows = ph.sp_n;
     // peer-to-peer halo: ghost rows of the state are written by their owners only
-    if (s->p2p && ph.epilogue == GDS_EPI_RHS && !ph.special) pp.n_rows = std::min<int64_t>(s->owned_rows, pp.n_rows);
+    if (s->p2p && s->owned_rows >= 0 && ph.epilogue == GDS_EPI_RHS && !ph.special)
+      pp.n_rows = std::min<int64_t>(s->owned_rows, pp.n_rows);
     pp.row0 = std::min<int64_t>(row0, pp.n_rows);
     if (row1 >= 0) pp.n_rows = std::min<int64_t>(row1, pp.n_rows);
     pp.steptab = s->d_steptab; pp.step_counter = s->d_counter;
@@ -1077,11 +1078,12 @@ static int enqueue_exchange(gds_system* s, int which) {
   pu.n_peers = wa.n_peers = (int32_t)s->peers.size();
   pu.src = mine[which];
   pu.src_idx = s->d_p2p_src; pu.dst_idx = s->d_p2p_dst;
-  pu.epoch = s->d_p2p_epoch; wa.epoch = s->d_p2p_epoch; wa.err = s->d_p2p_epoch + 1;
+  pu.epoch = s->d_p2p_epoch; wa.epoch = s->d_p2p_epoch; wa.err = s->d_p2p_epoch + 1; pu.err = s->d_p2p_epoch + 1;
   for (size_t q = 0; q < s->peers.size(); ++q) {
     const gds_system::Peer& pr = s->peers[q];
     pu.dst[q] = (double*)pr.mapped[which];
     pu.flag[q] = (int64_t*)pr.mapped[4] + s->my_rank;
+    pu.ready[q] = s->d_flags + 64 + pr.rank;
     pu.s0[q] = pr.send0; pu.s1[q] = pr.send1;
     wa.flag[q] = s->d_flags + pr.rank;
   }
@@ -1357,7 +1359,6 @@ extern "C" int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_p
   if (s->finalized) GDS_FAIL("attach the peers before gds_system_finalize (the exchange is part of the captured step)");
   if (n_peers < 0 || n_peers > GDS_MAX_PEERS) GDS_FAIL("at most 8 neighbouring ranks");
   if (my_rank < 0 || my_rank >= 64) GDS_FAIL("rank outside the flag table");
-  if (owned_rows < 0) GDS_FAIL("bad owned_rows");
   GDS_CUDA(cudaSetDevice(s->ctx->device));
   s->peers.clear();
   void* mine[5] = {s->Y[0], s->Y[1], s->XS[0], s->XS[1], s->d_flags};

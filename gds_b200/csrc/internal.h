@@ -299,7 +299,7 @@ struct gds_system {
   bool p2p = false;
   int my_rank = 0;
   int64_t owned_rows = -1;        // RHS passes stop here: ghost rows are written by the peers only
-  int64_t* d_flags = nullptr;     // [64] arrival flags, slot = sender's rank (written by peers over NVLink)
+  int64_t* d_flags = nullptr;     // [128] arrival flags (slot = sender's rank) and ready flags (64 + rank), written by peers
   int64_t* d_p2p_epoch = nullptr; // [2]: exchanges sent so far; error flag of the wait kernel
   int64_t* d_p2p_src = nullptr;
   int64_t* d_p2p_dst = nullptr;
@@ -310,7 +310,9 @@ struct PushParams {
   int32_t n_peers;
   const double* src;                 // my stage output
   double* dst[GDS_MAX_PEERS];        // the same logical buffer on each peer
-  int64_t* flag[GDS_MAX_PEERS];      // peer's arrival flag for this rank
+  int64_t* flag[GDS_MAX_PEERS];      // peer's arrival flag for this rank (its ready flag is 64 slots further)
+  const int64_t* ready[GDS_MAX_PEERS];  // this rank's ready flag written by each peer
+  int64_t* err;
   int64_t s0[GDS_MAX_PEERS], s1[GDS_MAX_PEERS];
   const int64_t* src_idx;
   const int64_t* dst_idx;

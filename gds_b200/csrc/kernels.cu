@@ -1162,8 +1162,9 @@ int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* a
 
 // ---------------------------------------------------------------------------------------------------
 // peer-to-peer halo exchange over NVLink, inside the captured step.
-// push: one block per neighbour stores this rank's boundary values straight into the neighbour's ghost rows
-// (peer-mapped memory), fences, and publishes the exchange number in the neighbour's flag slot.
+// push: one block per neighbour announces that this rank's stage is done (ready flag), waits for the neighbour's, stores
+// this rank's boundary values straight into the neighbour's ghost rows (peer-mapped memory), fences, and publishes the
+// exchange number in the neighbour's arrival flag.
 // wait: right after the push, one thread per neighbour polls the local flag slot until the neighbour's values of the
 // same exchange have arrived; only then may the next stage gather from the ghost rows.
 // ---------------------------------------------------------------------------------------------------
@@ -1171,6 +1172,21 @@ __global__ void __launch_bounds__(1024) push_kernel(const __grid_constant__ Push
   const int q = blockIdx.x;
   const double* __restrict__ src = p.src;
   double* dst = p.dst[q];
+  // Handshake before writing: the neighbour's own stage kernel may still be storing (meaningless) values into its ghost
+  // rows, so it first announces "my stage of this exchange is done" (ready flag, slot 64 + rank), and the push waits for it.
+  if (threadIdx.x == 0) {
+    const int64_t e = *p.epoch + 1;
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q] + 64), "l"(e) : "memory");
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int64_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.ready[q]) : "memory");
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { *p.err = 1 + q; break; }
+    } while (seen < e);
+  }
+  __syncthreads();
   for (int64_t i = p.s0[q] + threadIdx.x; i < p.s1[q]; i += 1024) dst[p.dst_idx[i]] = src[p.src_idx[i]];
   __threadfence_system();
   __syncthreads();

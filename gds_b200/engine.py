@@ -376,22 +376,22 @@ class StepEngine:
             mode = 'p2p' if dist.get_backend() == 'nccl' else 'host'
         if mode != 'p2p':
             return
-        if len(part.peers) > 8 or hasattr(part, 'gid_dom'):
-            return      # deep partitions (edge / face fields) use the host-driven exchange for now
-        blocks = [b for b, _ in self._halo_blocks()]
+        if len(part.peers) > 8:
+            return
+        deep = hasattr(part, 'gid_dom')
+        blocks = self._halo_blocks()
+        hx = HaloExchange(part, blocks)
         handles = (C.c_uint8 * 320)()
         check(lib.gds_system_ipc_export(self.h, handles))
-        recv_from = {}
-        for q in part.peers:
-            rows = part.n_own + part.recv_offsets[q] + np.arange(part.recv_counts[q], dtype=np.int64)
-            recv_from[q] = np.concatenate([off + rows for off in blocks]).astype(np.int64)
+        recv_from = {q: np.concatenate([off + part.recv_dom[d][q] for off, d in blocks]).astype(np.int64)
+                     for q in part.peers}
         mine = {'handles': bytes(handles), 'recv_from': recv_from}
         everyone = [None] * part.world
         dist.all_gather_object(everyone, mine)
         peers = [q for q in part.peers]
         src, dst, ptr_, hbytes = [], [], [0], b''
         for q in peers:
-            s_idx = np.concatenate([off + part.send_rows[q] for off in blocks]).astype(np.int64)
+            s_idx = np.concatenate([off + part.send_dom[d][q] for off, d in blocks]).astype(np.int64)
             d_idx = np.asarray(everyone[q]['recv_from'][part.rank], dtype=np.int64)
             assert s_idx.size == d_idx.size, 'halo lists of two neighbouring ranks disagree'
             src.append(s_idx); dst.append(d_idx); ptr_.append(ptr_[-1] + s_idx.size)
@@ -401,8 +401,10 @@ class StepEngine:
         ptr_arr = L.as_i64(np.asarray(ptr_))
         pr = L.as_i32(np.asarray(peers, dtype=np.int32))
         hb = (C.c_uint8 * max(1, len(hbytes))).from_buffer_copy(hbytes or b'\0')
+        # owned rows are a prefix of every block only in the node-only partitions; deep ones let the passes run over
+        # the ghost rows (the push handshake keeps what the owners send)
         check(lib.gds_system_p2p_attach(self.h, part.rank, len(peers), ptr(pr), hb, ptr(ptr_arr), ptr(src), ptr(dst),
-                                        part.n_own))
+                                        -1 if deep else part.n_own))
         self.p2p = True
 
     def p2p_status(self):

@@ -26,17 +26,20 @@ def main():
     import gds_b200
     from adaptors import product_api
     CASES = {
-        'heat': (lambda api: cases.case_heat_c1(api, n=96, nsteps=40, every=20), 96),
-        'heat_mixed': (cases.case_heat_mixed, 9),
-        'wave': (lambda api: cases.case_wave_c5(api, dims=(7, 8, 24), nsteps=20, every=10), 56),
-        'cml': (lambda api: cases.case_cml_c4(api, n=3000, iters=12, every=6), 1),
+        'heat': (lambda api: cases.case_heat_c1(api, n=96, nsteps=40, every=20), 96, 1),
+        'heat_mixed': (cases.case_heat_mixed, 9, 1),
+        'wave': (lambda api: cases.case_wave_c5(api, dims=(7, 8, 24), nsteps=20, every=10), 56, 1),
+        'cml': (lambda api: cases.case_cml_c4(api, n=3000, iters=12, every=6), 1, 1),
+        # edge / face fields: deep partitions (several ghost layers, owned rows not a prefix)
+        'hex_advdiff': (lambda api: cases.case_hex_advdiff_c2(api, m=8, n=10, nsteps=12, every=6), 1, 4),
+        'ns_cavity': (lambda api: cases.case_ns_cavity_c3(api, m=8, n=12, nsteps=12, every=6), 1, 2),
     }
     ok = True
-    for name, (fn, align) in CASES.items():
+    for name, (fn, align, hops) in CASES.items():
         results = {}
         for mode in ('p2p', 'nccl'):
             os.environ['GDS_B200_HALO'] = mode
-            cases.GRAPH_HOOK = lambda G: gds_b200.distribute(G, rank, world, align=align)
+            cases.GRAPH_HOOK = lambda G: gds_b200.distribute(G, rank, world, align=align, hops=hops)
             out = fn(product_api())
             cases.GRAPH_HOOK = None
             results[mode] = {k: np.asarray(v) for k, v in out.items()}
