@@ -37,8 +37,8 @@ OP = dict(
     ADD=16, SUB=17, MUL=18, DIV=19, POW=20, MAX=21, MIN=22, ATAN2=23,
     NEG=32, ABS=33, SIGN=34, SQRT=35, EXP=36, LOG=37, SIN=38, COS=39, TAN=40, TANH=41, SINH=42, COSH=43, ATAN=44,
     SQUARE=45, RECIP=46, POWI=47,
-    N_LAP=64, N_BDOT=65, N_INFLUX=66, N_OUTFLUX=67, N_ADVECT=68, N_LIE=69, N_EAGG=70,
-    E_GRADT=80, E_CURLT=81, E_ADVFIN=82, F_CURL=96,
+    N_LAP=64, N_BDOT=65, N_INFLUX=66, N_OUTFLUX=67, N_ADVECT=68, N_LIE=69, N_EAGG=70, N_EAGGT=71,
+    E_GRADT=80, E_CURLT=81, E_ADVFIN=82, E_ADVS1=83, F_CURL=96,
 )
 MAX_CODE, MAX_IMM, MAX_VEC, MAX_MASK, MAX_OUT, MAX_STACK = 96, 24, 16, 6, 4, 6
 

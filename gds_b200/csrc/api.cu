@@ -487,11 +487,15 @@ static int copy_pass(const gds_pass_desc* p, PassHost& ph) {
         if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
         if ((int)a >= p->n_vec || (int)b >= p->n_out) GDS_FAIL("operand index out of range");
         break;
+      case GDS_OP_N_EAGGT:
+        if (p->domain != GDS_NODES) GDS_FAIL("node gather in a non-node pass");
+        if ((int)a >= p->n_vec || (int)b >= p->n_out || (int)(ins >> 24) >= p->n_vec) GDS_FAIL("operand index out of range");
+        break;
       case GDS_OP_E_GRADT: case GDS_OP_E_CURLT:
         if (p->domain != GDS_EDGES) GDS_FAIL("edge gather in a non-edge pass");
         if ((int)a >= p->n_vec) GDS_FAIL("vector operand index out of range");
         push = 1; break;
-      case GDS_OP_E_ADVFIN:
+      case GDS_OP_E_ADVFIN: case GDS_OP_E_ADVS1:
         if (p->domain != GDS_EDGES) GDS_FAIL("edge gather in a non-edge pass");
         if ((int)a >= p->n_vec || (int)b >= p->n_vec) GDS_FAIL("vector operand index out of range");
         push = 1; break;

@@ -213,6 +213,45 @@ __device__ __forceinline__ double e_curlt(const GraphDev& g, const double* __res
   return UNITW ? acc : ld_stream_f64(g.e_omega + row) * acc;
 }
 
+// Tangent of the four aggregates in direction v with the flow directions (signs of y) held fixed -- what autograd sees
+// through sign() and relu() in advect_torch (gds.py:372-395): P1' = sum in*w*s_f*v_f, P2' = sum in*w*2*y_f*v_f, same for Q.
+template <bool UNITW>
+__device__ __forceinline__ double4 n_eaggt(const GraphDev& g, const double* __restrict__ y, const double* __restrict__ v,
+                                           int64_t row, int lane) {
+  SliceRange s = slice_of(g.n_soff, row, lane);
+  double p1 = 0, p2 = 0, q1 = 0, q2 = 0;
+#pragma unroll 2
+  for (uint32_t j = 0; j < s.width; ++j) {
+    int64_t slot = s.base + (int64_t)j * GDS_SLICE;
+    int32_t pk = ld_stream_i32(g.n_edge + slot);
+    double wj = UNITW ? ((pk >= 0) ? 1.0 : 0.0) : ld_stream_f64(g.n_w + slot);
+    int32_t e = (pk >= 0) ? (pk >> 1) : 0;
+    double sg = (pk & 1) ? 1.0 : -1.0;
+    double ye = ld_gather(y + e), ve = ld_gather(v + e);
+    double se = sgn(ye);
+    double dir = sg * se;
+    double a1 = wj * (se * ve), a2 = wj * (2.0 * ye * ve);
+    p1 += (dir > 0.0) ? a1 : 0.0;
+    p2 += (dir > 0.0) ? a2 : 0.0;
+    q1 += (dir < 0.0) ? a1 : 0.0;
+    q2 += (dir < 0.0) ? a2 : 0.0;
+  }
+  double d = __ldg(g.n_dinv + row);
+  return make_double4(d * p1, d * p2, d * q1, d * q2);
+}
+// S1_e = w_e (d_t P1_t - d_h Q1_h): the factor of y_e in the self-advection (0 where y_e = 0)
+template <bool UNITW>
+__device__ __forceinline__ double e_advs1(const GraphDev& g, const double* __restrict__ y,
+                                          const double* __restrict__ agg, int64_t row) {
+  double ye = ld_gather(y + row);
+  double s = sgn(ye);
+  int32_t u = ld_stream_i32(g.e_u + row), v = ld_stream_i32(g.e_v + row);
+  int32_t t = (s > 0.0) ? u : v, h = (s > 0.0) ? v : u;
+  const double2 at = __ldg(reinterpret_cast<const double2*>(agg) + 2 * (int64_t)t);
+  const double2 ah = __ldg(reinterpret_cast<const double2*>(agg) + 2 * (int64_t)h + 1);
+  double we = UNITW ? 1.0 : ld_stream_f64(g.e_w + row);
+  return (s == 0.0) ? 0.0 : we * (at.x - ah.x);
+}
 template <bool UNITW>
 __device__ __forceinline__ double e_advfin(const GraphDev& g, const double* __restrict__ y,
                                            const double* __restrict__ agg, int64_t row) {
@@ -395,6 +434,13 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
               dst[0] = make_double2(q.x, q.y);
               dst[1] = make_double2(q.z, q.w);
             } break;
+            case GDS_OP_N_EAGGT:
+            {
+              double4 q = n_eaggt<UNITW>(g, p.vec[a], p.vec[ins >> 24], row, lane);
+              double2* dst = reinterpret_cast<double2*>(p.out[b]) + 2 * row;
+              dst[0] = make_double2(q.x, q.y);
+              dst[1] = make_double2(q.z, q.w);
+            } break;
             default: break;
           }
         } else if (DOMAIN == GDS_EDGES) {
@@ -402,6 +448,7 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
             case GDS_OP_E_GRADT: PUSH(e_gradt<UNITW>(g, p.vec[a], row)); break;
             case GDS_OP_E_CURLT: PUSH(e_curlt<UNITW>(g, p.vec[a], row, lane)); break;
             case GDS_OP_E_ADVFIN: PUSH(e_advfin<UNITW>(g, p.vec[a], p.vec[b], row)); break;
+            case GDS_OP_E_ADVS1: PUSH(e_advs1<UNITW>(g, p.vec[a], p.vec[b], row)); break;
             default: break;
           }
         } else {

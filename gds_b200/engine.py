@@ -337,11 +337,13 @@ class StepEngine:
                     st.append(min(h - 1, level_of(p.vec[a]) - 1, level_of(p.vec[b]) - 1))
                 elif op == 'N_EAGG':
                     lv[id(p.out[b][0])] = min(h - 1, level_of(p.vec[a]) - 1)
+                elif op == 'N_EAGGT':
+                    lv[id(p.out[b][0])] = min(h - 1, level_of(p.vec[a]) - 1, level_of(p.vec[ins >> 24]) - 1)
                 elif op in ('E_GRADT', 'F_CURL'):
                     st.append(level_of(p.vec[a]))
                 elif op == 'E_CURLT':
                     st.append(min(h, level_of(p.vec[a])) - kf)
-                elif op == 'E_ADVFIN':
+                elif op in ('E_ADVFIN', 'E_ADVS1'):
                     st.append(min(level_of(p.vec[a]), level_of(p.vec[b])))
                 elif op == 'STORE':
                     lv[id(p.out[a][0])] = st[-1]

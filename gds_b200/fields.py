@@ -655,6 +655,28 @@ class edge_gds(gds):
         g = self._low
         return self._apply(lambda a: Gather('E_ADVFIN', g, a, EdgeAgg(g, a)), self._arg(y, L.EDGES), domains=(L.EDGES,))
 
+    def advect_jvp(self, v, y=None):
+        """J(y) v, the Jacobian of advect at y applied to the edge vector v (a matrix v: column by column), with the
+        flow directions sign(y) held fixed -- the derivative autograd takes through sign() and relu() in advect_torch
+        (gds.py:372-395).  Two gather passes like advect itself, no E x E matrix: from advect(y)_e = -(y_e S1_e + s_e S2_e),
+            (J v)_e = -v_e S1_e(y) - (y_e S1'_e + s_e S2'_e),
+        where S1', S2' are built from the tangent aggregates sum in*w*s_f*v_f and sum in*w*2*y_f*v_f."""
+        g = self._low
+
+        def build(a, d):
+            return Gather('E_ADVFIN', g, a, EdgeAgg(g, a, d)) - d * Gather('E_ADVS1', g, a, EdgeAgg(g, a))
+        return self._apply(build, self._arg(y, L.EDGES), v, domains=(L.EDGES, L.EDGES))
+
+    def advect_jac(self, y=None):
+        """Jacobian of the advective derivative as a dense E x E torch tensor (gds.py:391-395, where it is autograd
+        through dense operators); assembled from advect_jvp on the identity, so meant for the small graphs the
+        reference's Lyapunov analysis uses (examples/turbulence.py:252-268) -- at scale use advect_jvp directly."""
+        import torch
+        if isinstance(y, torch.Tensor):
+            y = y.detach().cpu().numpy()
+        y = np.asarray(self._arg(y, L.EDGES), dtype=float)
+        return torch.from_numpy(np.ascontiguousarray(self.advect_jvp(np.eye(self.ndim), y)))
+
 
     def leray_project(self, y=None, rtol=1e-13, max_iter=None, return_info=False):
         """Projection onto the divergence-free edge fields, y - B1^T pinv(B1 B1^T) B1 y (gds.py:249,414-427).  The
@@ -858,6 +880,34 @@ class System:
                 time.append(t)
         return np.array(time), {k: np.array(v) for k, v in data.items()}
 
+
+    def solve_to_disk(self, T: float, dt: float, folder: str, parent='runs'):
+        """system.py:59-95: step to T and leave one file per observable under parent/folder, each an array
+        [n_steps, ndim] of the states AFTER every step (no initial state), plus 't' [n_steps].  The reference writes
+        gzip-compressed hickle files; hickle is used when it is importable, otherwise the same arrays go to .npy.
+        The trajectory is recorded on the device (solve) and read back once; mesh dumps belong to the renderers."""
+        import glob
+        import os
+        assert os.path.isdir(parent), f'Parent directory "{parent}" does not exist'
+        path = parent + '/' + folder
+        if not os.path.isdir(path):
+            os.mkdir(path)
+        else:
+            for f in glob.glob(f'{path}/*.hkl') + glob.glob(f'{path}/*.npy'):
+                os.remove(f)
+        time, data = self.solve(T, dt)
+        dump = {'t': time[1:]}
+        dump.update({k: v[1:] for k, v in data.items()})
+        try:
+            import hickle as hkl
+        except ImportError:
+            hkl = None
+        for name, arr in dump.items():
+            if hkl is not None:
+                hkl.dump(np.asarray(arr), f'{path}/{name}.hkl', mode='w', compression='gzip')
+            else:
+                np.save(f'{path}/{name}.npy', np.asarray(arr))
+        return path
 
     def _solve_on_device(self, T, dt, every):
         """snapshots taken on the device inside the captured step, one read-back at the end; None when the stepper

@@ -188,10 +188,11 @@ class Gather(Expr):
     """one-hop incidence operator; `kind` is the opcode name, args are vectors on the source domain(s)"""
     OUT_DOMAIN = {'N_LAP': L.NODES, 'N_BDOT': L.NODES, 'N_INFLUX': L.NODES, 'N_OUTFLUX': L.NODES,
                   'N_ADVECT': L.NODES, 'N_LIE': L.NODES, 'E_GRADT': L.EDGES, 'E_CURLT': L.EDGES,
-                  'E_ADVFIN': L.EDGES, 'F_CURL': L.FACES}
+                  'E_ADVFIN': L.EDGES, 'E_ADVS1': L.EDGES, 'F_CURL': L.FACES}
     IN_DOMAINS = {'N_LAP': (L.NODES,), 'N_BDOT': (L.EDGES,), 'N_INFLUX': (L.EDGES,), 'N_OUTFLUX': (L.EDGES,),
                   'N_ADVECT': (L.EDGES, L.NODES), 'N_LIE': (L.EDGES, L.NODES), 'E_GRADT': (L.NODES,),
-                  'E_CURLT': (L.FACES,), 'E_ADVFIN': (L.EDGES, L.NODES), 'F_CURL': (L.EDGES,)}
+                  'E_CURLT': (L.FACES,), 'E_ADVFIN': (L.EDGES, L.NODES), 'E_ADVS1': (L.EDGES, L.NODES),
+                  'F_CURL': (L.EDGES,)}
 
     def __init__(self, kind, graph, *args):
         self.kind, self.graph, self.domain = kind, graph, self.OUT_DOMAIN[kind]
@@ -209,10 +210,12 @@ class Gather(Expr):
 
 
 class EdgeAgg(Expr):
-    """the four upwind node aggregates of an edge vector (pass 1 of edge self-advection); 4 values per node"""
+    """the four upwind node aggregates of an edge vector (pass 1 of edge self-advection); 4 values per node.
+    With a direction v: their tangent at y along v, the flow directions held fixed (Jacobian-vector product)."""
 
-    def __init__(self, graph, y):
-        self.graph, self.domain, self.args = graph, L.NODES, (y,)
+    def __init__(self, graph, y, v=None):
+        self.graph, self.domain = graph, L.NODES
+        self.args = (y,) if v is None else (y, v)
 
 
 def as_expr(x, domain=None, graph=None):
@@ -368,8 +371,8 @@ class Pass:
         self._imm_index = {}
         self._mask_index = {}
 
-    def emit(self, op, a=0, b=0, push=0, pop=0):
-        self.code.append(OP[op] | ((a & 0xff) << 8) | ((b & 0xff) << 16))
+    def emit(self, op, a=0, b=0, push=0, pop=0, c=0):
+        self.code.append(OP[op] | ((a & 0xff) << 8) | ((b & 0xff) << 16) | ((c & 0xff) << 24))
         self.depth += push - pop
         self.max_depth = max(self.max_depth, self.depth)
         if len(self.code) > L.MAX_CODE:
@@ -487,7 +490,10 @@ class Lowering:
             p = Pass(L.NODES, when, e.graph)
             ys = self.operand(p, e.args[0], for_gather=True)
             p.out.append((buf, 0))
-            p.emit('N_EAGG', ys, 0)
+            if len(e.args) == 2:
+                p.emit('N_EAGGT', ys, 0, c=self.operand(p, e.args[1], for_gather=True))
+            else:
+                p.emit('N_EAGG', ys, 0)
         else:
             buf = self._Buffer(self.ctx, rows)
             p = Pass(e.domain, when, e.graph)
@@ -564,14 +570,14 @@ class Lowering:
             p.max_depth = max(p.max_depth, p.depth)
         elif isinstance(e, Gather):
             slots = [self.operand(p, a, for_gather=True) for a in e.args]
-            if e.kind == 'E_ADVFIN':
-                p.emit('E_ADVFIN', slots[0], slots[1], push=1)
+            if e.kind in ('E_ADVFIN', 'E_ADVS1'):
+                p.emit(e.kind, slots[0], slots[1], push=1)
             elif len(slots) == 2:
                 p.emit(e.kind, slots[0], slots[1], push=1)
             else:
                 p.emit(e.kind, slots[0], push=1)
         elif isinstance(e, EdgeAgg):
-            raise TraceError('internal: edge aggregates are only consumed by E_ADVFIN')
+            raise TraceError('internal: edge aggregates are only consumed by E_ADVFIN / E_ADVS1')
         else:
             raise TraceError(f'cannot lower {type(e).__name__}')
 

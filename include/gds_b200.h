@@ -78,9 +78,12 @@ enum {
   GDS_OP_N_ADVECT = 68,   /* nodes: scalar advect(v=vec a, y=vec b)   gds.py:166-177                    */
   GDS_OP_N_LIE = 69,      /* nodes: lie_advect(v=vec a, y=vec b)      gds.py:179-189                    */
   GDS_OP_N_EAGG = 70,     /* nodes: 4 upwind aggregates of edge vec a -> out[b] as double4 (no push)    */
+  GDS_OP_N_EAGGT = 71,    /* nodes: tangent of those aggregates at y=vec a in direction vec c, flow signs fixed -> out[b]
+                           * (Jacobian-vector product of the self-advection, gds.py:372-395)           */
   GDS_OP_E_GRADT = 80,    /* edges: (B1^T v)[row], v on nodes         gds.py:154                        */
   GDS_OP_E_CURLT = 81,    /* edges: (B2^T v)[row], v on faces         gds.py:305                        */
   GDS_OP_E_ADVFIN = 82,   /* edges: self-advection from y=vec a, aggregates vec b   gds.py:326-345      */
+  GDS_OP_E_ADVS1 = 83,    /* edges: S1 factor of the self-advection, w_e (d_t P1_t - d_h Q1_h), y=vec a, aggregates vec b */
   GDS_OP_F_CURL = 96      /* faces: (B2 v)[row], v on edges           gds.py:294                        */
 };
 

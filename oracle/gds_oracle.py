@@ -717,6 +717,31 @@ class edge_gds(gds):
         return -(sp.csr_matrix(A) @ y)
 
 
+    def advect_jac(self, y=None, single_precision_operators=True):
+        """gds.py:372-395: Jacobian of advect_torch by autograd.  sign() and relu() have zero derivative almost
+        everywhere, so F (built from s = sign y) is a constant of the differentiation and
+            advect(y)_i = -sum_j F_ij (y_i s_j + s_i y_j) y_j
+            J_ik = -( delta_ik sum_j F_ij |y_j| + y_i F_ik s_k + 2 s_i F_ik y_k ).
+        The reference's torch copies of the operators are float32 (`incidence_torch`, `dual_weights_torch`,
+        gds.py:270-271): with `single_precision_operators` the entries of B and of the dual weights are rounded the same
+        way (the arithmetic itself stays float64, as torch promotes when y is float64)."""
+        if y is None: y = self.y
+        y = np.asarray(y, dtype=float)
+        s = np.sign(y)
+        B, dw = self.incidence, self.dual_weights
+        if single_precision_operators:
+            B = sp.csr_matrix(B.astype(np.float32).astype(np.float64))
+            dw = sp.csr_matrix(dw.astype(np.float32).astype(np.float64))
+        Bs = B @ sp.diags(s)
+        Bm, Bp = (-Bs).maximum(0), Bs.maximum(0)
+        F = np.asarray((Bm.T @ Bp - Bp.T @ Bm).multiply(dw).todense())
+        J = -(np.diag(F @ np.abs(y)) + (y[:, None] * F) * s[None, :] + 2.0 * (s[:, None] * F) * y[None, :])
+        return J
+
+    def advect_jvp(self, v, y=None):
+        """J(y) v in full float64 (no reference counterpart: the reference only forms the dense Jacobian)"""
+        return self.advect_jac(y, single_precision_operators=False) @ np.asarray(v, dtype=float)
+
     def leray_project(self, y=None):  # gds.py:249,414-419 (the Dirichlet branch, gds.py:420-427, is not runnable)
         if y is None: y = self.y
         assert self.dirichlet_indices.size == 0

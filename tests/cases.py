@@ -161,6 +161,21 @@ def operator_outputs(api, gname):
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+JAC_GRAPHS = ('hex_3x4', 'tri_4x6', 'hex_4x5_w')
+
+
+def jacobian_outputs(api, gname):
+    """Jacobian of the edge self-advection at a seeded state (gds.py:391-395: autograd through advect_torch; float64
+    state, the reference's float32 operator copies)."""
+    import torch
+    G = OP_GRAPHS[gname]()
+    ed = api.edge_gds(G)
+    y = np.random.default_rng(5).standard_normal(ed.ndim)
+    y[::7] = 0.0                                   # zero-flow edges: sign() == 0 rows and columns
+    J = ed.advect_jac(torch.from_numpy(y.copy()))
+    return {'in_y': y, 'jac': np.asarray(J.numpy() if hasattr(J, 'numpy') else J, dtype=float)}
+
+
 # ------------------------------------------------------------------------------------------------
 # trajectory cases
 # ------------------------------------------------------------------------------------------------

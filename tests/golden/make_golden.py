@@ -78,6 +78,13 @@ def main(argv):
         out = cases.operator_outputs(RefAPI, gname)
         np.savez_compressed(os.path.join(HERE, key + '.npz'), **out)
         print('wrote', key, {k: v.shape for k, v in out.items() if k.startswith('map') or k == 'n_faces'})
+    for gname in cases.JAC_GRAPHS:
+        key = f'jac_{gname}'
+        if want and key not in want:
+            continue
+        out = cases.jacobian_outputs(RefAPI, gname)
+        np.savez_compressed(os.path.join(HERE, key + '.npz'), **out)
+        print('wrote', key, out['jac'].shape)
     for cname, fn in cases.TRAJ_CASES.items():
         key = f'traj_{cname}'
         if want and key not in want:

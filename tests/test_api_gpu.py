@@ -169,3 +169,24 @@ def test_solve_records_on_the_device_and_matches_the_stepping_loop():
     assert np.array_equal(np.asarray(u1.y), np.asarray(u2.y))          # the fields carry on from the end of solve()
     s1.step(2.5e-3); s2.step(2.5e-3)
     assert np.array_equal(np.asarray(c1.y), np.asarray(c2.y))
+
+
+def test_solve_to_disk_layout(tmp_path):
+    """system.py:59-95: one array [n_steps, ndim] per observable with the states after every step, and 't'"""
+    def make(api):
+        G = cases.g_grid(6, 5)
+        T = api.node_gds(G)
+        api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=1e-2)
+        T.set_initial(y0=lambda x: float(x[0]) - 0.3 * x[1])
+        T.set_constraints(dirichlet=lambda t, x: np.sin(t) if x[0] == 0 else None)
+        return T, api.couple({'T': T})
+    T, sysobj = make(product_api())
+    path = sysobj.solve_to_disk(0.05, 0.01, 'run0', parent=str(tmp_path))
+    t, y = np.load(f'{path}/t.npy'), np.load(f'{path}/T.npy')
+    To, so = make(oracle_api())
+    want = []
+    for _ in range(t.size):
+        so.step(0.01)
+        want.append(np.array(To.y, copy=True))
+    assert y.shape == (t.size, T.ndim) and np.allclose(t, 0.01 * np.arange(1, t.size + 1))
+    assert rel_l2(y, np.array(want)) <= 1e-10

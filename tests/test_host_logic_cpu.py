@@ -105,6 +105,22 @@ def test_hodge_laplacian_and_advection_pass_structure():
     assert 'E_GRADT' in last and 'E_CURLT' in last and 'E_ADVFIN' in last
 
 
+def test_advection_jacobian_vector_product_pass_structure():
+    """advect_jvp inside a law (a linearised perturbation equation dv/dt = J(u) v): the aggregates of u and their
+    tangent along v are node passes, the rest is fused into edge passes"""
+    G = cases.g_hex(3, 4)
+    u = gds_b200.edge_gds(G)
+    base = np.random.default_rng(0).standard_normal(u.ndim)
+    u.set_evolution(dydt=lambda t, y: u.advect_jvp(y, base), max_step=1e-3)
+    passes = lower(u, u.dydt_fun)
+    # the base state is constant during a step: its aggregates and the S1 factor are hoisted out of the stages;
+    # per stage only the tangent aggregates (node pass) and one fused edge pass remain
+    assert [(p[0], p[1]) for p in passes] == [(L.NODES, L.WHEN_STEP), (L.EDGES, L.WHEN_STEP),
+                                              (L.NODES, L.WHEN_STAGE), (L.EDGES, L.WHEN_STAGE)]
+    assert passes[0][2][0] == 'N_EAGG' and 'E_ADVS1' in passes[1][2]
+    assert passes[2][2][0] == 'N_EAGGT' and 'E_ADVFIN' in passes[3][2] and 'E_ADVS1' not in passes[3][2]
+
+
 def test_data_dependent_control_flow_is_rejected():
     T = gds_b200.node_gds(cases.g_grid(4, 4))
     T.set_evolution(dydt=lambda t, y: y if y else -y, max_step=1e-2)

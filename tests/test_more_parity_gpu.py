@@ -37,6 +37,27 @@ def test_order2_with_dirichlet_hits_the_last_block():
     both(run)
 
 
+@pytest.mark.parametrize('gname', ['hex_3x4', 'tri_5x7_w'])
+def test_linearised_advection_perturbation_equation(gname):
+    """dv/dt = P-free tangent dynamics J(u) v - 0.2 v around a fixed flow u (the Lyapunov analysis of
+    examples/turbulence.py:252-268 as a law): advect_jvp inside a traced law, aggregates of u hoisted out of the stages"""
+    def run(api):
+        G = cases.OP_GRAPHS[gname]()
+        v = api.edge_gds(G)
+        rng = np.random.default_rng(3)
+        base = rng.standard_normal(v.ndim)
+        base[::5] = 0.0
+        v0 = rng.standard_normal(v.ndim)
+        api.evolve(v, dydt=lambda t, y: v.advect_jvp(y, base) - 0.2 * y, max_step=5e-3)
+        v.set_initial(y0=lambda e: v0[v.X[e]])
+        out = {}
+        for i in range(3):
+            v.step(0.02)
+            out[f'y{i}'] = np.array(v.y, copy=True)
+        return out
+    both(run)
+
+
 def test_map_mode_with_time_varying_dirichlet_and_time_argument():
     def run(api):
         G = cases.g_grid(6, 5)

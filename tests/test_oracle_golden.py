@@ -28,6 +28,22 @@ def test_operators_match_reference(gname):
             assert rel_l2(out[k], gold[k]) <= TOL, (k, rel_l2(out[k], gold[k]))
 
 
+@pytest.mark.parametrize('gname', list(cases.JAC_GRAPHS))
+def test_advection_jacobian_matches_reference(gname):
+    """gds.py:391-395.  The oracle rounds the operator entries to float32 exactly as the reference's torch copies do."""
+    gold = np.load(os.path.join(GOLD, f'jac_{gname}.npz'))
+    out = cases.jacobian_outputs(oracle_api(), gname)
+    assert np.array_equal(out['in_y'], gold['in_y'])
+    assert rel_l2(out['jac'], gold['jac']) <= TOL
+    # and the full-precision Jacobian (what the device path computes) is the derivative of the oracle's advect
+    G = cases.OP_GRAPHS[gname]()
+    ed = oracle_api().edge_gds(G)
+    y, live = gold['in_y'], gold['in_y'] != 0
+    v = np.random.default_rng(6).standard_normal(y.size) * live
+    fd = (ed.advect(y + 1e-7 * v) - ed.advect(y - 1e-7 * v)) / 2e-7
+    assert rel_l2(ed.advect_jvp(v, y), fd) <= 1e-7
+
+
 @pytest.mark.parametrize('cname', list(cases.TRAJ_CASES))
 def test_trajectories_match_reference(cname):
     gold = np.load(os.path.join(GOLD, f'traj_{cname}.npz'))

@@ -31,6 +31,25 @@ def test_operators_match_reference(gname):
             assert rel_l2(out[k], gold[k]) <= TOL, (k, rel_l2(out[k], gold[k]))
 
 
+@pytest.mark.parametrize('gname', list(cases.JAC_GRAPHS))
+def test_advection_jacobian(gname):
+    """edge_gds.advect_jac / advect_jvp (gds.py:391-395).  The reference differentiates through float32 copies of its
+    operators (gds.py:270-271), so its Jacobian carries ~1e-8 of rounding wherever a weight or 1/(deg-1) is not a dyadic
+    number; the device path computes in float64.  Bars: 1e-10 against the full-precision oracle on every graph, 1e-10
+    against the reference's golden Jacobian on the graph whose operator entries are exact in float32 (unit-weight
+    hexagons), 1e-6 (float32 resolution) on the others."""
+    gold = np.load(os.path.join(GOLD, f'jac_{gname}.npz'))
+    out = cases.jacobian_outputs(product_api(), gname)
+    assert np.array_equal(out['in_y'], gold['in_y'])
+    y = gold['in_y']
+    ed = oracle_api().edge_gds(cases.OP_GRAPHS[gname]())
+    assert rel_l2(out['jac'], ed.advect_jac(y, single_precision_operators=False)) <= TOL
+    assert rel_l2(out['jac'], gold['jac']) <= (TOL if gname == 'hex_3x4' else 1e-6)
+    pd = product_api().edge_gds(cases.OP_GRAPHS[gname]())
+    v = np.random.default_rng(6).standard_normal(y.size)
+    assert rel_l2(pd.advect_jvp(v, y), ed.advect_jvp(v, y)) <= TOL
+
+
 @pytest.mark.parametrize('cname', list(cases.TRAJ_CASES))
 def test_trajectories_match_reference(cname):
     gold = np.load(os.path.join(GOLD, f'traj_{cname}.npz'))
