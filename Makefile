@@ -8,7 +8,7 @@ CSRC := gds_b200/csrc
 LIB  := gds_b200/lib/libgds_b200.so
 SRCS := $(CSRC)/kernels.cu $(CSRC)/api.cu $(CSRC)/lower.cpp $(CSRC)/lattice.cpp
 HDRS := $(CSRC)/internal.h include/gds_b200.h
-NVFLAGS := -O3 -std=c++17 -lineinfo -fmad=false $(ARCH) -Iinclude -I$(CSRC) -Xcompiler -fPIC,-O3,-Wall -shared -cudart shared
+NVFLAGS := -O3 -std=c++17 -lineinfo -fmad=false $(EXTRA) $(ARCH) -Iinclude -I$(CSRC) -Xcompiler -fPIC,-O3,-Wall -shared -cudart shared
 
 all: $(LIB)
 

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libgds_b200.so')
+# GDS_B200_LIB: another build of the same library (kernel A/B runs); the default is the in-tree build
+LIB_PATH = os.environ.get('GDS_B200_LIB') or os.path.join(_HERE, 'lib', 'libgds_b200.so')
 
 
 class GdsError(RuntimeError):

@@ -75,6 +75,7 @@ struct GraphDev {
   const int32_t* n_nbr;   // neighbour node, padding = own row
   const int16_t* n_nbr16; // same slots as (neighbour - own row) when every difference fits 16 bits (lattices up to
                           // 32767 wide, locally numbered graphs): half the index bytes for the Laplacian kernels; else null
+  int32_t n_uniw;         // > 0: every slice of the node ELL has this width (slice s starts at slot s * n_uniw * 32)
   const int32_t* n_edge;  // (edge << 1) | (1 if this node is the head v of the edge), padding = -1
   const double* n_w;      // w_e, padding = 0
   const double* n_dinv;   // [V]

@@ -750,6 +750,13 @@ static void launch_lap(const PassParams& p, int64_t rows, cudaStream_t st) {
 // lapq: 4 CONSECUTIVE rows per thread, every index load one ld.global.nc.v4.s32 and every vector access a v2.f64
 // (needs 16-byte aligned operands); the faster form on unit-weight graphs, where no weight stream competes for registers
 #define LAPQ_BLOCK 128
+#ifndef LAPQ_MINB      // build-time knobs for A/B runs (make EXTRA=-DLAPQ_MINB=8 ...); the defaults are the measured best
+#define LAPQ_MINB 7
+#endif
+#ifndef LAPQ_UNROLL
+#define LAPQ_UNROLL 2
+#endif
+constexpr int kLapqUnroll = LAPQ_UNROLL;
 __device__ __forceinline__ int4 ld_stream_v4i32(const int32_t* p) {
   int4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -768,11 +775,29 @@ __device__ __forceinline__ double2 ld_plain_v2f64(const double* p) {
 __device__ __forceinline__ void st_v2f64(double* p, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
+// 256-bit accesses (sm_100: LDG.E.256 / STG.E.256), 32-byte aligned operands
+__device__ __forceinline__ void ld_stream_v4f64(const double* p, double (&x)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_plain_v4f64(const double* p, double (&x)[4]) {
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_gather_v4f64(const double* p, double (&x)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_v4f64(double* p, const double (&x)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+}
 // store 4 values of a quad; `full` = all four rows exist
-__device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, bool full, const double (&x)[4]) {
+template <bool V256>
+__device__ __forceinline__ void st_quad_v(double* p, int64_t r0, int64_t n_rows, bool full, const double (&x)[4]) {
   if (full) {
-    st_v2f64(p + r0, x[0], x[1]);
-    st_v2f64(p + r0 + 2, x[2], x[3]);
+    if (V256) {
+      st_v4f64(p + r0, x);
+    } else {
+      st_v2f64(p + r0, x[0], x[1]);
+      st_v2f64(p + r0 + 2, x[2], x[3]);
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -781,17 +806,30 @@ __device__ __forceinline__ void st_quad(double* p, int64_t r0, int64_t n_rows, b
 }
 
 
-template <bool UNITW, bool IDX16>
-__global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant__ PassParams p) {
+// RUNS: (a) every streamed vector is 32-byte aligned and moves as one 256-bit access per quad; (b) a quad whose four
+// neighbours in a slot are consecutive rows (a lattice direction: the four relative offsets are equal) gathers them as
+// ONE access -- a 256-bit load when the run is 32-byte aligned, the row's own registers plus one scalar for the +-1
+// directions, two 128-bit loads for other even offsets -- instead of four 8-byte gathers.  Same operands, same order
+// of additions: results are bit-identical to the scalar gathers.  (ncu on the scalar form: the L1 data pipe, 254
+// wavefronts per 128 rows, was the busiest unit at 67 %; a run costs 8 wavefronts per slot instead of ~40.)
+template <bool UNITW, bool IDX16, bool RUNS>
+__global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : 5) lapq_kernel(const __grid_constant__ PassParams p) {
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
   const bool full = r0 + 3 < p.n_rows;
   const GraphDev& g = p.g;
   const double* __restrict__ v = p.lap_v;
   // the four rows sit in one slice (32 % 4 == 0): entry j of rows r0..r0+3 is 16 contiguous bytes of indices
-  const uint32_t o0 = __ldg(g.n_soff + (r0 >> 5)), o1 = __ldg(g.n_soff + (r0 >> 5) + 1);
+  // (computed, not loaded, when all slices have one width: the index load then depends on nothing)
+  uint32_t o0, width;
+  if (RUNS && g.n_uniw) {
+    width = (uint32_t)g.n_uniw;
+    o0 = (uint32_t)(r0 >> 5) * width;
+  } else {
+    o0 = __ldg(g.n_soff + (r0 >> 5));
+    width = __ldg(g.n_soff + (r0 >> 5) + 1) - o0;
+  }
   const int64_t base = (int64_t)o0 * GDS_SLICE + (r0 & 31);
-  const uint32_t width = o1 - o0;
   // everything that does not depend on the gather is requested first (all buffers carry >= 4 doubles of slack, so
   // the 128-bit loads of a partial last quad stay inside their allocations)
   double yn[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0};
@@ -799,29 +837,43 @@ __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant_
   const int mode = p.stage_mode;
   if (p.epilogue == GDS_EPI_RHS) {
     if (mode != 4) {
-      double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
-      yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
+      if (RUNS) {
+        ld_stream_v4f64(p.yn + r0, yn);
+      } else {
+        double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
+        yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
+      }
     }
     if (mode == 1 || mode == 2) {
-      double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
-      ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
+      if (RUNS) {
+        ld_plain_v4f64(p.acc_in + r0, ac);
+      } else {
+        double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
+        ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
+      }
     }
     if (p.dmask) dbits = __ldg(p.dmask + (r0 >> 5)) >> (r0 & 31);
   }
   if (p.lap_mask) mbits = __ldg(p.lap_mask + (r0 >> 5)) >> (r0 & 31);
   if (p.lap_b) {
-    double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
-    bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
+    if (RUNS) {
+      ld_stream_v4f64(p.lap_b + r0, bb);
+    } else {
+      double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
+      bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
+    }
   }
   double c[4];
-  {
+  if (RUNS) {
+    ld_gather_v4f64(v + r0, c);
+  } else {
     double2 a = __ldg(reinterpret_cast<const double2*>(v + r0)), b = __ldg(reinterpret_cast<const double2*>(v + r0 + 2));
     c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
   }
   double s[4] = {0, 0, 0, 0};
   const int32_t* nb = g.n_nbr + base;
   const double* w = g.n_w + base;
-#pragma unroll 2
+#pragma unroll kLapqUnroll
   for (uint32_t j = 0; j < width; ++j) {
     int4 k;
     if (IDX16) {  // 4 x int16 (neighbour - row) in one 64-bit load
@@ -834,17 +886,38 @@ __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant_
     } else {
       k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
     }
-    if (UNITW) {
-      s[0] += ld_gather(v + k.x) - c[0];
-      s[1] += ld_gather(v + k.y) - c[1];
-      s[2] += ld_gather(v + k.z) - c[2];
-      s[3] += ld_gather(v + k.w) - c[3];
+    double gv[4];
+    const int32_t d = k.x - (int32_t)r0;
+    if (RUNS && (k.y == k.x + 1) & (k.z == k.x + 2) & (k.w == k.x + 3)) {
+      const double* q = v + k.x;
+      if ((d & 3) == 0) {
+        ld_gather_v4f64(q, gv);
+      } else if (d == 1) {
+        gv[0] = c[1]; gv[1] = c[2]; gv[2] = c[3]; gv[3] = ld_gather(q + 3);
+      } else if (d == -1) {
+        gv[0] = ld_gather(q); gv[1] = c[0]; gv[2] = c[1]; gv[3] = c[2];
+      } else if ((d & 1) == 0) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(q)), b = __ldg(reinterpret_cast<const double2*>(q + 2));
+        gv[0] = a.x; gv[1] = a.y; gv[2] = b.x; gv[3] = b.y;
+      } else {
+        gv[0] = ld_gather(q); gv[1] = ld_gather(q + 1); gv[2] = ld_gather(q + 2); gv[3] = ld_gather(q + 3);
+      }
     } else {
-      const double2 w01 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE), w23 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE + 2);
-      s[0] += w01.x * (ld_gather(v + k.x) - c[0]);
-      s[1] += w01.y * (ld_gather(v + k.y) - c[1]);
-      s[2] += w23.x * (ld_gather(v + k.z) - c[2]);
-      s[3] += w23.y * (ld_gather(v + k.w) - c[3]);
+      gv[0] = ld_gather(v + k.x); gv[1] = ld_gather(v + k.y); gv[2] = ld_gather(v + k.z); gv[3] = ld_gather(v + k.w);
+    }
+    if (UNITW) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] += gv[i] - c[i];
+    } else {
+      double wq[4];
+      if (RUNS) {
+        ld_stream_v4f64(w + (int64_t)j * GDS_SLICE, wq);
+      } else {
+        const double2 w01 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE), w23 = ld_stream_v2f64(w + (int64_t)j * GDS_SLICE + 2);
+        wq[0] = w01.x; wq[1] = w01.y; wq[2] = w23.x; wq[3] = w23.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i] += wq[i] * (gv[i] - c[i]);
     }
   }
   double k4[4];
@@ -856,7 +929,7 @@ __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant_
     val += p.lap_gamma;
     k4[i] = val;
   }
-  if (p.lap_store) st_quad(p.lap_store, r0, p.n_rows, full, k4);
+  if (p.lap_store) st_quad_v<RUNS>(p.lap_store, r0, p.n_rows, full, k4);
   if (p.epilogue != GDS_EPI_RHS) return;
   double h = 0.0;
   if (p.steptab) h = p.steptab[*p.step_counter].h;
@@ -868,32 +941,33 @@ __global__ void __launch_bounds__(LAPQ_BLOCK) lapq_kernel(const __grid_constant_
     case 0:
 #pragma unroll
       for (int i = 0; i < 4; ++i) { o1v[i] = k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
-      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
-      st_quad(p.xnext, r0, p.n_rows, full, o2v);
+      st_quad_v<RUNS>(p.acc_out, r0, p.n_rows, full, o1v);
+      st_quad_v<RUNS>(p.xnext, r0, p.n_rows, full, o2v);
       break;
     case 1:
 #pragma unroll
       for (int i = 0; i < 4; ++i) { o1v[i] = ac[i] + p.acc_w * k4[i]; o2v[i] = yn[i] + (p.a_next * h) * k4[i]; }
-      st_quad(p.acc_out, r0, p.n_rows, full, o1v);
-      st_quad(p.xnext, r0, p.n_rows, full, o2v);
+      st_quad_v<RUNS>(p.acc_out, r0, p.n_rows, full, o1v);
+      st_quad_v<RUNS>(p.xnext, r0, p.n_rows, full, o2v);
       break;
     case 2:
 #pragma unroll
       for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + (p.fin * h) * (ac[i] + k4[i]);
-      st_quad(p.ynew, r0, p.n_rows, full, o1v);
+      st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
       break;
     case 3:
 #pragma unroll
       for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
-      st_quad(p.ynew, r0, p.n_rows, full, o1v);
+      st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
       break;
     default:
-      st_quad(p.ynew, r0, p.n_rows, full, k4);
+      st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, k4);
       break;
   }
 }
 
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+static bool aligned32(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; }
 
 int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
   const int64_t rows = p.n_rows - p.row0;
@@ -912,12 +986,23 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
     if (quad_ok) {
       int64_t blocks = ((rows + 3) / 4 + LAPQ_BLOCK - 1) / LAPQ_BLOCK;
-      if (p.g.n_nbr16) {
-        if (unitw) lapq_kernel<true, true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
-        else lapq_kernel<false, true><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
-      } else {
-        if (unitw) lapq_kernel<true, false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
-        else lapq_kernel<false, false><<<(unsigned)blocks, LAPQ_BLOCK, 0, ctx->stream>>>(p);
+      // 256-bit accesses and run gathers need 32-byte aligned vectors (the engine lays fields out that way);
+      // GDS_B200_LAPQ_RUNS=0 keeps the 128-bit / scalar-gather form for A/B runs
+      static const char* runs_env = getenv("GDS_B200_LAPQ_RUNS");
+      bool runs = !(runs_env && !strcmp(runs_env, "0")) && aligned32(p.lap_v) && aligned32(p.lap_b) && aligned32(p.lap_store);
+      if (runs && p.epilogue == GDS_EPI_RHS)
+        runs = aligned32(p.yn) && aligned32(p.acc_in) && aligned32(p.acc_out) && aligned32(p.xnext) && aligned32(p.ynew);
+      const int variant = (unitw ? 4 : 0) | (p.g.n_nbr16 ? 2 : 0) | (runs ? 1 : 0);
+      const unsigned nb = (unsigned)blocks;
+      switch (variant) {
+        case 7: lapq_kernel<true, true, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 6: lapq_kernel<true, true, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 5: lapq_kernel<true, false, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 4: lapq_kernel<true, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 3: lapq_kernel<false, true, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 2: lapq_kernel<false, true, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        case 1: lapq_kernel<false, false, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        default: lapq_kernel<false, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
       }
       GDS_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
