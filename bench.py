@@ -441,7 +441,7 @@ def gpu_arm(args):
     builder, size_default, cpu_size = WORKLOADS[args.workload]
     size = args.size or size_default
     t_build = time.perf_counter()
-    prob = builder(product_api(), size, native=True, world=world, rank=rank)
+    prob = builder(product_api(), size, native=True, world=world, rank=rank, weighted=args.weighted)
     WORKLOAD_NAME[0] = prob['name']
     st, h, K, W = prob['stepper'], prob['h'], args.steps, args.warmup
     eng = st._ensure_engine()
@@ -508,7 +508,7 @@ def gpu_arm(args):
 
     # ---- the same lattice with random edge weights: kernel bytes == algorithmic bytes (N=1 only) --------------------
     weighted = None
-    if world == 1 and not args.no_weighted and args.workload == 'heat2d':
+    if world == 1 and not args.no_weighted and not args.weighted and args.workload == 'heat2d':
         del eng, st, fields, one_step
         prob.clear()
         pw = builder(product_api(), size, native=True, weighted=True)
@@ -559,6 +559,7 @@ def main():
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-weighted', action='store_true')
+    ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

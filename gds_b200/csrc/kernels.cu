@@ -616,8 +616,14 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 #define LAPT_BLOCK 128  // measured best on B200 (128 > 256 threads; register caps and deeper unrolling lose occupancy)
 #define LAPT_GROUP 128
 
+#ifndef LAPT_LATE      // build-time knobs for A/B runs, like LAPQ_*
+#define LAPT_LATE 0
+#endif
+#ifndef LAPT_MINB
+#define LAPT_MINB 5
+#endif
 template <bool UNITW, int MODE, bool CHAINED, bool IDX16>
-__global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __grid_constant__ PassParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t group = p.row0 + ((int64_t)blockIdx.x * (LAPT_BLOCK / 32) + (threadIdx.x >> 5)) * LAPT_GROUP;
   if (group + LAPT_GROUP > p.n_rows) return;
@@ -626,19 +632,51 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
   const int64_t r = group + lane;  // this lane's row in slice i is r + 32 i
   constexpr bool RHS = MODE != 5;
   // slice offsets of the 4 slices: 16-byte aligned (group/32 is a multiple of 4)
-  const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(g.n_soff + (group >> 5)));
-  const uint32_t o5 = __ldg(g.n_soff + (group >> 5) + 4);
-  const uint32_t off[5] = {o4.x, o4.y, o4.z, o4.w, o5};
+  // (computed when every slice has one width: the index loads then depend on nothing)
+  uint32_t off[5];
+  if (g.n_uniw) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) off[i] = ((uint32_t)(group >> 5) + i) * (uint32_t)g.n_uniw;
+  } else {
+    const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(g.n_soff + (group >> 5)));
+    off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w;
+    off[4] = __ldg(g.n_soff + (group >> 5) + 4);
+  }
   double yn[4], ac[4], bb[4], c[4], s[4];
   uint32_t dbit[4], mbit[4], width[4];
   const int32_t* nb[4];
   const int16_t* nb16[4];
   const double* wp[4];
   uint32_t wmax = 0;
+  // the stage vectors (y_n, accumulator, b, masks) are requested before the gather loop (LAPT_LATE 0) or after it
+  // (LAPT_LATE 1: fewer live registers, more resident warps, one more dependent round trip)
+  auto load_streams = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (RHS && MODE != 4) yn[i] = ld_stream_f64(p.yn + r + 32 * i);
+      if (MODE == 1 || MODE == 2) ac[i] = ld_plain_f64(p.acc_in + r + 32 * i);
+    }
+    if (p.lap_b) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
+        if (CHAINED) bb[i] = chain_apply(p.lap_bchain, bb[i]);
+        bb[i] *= p.lap_beta;
+      }
+    }
+    if (p.lap_b2) {  // second additive vector: folded into bb (beta * g(b) + beta2 * b2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bb[i] = (p.lap_b ? bb[i] : 0.0) + p.lap_beta2 * ld_stream_f64(p.lap_b2 + r + 32 * i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dbit[i] = (RHS && p.dmask) ? ((__ldg(p.dmask + (group >> 5) + i) >> lane) & 1u) : 0u;
+      mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (group >> 5) + i) >> lane) & 1u) : 0u;
+    }
+  };
+  if (!LAPT_LATE) load_streams();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (RHS && MODE != 4) yn[i] = ld_stream_f64(p.yn + r + 32 * i);
-    if (MODE == 1 || MODE == 2) ac[i] = ld_plain_f64(p.acc_in + r + 32 * i);
     c[i] = ld_gather(v + r + 32 * i);
     if (CHAINED) c[i] = chain_apply(p.lap_chain, c[i]);
     s[i] = 0.0;
@@ -647,23 +685,6 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
     nb[i] = g.n_nbr + (int64_t)off[i] * GDS_SLICE + lane;
     if (IDX16) nb16[i] = g.n_nbr16 + (int64_t)off[i] * GDS_SLICE + lane;
     if (!UNITW) wp[i] = g.n_w + (int64_t)off[i] * GDS_SLICE + lane;
-  }
-  if (p.lap_b) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      bb[i] = ld_stream_f64(p.lap_b + r + 32 * i);
-      if (CHAINED) bb[i] = chain_apply(p.lap_bchain, bb[i]);
-      bb[i] *= p.lap_beta;
-    }
-  }
-  if (p.lap_b2) {  // second additive vector: folded into bb (beta * g(b) + beta2 * b2)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) bb[i] = (p.lap_b ? bb[i] : 0.0) + p.lap_beta2 * ld_stream_f64(p.lap_b2 + r + 32 * i);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    dbit[i] = (RHS && p.dmask) ? ((__ldg(p.dmask + (group >> 5) + i) >> lane) & 1u) : 0u;
-    mbit[i] = p.lap_mask ? ((__ldg(p.lap_mask + (group >> 5) + i) >> lane) & 1u) : 0u;
   }
   // all index loads of a chunk of CH columns are issued before the first gather that depends on them: the chain is
   // slice offsets -> indices -> gathers, once per chunk (the 2-D lattices have 4 columns: one chunk)
@@ -690,6 +711,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK) lapT_kernel(const __grid_constant_
         s[i] += UNITW ? d : w[jj][i] * d;
       }
   }
+  if (LAPT_LATE) load_streams();
   double h = 0.0;
   if (MODE <= 3 && p.steptab) h = p.steptab[*p.step_counter].h;
 #pragma unroll
@@ -751,12 +773,18 @@ static void launch_lap(const PassParams& p, int64_t rows, cudaStream_t st) {
 // (needs 16-byte aligned operands); the faster form on unit-weight graphs, where no weight stream competes for registers
 #define LAPQ_BLOCK 128
 #ifndef LAPQ_MINB      // build-time knobs for A/B runs (make EXTRA=-DLAPQ_MINB=8 ...); the defaults are the measured best
-#define LAPQ_MINB 7
+#define LAPQ_MINB 10
+#endif
+#ifndef LAPQ_MINB_W    // the weighted instantiations carry 4 weights per slot more
+#define LAPQ_MINB_W 8
 #endif
 #ifndef LAPQ_UNROLL
 #define LAPQ_UNROLL 2
 #endif
 constexpr int kLapqUnroll = LAPQ_UNROLL;
+#ifndef LAPQ_LATE      // 1: request the stage vectors (y_n, accumulator, b) after the gather loop instead of before it --
+#define LAPQ_LATE 1    // fewer live registers, one more dependent round trip
+#endif
 __device__ __forceinline__ int4 ld_stream_v4i32(const int32_t* p) {
   int4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -813,7 +841,7 @@ __device__ __forceinline__ void st_quad_v(double* p, int64_t r0, int64_t n_rows,
 // of additions: results are bit-identical to the scalar gathers.  (ncu on the scalar form: the L1 data pipe, 254
 // wavefronts per 128 rows, was the busiest unit at 67 %; a run costs 8 wavefronts per slot instead of ~40.)
 template <bool UNITW, bool IDX16, bool RUNS>
-__global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : 5) lapq_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) lapq_kernel(const __grid_constant__ PassParams p) {
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
   const bool full = r0 + 3 < p.n_rows;
@@ -822,7 +850,7 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : 5) lapq_kernel
   // the four rows sit in one slice (32 % 4 == 0): entry j of rows r0..r0+3 is 16 contiguous bytes of indices
   // (computed, not loaded, when all slices have one width: the index load then depends on nothing)
   uint32_t o0, width;
-  if (RUNS && g.n_uniw) {
+  if (g.n_uniw) {
     width = (uint32_t)g.n_uniw;
     o0 = (uint32_t)(r0 >> 5) * width;
   } else {
@@ -835,34 +863,37 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : 5) lapq_kernel
   double yn[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0};
   uint32_t dbits = 0u, mbits = 0u;
   const int mode = p.stage_mode;
-  if (p.epilogue == GDS_EPI_RHS) {
-    if (mode != 4) {
+  auto load_streams = [&]() {
+    if (p.epilogue == GDS_EPI_RHS) {
+      if (mode != 4) {
+        if (RUNS) {
+          ld_stream_v4f64(p.yn + r0, yn);
+        } else {
+          double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
+          yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
+        }
+      }
+      if (mode == 1 || mode == 2) {
+        if (RUNS) {
+          ld_plain_v4f64(p.acc_in + r0, ac);
+        } else {
+          double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
+          ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
+        }
+      }
+      if (p.dmask) dbits = __ldg(p.dmask + (r0 >> 5)) >> (r0 & 31);
+    }
+    if (p.lap_mask) mbits = __ldg(p.lap_mask + (r0 >> 5)) >> (r0 & 31);
+    if (p.lap_b) {
       if (RUNS) {
-        ld_stream_v4f64(p.yn + r0, yn);
+        ld_stream_v4f64(p.lap_b + r0, bb);
       } else {
-        double2 a = ld_stream_v2f64(p.yn + r0), b = ld_stream_v2f64(p.yn + r0 + 2);
-        yn[0] = a.x; yn[1] = a.y; yn[2] = b.x; yn[3] = b.y;
+        double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
+        bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
       }
     }
-    if (mode == 1 || mode == 2) {
-      if (RUNS) {
-        ld_plain_v4f64(p.acc_in + r0, ac);
-      } else {
-        double2 a = ld_plain_v2f64(p.acc_in + r0), b = ld_plain_v2f64(p.acc_in + r0 + 2);
-        ac[0] = a.x; ac[1] = a.y; ac[2] = b.x; ac[3] = b.y;
-      }
-    }
-    if (p.dmask) dbits = __ldg(p.dmask + (r0 >> 5)) >> (r0 & 31);
-  }
-  if (p.lap_mask) mbits = __ldg(p.lap_mask + (r0 >> 5)) >> (r0 & 31);
-  if (p.lap_b) {
-    if (RUNS) {
-      ld_stream_v4f64(p.lap_b + r0, bb);
-    } else {
-      double2 a = ld_stream_v2f64(p.lap_b + r0), b = ld_stream_v2f64(p.lap_b + r0 + 2);
-      bb[0] = a.x; bb[1] = a.y; bb[2] = b.x; bb[3] = b.y;
-    }
-  }
+  };
+  if (!LAPQ_LATE) load_streams();
   double c[4];
   if (RUNS) {
     ld_gather_v4f64(v + r0, c);
@@ -920,6 +951,7 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : 5) lapq_kernel
       for (int i = 0; i < 4; ++i) s[i] += wq[i] * (gv[i] - c[i]);
     }
   }
+  if (LAPQ_LATE) load_streams();
   double k4[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
