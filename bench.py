@@ -73,12 +73,12 @@ def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
     m_op = 12 * (V + 2 * E) + 4 * (V + 1)                       # L0 as CSR (fp64 values, int32 indices)
     # bytes the kernel's own layout moves per step: 4 ELL columns of int32 indices (+ fp64 weights if weighted) per
     # stage, plus the RK4 vector traffic (x / y_n / acc reads, acc / x_next / y_new writes; stage 1 reads x = y_n once)
-    # (unit weights on a grid at most 32767 wide: the quad kernel reads 16-bit relative indices, 8 B per row and stage)
-    k_op = ((8 if (not weighted and n <= 32767) else 16) + (32 if weighted else 0)) * V
+    # (a grid at most 32767 wide: the quad kernel reads 16-bit relative indices, 8 B per row and stage)
+    k_op = ((8 if n <= 32767 else 16) + (32 if weighted else 0)) * V
     return dict(stepper=T, fields=[T], h=h, n_state=n_own, V=V, E=E, F=0,
                 bytes_per_step=4 * m_op + 136 * V, bytes_per_launch=(4 * m_op + 136 * V) / 4.0,
                 kernel_bytes_per_launch=(4 * k_op + 136 * V) / 4.0,
-                dominant_class=0, kernel='lapq_kernel<unit weights>' if not weighted else 'lapT_kernel<weighted>',
+                dominant_class=0, kernel='lapq_kernel<unit weights>' if not weighted else 'lapq_kernel<weighted>',
                 name=f'heat RK4 h=1e-2 on grid_2d_graph({m},{n}) (V={m * n}, E={2 * m * n - m - n}), Dirichlet static+time-varying'
                      + (', random edge weights' if weighted else '')
                      + (f', {world} slabs of {n}x{n} with per-stage halo exchange' if world > 1 else ''))

@@ -617,10 +617,10 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 #define LAPT_GROUP 128
 
 #ifndef LAPT_LATE      // build-time knobs for A/B runs, like LAPQ_*
-#define LAPT_LATE 0
+#define LAPT_LATE 1
 #endif
 #ifndef LAPT_MINB
-#define LAPT_MINB 5
+#define LAPT_MINB 8
 #endif
 template <bool UNITW, int MODE, bool CHAINED, bool IDX16>
 __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __grid_constant__ PassParams p) {
@@ -1009,10 +1009,13 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // full 128-row groups in lapT, the remainder (< 128 rows) in the generic kernel
     if (rows / 32 > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
     PassParams q = p;
-    // measured on B200 (same box, heat RK4 on a 7072^2 grid): unit weights 0.528 ms/launch with the 128-bit quad kernel
-    // vs 0.558 ms with lapT; weighted 0.869 ms vs 0.806 ms.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
+    // measured on B200, same box, heat RK4 on a 7072^2 grid, ms per launch (profiles/README.md):
+    //   unit weights: quad 0.361 (scalar-gather form with early stream loads, 64 registers: 0.50), lapT 0.56
+    //   random weights: quad 0.606, lapT 0.674 (early stream loads, 96 registers: 0.787)
+    // so the quad kernel takes every plain L0 form; lapT keeps pointwise chains, a second additive vector and
+    // operands that are not 16-byte aligned.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
-    const bool use_quad = (force ? !strcmp(force, "quad") : unitw) && p.lap_chain.n == 0 && p.lap_bchain.n == 0 && !p.lap_b2;
+    const bool use_quad = (force ? !strcmp(force, "quad") : true) && p.lap_chain.n == 0 && p.lap_bchain.n == 0 && !p.lap_b2;
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
