@@ -466,6 +466,11 @@ def gpu_arm(args):
     n_total = prob['n_state'] * world
     value = n_total * K / (ms * 1e-3)
     roof = roofline_of(prob, eng, K, h, ms / K)
+    if world > 1:   # GPUs of one box differ by several per cent; the step runs at the pace of the slowest
+        mine = torch.tensor([roof['launch_ms']], dtype=torch.float64, device='cuda')
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        roof['launch_ms_per_rank'] = [float(x.item()) for x in every]
     try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             roof['traffic'] = json.load(fh).get(args.workload, {}).get(str(size))

@@ -314,6 +314,7 @@ struct PushParams {
   int64_t* flag[GDS_MAX_PEERS];      // peer's arrival flag for this rank (its ready flag is 64 slots further)
   const int64_t* ready[GDS_MAX_PEERS];  // this rank's ready flag written by each peer
   int64_t* err;
+  int32_t handshake;                 // wait for the receiver's ready flag before storing (deep partitions only)
   int64_t s0[GDS_MAX_PEERS], s1[GDS_MAX_PEERS];
   const int64_t* src_idx;
   const int64_t* dst_idx;

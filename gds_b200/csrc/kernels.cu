@@ -697,7 +697,10 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool on = j0 + jj < width[i];  // warp-uniform
-        if (IDX16) k[jj][i] = (int32_t)(r + 32 * i) + (on ? ld_stream_i16(nb16[i] + (j0 + jj) * GDS_SLICE) : 0);
+        if (IDX16) {
+          const int32_t d16 = on ? ld_stream_i16(nb16[i] + (j0 + jj) * GDS_SLICE) : 0;
+          k[jj][i] = (d16 == -32768) ? ld_stream_i32(nb[i] + (j0 + jj) * GDS_SLICE) : (int32_t)(r + 32 * i) + d16;
+        }
         else k[jj][i] = on ? ld_stream_i32(nb[i] + (j0 + jj) * GDS_SLICE) : (int32_t)(r + 32 * i);
         if (!UNITW) w[jj][i] = on ? ld_stream_f64(wp[i] + (j0 + jj) * GDS_SLICE) : 0.0;
       }
@@ -909,11 +912,17 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) l
     int4 k;
     if (IDX16) {  // 4 x int16 (neighbour - row) in one 64-bit load
       const int2 raw = ld_stream_v2i32(g.n_nbr16 + base + (int64_t)j * GDS_SLICE);
-      const int32_t rr = (int32_t)r0;
-      k.x = rr + (int32_t)(int16_t)(raw.x & 0xffff);
-      k.y = rr + 1 + (raw.x >> 16);
-      k.z = rr + 2 + (int32_t)(int16_t)(raw.y & 0xffff);
-      k.w = rr + 3 + (raw.y >> 16);
+      const uint32_t ux = (uint32_t)raw.x, uy = (uint32_t)raw.y;
+      const bool escape = ((ux & 0xffffu) == 0x8000u) | ((ux >> 16) == 0x8000u) | ((uy & 0xffffu) == 0x8000u) | ((uy >> 16) == 0x8000u);
+      if (escape) {  // a difference that does not fit 16 bits (rare): this quad's indices come from the int32 array
+        k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
+      } else {
+        const int32_t rr = (int32_t)r0;
+        k.x = rr + (int32_t)(int16_t)(raw.x & 0xffff);
+        k.y = rr + 1 + (raw.x >> 16);
+        k.z = rr + 2 + (int32_t)(int16_t)(raw.y & 0xffff);
+        k.w = rr + 3 + (raw.y >> 16);
+      }
     } else {
       k = ld_stream_v4i32(nb + (int64_t)j * GDS_SLICE);
     }
@@ -1339,9 +1348,9 @@ __global__ void __launch_bounds__(1024) push_kernel(const __grid_constant__ Push
   const int q = blockIdx.x;
   const double* __restrict__ src = p.src;
   double* dst = p.dst[q];
-  // Handshake before writing: the neighbour's own stage kernel may still be storing (meaningless) values into its ghost
-  // rows, so it first announces "my stage of this exchange is done" (ready flag, slot 64 + rank), and the push waits for it.
-  if (threadIdx.x == 0) {
+  // Handshake before writing (deep partitions, whose passes also run over ghost rows): the neighbour's own stage kernel
+  // may still be storing (meaningless) values into its ghost rows, so it first announces "my stage of this exchange is done" (ready flag, slot 64 + rank), and the push waits for it.
+  if (p.handshake && threadIdx.x == 0) {
     const int64_t e = *p.epoch + 1;
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q] + 64), "l"(e) : "memory");
     unsigned long long t0, t1;
