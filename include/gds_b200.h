@@ -245,9 +245,10 @@ int gds_halo_unpack(gds_halo* h, const void* buf_dev, void* vec_dev);
  *      64 bytes each; FLAGS holds 128 words), the host transport distributes them, every rank attaches its neighbours BEFORE
  *      gds_system_finalize; then gds_system_step replays the step graph as on one GPU.  src_idx: positions in this
  *      rank's state of the values sent to neighbour q (send_ptr[q] .. send_ptr[q+1]); dst_idx: where they land in the
- *      neighbour's state.  Every push first waits for the neighbour's "my stage is done" flag, so a neighbour's own
- *      kernels never overwrite what was pushed; owned_rows >= 0 additionally stops the RHS passes at that row (owned rows
- *      first), owned_rows < 0 lets them run over the ghost rows as well (deep partitions: owned rows are not a prefix).
+ *      neighbour's state.  owned_rows >= 0 (owned rows first): the RHS passes stop at that row, so ghost rows are written
+ *      by their owners' pushes only.  owned_rows < 0 (deep partitions: owned rows are not a prefix): the passes run over
+ *      the ghost rows as well, and every push first waits for the neighbour's "my stage is done" flag, so a neighbour's
+ *      own kernels never overwrite what was pushed.
  *      The wait gives up after 20 s (a dead peer) and raises the error flag read by gds_system_p2p_status. --------- */
 int gds_system_ipc_export(gds_system* s, uint8_t* handles /* 5 x 64 bytes */);
 int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_peers, const int32_t* peer_rank,
