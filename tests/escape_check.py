@@ -36,5 +36,12 @@ def check(name, G):
 if __name__ == '__main__':
     G2 = nx.grid_2d_graph(200, 200)
     G2.add_edge((0, 0), (199, 199))
-    good = check('cycle_40000', nx.cycle_graph(40000)) & check('grid_200x200_plus_long_edge', G2)
+    # the local graph of a slab behind the first: its ghost lattice row is numbered AFTER the owned rows, so a whole row of
+    # neighbours is > 32767 rows away (escapes that are aligned runs) -- here: a 200 x 200 grid whose first row comes last
+    H = nx.grid_2d_graph(200, 200)
+    G3 = nx.Graph()
+    G3.add_nodes_from([n for n in H.nodes() if n[0] > 0] + [n for n in H.nodes() if n[0] == 0])
+    G3.add_edges_from(H.edges())
+    good = (check('cycle_40000', nx.cycle_graph(40000)) & check('grid_200x200_plus_long_edge', G2)
+            & check('grid_200x200_first_row_last', G3))
     sys.exit(0 if good else 1)
