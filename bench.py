@@ -354,6 +354,24 @@ def cpu_baseline(workload, size, budget_s=12.0):
                       f'{os.cpu_count()} host cores)'}
 
 
+_REAL_STDOUT = [None]
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout at
+    the first collective), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a saved
+    copy of the real stdout."""
+    sys.stdout.flush()
+    _REAL_STDOUT[0] = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    fd = _REAL_STDOUT[0] if _REAL_STDOUT[0] is not None else 1
+    os.write(fd, (line + '\n').encode())
+
+
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -365,7 +383,7 @@ def reference_arm(args):
     cb = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
           'sample': f'{prob["name"]}; oracle/gds_oracle.py (numpy/scipy restatement of the reference, 1 thread of '
                     f'{os.cpu_count()} host cores: scipy CSR SpMV is single-threaded)'}
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -543,7 +561,7 @@ def gpu_arm(args):
                        'dof_stage_evals_per_sec': 4 * value, 'build_seconds': t_build},
             'roofline': roof, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -566,6 +584,7 @@ def main():
     ap.add_argument('--no-weighted', action='store_true')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         reference_arm(args)

@@ -73,8 +73,9 @@ struct GraphDev {
   // node incidence, sliced-ELL over nodes
   const uint32_t* n_soff;
   const int32_t* n_nbr;   // neighbour node, padding = own row
-  const int16_t* n_nbr16; // same slots as (neighbour - own row) when every difference fits 16 bits (lattices up to
-                          // 32767 wide, locally numbered graphs): half the index bytes for the Laplacian kernels; else null
+  const int16_t* n_nbr16; // same slots as (neighbour - own row) in 16 bits (lattices up to 32767 wide, locally numbered
+                          // graphs): half the index bytes for the quad Laplacian kernel.  -32768 = escape: the difference
+                          // does not fit, read n_nbr.  Null when more than 1 slot in 64 would escape
   int32_t n_uniw;         // > 0: every slice of the node ELL has this width (slice s starts at slot s * n_uniw * 32)
   const int32_t* n_edge;  // (edge << 1) | (1 if this node is the head v of the edge), padding = -1
   const double* n_w;      // w_e, padding = 0
