@@ -85,6 +85,13 @@ def main(argv):
         out = cases.jacobian_outputs(RefAPI, gname)
         np.savez_compressed(os.path.join(HERE, key + '.npz'), **out)
         print('wrote', key, out['jac'].shape)
+    for cname, fn in cases.QUIRK_CASES.items():
+        key = f'quirk_{cname}'
+        if want and key not in want:
+            continue
+        out = fn(RefAPI)
+        np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
+        print('wrote', key, {k: np.shape(v) for k, v in out.items()})
     for cname, fn in cases.TRAJ_CASES.items():
         key = f'traj_{cname}'
         if want and key not in want:

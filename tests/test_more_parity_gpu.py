@@ -1,6 +1,7 @@
 """More stepping parity against the CPU oracle: corners of the reference semantics and operator
 combinations the BASELINE cases do not reach."""
 import math
+import os
 
 import networkx as nx
 import numpy as np
@@ -21,20 +22,22 @@ def both(run):
         assert rel_l2(a[k], b[k]) <= TOL, (k, rel_l2(a[k], b[k]))
 
 
-def test_order2_with_dirichlet_hits_the_last_block():
-    """Appendix B.4: for order=2 the Dirichlet overwrite lands on the derivative block (fds.py:196,362)"""
-    def run(api):
-        G = cases.g_grid(7, 6)
-        a = api.node_gds(G)
-        api.evolve(a, dydt=lambda t, y: 0.8 * a.laplacian(), order=2, max_step=0.05)
-        a.set_initial(y0=lambda x: math.sin(x[0]) * math.cos(x[1]))
-        a.set_constraints(dirichlet=lambda t, x: 0.3 * math.cos(t) if x[0] == 0 else None)
-        out = {}
-        for i in range(3):
-            a.step(0.1)
-            out[f'y{i}'] = np.array(a.y, copy=True)
-        return out
-    both(run)
+@pytest.mark.parametrize('cname', list(cases.QUIRK_CASES))
+def test_quirk_cases(cname):
+    """order-2 Dirichlet on the last block (App. B.4), recurrence maps with time-varying Dirichlet values, the smallest
+    max_step of a coupled system (fds.py:437), free / normal rows and fluxes, lie_advect + bilaplacian, face fields,
+    accepted-state vs stage-state operators (App. B.3): against the CPU oracle AND against golden vectors produced by the
+    unmodified reference (tests/golden/quirk_*.npz)"""
+    run = cases.QUIRK_CASES[cname]
+    got, want = run(product_api()), run(oracle_api())
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', f'quirk_{cname}.npz'))
+    assert set(got) == set(want) == set(gold.files)
+    for k in want:
+        assert np.shape(got[k]) == np.shape(want[k]), k
+        assert rel_l2(got[k], want[k]) <= TOL, (k, rel_l2(got[k], want[k]))
+        assert rel_l2(got[k], gold[k]) <= TOL, (k, rel_l2(got[k], gold[k]))
+    if cname == 'accepted_vs_stage':
+        assert rel_l2(got['accepted'], got['stage']) > 1e-3
 
 
 @pytest.mark.parametrize('gname', ['hex_3x4', 'tri_5x7_w'])
@@ -56,109 +59,6 @@ def test_linearised_advection_perturbation_equation(gname):
             out[f'y{i}'] = np.array(v.y, copy=True)
         return out
     both(run)
-
-
-def test_map_mode_with_time_varying_dirichlet_and_time_argument():
-    def run(api):
-        G = cases.g_grid(6, 5)
-        x = api.node_gds(G)
-        api.evolve_map(x, map_fun=lambda t, y: 0.5 * y + 0.1 * x.laplacian(y) + 0.01 * t, dt=1.0)
-        x.set_initial(y0=lambda p: 0.1 * p[0] - 0.05 * p[1])
-        x.set_constraints(dirichlet=lambda t, p: math.sin(0.3 * t) if p[1] == 0 else None)
-        out = {}
-        for i in range(5):
-            x.step(1.0)
-            out[f'y{i}'] = np.array(x.y, copy=True)
-        return out
-    both(run)
-
-
-def test_euler_coupled_fields_with_different_max_steps():
-    """coupled_fds uses the smallest max_step of its systems (fds.py:437)"""
-    def run(api):
-        G = cases.g_hex(3, 3)
-        u, c = api.edge_gds(G), api.node_gds(G)
-        api.evolve(u, dydt=lambda t, y: -0.2 * y + 0.05 * u.laplacian(y), max_step=4e-3, scheme='euler')
-        api.evolve(c, dydt=lambda t, y: -c.advect(u, y) + 0.1 * u.div(), max_step=1e-3, scheme='euler')
-        r = np.random.default_rng(5)
-        u0, c0 = r.standard_normal(u.ndim), r.random(c.ndim)
-        u.set_initial(y0=lambda e: u0[u.X[e]])
-        c.set_initial(y0=lambda x: c0[c.X[x]])
-        s = api.couple({'u': u, 'c': c})
-        out = {}
-        for i in range(3):
-            s.step(2.5e-3)
-            out[f'u{i}'], out[f'c{i}'] = np.array(u.y, copy=True), np.array(c.y, copy=True)
-        out['t'] = np.array([s.t])
-        return out
-    both(run)
-
-
-def test_edge_law_with_free_and_normal_rows_and_fluxes():
-    def run(api):
-        G = cases.add_weights(cases.g_tri(4, 6), 8)
-        u, p = api.edge_gds(G), api.node_gds(G)
-        E = u.ndim
-        free, normal = np.arange(1, E, 7), np.arange(3, E, 5)
-        api.evolve_nil(p)
-        p.set_initial(y0=lambda x: 0.2 * x[0] - 0.1 * x[1])
-        api.evolve(u, dydt=lambda t, y: 0.3 * u.laplacian(y, free=free, normal=normal) - 0.5 * p.grad() + 0.05 * u.dd_(y),
-                   max_step=2e-3)
-        u0 = np.random.default_rng(6).standard_normal(E)
-        u.set_initial(y0=lambda e: u0[u.X[e]])
-        u.set_constraints(dirichlet={list(u.X.keys())[2]: 0.7})
-        s = api.couple({'u': u, 'p': p})
-        for _ in range(4):
-            s.step(2e-3)
-        return {'u': np.array(u.y, copy=True), 'influx': np.asarray(u.influx()).ravel(),
-                'outflux': np.asarray(u.outflux()).ravel(), 'curl': np.asarray(u.curl())}
-    both(run)
-
-
-def test_node_law_with_lie_advect_and_bilaplacian():
-    def run(api):
-        G = cases.g_grid(6, 7)
-        v, T = api.edge_gds(G), api.node_gds(G)
-        api.evolve_nil(v)
-        v0 = np.random.default_rng(7).standard_normal(v.ndim)
-        v.set_initial(y0=lambda e: v0[v.X[e]])
-        api.evolve(T, dydt=lambda t, y: -0.4 * T.lie_advect(v, y) - 0.01 * T.bilaplacian(y) + 0.2 * T.laplacian(y),
-                   max_step=1e-3)
-        T.set_initial(y0=lambda x: math.exp(-((x[0] - 3) ** 2 + (x[1] - 3) ** 2) / 4))
-        T.set_constraints(dirichlet={(0, 0): 0.0}, neumann={(5, 6): 0.3})
-        for _ in range(4):
-            T.step(1e-3)
-        return {'T': np.array(T.y, copy=True)}
-    both(run)
-
-
-def test_face_field_diffusion():
-    def run(api):
-        G = cases.g_hex(3, 4)
-        w = api.face_gds(G)
-        api.evolve(w, dydt=lambda t, y: 0.2 * w.laplacian(y) - 0.1 * y, max_step=5e-3)
-        w0 = np.random.default_rng(8).standard_normal(w.ndim)
-        w.set_initial(y0=lambda f: w0[w.X[f]])
-        for _ in range(3):
-            w.step(5e-3)
-        return {'w': np.array(w.y, copy=True)}
-    both(run)
-
-
-def test_accepted_state_vs_stage_argument_differ_like_the_reference():
-    """Appendix B.3: `T.laplacian()` (accepted state) and `T.laplacian(y)` (stage state) are different laws"""
-    def run(api, stage):
-        G = cases.g_grid(4, 4)
-        T = api.node_gds(G)
-        api.evolve(T, dydt=(lambda t, y: T.laplacian(y)) if stage else (lambda t, y: T.laplacian()), max_step=5e-2)
-        T.set_initial(y0=lambda x: float(x == (1, 1)))
-        for _ in range(10):
-            T.step(5e-2)
-        return np.array(T.y, copy=True)
-    a0, a1 = run(product_api(), False), run(product_api(), True)
-    b0, b1 = run(oracle_api(), False), run(oracle_api(), True)
-    assert rel_l2(a0, b0) <= TOL and rel_l2(a1, b1) <= TOL
-    assert rel_l2(a0, a1) > 1e-3
 
 
 def test_navier_stokes_with_pressure_solve_every_step():

@@ -44,6 +44,19 @@ def test_advection_jacobian_matches_reference(gname):
     assert rel_l2(ed.advect_jvp(v, y), fd) <= 1e-7
 
 
+@pytest.mark.parametrize('cname', list(cases.QUIRK_CASES))
+def test_quirk_cases_match_reference(cname):
+    """corners of the reference semantics: order-2 Dirichlet on the last block, recurrence maps with
+    time-varying Dirichlet values, smallest max_step of a coupled system, free / normal rows, lie_advect + bilaplacian,
+    face fields, accepted-state vs stage-state operators -- each run on the UNMODIFIED reference"""
+    gold = np.load(os.path.join(GOLD, f'quirk_{cname}.npz'))
+    out = cases.QUIRK_CASES[cname](oracle_api())
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        assert np.shape(out[k]) == gold[k].shape, k
+        assert rel_l2(out[k], gold[k]) <= TOL, (cname, k, rel_l2(out[k], gold[k]))
+
+
 @pytest.mark.parametrize('cname', list(cases.TRAJ_CASES))
 def test_trajectories_match_reference(cname):
     gold = np.load(os.path.join(GOLD, f'traj_{cname}.npz'))
