@@ -614,6 +614,9 @@ class node_gds(gds):
         self.dirichlet_laplacian = (sp.diags(keep) @ self.vertex_laplacian).tocsr()
         self.neumann_correction[self.neumann_indices] = self.neumann_values
 
+    def partial(self, e):  # gds.py:149-150
+        return np.sqrt(self.edge_weights[self.edges[e]]) * (self(e[1]) - self(e[0]))
+
     def grad(self, y=None):  # gds.py:152-154
         if y is None: y = self.y
         return self.incidence.T @ y

@@ -484,3 +484,65 @@ QUIRK_CASES = {
     'face_diffusion': quirk_face_diffusion,
     'accepted_vs_stage': quirk_accepted_vs_stage,
 }
+
+
+# ------------------------------------------------------------------------------------------------
+# the rest of the drop-in surface (System.solve, project=, fields outside the system, point reads, derived observables,
+# single-edge differences); golden vectors from the unmodified reference in tests/golden/api_*.npz
+# ------------------------------------------------------------------------------------------------
+def _api_heat(api, n=10):
+    G = g_grid(n, n)
+    T = api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=2e-3)
+    T.set_initial(y0=lambda x: math.exp(-((x[0] - 4) ** 2 + (x[1] - 5) ** 2) / 6))
+    T.set_constraints(dirichlet=lambda t, x: math.cos(t) if x[0] == 0 else None)
+    return T
+
+
+def api_solve(api):
+    """System.solve (system.py:38-57): states after every call of step(dt), initial state first"""
+    T = _api_heat(api)
+    t, data = api.couple({'T': T}).solve(0.02, 0.004)
+    return {'t': np.asarray(t, dtype=float), 'T': np.asarray(data['T'], dtype=float)}
+
+
+def api_user_projection(api):
+    """project= is arbitrary host code applied after every step (fds.py:363)"""
+    T = _api_heat(api, n=8)
+    T.set_constraints(dirichlet={(0, 0): 1.0}, project=lambda y: np.clip(y, 0.0, 0.6))
+    T.step(0.01)
+    return {'T': np.array(T.y, copy=True)}
+
+
+def api_external_field(api):
+    """a law may read a field outside its system; step(dt) spans several max_steps"""
+    G = g_grid(7, 9)
+    src, T = api.node_gds(G), api.node_gds(G)
+    api.evolve_nil(src)
+    src.set_initial(y0=lambda x: 0.1 * x[0] - 0.05 * x[1])
+    api.evolve(T, dydt=lambda t, y: T.laplacian(y) + 2.0 * src.y - y * t, max_step=3e-3)
+    T.set_initial(y0=lambda x: float(x[0] == 3))
+    for _ in range(3):
+        T.step(1e-2)
+    return {'T': np.array(T.y, copy=True), 't': np.array([T.t])}
+
+
+def api_point_reads(api):
+    """oriented point reads (gds.py:273-274), curl of the evolved field, single-edge difference (gds.py:149-150)"""
+    G = add_weights(g_hex(3, 4), 2)
+    u, c = api.edge_gds(G), api.node_gds(G)
+    rng = np.random.default_rng(3)
+    y0 = rng.standard_normal(u.ndim)
+    api.evolve(u, dydt=lambda t, y: 0.1 * u.laplacian(y), max_step=1e-3)
+    u.set_initial(y0=lambda e: y0[u.X[e]])
+    u.step(3e-3)
+    e = list(u.X.keys())[5]
+    x = rng.standard_normal(c.ndim)
+    api.evolve_nil(c)
+    c.set_initial(y0=lambda n: x[c.X[n]])
+    return {'read': np.array([u(e), u((e[1], e[0]))]), 'curl': np.asarray(u.curl(), dtype=float),
+            'partial': np.array([c.partial(e)]), 'y': np.array(u.y, copy=True)}
+
+
+API_CASES = {'solve': api_solve, 'user_projection': api_user_projection, 'external_field': api_external_field,
+             'point_reads': api_point_reads}

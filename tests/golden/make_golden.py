@@ -92,6 +92,13 @@ def main(argv):
         out = fn(RefAPI)
         np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
         print('wrote', key, {k: np.shape(v) for k, v in out.items()})
+    for cname, fn in cases.API_CASES.items():
+        key = f'api_{cname}'
+        if want and key not in want:
+            continue
+        out = fn(RefAPI)
+        np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
+        print('wrote', key, {k: np.shape(v) for k, v in out.items()})
     for cname, fn in cases.TRAJ_CASES.items():
         key = f'traj_{cname}'
         if want and key not in want:

@@ -190,3 +190,20 @@ def test_solve_to_disk_layout(tmp_path):
         want.append(np.array(To.y, copy=True))
     assert y.shape == (t.size, T.ndim) and np.allclose(t, 0.01 * np.arange(1, t.size + 1))
     assert rel_l2(y, np.array(want)) <= 1e-10
+
+
+_UNSEEN = pytest.mark.xfail(strict=False, reason='added after the last GPU session of round 1: first run pending')
+
+
+@pytest.mark.parametrize('cname', ['solve', 'user_projection', 'external_field',
+                                   pytest.param('point_reads', marks=_UNSEEN)])
+def test_api_surface_matches_reference_golden(cname):
+    """the same API cases against golden vectors produced by the UNMODIFIED reference (tests/golden/api_*.npz; the oracle
+    matches them on the CPU, tests/test_oracle_golden.py)"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', f'api_{cname}.npz'))
+    out = cases.API_CASES[cname](product_api())
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        assert np.shape(out[k]) == gold[k].shape, k
+        assert rel_l2(out[k], gold[k]) <= 1e-10, (cname, k, rel_l2(out[k], gold[k]))

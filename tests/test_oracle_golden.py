@@ -57,6 +57,18 @@ def test_quirk_cases_match_reference(cname):
         assert rel_l2(out[k], gold[k]) <= TOL, (cname, k, rel_l2(out[k], gold[k]))
 
 
+@pytest.mark.parametrize('cname', list(cases.API_CASES))
+def test_api_surface_matches_reference(cname):
+    """System.solve, project=, fields outside the system, oriented point reads, curl of an evolved field, single-edge
+    differences -- each run on the UNMODIFIED reference"""
+    gold = np.load(os.path.join(GOLD, f'api_{cname}.npz'))
+    out = cases.API_CASES[cname](oracle_api())
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        assert np.shape(out[k]) == gold[k].shape, k
+        assert rel_l2(out[k], gold[k]) <= TOL, (cname, k, rel_l2(out[k], gold[k]))
+
+
 @pytest.mark.parametrize('cname', list(cases.TRAJ_CASES))
 def test_trajectories_match_reference(cname):
     gold = np.load(os.path.join(GOLD, f'traj_{cname}.npz'))
