@@ -546,3 +546,59 @@ def api_point_reads(api):
 
 API_CASES = {'solve': api_solve, 'user_projection': api_user_projection, 'external_field': api_external_field,
              'point_reads': api_point_reads}
+
+
+# ------------------------------------------------------------------------------------------------
+# empty / tiny / ragged graphs, sizes off the 32- and 128-row boundaries; golden vectors from the unmodified reference
+# in tests/golden/ragged_*.npz for every graph the reference can construct
+# ------------------------------------------------------------------------------------------------
+def _nofaces(G):
+    G.faces = []
+    return G
+
+
+def star(k, seed=None):
+    G = nx.star_graph(k)
+    if seed is not None:
+        rng = np.random.default_rng(seed)
+        for u, v in G.edges():
+            G[u][v]['weight'] = float(rng.uniform(0.5, 2.0))
+    return _nofaces(G)
+
+
+RAGGED = {
+    'single_node': lambda: _nofaces(nx.empty_graph(1)),
+    'isolated_nodes': lambda: _nofaces(nx.empty_graph(5)),
+    'single_edge': lambda: _nofaces(nx.path_graph(2)),
+    'path_33': lambda: _nofaces(nx.path_graph(33)),
+    'path_129': lambda: _nofaces(nx.path_graph(129)),
+    'cycle_127': lambda: _nofaces(nx.cycle_graph(127)),
+    'star_200': lambda: star(200),
+    'star_70_weighted': lambda: star(70, seed=3),
+    'complete_40': lambda: _nofaces(nx.complete_graph(40)),
+    'grid_5x26_plus_isolated': lambda: _nofaces(nx.disjoint_union(nx.convert_node_labels_to_integers(nx.grid_2d_graph(5, 26)),
+                                                                  nx.empty_graph(3))),
+}
+
+
+def run_ops(api, G):
+    rng = np.random.default_rng(99)
+    nd, ed = api.node_gds(G), api.edge_gds(G)
+    V, E = nd.ndim, ed.ndim
+    yv, ye = rng.standard_normal(V), rng.standard_normal(E)
+    if E:
+        ye[::5] = 0.0
+    out = {'lap': nd.laplacian(yv), 'bilap': nd.bilaplacian(yv)}
+    if E:
+        out.update(grad=nd.grad(yv), nadv=nd.advect(ye, yv), lie=nd.lie_advect(ye, yv), div=ed.div(ye),
+                   influx=np.asarray(ed.influx(ye)).ravel(), outflux=np.asarray(ed.outflux(ye)).ravel(),
+                   dd=ed.dd_(ye), eadv=ed.advect(ye), elap=ed.laplacian(ye))
+    # a few RK4 steps of a nonlinear law with a Dirichlet node
+    api.evolve(nd, dydt=lambda t, y: nd.laplacian(y) - 0.1 * y ** 3, max_step=1e-3)
+    nd.set_initial(y0=lambda x: yv[nd.X[x]])
+    first = next(iter(nd.X))
+    nd.set_constraints(dirichlet={first: 0.5})
+    for _ in range(3):
+        nd.step(2.5e-3)
+    out['traj'] = np.array(nd.y, copy=True)
+    return out

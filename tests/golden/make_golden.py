@@ -92,6 +92,17 @@ def main(argv):
         out = fn(RefAPI)
         np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
         print('wrote', key, {k: np.shape(v) for k, v in out.items()})
+    for gname, make in cases.RAGGED.items():
+        key = f'ragged_{gname}'
+        if want and key not in want:
+            continue
+        try:
+            out = cases.run_ops(RefAPI, make())
+        except Exception as exc:      # degenerate graphs the reference cannot construct (no edges, ...)
+            print('reference cannot run', key, '-', type(exc).__name__, str(exc)[:80])
+            continue
+        np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
+        print('wrote', key, sorted(out))
     for cname, fn in cases.API_CASES.items():
         key = f'api_{cname}'
         if want and key not in want:

@@ -57,6 +57,19 @@ def test_quirk_cases_match_reference(cname):
         assert rel_l2(out[k], gold[k]) <= TOL, (cname, k, rel_l2(out[k], gold[k]))
 
 
+@pytest.mark.parametrize('gname', list(cases.RAGGED))
+def test_ragged_and_tiny_graphs_match_reference(gname):
+    """a single node, isolated nodes, one edge, paths and cycles off the 32 / 128-row boundaries, stars (degree-1 nodes:
+    the inf -> 0 rule of the dual weights, gds.py:253-257), a complete graph, a grid with isolated nodes -- every operator
+    and a few RK4 steps of a nonlinear law, each run on the UNMODIFIED reference"""
+    gold = np.load(os.path.join(GOLD, f'ragged_{gname}.npz'))
+    out = cases.run_ops(oracle_api(), cases.RAGGED[gname]())
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        assert np.shape(out[k]) == gold[k].shape, k
+        assert rel_l2(out[k], gold[k]) <= TOL, (gname, k, rel_l2(out[k], gold[k]))
+
+
 @pytest.mark.parametrize('cname', list(cases.API_CASES))
 def test_api_surface_matches_reference(cname):
     """System.solve, project=, fields outside the system, oriented point reads, curl of an evolved field, single-edge

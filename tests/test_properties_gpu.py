@@ -2,6 +2,7 @@
 size-independent properties at BASELINE.json's full sizes (where the oracle would take too long):
 conservation, linearity, curl o grad = 0, 2-homogeneity of the edge self-advection."""
 import math
+import os
 
 import networkx as nx
 import numpy as np
@@ -12,56 +13,8 @@ from adaptors import oracle_api, product_api, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def _nofaces(G):
-    G.faces = []
-    return G
-
-
-def star(k, seed=None):
-    G = nx.star_graph(k)
-    if seed is not None:
-        rng = np.random.default_rng(seed)
-        for u, v in G.edges():
-            G[u][v]['weight'] = float(rng.uniform(0.5, 2.0))
-    return _nofaces(G)
-
-
-RAGGED = {
-    'single_node': lambda: _nofaces(nx.empty_graph(1)),
-    'isolated_nodes': lambda: _nofaces(nx.empty_graph(5)),
-    'single_edge': lambda: _nofaces(nx.path_graph(2)),
-    'path_33': lambda: _nofaces(nx.path_graph(33)),
-    'path_129': lambda: _nofaces(nx.path_graph(129)),
-    'cycle_127': lambda: _nofaces(nx.cycle_graph(127)),
-    'star_200': lambda: star(200),
-    'star_70_weighted': lambda: star(70, seed=3),
-    'complete_40': lambda: _nofaces(nx.complete_graph(40)),
-    'grid_5x26_plus_isolated': lambda: _nofaces(nx.disjoint_union(nx.convert_node_labels_to_integers(nx.grid_2d_graph(5, 26)),
-                                                                  nx.empty_graph(3))),
-}
-
-
-def run_ops(api, G):
-    rng = np.random.default_rng(99)
-    nd, ed = api.node_gds(G), api.edge_gds(G)
-    V, E = nd.ndim, ed.ndim
-    yv, ye = rng.standard_normal(V), rng.standard_normal(E)
-    if E:
-        ye[::5] = 0.0
-    out = {'lap': nd.laplacian(yv), 'bilap': nd.bilaplacian(yv)}
-    if E:
-        out.update(grad=nd.grad(yv), nadv=nd.advect(ye, yv), lie=nd.lie_advect(ye, yv), div=ed.div(ye),
-                   influx=np.asarray(ed.influx(ye)).ravel(), outflux=np.asarray(ed.outflux(ye)).ravel(),
-                   dd=ed.dd_(ye), eadv=ed.advect(ye), elap=ed.laplacian(ye))
-    # a few RK4 steps of a nonlinear law with a Dirichlet node
-    api.evolve(nd, dydt=lambda t, y: nd.laplacian(y) - 0.1 * y ** 3, max_step=1e-3)
-    nd.set_initial(y0=lambda x: yv[nd.X[x]])
-    first = next(iter(nd.X))
-    nd.set_constraints(dirichlet={first: 0.5})
-    for _ in range(3):
-        nd.step(2.5e-3)
-    out['traj'] = np.array(nd.y, copy=True)
-    return out
+import cases
+from cases import RAGGED, run_ops
 
 
 @pytest.mark.parametrize('name', list(RAGGED))
@@ -72,11 +25,16 @@ def test_ragged_and_tiny_graphs_match_oracle(name):
     for k in want:
         assert np.shape(got[k]) == np.shape(want[k]), k
         assert rel_l2(got[k], want[k]) <= 1e-10, (name, k, rel_l2(got[k], want[k]))
+    gold_file = os.path.join(os.path.dirname(__file__), 'golden', f'ragged_{name}.npz')
+    if os.path.exists(gold_file):      # the unmodified reference on the same graph (it cannot construct all of them)
+        gold = np.load(gold_file)
+        assert set(gold.files) == set(got)
+        for k in gold.files:
+            assert rel_l2(got[k], gold[k]) <= 1e-10, (name, k, rel_l2(got[k], gold[k]))
 
 
 def test_matrix_right_hand_side():
     """operators accept a matrix of columns, e.g. laplacian(np.eye(n)) to extract the operator (examples/fluid.py:350)"""
-    import cases
     G = cases.g_hex(3, 4)
     a, b = product_api().edge_gds(G), oracle_api().edge_gds(cases.g_hex(3, 4))
     I = np.eye(a.ndim)
