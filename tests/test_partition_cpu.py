@@ -237,3 +237,59 @@ def test_deep_partition_recomputes_two_hop_operators_on_the_ghost_layers(kind, d
         got = _hodge1(p.n_loc, p.edge_u.astype(np.int64), p.edge_v.astype(np.int64), lf, v)
         own = p.owned_dom[1]
         assert np.allclose(got[own], want[p.edge_gid[own]], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('world,hops', [(2, 2), (3, 2), (4, 3)])
+def test_deep_partition_is_enough_for_the_edge_self_advection(world, hops):
+    """The two-pass nonlinear operator (node aggregates with weighted degrees, then the edge formula; gds.py:326-345) on
+    an IRREGULAR weighted graph: with two ghost layers every rank gets its OWNED edges right from its local graph alone
+    -- the aggregates at the far endpoint of an owned edge need that endpoint's whole star, one layer further out."""
+    import networkx as nx
+    from oracle import gds_oracle
+    from gds_b200.partition import DeepPartition
+    G = nx.random_geometric_graph(260, 0.11, seed=9)
+    G = nx.convert_node_labels_to_integers(G.subgraph(max(nx.connected_components(G), key=len)).copy())
+    # number the nodes along x so that index ranges are spatial slabs
+    order = sorted(G.nodes(), key=lambda n: G.nodes[n]['pos'][0])
+    G = nx.relabel_nodes(G, {n: i for i, n in enumerate(order)})
+    H = nx.Graph()
+    H.add_nodes_from(range(G.number_of_nodes()))
+    rng = np.random.default_rng(2)
+    H.add_weighted_edges_from((min(u, v), max(u, v), float(rng.uniform(0.5, 2.0))) for u, v in G.edges())
+    H.faces = []
+    full = gds_oracle.edge_gds(H)
+    eu = np.array([u for u, v in H.edges()], dtype=np.int64)
+    ev = np.array([v for u, v in H.edges()], dtype=np.int64)
+    w = np.array([d['weight'] for _, _, d in H.edges(data=True)])
+    V, E = H.number_of_nodes(), eu.size
+    y = rng.standard_normal(E)
+    y[::9] = 0.0
+    want = full.advect(y)
+    bounds = split_bounds(V, world)
+    def local_advect(p):
+        """the oracle's operator on the rank's local graph, in the partition's own edge order and orientation
+        (networkx lists the edges of a rebuilt graph in adjacency order, possibly reversed: an edge vector changes
+        sign with the orientation of its edge)"""
+        L = nx.Graph()
+        L.add_nodes_from(range(p.n_loc))
+        L.add_weighted_edges_from((int(a), int(b), float(c)) for a, b, c in zip(p.edge_u, p.edge_v, p.weights))
+        L.faces = []
+        loc = gds_oracle.edge_gds(L)
+        keys = list(loc.edges.keys())
+        idx = np.array([loc.edges[(int(a), int(b))] for a, b in zip(p.edge_u, p.edge_v)])
+        sgn = np.array([1.0 if keys[j] == (int(a), int(b)) else -1.0 for j, a, b in zip(idx, p.edge_u, p.edge_v)])
+        y_loc = np.zeros(p.E_loc)
+        y_loc[idx] = sgn * y[p.edge_gid]
+        return sgn * loc.advect(y_loc)[idx]
+
+    one_layer_ok = []
+    for r in range(world):
+        p = DeepPartition(r, world, V, eu, ev, w, bounds, hops)
+        got, own = local_advect(p), p.owned_dom[1]
+        assert own.any() and np.allclose(got[own], want[p.edge_gid[own]], rtol=0, atol=1e-12)
+        p1 = DeepPartition(r, world, V, eu, ev, w, bounds, 1)
+        o1 = p1.owned_dom[1]
+        one_layer_ok.append(np.allclose(local_advect(p1)[o1], want[p1.edge_gid[o1]], rtol=0, atol=1e-9))
+    # one layer is NOT enough for a rank that owns a cut edge (its far endpoint's star is incomplete); the last rank owns
+    # none (an edge belongs to the owner of its tail = lower index) and gets away with it
+    assert not all(one_layer_ok) and one_layer_ok[-1]
