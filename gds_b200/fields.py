@@ -311,7 +311,7 @@ class fds(Observable, Steppable):
             return self._coupled.t
         if self.iter_mode is IterationMode.dydt and self._engine is not None:
             return self._engine.t
-        return self._t if self.iter_mode is not IterationMode.none else self.t0
+        return self._t if self.iter_mode is not IterationMode.none else None     # fds.py:385-392: no branch, None
 
     @property
     def dt(self):

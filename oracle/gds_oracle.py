@@ -554,7 +554,9 @@ class fds:
         return self._y
 
     @property
-    def t(self):
+    def t(self):  # fds.py:385-392 (no branch for a field without a law: None)
+        if self.iter_mode is IterationMode.none:
+            return None
         if self.iter_mode is IterationMode.dydt:
             return self.integrator.t
         return self._t
@@ -631,6 +633,7 @@ class node_gds(gds):
 
     def advect(self, v_field, y=None):  # gds.py:166-177
         if isinstance(v_field, edge_gds):
+            assert v_field.G is self.G, 'Incompatible domains'   # gds.py:168
             v_field = v_field.y
         if y is None: y = self.y
         B = self.incidence
@@ -640,6 +643,7 @@ class node_gds(gds):
 
     def lie_advect(self, v_field, y=None):  # gds.py:179-189
         if isinstance(v_field, edge_gds):
+            assert v_field.G is self.G, 'Incompatible domains'   # gds.py:184
             v_field = v_field.y
         if y is None: y = self.y
         B = self.incidence

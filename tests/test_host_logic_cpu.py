@@ -240,3 +240,81 @@ def test_affine_split_of_an_lhs_law():
         bad = pressure.laplacian(Stage(pressure)) * Stage(pressure)
     with pytest.raises(TraceError):
         split_affine(bad, pressure)
+
+
+def _misuses(mod, integrators):
+    """the API preconditions of the path (fds.py:72,95,149,189,243,412-414,435; gds.py:168): each entry provokes one"""
+    def two_laws():
+        T = mod.node_gds(cases.g_grid(3, 3))
+        T.set_evolution(dydt=lambda t, y: y, map_fun=lambda t, y: y)
+
+    def no_law():
+        mod.node_gds(cases.g_grid(3, 3)).set_evolution()
+
+    def initial_before_law():
+        mod.node_gds(cases.g_grid(3, 3)).set_initial(y0=lambda x: 0.)
+
+    def constraints_before_law():
+        mod.node_gds(cases.g_grid(3, 3)).set_constraints(dirichlet={(0, 0): 1.})
+
+    def overlap():
+        T = mod.node_gds(cases.g_grid(3, 3))
+        T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2, integrator=integrators[0])
+        T.set_constraints(dirichlet={(0, 0): 1., (0, 1): 2.}, neumann={(0, 1): 0.5})
+
+    def couple_nothing():
+        mod.couple({})
+
+    def couple_without_law():
+        mod.couple({'T': mod.node_gds(cases.g_grid(3, 3))})
+
+    def couple_late():
+        T = mod.node_gds(cases.g_grid(3, 3))
+        T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2, integrator=integrators[0])
+        T.set_initial(t0=1.0, y0=lambda x: 1.)
+        mod.couple({'T': T})
+
+    def incompatible_domains():
+        T = mod.node_gds(cases.g_grid(3, 3))
+        v = mod.edge_gds(cases.g_grid(4, 4))
+        T.advect(v, np.zeros(T.ndim))
+    return {'two_laws': two_laws, 'no_law': no_law, 'initial_before_law': initial_before_law,
+            'constraints_before_law': constraints_before_law, 'overlap': overlap, 'couple_nothing': couple_nothing,
+            'couple_without_law': couple_without_law, 'couple_late': couple_late,
+            'incompatible_domains': incompatible_domains}
+
+
+def test_api_preconditions_raise_like_the_reference():
+    """same misuse, same exception type and (where the reference gives one) same message as the oracle, which restates
+    the reference's asserts; tests/test_golden_fresh_cpu.py-style check against the reference itself below"""
+    ours = _misuses(gds_b200, (gds_b200.Integrators.rk4,))
+    theirs = _misuses(gds_oracle, (gds_oracle.Integrators.rk4,))
+    for name in ours:
+        with pytest.raises(AssertionError) as a:
+            ours[name]()
+        with pytest.raises(AssertionError) as b:
+            theirs[name]()
+        ma, mb = str(a.value).split('\n')[0], str(b.value).split('\n')[0]
+        if name == 'overlap':       # the message lists the overlapping points: compare up to the list
+            ma, mb = ma.split(' on ')[0], mb.split(' on ')[0]
+        assert ma == mb, (name, ma, mb)
+    T = gds_b200.node_gds(cases.g_grid(3, 3))
+    with pytest.raises(ValueError, match='Unsupported integrator type'):         # fds.py:95
+        T.set_evolution(dydt=lambda t, y: y, integrator='no such integrator')
+
+
+@pytest.mark.skipif(not __import__('os').path.isdir('/root/reference/gds'), reason='reference not mounted')
+def test_api_preconditions_raise_like_the_unmodified_reference():
+    from oracle.ref_harness import load_reference
+    ref = load_reference()
+    theirs = _misuses(ref, (ref.Integrators.implicit_midpoint,))
+    ours = _misuses(gds_b200, (gds_b200.Integrators.rk4,))
+    for name in ours:
+        with pytest.raises(AssertionError) as a:
+            ours[name]()
+        with pytest.raises(AssertionError) as b:
+            theirs[name]()
+        ma, mb = str(a.value).split('\n')[0], str(b.value).split('\n')[0]
+        if name == 'overlap':
+            ma, mb = ma.split(' on ')[0], mb.split(' on ')[0]
+        assert ma == mb, (name, ma, mb)
