@@ -57,3 +57,42 @@ def test_trajectory_golden_is_fresh(ref_api):
 def test_jacobian_and_ragged_golden_are_fresh(ref_api):
     _same(cases.jacobian_outputs(ref_api, 'hex_3x4'), os.path.join(GOLD, 'jac_hex_3x4.npz'))
     _same(cases.run_ops(ref_api, cases.RAGGED['star_70_weighted']()), os.path.join(GOLD, 'ragged_star_70_weighted.npz'))
+
+
+@pytest.mark.parametrize('gname', ['grid_6x7', 'hex_3x4', 'tri_4x6', 'rgg_60'])
+def test_public_index_maps_and_boundary_bookkeeping_equal_the_reference(gname, monkeypatch):
+    """the public attributes examples and renderers read -- X, iX, nodes, edges, faces, ndim, X_dirichlet,
+    dirichlet_indices / values, X_neumann, dynamic flags (gds.py:16-55, fds.py:175-243) -- from the host mirror on a
+    host-only context against the unmodified reference, same graph, same boundary conditions"""
+    import math
+    import gds_b200
+    from oracle.ref_harness import load_reference
+    ref = load_reference()
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    try:
+        for kind in ('node_gds', 'edge_gds', 'face_gds'):
+            a, b = getattr(gds_b200, kind)(cases.OP_GRAPHS[gname]()), getattr(ref, kind)(cases.OP_GRAPHS[gname]())
+            assert a.ndim == b.ndim
+            assert list(a.X.items()) == list(b.X.items())
+            assert list(a.iX.items()) == list(b.iX.items())
+            assert list(a.nodes.items()) == list(b.nodes.items())
+            assert list(a.edges.items()) == list(b.edges.items())
+            assert list(a.faces.items()) == list(b.faces.items())
+            if a.ndim == 0:
+                continue
+            pts = list(a.X.keys())
+            static = {pts[i]: 0.25 * i for i in range(0, len(pts), 5)}
+            dyn = lambda t, x, pts=pts: math.sin(t + 0.1 * len(str(x))) if x in pts[2::7] else None   # noqa: E731
+            for f, mod in ((a, gds_b200), (b, ref)):
+                f.set_evolution(dydt=lambda t, y: 0 * y, max_step=1e-2,
+                                integrator=(gds_b200.Integrators.rk4 if mod is gds_b200 else ref.Integrators.implicit_midpoint))
+                f.set_constraints(dirichlet=mod.combine_bcs(static, dyn),
+                                  neumann=({pts[1]: -0.5} if kind == 'node_gds' else {}))
+            assert list(a.X_dirichlet) == list(b.X_dirichlet)
+            assert np.array_equal(a.dirichlet_indices, b.dirichlet_indices)
+            assert np.allclose(a.dirichlet_values, b.dirichlet_values, rtol=0, atol=0)
+            assert list(a.X_neumann) == list(b.X_neumann) and np.array_equal(a.neumann_indices, b.neumann_indices)
+            assert a.dynamic_dirichlet == b.dynamic_dirichlet and a.dynamic_neumann == b.dynamic_neumann
+    finally:
+        gds_b200.Context._default.clear()
