@@ -45,3 +45,21 @@ def test_host_only_context_never_computes():
         assert 'host-only' in str(e)
     else:
         raise AssertionError('download on a host-only context must fail')
+
+
+def test_python_constants_equal_the_header():
+    """opcodes, domains, schemes, operand kinds and limits mirrored in gds_b200/_lib.py are the header's values"""
+    src = open(os.path.join(ROOT, 'include', 'gds_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r'\b(GDS_[A-Z0-9_]+)\s*=\s*(-?\d+)', src)}
+    defines = {k: int(v) for k, v in re.findall(r'#define\s+(GDS_[A-Z0-9_]+)\s+(\d+)\s*$', src, flags=re.M)}
+    ops = {k[len('GDS_OP_'):]: v for k, v in enums.items() if k.startswith('GDS_OP_')}
+    assert ops == dict(L.OP), (set(ops) ^ set(L.OP))
+    for name in ('NODES', 'EDGES', 'FACES', 'SCHEME_EULER', 'SCHEME_RK4', 'SCHEME_MAP', 'WHEN_STAGE', 'WHEN_STEP',
+                 'EPI_NONE', 'EPI_RHS', 'VEC_BUF', 'VEC_STATE', 'VEC_STAGE'):
+        assert enums['GDS_' + name] == getattr(L, name), name
+    for name in ('MAX_CODE', 'MAX_IMM', 'MAX_VEC', 'MAX_MASK', 'MAX_OUT'):
+        assert defines['GDS_' + name] == getattr(L, name), name
+    from gds_b200.trace import Lowering
+    chain = {k[len('GDS_CHAIN_'):]: v for k, v in enums.items() if k.startswith('GDS_CHAIN_')}
+    assert chain == Lowering.CHAIN
