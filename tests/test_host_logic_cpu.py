@@ -151,6 +151,25 @@ def test_row_program_validation_in_the_library():
     d.code = code
     rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
     assert rc != 0 and b'non-edge pass' in L.lib.gds_last_error()
+    # tangent aggregates: the direction vector (operand c) and the output slot are checked like every other operand
+    code = (C.c_uint32 * 2)(L.OP['N_EAGGT'] | (0 << 8) | (0 << 16) | (3 << 24), 0)
+    d.code = code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'out of range' in L.lib.gds_last_error()
+    d.domain = L.EDGES
+    code = (C.c_uint32 * 2)(L.OP['E_ADVS1'] | (0 << 8) | (1 << 16), 0)    # aggregates operand missing
+    d.code = code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'out of range' in L.lib.gds_last_error()
+    d.domain = L.NODES
+    code = (C.c_uint32 * 2)(L.OP['E_ADVS1'], 0)                           # edge operator in a node pass
+    d.code = code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'non-edge pass' in L.lib.gds_last_error()
+    code = (C.c_uint32 * 2)(250, 0)                                        # not an opcode
+    d.code = code
+    rc = L.lib.gds_pass_run(ctx.h, dev.h, C.byref(d), 0.0)
+    assert rc != 0 and b'unknown opcode' in L.lib.gds_last_error()
 
 
 def kernel_kinds(field, law, scheme='rk4'):
