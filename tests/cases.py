@@ -602,3 +602,27 @@ def run_ops(api, G):
         nd.step(2.5e-3)
     out['traj'] = np.array(nd.y, copy=True)
     return out
+
+
+def fuzz_graphs():
+    """random / irregular graphs: components, isolated nodes, leaves, hubs, weights, shuffled labels"""
+    rng = np.random.default_rng(17)
+
+    def weighted(G, seed):
+        r = np.random.default_rng(seed)
+        for u, v in G.edges():
+            G[u][v]['weight'] = float(r.uniform(0.3, 3.0))
+        return G
+    out = {
+        'gnp_40': nx.gnp_random_graph(40, 0.12, seed=4),                       # isolated nodes, several components
+        'gnp_60_weighted': weighted(nx.gnp_random_graph(60, 0.08, seed=5), 1),
+        'regular_3_50': nx.random_regular_graph(3, 50, seed=6),
+        'barbell': nx.barbell_graph(7, 4),
+        'wheel_weighted': weighted(nx.wheel_graph(23), 2),
+        'ladder': nx.ladder_graph(19),
+        'tree': nx.bfs_tree(nx.gnp_random_graph(45, 0.2, seed=8), 0).to_undirected(),
+        'shuffled_labels': nx.relabel_nodes(nx.cycle_graph(31), dict(zip(range(31), rng.permutation(31).tolist()))),
+    }
+    for G in out.values():
+        G.faces = []
+    return out

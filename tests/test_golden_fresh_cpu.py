@@ -96,3 +96,16 @@ def test_public_index_maps_and_boundary_bookkeeping_equal_the_reference(gname, m
             assert a.dynamic_dirichlet == b.dynamic_dirichlet and a.dynamic_neumann == b.dynamic_neumann
     finally:
         gds_b200.Context._default.clear()
+
+
+@pytest.mark.parametrize('gname', list(cases.fuzz_graphs()))
+def test_oracle_equals_the_live_reference_on_irregular_graphs(ref_api, gname):
+    """no committed vectors here: the oracle and the unmodified reference run side by side on random / irregular graphs
+    (components, isolated nodes, leaves, hubs, weights, shuffled labels), every operator and a short nonlinear trajectory"""
+    from adaptors import oracle_api, rel_l2
+    want = cases.run_ops(ref_api, cases.fuzz_graphs()[gname])
+    got = cases.run_ops(oracle_api(), cases.fuzz_graphs()[gname])
+    assert set(want) == set(got)
+    for k in want:
+        assert np.shape(got[k]) == np.shape(want[k]), k
+        assert rel_l2(got[k], want[k]) <= 1e-12, (gname, k, rel_l2(got[k], want[k]))

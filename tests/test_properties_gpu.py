@@ -33,6 +33,21 @@ def test_ragged_and_tiny_graphs_match_oracle(name):
             assert rel_l2(got[k], gold[k]) <= 1e-10, (name, k, rel_l2(got[k], gold[k]))
 
 
+_UNSEEN = pytest.mark.xfail(strict=False, reason='added after the last GPU session of round 1: first run pending')
+
+
+@_UNSEEN
+@pytest.mark.parametrize('gname', list(cases.fuzz_graphs()))
+def test_irregular_graphs_match_oracle(gname):
+    """random / irregular graphs (the oracle equals the live reference on them, tests/test_golden_fresh_cpu.py)"""
+    want = run_ops(oracle_api(), cases.fuzz_graphs()[gname])
+    got = run_ops(product_api(), cases.fuzz_graphs()[gname])
+    assert set(want) == set(got)
+    for k in want:
+        assert np.shape(got[k]) == np.shape(want[k]), k
+        assert rel_l2(got[k], want[k]) <= 1e-10, (gname, k, rel_l2(got[k], want[k]))
+
+
 def test_matrix_right_hand_side():
     """operators accept a matrix of columns, e.g. laplacian(np.eye(n)) to extract the operator (examples/fluid.py:350)"""
     G = cases.g_hex(3, 4)
