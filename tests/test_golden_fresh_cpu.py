@@ -109,3 +109,54 @@ def test_oracle_equals_the_live_reference_on_irregular_graphs(ref_api, gname):
     for k in want:
         assert np.shape(got[k]) == np.shape(want[k]), k
         assert rel_l2(got[k], want[k]) <= 1e-12, (gname, k, rel_l2(got[k], want[k]))
+
+
+def _graph_equal(A, B):
+    assert list(A.nodes()) == list(B.nodes())
+    assert list(A.edges()) == list(B.edges())
+    pa, pb = nx_attr(A, 'pos'), nx_attr(B, 'pos')
+    assert set(pa) == set(pb)
+    for v in pa:
+        assert np.array_equal(np.asarray(pa[v], dtype=float), np.asarray(pb[v], dtype=float)), v
+
+
+def nx_attr(G, key):
+    import networkx as nx
+    return nx.get_node_attributes(G, key)
+
+
+@pytest.mark.parametrize('maker,args,kw', [
+    ('square_lattice', (5, 8), {}), ('square_lattice', (6, 4), {'diagonals': True}),
+    ('triangular_lattice', (4, 7), {}), ('triangular_lattice', (5, 6), {}),
+    ('hexagonal_lattice', (3, 4), {}), ('hexagonal_lattice', (2, 5), {'with_faces': False}),
+])
+def test_lattice_helpers_equal_the_reference(maker, args, kw, monkeypatch):
+    """the domain builders of the examples (generators.py:42-200,396-429,444-534): same nodes, G.edges() order, positions,
+    faces, boundary sub-graphs (with_boundaries and get_planar_boundary) and outer face as the unmodified reference"""
+    import gds_b200
+    from oracle.ref_harness import load_reference
+    ref = load_reference()
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    try:
+        Ga, sides_a = getattr(gds_b200, maker)(*args, with_boundaries=True, **kw)
+        Gb, sides_b = getattr(ref, maker)(*args, with_boundaries=True, **kw)
+        _graph_equal(Ga, Gb)
+        for a, b in zip(sides_a, sides_b):
+            assert list(a.nodes()) == list(b.nodes()) and list(a.edges()) == list(b.edges())
+        assert hasattr(Ga, 'faces') == hasattr(Gb, 'faces')
+        if hasattr(Gb, 'faces'):
+            assert [tuple(f) for f in Ga.faces] == [tuple(f) for f in Gb.faces]
+        for a, b in zip(gds_b200.get_planar_boundary(Ga), ref.get_planar_boundary(Gb)):
+            assert list(a.nodes()) == list(b.nodes()) and list(a.edges()) == list(b.edges())
+        fa, oa = gds_b200.embedded_faces(getattr(gds_b200, maker)(*args, **kw))
+        fb, ob = ref.embedded_faces(getattr(ref, maker)(*args, **kw))
+        assert [tuple(f) for f in fa] == [tuple(f) for f in fb] and tuple(oa) == tuple(ob)
+        wa = gds_b200.set_edge_weights(Ga, lambda e: 1.0 + 0.1 * len(str(e)))
+        wb = ref.set_edge_weights(Gb, lambda e: 1.0 + 0.1 * len(str(e)))
+        assert gds_b200.get_edge_weights(wa) == ref.get_edge_weights(wb)
+        assert gds_b200.get_edge_lengths(Ga) == ref.get_edge_lengths(Gb)
+        some = list(Ga.nodes())[::3]
+        assert list(gds_b200.edge_domain(Ga, some)) == list(ref.edge_domain(Gb, some))
+    finally:
+        gds_b200.Context._default.clear()
