@@ -19,7 +19,7 @@ from .partition import Partition, HaloExchange, split_bounds  # noqa: F401
 from .engine import StepEngine, step_table  # noqa: F401
 from .lattices import (set_grid_graph_layout, square_lattice, triangular_lattice, hexagonal_lattice,  # noqa: F401
                        get_planar_boundary, embedded_faces, get_edge_weights, set_edge_weights, get_edge_lengths,
-                       edge_domain, remove_edges, remove_pos)
+                       edge_domain, remove_edges, remove_pos, degree_matrix)
 from .fields import (fds, gds, GraphObservable, node_gds, edge_gds, simplex_gds, face_gds, coupled_fds, couple,  # noqa: F401
                      System, BoundarySpec)
 

@@ -15,7 +15,7 @@ import numpy as np
 
 __all__ = ['set_grid_graph_layout', 'square_lattice', 'triangular_lattice', 'hexagonal_lattice', 'get_planar_boundary',
            'embedded_faces', 'get_edge_weights', 'set_edge_weights', 'get_edge_lengths', 'edge_domain', 'remove_edges',
-           'remove_pos']
+           'remove_pos', 'degree_matrix']
 
 
 def set_grid_graph_layout(G: nx.Graph):
@@ -201,3 +201,16 @@ def remove_pos(G):
     for v in G.nodes():
         G.nodes[v].pop('pos', None)
     return G
+
+
+def degree_matrix(G):
+    """diagonal matrix of the weighted degrees, sum over incident edges of their 'weight' (gds/utils/graph/common.py:5-10)"""
+    import scipy.sparse as sp
+    index = {v: i for i, v in enumerate(G.nodes())}
+    deg = np.zeros(len(index))
+    for u, v, d in G.edges(data=True):
+        w = d.get('weight', 1)
+        deg[index[u]] += w
+        if u != v:
+            deg[index[v]] += w
+    return sp.diags(deg, format='csr')

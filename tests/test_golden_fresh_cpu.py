@@ -156,6 +156,7 @@ def test_lattice_helpers_equal_the_reference(maker, args, kw, monkeypatch):
         wb = ref.set_edge_weights(Gb, lambda e: 1.0 + 0.1 * len(str(e)))
         assert gds_b200.get_edge_weights(wa) == ref.get_edge_weights(wb)
         assert gds_b200.get_edge_lengths(Ga) == ref.get_edge_lengths(Gb)
+        assert np.array_equal(gds_b200.degree_matrix(Ga).toarray(), ref.degree_matrix(Gb).toarray())
         some = list(Ga.nodes())[::3]
         assert list(gds_b200.edge_domain(Ga, some)) == list(ref.edge_domain(Gb, some))
     finally:
