@@ -58,6 +58,53 @@ class BoundarySpec:
 # ------------------------------------------------------------------------------------------------
 # fds (gds/fds.py:14-400)
 # ------------------------------------------------------------------------------------------------
+class DeviceIntegrator:
+    """Solver-object view of a device-stepped field: the attributes the reference reads and writes on its
+    scipy.integrate.OdeSolver / gds.ode.midpoint.ImplicitMidpoint objects (gds/ode/midpoint.py:10-32; fds.py:157,171,196,
+    285-286,362-363) -- `t`, `y` (the whole state vector, every order block; materialised on access, assignable),
+    `t_bound`, `status`, `max_step`, `step()` = ONE internal step of min(max_step, t_bound - t) -- over the captured
+    step, for code that drives the solver object itself instead of calling `step(dt)`."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.t_bound = np.inf
+        self.status = 'running'
+
+    @property
+    def max_step(self):
+        return self._owner.max_step
+
+    @property
+    def t(self):
+        return self._owner.t
+
+    @property
+    def y(self):
+        o = self._owner
+        if o._engine is not None:
+            return np.array(o._engine.read(o, full=True), copy=True)
+        return np.array(o._host_state, copy=True)
+
+    @y.setter
+    def y(self, value):
+        o = self._owner
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float64).ravel())
+        assert a.size == o.ndim * o._order(), 'state vector has the wrong length'
+        if o._engine is not None:
+            o._engine.write(o, a)
+        else:
+            o._host_state = a.copy()
+        o._bump()
+
+    def step(self):
+        if self.status != 'running':
+            raise RuntimeError('Attempt to step on a failed or finished solver.')     # scipy's OdeSolver.step
+        o = self._owner
+        o.step(min(self.max_step, self.t_bound - o.t))
+        if self.t_bound - o.t <= 1e-14 * max(1.0, abs(self.t_bound)):      # t + (t_bound - t) may miss t_bound by an ulp
+            self.status = 'finished'
+
+
 class fds(Observable, Steppable):
     def __init__(self, X):
         Observable.__init__(self, X)
@@ -316,6 +363,17 @@ class fds(Observable, Steppable):
     @property
     def dt(self):
         return self._dt if self.iter_mode in (IterationMode.dydt, IterationMode.map) else 1e-3
+
+    @property
+    def integrator(self):
+        """the solver object of a `dydt=` field (fds.py:84-95 creates one per field); other modes have none"""
+        if self.iter_mode is not IterationMode.dydt:
+            raise AttributeError('integrator')
+        if self._coupled is not None:
+            raise Exception('this field is advanced by its coupled system; that system owns the integrator')
+        if self.__dict__.get('_integrator') is None:
+            self.__dict__['_integrator'] = DeviceIntegrator(self)
+        return self.__dict__['_integrator']
 
     def system(self, name: str) -> 'System':
         return System(self, {name: self})

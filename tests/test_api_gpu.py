@@ -207,3 +207,24 @@ def test_api_surface_matches_reference_golden(cname):
     for k in gold.files:
         assert np.shape(out[k]) == gold[k].shape, k
         assert rel_l2(out[k], gold[k]) <= 1e-10, (cname, k, rel_l2(out[k], gold[k]))
+
+
+@_UNSEEN
+def test_solver_object_facade_steps_like_step():
+    """driving obs.integrator by hand (t_bound, status, step()) is the loop fds.step runs (fds.py:284-290)"""
+    a, b = heat(product_api()), heat(product_api())
+    a.step(0.011)                                         # 5 internal steps of 2e-3 and one of 1e-3
+    it = b.integrator
+    it.t_bound = 0.011
+    n = 0
+    while it.status == 'running':
+        it.step()
+        n += 1
+    assert n == 6 and b.t == pytest.approx(a.t, abs=1e-15) and it.t == b.t
+    assert np.array_equal(np.asarray(a.y), np.asarray(b.y)) and np.array_equal(it.y[:b.ndim], np.asarray(b.y))
+    with pytest.raises(RuntimeError):
+        it.step()
+    y = it.y
+    y[3] += 1.0
+    it.y = y                                              # assignment reaches the device state
+    assert b.y[3] == pytest.approx(y[3])

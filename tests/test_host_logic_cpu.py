@@ -337,3 +337,23 @@ def test_api_preconditions_raise_like_the_unmodified_reference():
         if name == 'overlap':
             ma, mb = ma.split(' on ')[0], mb.split(' on ')[0]
         assert ma == mb, (name, ma, mb)
+
+
+def test_solver_object_facade_host_side():
+    """obs.integrator mirrors the solver-object attributes the reference touches (gds/ode/midpoint.py:10-32): state
+    vector with every order block, assignable; t, t_bound, status, max_step; fields without a `dydt=` law have none"""
+    T = gds_b200.node_gds(cases.g_grid(4, 5))
+    T.set_evolution(dydt=lambda t, y: T.laplacian(), order=2, max_step=2e-2)
+    T.set_initial(y0=lambda x: float(x[0]) + 0.1 * x[1])
+    it = T.integrator
+    assert it is T.integrator and it.status == 'running' and it.t_bound == np.inf and it.max_step == 2e-2
+    assert it.t == 0. and it.y.shape == (2 * T.ndim,) and np.array_equal(it.y[:T.ndim], T.y)
+    new = np.arange(2 * T.ndim, dtype=float)
+    it.y = new
+    assert np.array_equal(it.y, new) and np.array_equal(np.asarray(T.y), new[:T.ndim])
+    it.y[0] = -1.0                                        # a copy: writes go through the setter only
+    assert T.y[0] == 0.0
+    M = gds_b200.node_gds(cases.g_grid(3, 3))
+    M.set_evolution(map_fun=lambda t, y: 0.5 * y)
+    with pytest.raises(AttributeError):
+        M.integrator
