@@ -59,20 +59,21 @@ class BoundarySpec:
 # fds (gds/fds.py:14-400)
 # ------------------------------------------------------------------------------------------------
 class DeviceIntegrator:
-    """Solver-object view of a device-stepped field: the attributes the reference reads and writes on its
-    scipy.integrate.OdeSolver / gds.ode.midpoint.ImplicitMidpoint objects (gds/ode/midpoint.py:10-32; fds.py:157,171,196,
-    285-286,362-363) -- `t`, `y` (the whole state vector, every order block; materialised on access, assignable),
-    `t_bound`, `status`, `max_step`, `step()` = ONE internal step of min(max_step, t_bound - t) -- over the captured
-    step, for code that drives the solver object itself instead of calling `step(dt)`."""
+    """Solver-object view of a device-stepped field or coupled system: the attributes the reference reads and writes on
+    its scipy.integrate.OdeSolver / gds.ode.midpoint.ImplicitMidpoint objects (gds/ode/midpoint.py:10-32;
+    fds.py:157,171,196,285-286,362-363,443-444) -- `t`, `y` (the whole state vector: every order block of every coupled
+    field, in coupling order; materialised on access, assignable), `t_bound`, `status`, `max_step`, `step()` = ONE
+    internal step of min(max_step, t_bound - t) -- over the captured step, for code that drives the solver object
+    itself instead of calling `step(dt)`."""
 
-    def __init__(self, owner):
-        self._owner = owner
+    def __init__(self, owner, members, max_step):
+        self._owner, self._members, self._max_step = owner, members, max_step
         self.t_bound = np.inf
         self.status = 'running'
 
     @property
     def max_step(self):
-        return self._owner.max_step
+        return self._max_step()
 
     @property
     def t(self):
@@ -80,21 +81,23 @@ class DeviceIntegrator:
 
     @property
     def y(self):
-        o = self._owner
-        if o._engine is not None:
-            return np.array(o._engine.read(o, full=True), copy=True)
-        return np.array(o._host_state, copy=True)
+        parts = [np.asarray(m._engine.read(m, full=True) if m._engine is not None else m._host_state, dtype=np.float64)
+                 for m in self._members]
+        return np.concatenate(parts) if len(parts) > 1 else np.array(parts[0], copy=True)
 
     @y.setter
     def y(self, value):
-        o = self._owner
         a = np.ascontiguousarray(np.asarray(value, dtype=np.float64).ravel())
-        assert a.size == o.ndim * o._order(), 'state vector has the wrong length'
-        if o._engine is not None:
-            o._engine.write(o, a)
-        else:
-            o._host_state = a.copy()
-        o._bump()
+        assert a.size == sum(m.ndim * m._order() for m in self._members), 'state vector has the wrong length'
+        at = 0
+        for m in self._members:
+            n = m.ndim * m._order()
+            if m._engine is not None:
+                m._engine.write(m, a[at:at + n])
+            else:
+                m._host_state = a[at:at + n].copy()
+            m._bump()
+            at += n
 
     def step(self):
         if self.status != 'running':
@@ -372,7 +375,7 @@ class fds(Observable, Steppable):
         if self._coupled is not None:
             raise Exception('this field is advanced by its coupled system; that system owns the integrator')
         if self.__dict__.get('_integrator') is None:
-            self.__dict__['_integrator'] = DeviceIntegrator(self)
+            self.__dict__['_integrator'] = DeviceIntegrator(self, [self], lambda: self.max_step)
         return self.__dict__['_integrator']
 
     def system(self, name: str) -> 'System':
@@ -843,6 +846,15 @@ class coupled_fds(Steppable):
             s._coupled = self
             s._dev_y = Buffer(s._low.ctx, s.ndim, s._low.to_dev(s._domain_code, s._host_state[:s.ndim]))
             s._dev_y_cache = None
+
+    @property
+    def integrator(self):
+        """the one solver object of the coupled continuous fields (fds.py:441-447)"""
+        if not self.has_integrator:
+            raise AttributeError('integrator')
+        if self.__dict__.get('_integrator') is None:
+            self.__dict__['_integrator'] = DeviceIntegrator(self, self.cont, lambda: self.dydt_max_step)
+        return self.__dict__['_integrator']
 
     def _ensure_engine(self, record=False):
         if self._engine is not None and record and not self._engine.record:

@@ -357,3 +357,16 @@ def test_solver_object_facade_host_side():
     M.set_evolution(map_fun=lambda t, y: 0.5 * y)
     with pytest.raises(AttributeError):
         M.integrator
+    # a coupled system has ONE solver object over the concatenated state, in coupling order (fds.py:439-447)
+    G = cases.g_hex(2, 2)
+    u, c = gds_b200.edge_gds(G), gds_b200.node_gds(G)
+    u.set_evolution(dydt=lambda t, y: -y, max_step=4e-3)
+    c.set_evolution(dydt=lambda t, y: c.laplacian(y), max_step=1e-3)
+    u.set_initial(y0=lambda e: 1.0)
+    c.set_initial(y0=lambda x: 2.0)
+    st = gds_b200.couple({'u': u, 'c': c}).stepper
+    ci = st.integrator
+    assert ci.max_step == 1e-3 and ci.t == 0. and ci.y.shape == (u.ndim + c.ndim,)
+    assert np.all(ci.y[:u.ndim] == 1.0) and np.all(ci.y[u.ndim:] == 2.0)
+    with pytest.raises(Exception):
+        u.integrator                      # the coupled system owns the solver object
