@@ -34,7 +34,7 @@ UNIT = 'DOF-updates/s'
 # ------------------------------------------------------------------------------------------------
 # workloads: the same definition drives the CUDA product and the CPU oracle
 # ------------------------------------------------------------------------------------------------
-def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
+def heat2d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True):
     """BASELINE config 1 law on a grid (README.md:208-211 / examples/heat.py:56-63), RK4 h = 1e-2.  With `world` ranks
     the grid is (n*world) x n, cut into `world` slabs of n x n nodes (weak scaling: fixed work per GPU)."""
     h = 1e-2
@@ -45,7 +45,7 @@ def heat2d_problem(api, n, native, world=1, rank=0, weighted=False):
         if weighted:   # same lattice with random edge weights: the general (weighted) operator layout
             wts = np.random.default_rng(5).uniform(0.5, 2.0, 2 * n * (n - 1) if world == 1 else 0)
         G = gds_b200.NativeGraph('grid_2d', m, n, weights=wts)
-        if world > 1:
+        if world > 1 and distribute:
             gds_b200.distribute(G, rank, world)
         T = api.node_gds(G)
         api.evolve(T, dydt=lambda t, y: T.laplacian(y), max_step=h)
@@ -89,7 +89,7 @@ def _edges_inside(eu, ev, node_mask):
     return np.nonzero(node_mask[eu] & node_mask[ev])[0]
 
 
-def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
+def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True):
     """BASELINE config 2: edge diffusion (Hodge-1 Laplacian, Dirichlet 0 on top/bottom boundary edges) coupled with node
     advection-diffusion (Neumann -0.1 on the top row) on hexagonal_lattice_graph(n, n), RK4 h = 1e-3 (tests/cases.py
     case_hex_advdiff_c2 is the same law at small size, checked against the reference)."""
@@ -100,7 +100,7 @@ def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False):
         # with `world` ranks: hexagonal_lattice_graph(n, n*world) cut into node-index ranges (vertical strips), 4 ghost
         # layers (hexagons: the edge <- face gather needs 3), edge and node state exchanged after every stage
         G = gds_b200.NativeGraph('hexagonal', n, n * world)
-        if world > 1:
+        if world > 1 and distribute:
             gds_b200.distribute(G, rank, world, hops=4)
         u, c = api.edge_gds(G), api.node_gds(G)
         hg = G.hostgraph(with_faces=True)
@@ -221,14 +221,14 @@ def cml_problem(api, n, native, world=1, rank=0, weighted=False):
                 name=f'coupled map lattice, random_geometric_graph({n}) (E={E}), map mode')
 
 
-def wave3d_problem(api, n, native, world=1, rank=0, weighted=False):
+def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True):
     """BASELINE config 5 law: wave equation, order 2, accepted-state Laplacian (examples/wave.py:14) on grid_graph([n]*3)"""
     assert not weighted
     h = 0.1
     if native:
         import gds_b200
         G = gds_b200.NativeGraph('grid', n, n, n * world)
-        if world > 1:
+        if world > 1 and distribute:
             gds_b200.distribute(G, rank, world)
     else:
         import cases
@@ -400,8 +400,15 @@ def time_steps(eng, ctx, K, h, barrier, device, world, dist, torch, est_ms=2.0):
     """K steps with the state resident in HBM: CUDA events on the library's stream, max over ranks.  The clock sampler
     (100 ms period) needs load for longer than the timed region, so the same steps first run untimed for about 0.3 s
     and the timed K steps follow without a gap."""
+    n_pre = max(1, min(2000, int(0.3 / max(1e-6, est_ms * 1e-3))))
+    if world > 1:
+        # every rank must enqueue the SAME number of steps: the fused halo exchange pairs them up one by one, and
+        # `est_ms` is a rank-local measurement
+        tt = torch.tensor([n_pre], dtype=torch.int64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        n_pre = int(tt.item())
     with ClockSampler(device) as clk:
-        eng.run(eng.plan_steps(max(1, min(2000, int(0.3 / max(1e-6, est_ms * 1e-3)))), h))
+        eng.run(eng.plan_steps(n_pre, h))
         plan = eng.plan_steps(K, h)
         launches0, _ = ctx.counters()
         barrier()
@@ -415,6 +422,61 @@ def time_steps(eng, ctx, K, h, barrier, device, world, dist, torch, est_ms=2.0):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     return ms, int(launches1 - launches0), clk.summary()
+
+
+def verify_partitioned(eng, builder, args, world, rank, dist, torch):
+    """Correctness of the partitioned run, checked in the bench itself (the driver only sees this line at N > 1):
+    (1) halo_check -- after the timed steps every rank fetches, over NCCL send/recv, the rows its neighbours own and
+        compares them bit for bit with the ghost rows the fused peer-to-peer exchange left on it (full bench size);
+    (2) slab_check -- the same law on a small lattice (slabs still > 32767 rows, so ghost rows sit behind the 16-bit
+        index escape), 6 steps partitioned over all ranks vs. the whole lattice on rank 0's GPU alone: owned rows of
+        every rank bit-identical;
+    (3) the error flag and exchange count of the fused exchange."""
+    from adaptors import product_api
+    out = {'transport': 'p2p' if getattr(eng, 'p2p', False) else 'host', 'overlap_split': getattr(eng, 'overlap', None)}
+    eng.sync()
+    bad = torch.tensor([eng.halo_check()], dtype=torch.int64, device='cuda')
+    dist.all_reduce(bad)
+    out['halo_check'] = 'bit-identical' if int(bad.item()) == 0 else f'{int(bad.item())} ghost values differ from their owners'
+    if getattr(eng, 'p2p', False):
+        ex, err = eng.p2p_status()
+        st = torch.tensor([ex, err], dtype=torch.int64, device='cuda')
+        every = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(every, st)
+        out['p2p'] = {'exchanges_per_rank': [int(x[0].item()) for x in every], 'error': max(int(x[1].item()) for x in every)}
+    small = {'heat2d': 512, 'wave3d': 48, 'hex_advdiff': 24}.get(args.workload)
+    slab_ok = True
+    if small is not None and not args.no_slab_check:
+        steps = 6
+        prob = builder(product_api(), small, native=True, world=world, rank=rank)
+        e2 = prob['stepper']._ensure_engine()
+        e2.run(e2.plan_steps(steps, prob['h']))
+        e2.sync()
+        mine = [(np.asarray(fl.global_ids)[fl.owned_mask], np.asarray(fl.y_owned)) for fl in prob['fields']]
+        bad2 = torch.tensor([e2.halo_check()], dtype=torch.int64, device='cuda')
+        dist.all_reduce(bad2)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        verdict = [1]
+        if rank == 0:
+            one = builder(product_api(), small, native=True, world=world, rank=0, distribute=False)
+            e1 = one['stepper']._ensure_engine()
+            e1.run(e1.plan_steps(steps, one['h']))
+            e1.sync()
+            for k, fl in enumerate(one['fields']):
+                want = np.asarray(fl.y)
+                got = np.full_like(want, np.nan)
+                for r in range(world):
+                    gid, val = gathered[r][k]
+                    got[gid] = val
+                if not np.array_equal(got, want):
+                    verdict[0] = 0
+        dist.broadcast_object_list(verdict, src=0)
+        slab_ok = bool(verdict[0]) and int(bad2.item()) == 0
+        out['slab_check'] = (('bit-identical' if slab_ok else 'MISMATCH') + f' ({prob["name"]}; {steps} steps, {world} ranks vs one GPU;'
+                             f' overlap split {getattr(e2, "overlap", None)}, ghost rows vs owners: {int(bad2.item())} differ)')
+    out['ok'] = int(bad.item()) == 0 and slab_ok and out.get('p2p', {}).get('error', 0) == 0
+    return out
 
 
 def roofline_of(prob, eng, K, h, ms_step):
@@ -483,6 +545,9 @@ def gpu_arm(args):
     ms, launches, clocks = time_steps(eng, ctx, K, h, barrier, local, world, dist, torch, est_ms=est)
     n_total = prob['n_state'] * world
     value = n_total * K / (ms * 1e-3)
+    multi = None
+    if world > 1:
+        multi = verify_partitioned(eng, builder, args, world, rank, dist, torch)
     roof = roofline_of(prob, eng, K, h, ms / K)
     if world > 1:   # GPUs of one box differ by several per cent; the step runs at the pace of the slowest
         mine = torch.tensor([roof['launch_ms']], dtype=torch.float64, device='cuda')
@@ -561,9 +626,15 @@ def gpu_arm(args):
                        'dof_stage_evals_per_sec': 4 * value, 'build_seconds': t_build},
             'roofline': roof, 'cpu_baseline': cb, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
+        if multi is not None:
+            out['multi_gpu'] = multi
         emit(json.dumps(out))
     if world > 1:
+        if getattr(eng, 'p2p', False):
+            eng.sync()          # raises if an exchange of the e2e steps timed out
         dist.destroy_process_group()
+        if multi is not None and not multi['ok']:
+            raise SystemExit('bench.py: partitioned run is NOT bit-identical (see multi_gpu in the JSON line)')
 
 
 WORKLOAD_NAME = [None]
@@ -582,6 +653,7 @@ def main():
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-weighted', action='store_true')
+    ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     args = ap.parse_args()
     claim_stdout()

@@ -121,6 +121,8 @@ _sig('gds_halo_unpack', c_vp, c_vp, c_vp)
 _sig('gds_system_ipc_export', c_vp, c_vp)
 _sig('gds_system_p2p_attach', c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64)
 _sig('gds_system_p2p_status', c_vp, P(c_i64), P(c_i64))
+_sig('gds_system_p2p_error', c_vp, P(c_i64))
+_sig('gds_system_p2p_set_overlap', c_vp, c_i64, c_i64)
 _sig('gds_system_info', c_vp, P(c_i64), P(c_i64))
 _sig('gds_hostgraph_lattice', c_i32, c_i64, c_i64, c_i64, c_f64, c_i32, P(c_vp))
 _sig('gds_hostgraph_from_graph', c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp))
@@ -140,6 +142,7 @@ EXPORTED = [
     'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',
     'gds_halo_create', 'gds_halo_destroy', 'gds_halo_pack', 'gds_halo_unpack',
     'gds_system_ipc_export', 'gds_system_p2p_attach', 'gds_system_p2p_status',
+    'gds_system_p2p_error', 'gds_system_p2p_set_overlap',
     'gds_system_enable_recording', 'gds_system_set_trajectory', 'gds_system_step_record',
     'gds_hostgraph_lattice', 'gds_hostgraph_from_graph', 'gds_hostgraph_sizes', 'gds_hostgraph_copy',
     'gds_hostgraph_destroy', 'gds_graph_create_from_host',

@@ -39,6 +39,9 @@ extern "C" int gds_ctx_create(int device, gds_ctx** out) {
   c->stream = c->own_stream;
   GDS_CUDA(cudaEventCreate(&c->ev0));
   GDS_CUDA(cudaEventCreate(&c->ev1));
+  GDS_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  GDS_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  GDS_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -56,6 +59,9 @@ extern "C" int gds_ctx_destroy(gds_ctx* c) {
   if (c->flush_buf) cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->side_stream);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
@@ -857,6 +863,7 @@ extern "C" int gds_cg_solve(gds_ctx* c, gds_graph* g, const gds_pass_desc* apply
 // ---------------------------------------------------------------------------------------------------
 // systems
 // ---------------------------------------------------------------------------------------------------
+#define GDS_FLAGS_BYTES (2u << 20)
 extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int32_t scheme, gds_system** out) {
   if (!c || !g || !out || n_state <= 0) GDS_FAIL("bad argument");
   if (scheme != GDS_SCHEME_EULER && scheme != GDS_SCHEME_RK4 && scheme != GDS_SCHEME_MAP) GDS_FAIL("unknown scheme");
@@ -882,10 +889,19 @@ extern "C" int gds_system_create(gds_ctx* c, gds_graph* g, int64_t n_state, int3
   }
   GDS_CUDA(cudaMalloc((void**)&s->d_counter, 2 * sizeof(int64_t)));   // [step, block ticket of the tail kernel]
   GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(int64_t), c->stream));
-  GDS_CUDA(cudaMalloc((void**)&s->d_flags, 128 * sizeof(int64_t)));
-  GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, 128 * sizeof(int64_t), c->stream));
+  // the flag table is exported through CUDA IPC: it gets a whole 2 MiB allocation of its own, so that its handle can
+  // never refer to a block shared with other small allocations
+  GDS_CUDA(cudaMalloc((void**)&s->d_flags, GDS_FLAGS_BYTES));
+  GDS_CUDA(cudaMemsetAsync(s->d_flags, 0, GDS_FLAGS_BYTES, c->stream));
   GDS_CUDA(cudaMalloc((void**)&s->d_p2p_epoch, 2 * sizeof(int64_t)));
   GDS_CUDA(cudaMemsetAsync(s->d_p2p_epoch, 0, 2 * sizeof(int64_t), c->stream));
+  GDS_CUDA(cudaHostAlloc((void**)&s->h_p2p_err, sizeof(int64_t), cudaHostAllocMapped));
+  *s->h_p2p_err = 0;
+  GDS_CUDA(cudaHostGetDevicePointer((void**)&s->d_p2p_err_host, s->h_p2p_err, 0));
+  if (const char* e = getenv("GDS_B200_P2P_TIMEOUT_MS")) {
+    const double ms = atof(e);
+    if (ms > 0.0) s->p2p_timeout_ns = (uint64_t)(ms * 1e6);
+  }
   *out = s;
   return 0;
 }
@@ -903,9 +919,11 @@ extern "C" int gds_system_destroy(gds_system* s) {
   cudaFree(s->ACC);
   cudaFree(s->d_dir_idx_static); cudaFree(s->d_dir_val_static); cudaFree(s->d_dir_idx_dyn);
   cudaFree(s->d_bc_tab); cudaFree(s->d_steptab); cudaFree(s->d_counter);
+  cudaFree(s->d_dir_phase_static); cudaFree(s->d_dir_phase_dyn);
   for (auto& pr : s->peers)
     for (void* m : pr.mapped) if (m) cudaIpcCloseMemHandle(m);
   cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst);
+  if (s->h_p2p_err) cudaFreeHost(s->h_p2p_err);
   cudaFree(s->d_rec); cudaFree(s->d_traj);
   delete s;
   return 0;
@@ -1040,7 +1058,8 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
     GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
     if (ph.special) pp.n_rows = ph.sp_n;
     // peer-to-peer halo: ghost rows of the state are written by their owners only
-    if (s->p2p && s->owned_rows >= 0 && ph.epilogue == GDS_EPI_RHS && !ph.special)
+    // (the order-k block shift too: its ghost rows arrive with the derivative block's push like any other)
+    if (s->p2p && s->owned_rows >= 0 && ph.epilogue == GDS_EPI_RHS && ph.special != 2)
       pp.n_rows = std::min<int64_t>(s->owned_rows, pp.n_rows);
     pp.row0 = std::min<int64_t>(row0, pp.n_rows);
     if (row1 >= 0) pp.n_rows = std::min<int64_t>(row1, pp.n_rows);
@@ -1069,15 +1088,18 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
   return 0;
 }
 
-// Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter
-static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
+// Dirichlet overwrite (fds.py:289-290,362; coupled: fds.py:486-488), then advance the step counter.
+// phase < 0: all of it.  With the overlap split the overwrite of the rows in the boundary ranges (phase 1) runs before
+// the push of the new accepted state, the rest (phase 0) and the counter after the interior rows have finished.
+static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt, int phase = -1) {
   gds_ctx* c = s->ctx;
   double* ynew = s->Y[cur ^ 1];
   if (lt) GDS_TRY(lt->begin(3));
   const bool rec = s->recording && !lt;   // the snapshot reads the step counter after the overwrite: advance it last
+  const bool last = phase != 1;
   GDS_TRY(launch_tail(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, s->n_dir_static, s->d_dir_idx_dyn, s->d_bc_tab,
-                      s->n_dir_dyn, s->d_counter, rec ? 0 : 1));
-  if (rec) {
+                      s->n_dir_dyn, s->d_counter, (rec || !last) ? 0 : 1, s->d_dir_phase_static, s->d_dir_phase_dyn, phase));
+  if (rec && last) {
     GDS_TRY(launch_record(c, ynew, s->d_traj, s->d_rec, s->d_counter, s->n_state));
     GDS_TRY(launch_advance_counter(c, s->d_counter));
   }
@@ -1086,18 +1108,17 @@ static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt) {
 }
 
 // peer-to-peer halo: push this rank's boundary values of buffer `which` (0/1 = Y, 2/3 = XS) into the neighbours' ghost
-// rows, then wait for theirs
-static int enqueue_exchange(gds_system* s, int which) {
+// rows (enqueue_push), then wait for theirs (enqueue_wait)
+static int enqueue_push(gds_system* s, int which) {
   if (!s->p2p || s->peers.empty()) return 0;
   const double* mine[4] = {s->Y[0], s->Y[1], s->XS[0], s->XS[1]};
   PushParams pu;
-  WaitParams wa;
   memset(&pu, 0, sizeof(pu));
-  memset(&wa, 0, sizeof(wa));
-  pu.n_peers = wa.n_peers = (int32_t)s->peers.size();
+  pu.n_peers = (int32_t)s->peers.size();
   pu.src = mine[which];
   pu.src_idx = s->d_p2p_src; pu.dst_idx = s->d_p2p_dst;
-  pu.epoch = s->d_p2p_epoch; wa.epoch = s->d_p2p_epoch; wa.err = s->d_p2p_epoch + 1; pu.err = s->d_p2p_epoch + 1;
+  pu.epoch = s->d_p2p_epoch; pu.err = s->d_p2p_epoch + 1; pu.err_host = s->d_p2p_err_host;
+  pu.timeout_ns = s->p2p_timeout_ns;
   // node-only partitions stop their RHS passes at the owned rows, so nothing but the owners' pushes ever writes a ghost
   // row and no handshake is needed (it costs a second cross-GPU round trip per exchange: 0.32 vs 0.05 ms per RK4 step)
   pu.handshake = s->owned_rows < 0 ? 1 : 0;
@@ -1107,26 +1128,95 @@ static int enqueue_exchange(gds_system* s, int which) {
     pu.flag[q] = (int64_t*)pr.mapped[4] + s->my_rank;
     pu.ready[q] = s->d_flags + 64 + pr.rank;
     pu.s0[q] = pr.send0; pu.s1[q] = pr.send1;
-    wa.flag[q] = s->d_flags + pr.rank;
   }
-  GDS_TRY(launch_push(s->ctx, pu));
+  return launch_push(s->ctx, pu);
+}
+
+static int enqueue_wait(gds_system* s) {
+  if (!s->p2p || s->peers.empty()) return 0;
+  WaitParams wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.n_peers = (int32_t)s->peers.size();
+  wa.epoch = s->d_p2p_epoch; wa.err = s->d_p2p_epoch + 1; wa.err_host = s->d_p2p_err_host;
+  wa.timeout_ns = s->p2p_timeout_ns;
+  for (size_t q = 0; q < s->peers.size(); ++q) wa.flag[q] = s->d_flags + s->peers[q].rank;
   return launch_wait(s->ctx, wa);
 }
 
-// enqueue every kernel of one step reading Y[cur], writing Y[cur^1]
+static bool overlapped(const gds_system* s) {
+  return s->p2p && !s->peers.empty() && s->owned_rows >= 0 && s->ov_lo_end >= 0 && s->ov_hi_begin >= s->ov_lo_end;
+}
+
+// enqueue every kernel of one step reading Y[cur], writing Y[cur^1].
+// With a peer-to-peer halo and an overlap split (gds_system_p2p_set_overlap) a stage is
+//     main stream:  boundary rows [0, lo) and [hi, owned)  ->  push  ---------.
+//     side stream:  interior rows [lo, hi)  ----------------------------------+->  wait  ->  next stage
+// so the NVLink stores and the flag round trip hide behind the interior rows.  Interior rows neither are sent nor read
+// a ghost row, so a neighbour that runs one exchange ahead can never touch what they read.  Both branches are captured
+// into the one step graph.  Timed stepping (`lt`) keeps one launch per pass and runs the exchange between the event pairs.
 static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
+  gds_ctx* c = s->ctx;
   GDS_TRY(enqueue_prestep(s, cur, lt));
   const int ns = n_stages_of(s);
+  const bool ov = overlapped(s) && !lt;
   for (int st = 0; st < ns; ++st) {
+    const int which = (st < ns - 1) ? 2 + (st & 1) : (cur ^ 1);   // x_next of this stage / the new accepted state
+    if (ov) {
+      cudaStream_t main_stream = c->stream;
+      GDS_CUDA(cudaEventRecord(c->ev_fork, main_stream));
+      GDS_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+      c->stream = c->side_stream;
+      int rc = enqueue_stage(s, cur, st, nullptr, s->ov_lo_end, s->ov_hi_begin);
+      c->stream = main_stream;
+      GDS_TRY(rc);
+      GDS_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
+      GDS_TRY(enqueue_stage(s, cur, st, nullptr, 0, s->ov_lo_end));
+      GDS_TRY(enqueue_stage(s, cur, st, nullptr, s->ov_hi_begin, -1));
+      // the Dirichlet overwrite belongs to the new accepted state and Dirichlet rows may be among the rows sent: the
+      // overwrite of the boundary ranges runs before the push, the rest after the interior rows
+      if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, nullptr, 1));
+      GDS_TRY(enqueue_push(s, which));
+      GDS_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
+      if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, nullptr, 0));
+      GDS_TRY(enqueue_wait(s));
+      continue;
+    }
     GDS_TRY(enqueue_stage(s, cur, st, lt));
-    if (st < ns - 1 && !lt) GDS_TRY(enqueue_exchange(s, 2 + (st & 1)));   // x_next of this stage
+    if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, lt));
+    GDS_TRY(enqueue_push(s, which));
+    GDS_TRY(enqueue_wait(s));
   }
-  GDS_TRY(enqueue_tail(s, cur, lt));
-  if (!lt) GDS_TRY(enqueue_exchange(s, cur ^ 1));                          // the new accepted state
   return 0;
 }
 
 #define GDS_STEP_CAPACITY 4096  // steps per table upload; longer runs are chunked
+
+// overlap split: phase of every Dirichlet entry = 1 when its row lies in the boundary ranges of the pass that advances it
+static int classify_dirichlet(gds_system* s) {
+  auto phase_of = [&](int64_t idx) -> uint8_t {
+    for (const PassHost& ph : s->passes) {
+      if (ph.epilogue != GDS_EPI_RHS) continue;
+      const int64_t rows = ph.special ? ph.sp_n : domain_rows(s->g, ph.domain);
+      if (idx < ph.state_offset || idx >= ph.state_offset + rows) continue;
+      const int64_t row = idx - ph.state_offset;
+      return (row < s->ov_lo_end || row >= s->ov_hi_begin) ? 1 : 0;
+    }
+    return 0;
+  };
+  auto build = [&](const int64_t* d_idx, int64_t n, uint8_t** d_out) -> int {
+    if (n <= 0) return 0;
+    std::vector<int64_t> idx((size_t)n);
+    GDS_CUDA(cudaMemcpy(idx.data(), d_idx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> ph((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ph[i] = phase_of(idx[i]);
+    GDS_CUDA(cudaMalloc((void**)d_out, (size_t)n));
+    GDS_CUDA(cudaMemcpy(*d_out, ph.data(), (size_t)n, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  GDS_TRY(build(s->d_dir_idx_static, s->n_dir_static, &s->d_dir_phase_static));
+  GDS_TRY(build(s->d_dir_idx_dyn, s->n_dir_dyn, &s->d_dir_phase_dyn));
+  return 0;
+}
 
 extern "C" int gds_system_finalize(gds_system* s) {
   if (!s) GDS_FAIL("null system");
@@ -1158,6 +1248,7 @@ extern "C" int gds_system_finalize(gds_system* s) {
     GDS_CUDA(cudaMemset(s->d_traj, 0, sizeof(double*)));
   }
   if (c->stream != c->own_stream) GDS_FAIL("finalize on the context's own stream (an external stream cannot be captured here)");
+  if (overlapped(s)) GDS_TRY(classify_dirichlet(s));
   for (int cur = 0; cur < 2; ++cur) {
     int64_t before = c->kernel_launches;
     GDS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -1419,6 +1510,24 @@ extern "C" int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t*
   GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
   if (exchanges) *exchanges = h[0];
   if (error) *error = h[1];
+  return 0;
+}
+
+// the same error flag read from its mirror in mapped host memory: no stream synchronisation, so the host can look before
+// every call; it shows failures of work that has completed
+extern "C" int gds_system_p2p_error(gds_system* s, int64_t* error) {
+  if (!s || !error) GDS_FAIL("bad argument");
+  *error = s->h_p2p_err ? *reinterpret_cast<volatile int64_t*>(s->h_p2p_err) : 0;
+  return 0;
+}
+
+extern "C" int gds_system_p2p_set_overlap(gds_system* s, int64_t lo_end, int64_t hi_begin) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("set the overlap split before gds_system_finalize");
+  if (!s->p2p || s->owned_rows < 0) GDS_FAIL("the overlap split needs a peer-to-peer halo whose owned rows come first");
+  if (lo_end < 0 || hi_begin < lo_end || hi_begin > s->owned_rows || (lo_end & 127) || (hi_begin & 127))
+    GDS_FAIL("need 0 <= lo_end <= hi_begin <= owned_rows, both multiples of 128");
+  s->ov_lo_end = lo_end; s->ov_hi_begin = hi_begin;
   return 0;
 }
 

@@ -215,6 +215,10 @@ struct gds_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // second stream + fork / join events: the interior rows of a stage run beside the boundary rows and their push
+  // (gds_system_p2p_set_overlap); both are captured into the step graph as two branches
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t kernel_launches = 0;
   int64_t graph_replays = 0;
   void* flush_buf = nullptr;
@@ -276,6 +280,8 @@ struct gds_system {
   int64_t* d_dir_idx_static = nullptr;
   double* d_dir_val_static = nullptr;
   int64_t* d_dir_idx_dyn = nullptr;
+  uint8_t* d_dir_phase_static = nullptr;  // overlap split: 1 = the entry's row is in the boundary ranges
+  uint8_t* d_dir_phase_dyn = nullptr;
   double* d_bc_tab = nullptr;   // [cap_steps x n_dir_dyn]
   StepRec* d_steptab = nullptr; // [cap_steps]
   int64_t cap_steps = 0;
@@ -305,6 +311,13 @@ struct gds_system {
   int64_t* d_p2p_epoch = nullptr; // [2]: exchanges sent so far; error flag of the wait kernel
   int64_t* d_p2p_src = nullptr;
   int64_t* d_p2p_dst = nullptr;
+  // the error flag again in pinned, device-mapped host memory: the host polls it without synchronising the stream
+  int64_t* h_p2p_err = nullptr;   // host address
+  int64_t* d_p2p_err_host = nullptr;  // the same word as seen from the device
+  uint64_t p2p_timeout_ns = 20000000000ull;
+  // overlap: rows [0, ov_lo_end) and [ov_hi_begin, owned_rows) hold every row that is sent to / reads from a neighbour;
+  // they run first, their push follows at once, the interior rows run on a second stream meanwhile (-1: no overlap)
+  int64_t ov_lo_end = -1, ov_hi_begin = -1;
 };
 
 #define GDS_MAX_PEERS 8
@@ -315,6 +328,8 @@ struct PushParams {
   int64_t* flag[GDS_MAX_PEERS];      // peer's arrival flag for this rank (its ready flag is 64 slots further)
   const int64_t* ready[GDS_MAX_PEERS];  // this rank's ready flag written by each peer
   int64_t* err;
+  int64_t* err_host;                 // mirror of the error flag in mapped host memory (polled by the host)
+  uint64_t timeout_ns;
   int32_t handshake;                 // wait for the receiver's ready flag before storing (deep partitions only)
   int64_t s0[GDS_MAX_PEERS], s1[GDS_MAX_PEERS];
   const int64_t* src_idx;
@@ -326,6 +341,8 @@ struct WaitParams {
   const int64_t* flag[GDS_MAX_PEERS];  // my flags, one per neighbour
   const int64_t* epoch;
   int64_t* err;
+  int64_t* err_host;
+  uint64_t timeout_ns;
 };
 int launch_record(gds_ctx* ctx, const double* y, double* const* traj, const int64_t* rec, const int64_t* counter, int64_t n);
 int launch_push(gds_ctx* ctx, const PushParams& p);
@@ -337,7 +354,8 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
                      int64_t n, int64_t n_dyn_stride, const int64_t* counter);
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
 int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
-                const double* tab, int64_t nd, int64_t* counter, int advance);
+                const double* tab, int64_t nd, int64_t* counter, int advance, const uint8_t* sphase = nullptr,
+                const uint8_t* dphase = nullptr, int phase = -1);
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode);

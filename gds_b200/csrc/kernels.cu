@@ -1132,11 +1132,17 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
 __global__ void __launch_bounds__(256) tail_kernel(double* __restrict__ y, const int64_t* __restrict__ sidx,
                                                    const double* __restrict__ sval, int64_t ns,
                                                    const int64_t* __restrict__ didx, const double* __restrict__ tab,
-                                                   int64_t nd, int64_t* counter, int advance) {
+                                                   int64_t nd, int64_t* counter, int advance,
+                                                   const uint8_t* __restrict__ sphase, const uint8_t* __restrict__ dphase,
+                                                   int phase) {
   const int64_t step = counter[0];
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < ns) y[sidx[i]] = sval[i];
-  else if (i < ns + nd) y[didx[i - ns]] = tab[step * nd + (i - ns)];
+  // phase >= 0: only the entries of that phase (overlap split: boundary ranges first, the rest after the interior rows)
+  if (i < ns) {
+    if (phase < 0 || !sphase || sphase[i] == phase) y[sidx[i]] = sval[i];
+  } else if (i < ns + nd) {
+    if (phase < 0 || !dphase || dphase[i - ns] == phase) y[didx[i - ns]] = tab[step * nd + (i - ns)];
+  }
   if (!advance) return;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1147,10 +1153,11 @@ __global__ void __launch_bounds__(256) tail_kernel(double* __restrict__ y, const
 }
 
 int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
-                const double* tab, int64_t nd, int64_t* counter, int advance) {
+                const double* tab, int64_t nd, int64_t* counter, int advance, const uint8_t* sphase,
+                const uint8_t* dphase, int phase) {
   if (ns + nd <= 0 && !advance) return 0;
   const unsigned blocks = (unsigned)std::max<int64_t>(1, (ns + nd + 255) / 256);
-  tail_kernel<<<blocks, 256, 0, ctx->stream>>>(y, sidx, sval, ns, didx, tab, nd, counter, advance);
+  tail_kernel<<<blocks, 256, 0, ctx->stream>>>(y, sidx, sval, ns, didx, tab, nd, counter, advance, sphase, dphase, phase);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;
@@ -1344,23 +1351,36 @@ int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* a
 // wait: right after the push, one thread per neighbour polls the local flag slot until the neighbour's values of the
 // same exchange have arrived; only then may the next stage gather from the ghost rows.
 // ---------------------------------------------------------------------------------------------------
+// A wait that has timed out (a peer stopped, or the ranks enqueued different numbers of steps) raises the error flag --
+// in device memory for the kernels that follow, in mapped host memory for the host, which polls it without a
+// synchronisation -- and every later push / wait of this system returns at once instead of spinning again: a protocol
+// failure costs ONE timeout, and the next host call on the system raises (gds_system_p2p_error).
+__device__ __forceinline__ void p2p_raise(int64_t* err, int64_t* err_host, int64_t code) {
+  *err = code;
+  *reinterpret_cast<volatile int64_t*>(err_host) = code;
+  __threadfence_system();
+}
+
 __global__ void __launch_bounds__(1024) push_kernel(const __grid_constant__ PushParams p) {
   const int q = blockIdx.x;
   const double* __restrict__ src = p.src;
   double* dst = p.dst[q];
   // Handshake before writing (deep partitions, whose passes also run over ghost rows): the neighbour's own stage kernel
-  // may still be storing (meaningless) values into its ghost rows, so it first announces "my stage of this exchange is done" (ready flag, slot 64 + rank), and the push waits for it.
+  // may still be storing (meaningless) values into its ghost rows, so it first announces "my stage of this exchange is
+  // done" (ready flag, slot 64 + rank), and the push waits for it.
   if (p.handshake && threadIdx.x == 0) {
     const int64_t e = *p.epoch + 1;
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q] + 64), "l"(e) : "memory");
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    int64_t seen;
-    do {
-      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.ready[q]) : "memory");
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { *p.err = 1 + q; break; }
-    } while (seen < e);
+    if (*reinterpret_cast<volatile int64_t*>(p.err) == 0) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      int64_t seen;
+      do {
+        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.ready[q]) : "memory");
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > p.timeout_ns) { p2p_raise(p.err, p.err_host, 101 + q); break; }
+      } while (seen < e);
+    }
   }
   __syncthreads();
   for (int64_t i = p.s0[q] + threadIdx.x; i < p.s1[q]; i += 1024) dst[p.dst_idx[i]] = src[p.src_idx[i]];
@@ -1376,14 +1396,14 @@ __global__ void wait_kernel(const __grid_constant__ WaitParams p) {
   // exchange number being completed = exchanges completed so far + 1 (the push just before used the same number)
   const int q = threadIdx.x;
   const int64_t expect = *p.epoch + 1;
-  if (q < p.n_peers) {
+  if (q < p.n_peers && *reinterpret_cast<volatile int64_t*>(p.err) == 0) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     int64_t seen;
     do {
       asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.flag[q]) : "memory");
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { *p.err = 1 + q; break; }   // 20 s: a peer died; do not hang the GPU
+      if (t1 - t0 > p.timeout_ns) { p2p_raise(p.err, p.err_host, 1 + q); break; }   // a peer stopped: do not hang the GPU
     } while (seen < expect);
   }
   __threadfence_system();

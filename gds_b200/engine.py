@@ -37,6 +37,26 @@ def step_table(t, t_bound, max_step):
     return np.asarray(ts, dtype=np.float64), np.asarray(hs, dtype=np.float64), t
 
 
+def overlap_split(send_rows, n_own, max_fraction=0.25):
+    """(lo_end, hi_begin), multiples of 128, such that [0, lo_end) and [hi_begin, n_own) hold every row in `send_rows`
+    (the owned rows adjacent to a cut: they are sent to, and read ghost rows from, a neighbour) and are as short as
+    possible -- the cut goes through the widest gap between boundary rows.  None when the two ranges would cover more than
+    `max_fraction` of the owned rows (nothing to hide the exchange behind)."""
+    r = np.unique(np.asarray(send_rows, dtype=np.int64))
+    if r.size == 0 or n_own < 1024:
+        return None
+    lo = np.concatenate([[0], (r + 128) // 128 * 128])                     # lo_end if rows r[:i] go to the low range
+    hi = np.concatenate([r // 128 * 128, [n_own // 128 * 128]])            # hi_begin if rows r[i:] go to the high range
+    ok = hi >= lo
+    if not ok.any():
+        return None
+    cost = np.where(ok, lo + (n_own - hi), np.iinfo(np.int64).max)
+    i = int(np.argmin(cost))
+    if cost[i] > max_fraction * n_own:
+        return None
+    return int(lo[i]), int(hi[i])
+
+
 class StepEngine:
     """Compiled system of one or more fields advanced together."""
 
@@ -145,6 +165,7 @@ class StepEngine:
             self.n_dyn = i.size
             check(lib.gds_system_set_dirichlet(self.h, ptr(i), None, i.size, 1))
         self.p2p = False
+        self.overlap = None
         self._stream = None
         if self.record:
             check(lib.gds_system_enable_recording(self.h))
@@ -191,6 +212,7 @@ class StepEngine:
             a = np.empty(f.ndim * f._order(), dtype=np.float64)
             check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], a.size))
             f._host_state = self._blocks_from_dev(f, a)
+        self._check_p2p()
 
     def read(self, f, full=False):
         """current state slice of field f as a host array (cached until the next step)"""
@@ -200,6 +222,7 @@ class StepEngine:
             n = f.ndim * (f._order() if full else 1)
             a = np.empty(n, dtype=np.float64)
             check(lib.gds_system_get_state(self.h, ptr(a), self.offsets[id(f)], n))
+            self._check_p2p()
             self._read_cache[key] = self._blocks_from_dev(f, a)
         return self._read_cache[key]
 
@@ -214,6 +237,7 @@ class StepEngine:
             np.take(tmp, f._low.p2i, out=out)
             return out
         check(lib.gds_system_get_state(self.h, ptr(out), self.offsets[id(f)], out.size))
+        self._check_p2p()
         return out
 
     def write(self, f, values, offset=0):
@@ -253,6 +277,7 @@ class StepEngine:
 
     def _launch(self, ts, hs, t_after):
         self._bind_stream()
+        self._check_p2p()
         bc = self._bc_table(t_after)
         if self.part is not None and not self.p2p:
             self._run_partitioned(ts, hs, bc)
@@ -289,6 +314,7 @@ class StepEngine:
         if ts.size == 0:
             return
         self._bind_stream()
+        self._check_p2p()
         if self.part is not None and not self.p2p:
             self._run_partitioned(ts, hs, bc)
         else:   # one GPU, or peer-to-peer halo fused into the captured step
@@ -366,30 +392,31 @@ class StepEngine:
         handles of their state buffers and the positions of their ghost rows, and the library fuses a push / wait pair
         into the captured step after every stage -- boundary values cross NVLink by direct stores into the neighbour's
         memory, with no host and no NCCL on the data path.  Otherwise (gloo test transport, GDS_B200_HALO=nccl) the
-        host drives pack -> send/recv -> unpack between the stages."""
+        host drives pack -> send/recv -> unpack between the stages.
+        The transport is agreed on COLLECTIVELY: every rank takes part in the one all_gather below, and the fused halo
+        is used only if every rank can use it (at most 8 neighbours each, same GDS_B200_HALO)."""
         import os
         import torch.distributed as dist
-        from .partition import HaloExchange
         part = self.part
         mode = os.environ.get('GDS_B200_HALO', '')
         if not (dist.is_available() and dist.is_initialized() and part.world > 1):
             return
         if not mode:
             mode = 'p2p' if dist.get_backend() == 'nccl' else 'host'
-        if mode != 'p2p':
-            return
-        if len(part.peers) > 8:
-            return
+        want = mode == 'p2p' and len(part.peers) <= 8 and part.world <= 64
         deep = hasattr(part, 'gid_dom')
         blocks = self._halo_blocks()
-        hx = HaloExchange(part, blocks)
-        handles = (C.c_uint8 * 320)()
-        check(lib.gds_system_ipc_export(self.h, handles))
-        recv_from = {q: np.concatenate([off + part.recv_dom[d][q] for off, d in blocks]).astype(np.int64)
-                     for q in part.peers}
-        mine = {'handles': bytes(handles), 'recv_from': recv_from}
+        mine = {'want': want}
+        if want:
+            handles = (C.c_uint8 * 320)()
+            check(lib.gds_system_ipc_export(self.h, handles))
+            mine['handles'] = bytes(handles)
+            mine['recv_from'] = {q: np.concatenate([off + part.recv_dom[d][q] for off, d in blocks]).astype(np.int64)
+                                 for q in part.peers}
         everyone = [None] * part.world
         dist.all_gather_object(everyone, mine)
+        if not all(e['want'] for e in everyone):
+            return
         peers = [q for q in part.peers]
         src, dst, ptr_, hbytes = [], [], [0], b''
         for q in peers:
@@ -408,12 +435,32 @@ class StepEngine:
         check(lib.gds_system_p2p_attach(self.h, part.rank, len(peers), ptr(pr), hb, ptr(ptr_arr), ptr(src), ptr(dst),
                                         -1 if deep else part.n_own))
         self.p2p = True
+        self.overlap = None
+        if not deep and peers and os.environ.get('GDS_B200_OVERLAP', '1') != '0':
+            split = overlap_split(np.concatenate([part.send_rows[q] for q in peers]), part.n_own)
+            if split is not None:
+                check(lib.gds_system_p2p_set_overlap(self.h, split[0], split[1]))
+                self.overlap = split
 
     def p2p_status(self):
-        """(exchanges completed, error flag) of the fused peer-to-peer halo"""
+        """(exchanges completed, error flag) of the fused peer-to-peer halo (synchronises the stream)"""
         a, b = L.c_i64(), L.c_i64()
         check(lib.gds_system_p2p_status(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def _check_p2p(self):
+        """raise if an exchange of the fused halo has timed out (read from mapped host memory: no synchronisation, so
+        it is looked at before every enqueue and after every read-back)"""
+        if not self.p2p:
+            return
+        e = L.c_i64()
+        check(lib.gds_system_p2p_error(self.h, C.byref(e)))
+        if e.value:
+            k = e.value - 1 if e.value < 100 else e.value - 101
+            who = self.part.peers[k] if 0 <= k < len(self.part.peers) else '?'
+            raise L.GdsError(f'peer-to-peer halo exchange timed out waiting for rank {who} (code {e.value}): a peer '
+                             f'stopped or the ranks enqueued different numbers of steps; the state of rank '
+                             f'{self.part.rank} is not valid any more')
 
     def _setup_partitioned(self):
         """halo lists over every state block, exchange buffers, and the transport stream"""
@@ -520,9 +567,13 @@ class StepEngine:
 
     def run_timed(self, plan):
         """like run(), but kernel by kernel with CUDA events around every launch: returns (ms, launches) per class
-        [node passes, edge passes, face passes, per-step tail] (measurement aid, synchronises)"""
+        [node passes, edge passes, face passes, per-step tail] (measurement aid, synchronises).  The fused peer-to-peer
+        exchange runs between the event pairs; the host-driven halo cannot be interleaved here."""
         ts, hs, t_after, t_new, bc = plan
+        if self.part is not None and not self.p2p:
+            raise NotImplementedError('timed stepping of a partitioned engine needs the peer-to-peer halo')
         self._bind_stream()
+        self._check_p2p()
         ms, cnt = np.zeros(4, dtype=np.float64), np.zeros(4, dtype=np.int64)
         check(lib.gds_system_step_timed(self.h, ts.size, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None,
                                         ptr(ms), ptr(cnt)))
@@ -561,3 +612,24 @@ class StepEngine:
 
     def sync(self):
         self.ctx.sync()
+        self._check_p2p()
+
+    def halo_check(self):
+        """Partitioned engines: fetch, over the host-driven transport (NCCL send/recv), the rows this rank's neighbours
+        own and compare them BIT FOR BIT with the ghost rows the stepping left here.  Returns the number of ghost values
+        that differ on this rank (0 everywhere = every ghost row equals its owner's row)."""
+        if self.part is None or not self.part.peers:
+            return 0
+        torch = self._torch
+        self._bind_stream()
+        state = self._state_ptr()
+        have = torch.empty_like(self._recv)
+        check(lib.gds_halo_pack(self._halo[1], state, have.data_ptr()))           # my ghost rows as they are
+        check(lib.gds_halo_pack(self._halo[0], state, self._send.data_ptr()))     # my boundary rows for the neighbours
+        with torch.cuda.stream(self._stream):
+            for r in self.hx.exchange(self._send, self._recv):
+                r.wait()
+            self._stream.synchronize()
+            bad = int((have.view(torch.int64) != self._recv.view(torch.int64)).sum().item()) if self.hx.n_recv else 0
+        self._check_p2p()
+        return bad

@@ -249,12 +249,22 @@ int gds_halo_unpack(gds_halo* h, const void* buf_dev, void* vec_dev);
  *      by their owners' pushes only.  owned_rows < 0 (deep partitions: owned rows are not a prefix): the passes run over
  *      the ghost rows as well, and every push first waits for the neighbour's "my stage is done" flag, so a neighbour's
  *      own kernels never overwrite what was pushed.
- *      The wait gives up after 20 s (a dead peer) and raises the error flag read by gds_system_p2p_status. --------- */
+ *      The wait gives up after 20 s (a dead peer, or ranks that enqueued different numbers of steps) and raises the error
+ *      flag read by gds_system_p2p_status / gds_system_p2p_error; later exchanges then return at once. --------------- */
 int gds_system_ipc_export(gds_system* s, uint8_t* handles /* 5 x 64 bytes */);
 int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_peers, const int32_t* peer_rank,
                           const uint8_t* peer_handles /* n_peers x 5 x 64 */, const int64_t* send_ptr,
                           const int64_t* src_idx, const int64_t* dst_idx, int64_t owned_rows);
 int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t* error);
+/* the error flag alone, read from its mirror in mapped host memory WITHOUT synchronising the stream (the host looks before
+ * every call).  0 = fine; k in 1..8: the wait for neighbour k-1 timed out; 101..108: the handshake with neighbour k-101.
+ * After the first timeout (GDS_B200_P2P_TIMEOUT_MS, default 20000) every later exchange of the system returns at once. */
+int gds_system_p2p_error(gds_system* s, int64_t* error);
+/* Overlap of the exchange with the interior rows (node-only partitions, owned_rows >= 0; call between p2p_attach and
+ * finalize).  Rows [0, lo_end) and [hi_begin, owned_rows) must hold every row that is sent to or reads from a neighbour;
+ * per stage they run first and are pushed at once while rows [lo_end, hi_begin) run on a second stream -- both branches
+ * are part of the one captured step.  lo_end, hi_begin: multiples of 128. */
+int gds_system_p2p_set_overlap(gds_system* s, int64_t lo_end, int64_t hi_begin);
 /* algorithmic facts for the roofline: kernels per step and device bytes held */
 int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
 

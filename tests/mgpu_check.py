@@ -27,6 +27,10 @@ def main():
     from adaptors import product_api
     CASES = {
         'heat': (lambda api: cases.case_heat_c1(api, n=96, nsteps=40, every=20), 96, 1),
+        # slabs of > 32767 owned rows on up to 8 ranks: the ghost lattice rows sit behind the 16-bit index escape, and the
+        # peer-to-peer transport splits every stage into boundary rows -> push || interior rows
+        'heat_big': (lambda api: cases.case_heat_c1(api, n=528, nsteps=10, every=5), 528, 1),
+        'wave_big': (lambda api: cases.case_wave_c5(api, dims=(16, 16, 128), nsteps=10, every=5), 256, 1),
         'heat_mixed': (cases.case_heat_mixed, 9, 1),
         'wave': (lambda api: cases.case_wave_c5(api, dims=(7, 8, 24), nsteps=20, every=10), 56, 1),
         'cml': (lambda api: cases.case_cml_c4(api, n=3000, iters=12, every=6), 1, 1),

@@ -192,11 +192,10 @@ def test_solve_to_disk_layout(tmp_path):
     assert rel_l2(y, np.array(want)) <= 1e-10
 
 
-_UNSEEN = pytest.mark.xfail(strict=False, reason='added after the last GPU session of round 1: first run pending')
 
 
 @pytest.mark.parametrize('cname', ['solve', 'user_projection', 'external_field',
-                                   pytest.param('point_reads', marks=_UNSEEN)])
+                                   'point_reads'])
 def test_api_surface_matches_reference_golden(cname):
     """the same API cases against golden vectors produced by the UNMODIFIED reference (tests/golden/api_*.npz; the oracle
     matches them on the CPU, tests/test_oracle_golden.py)"""
@@ -209,7 +208,6 @@ def test_api_surface_matches_reference_golden(cname):
         assert rel_l2(out[k], gold[k]) <= 1e-10, (cname, k, rel_l2(out[k], gold[k]))
 
 
-@_UNSEEN
 def test_solver_object_facade_steps_like_step():
     """driving obs.integrator by hand (t_bound, status, step()) is the loop fds.step runs (fds.py:284-290)"""
     a, b = heat(product_api()), heat(product_api())

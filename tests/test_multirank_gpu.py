@@ -1,7 +1,11 @@
-"""The partitioned stepping path (stage-by-stage enqueue + halo pack / exchange / unpack) on ONE GPU: two ranks share
-cuda:0 and exchange through gloo (NCCL cannot put two ranks on one device; the transport is the only difference from
-the multi-GPU run).  Assembled results must match the CPU oracle of the undistributed problem to 1e-10, and the
-undistributed CUDA run bit for bit (same summation order in every owned row)."""
+"""The partitioned stepping path on ONE GPU: two or three ranks (processes) share cuda:0.
+  * transport 'host': stage-by-stage enqueue + halo pack / exchange / unpack, exchanged through gloo (NCCL cannot put two
+    ranks on one device);
+  * transport 'p2p': the production path of the multi-GPU run -- the push / wait kernels fused into the captured step
+    store straight into the neighbour's state buffers, mapped through CUDA IPC (which works between processes that share a
+    device; the GPU time-slices the ranks, so a spinning wait kernel is preempted for the rank it waits for).
+Assembled results must match the CPU oracle of the undistributed problem to 1e-10, and the undistributed CUDA run bit for
+bit (same summation order in every owned row)."""
 import os
 
 import numpy as np
@@ -22,6 +26,9 @@ CASES = {
     'cml': (lambda api: cases.case_cml_c4(api, n=600, iters=12, every=6), 1, 1),
     'hex_advdiff': (lambda api: cases.case_hex_advdiff_c2(api, m=8, n=10, nsteps=12, every=6), 1, 4),
     'ns_cavity': (lambda api: cases.case_ns_cavity_c3(api, m=8, n=12, nsteps=12, every=6), 1, 2),
+    # slabs of >= 1024 owned rows: the p2p transport splits every stage into boundary rows -> push || interior rows
+    'heat_overlap': (lambda api: cases.case_heat_c1(api, n=64, nsteps=12, every=6), 64, 1),
+    'wave_overlap': (lambda api: cases.case_wave_c5(api, dims=(8, 8, 48), nsteps=10, every=5), 64, 1),
 }
 
 
@@ -34,30 +41,48 @@ def _rd_grid(api):
     return cases._snap(T, {'T': T}, 5e-3, 20, 10)
 
 
-def _worker(rank, world, port, name, ret):
+def _worker(rank, world, port, name, transport, ret):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), GDS_B200_DEVICE='0')
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), GDS_B200_DEVICE='0', GDS_B200_HALO=transport)
     torch.cuda.set_device(0)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         import gds_b200
+        from gds_b200 import engine as E
         fn, align, hops = CASES[name]
         cases.GRAPH_HOOK = lambda G: gds_b200.distribute(G, rank, world, align=align, hops=hops)
+        seen = []
+        build = E.StepEngine._build
+
+        def spy(self):
+            build(self)
+            seen.append((bool(self.p2p), self.overlap))
+        E.StepEngine._build = spy
         out = fn(product_api())
         ret[rank] = {k: np.asarray(v) for k, v in out.items()}
+        ret[f'engine{rank}'] = seen
     finally:
         cases.GRAPH_HOOK = None
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('name', list(CASES))
-@pytest.mark.parametrize('world', [2, 3])
-def test_partitioned_matches_undistributed(name, world):
+# host transport: every small case on 2 and 3 ranks; p2p: every case on 2 ranks, two of them on 3 (middle rank: 2 neighbours)
+RUNS = ([(n, w, 'host') for n in CASES if not n.endswith('_overlap') for w in (2, 3)]
+        + [(n, 2, 'p2p') for n in CASES] + [('heat', 3, 'p2p'), ('hex_advdiff', 3, 'p2p')])
+
+
+@pytest.mark.parametrize('name,world,transport', RUNS)
+def test_partitioned_matches_undistributed(name, world, transport):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() + hash(name) + world) % 1500
+    port = 29500 + (os.getpid() + hash(name) + world + (7 if transport == 'p2p' else 0)) % 1500
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, name, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, name, transport, ret), nprocs=world, join=True)
+    for r in range(world):
+        # the transport asked for is the one that ran; the large slabs took the overlap split
+        assert all(p2p == (transport == 'p2p') for p2p, _ in ret[f'engine{r}']), ret[f'engine{r}']
+        if transport == 'p2p' and name.endswith('_overlap') and world == 2:
+            assert all(ov is not None for _, ov in ret[f'engine{r}']), ret[f'engine{r}']
     fn = CASES[name][0]
     want = fn(oracle_api())
     single = fn(product_api())
@@ -74,3 +99,48 @@ def test_partitioned_matches_undistributed(name, world):
         assert np.array_equal(got, single[k]), (name, k, 'partitioned result differs from the one-GPU result')
         for i in range(want[k].shape[0]):
             assert rel_l2(got[i], want[k][i]) <= 1e-10
+
+
+def _timeout_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), GDS_B200_DEVICE='0', GDS_B200_HALO='p2p',
+                      GDS_B200_P2P_TIMEOUT_MS='1500')
+    torch.cuda.set_device(0)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import gds_b200
+        G = gds_b200.distribute(cases.g_grid(24, 24), rank, world, align=24)
+        T = gds_b200.node_gds(G)
+        T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2, integrator=gds_b200.Integrators.rk4)
+        T.set_initial(y0=lambda x: float(x[0] + x[1]))
+        eng = T._ensure_engine()
+        assert eng.p2p
+        # rank 1 takes one step fewer: rank 0's last step waits for values that never come
+        eng.run(eng.plan_steps(3 if rank == 0 else 2, 1e-2))
+        try:
+            eng.sync()
+            ret[rank] = 'ok'
+        except gds_b200.GdsError as e:
+            ret[rank] = str(e)
+        if rank == 0:          # once raised, the flag stays up: every later call refuses to go on
+            try:
+                eng.run(eng.plan_steps(1, 1e-2))
+                ret['again'] = 'ok'
+            except gds_b200.GdsError as e:
+                ret['again'] = str(e)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unmatched_exchange_raises_instead_of_returning_stale_ghosts():
+    """a rank whose neighbour stops delivering must not hand out its state: the wait kernel gives up after the timeout
+    (1.5 s here, 20 s by default), later exchanges return at once, and the next host call on the engine raises"""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + 977) % 1500
+    ret = mp.Manager().dict()
+    mp.spawn(_timeout_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert 'timed out waiting for rank 1' in ret[0], ret[0]
+    assert 'timed out' in ret['again'], ret['again']
+    assert ret[1] == 'ok'

@@ -33,10 +33,8 @@ def test_ragged_and_tiny_graphs_match_oracle(name):
             assert rel_l2(got[k], gold[k]) <= 1e-10, (name, k, rel_l2(got[k], gold[k]))
 
 
-_UNSEEN = pytest.mark.xfail(strict=False, reason='added after the last GPU session of round 1: first run pending')
 
 
-@_UNSEEN
 @pytest.mark.parametrize('gname', list(cases.fuzz_graphs()))
 def test_irregular_graphs_match_oracle(gname):
     """random / irregular graphs (the oracle equals the live reference on them, tests/test_golden_fresh_cpu.py)"""
