@@ -213,7 +213,7 @@ def cml_problem(api, n, native, world=1, rank=0, weighted=False):
     y0 = np.random.default_rng(2).uniform(-1, 1, n)
     x.set_initial(y0=y0 if native else (lambda v: y0[v]))
     V = n
-    E = x._low.E if native else x.low.E
+    E = x._low.E if native else G.number_of_edges()
     per_step = 12 * (V + 2 * E) + 4 * V + 16 * V
     return dict(stepper=x, fields=[x], h=1.0, n_state=V, V=V, E=E, F=0, bytes_per_step=per_step,
                 bytes_per_launch=per_step, kernel_bytes_per_launch=(4 * 2 * E + 8 * 4) * 1.0 + 24 * V,
@@ -326,10 +326,32 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_run(workload, size, steps, warmup):
-    from adaptors import oracle_api
+# sizes the UNMODIFIED reference can hold (it densifies the |V| x |E| incidence matrix, gds/gds.py:145,265-267, and
+# assembles edge operators with O(E^2) Python loops): heat2d 100 is BASELINE config 1 exactly
+REF_SIZES = {'heat2d': 100, 'hex_advdiff': 12, 'ns_cavity': 12, 'cml': 3000, 'wave3d': 16}
+
+
+def reference_available():
+    try:
+        from oracle.ref_harness import reference_root
+        return reference_root() is not None
+    except Exception:
+        return False
+
+
+def cpu_run(workload, size, steps, warmup, kind='port'):
+    """kind 'reference': the unmodified reference (oracle/_ref or /root/reference) driven by a fixed-step RK4 solver
+    object; 'port': the oracle (numpy / scipy restatement)"""
+    if kind == 'reference':
+        import warnings
+        warnings.simplefilter('ignore')
+        from oracle.ref_api import make_ref_api
+        api = make_ref_api()
+    else:
+        from adaptors import oracle_api
+        api = oracle_api()
     builder = WORKLOADS[workload][0]
-    prob = builder(oracle_api(), size, native=False)
+    prob = builder(api, size, native=False)
     st, h = prob['stepper'], prob['h']
     for _ in range(warmup):
         st.step(h)
@@ -340,18 +362,30 @@ def cpu_run(workload, size, steps, warmup):
     return prob, el
 
 
-def cpu_baseline(workload, size, budget_s=12.0):
-    """bounded sample of the same law on the host: oracle port (scipy CSR SpMV, single thread)"""
-    prob, el1 = cpu_run(workload, size, steps=3, warmup=1)
-    steps = int(max(3, min(400, budget_s / max(el1 / 3, 1e-6))))
+def _cpu_sample(workload, size, kind, budget_s):
+    prob, el1 = cpu_run(workload, size, steps=3, warmup=1, kind=kind)
+    steps = int(max(3, min(2000, budget_s / max(el1 / 3, 1e-6))))
     st, h = prob['stepper'], prob['h']
     t0 = time.perf_counter()
     for _ in range(steps):
         st.step(h)
     el = time.perf_counter() - t0
-    return {'value': prob['n_state'] * steps / el, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-            'sample': f'{prob["name"]}; {steps} steps in {el:.2f} s (oracle/gds_oracle.py, scipy CSR, 1 thread of '
-                      f'{os.cpu_count()} host cores)'}
+    what = ('the unmodified reference (asrvsn/gds, oracle/_ref) with an RK4 solver object swapped in; its stepping path is '
+            'scipy CSR SpMV + numpy, single-threaded' if kind == 'reference'
+            else 'oracle/gds_oracle.py, scipy CSR, single-threaded')
+    return {'value': prob['n_state'] * steps / el, 'unit': UNIT, 'cores': 1, 'kind': kind,
+            'sample': f'{prob["name"]}; {steps} steps in {el:.2f} s ({what}; {os.cpu_count()} host cores present)'}
+
+
+def cpu_baseline(workload, size, budget_s=12.0):
+    """bounded samples of the same law on the host: the reference itself at the size it can hold (BASELINE config 1 for
+    the heat law) when oracle/_ref is present, and the oracle port at a larger size"""
+    port = _cpu_sample(workload, size, 'port', budget_s)
+    if not reference_available():
+        return port
+    ref = _cpu_sample(workload, REF_SIZES[workload], 'reference', budget_s)
+    ref['port'] = port
+    return ref
 
 
 _REAL_STDOUT = [None]
@@ -373,21 +407,28 @@ def emit(line):
 
 
 def reference_arm(args):
+    """the reference's own CPU implementation of the path on the host cores: the UNMODIFIED reference where oracle/_ref
+    (or /root/reference) is present -- at the size it can hold -- else the oracle port"""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     workload = args.workload
-    size = args.cpu_size or WORKLOADS[workload][2]
-    prob, el = cpu_run(workload, size, args.steps, args.warmup)
+    kind = 'reference' if reference_available() and not args.cpu_size else 'port'
+    size = REF_SIZES[workload] if kind == 'reference' else (args.cpu_size or WORKLOADS[workload][2])
+    prob, el = cpu_run(workload, size, args.steps, args.warmup, kind=kind)
     v = prob['n_state'] * args.steps / el
-    cb = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-          'sample': f'{prob["name"]}; oracle/gds_oracle.py (numpy/scipy restatement of the reference, 1 thread of '
-                    f'{os.cpu_count()} host cores: scipy CSR SpMV is single-threaded)'}
+    what = ('the unmodified reference (asrvsn/gds, imported from oracle/_ref) with an RK4 solver object swapped in '
+            '(gds/ode/midpoint.py protocol)' if kind == 'reference'
+            else 'oracle/gds_oracle.py (numpy/scipy restatement of the reference)')
+    cb = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': kind,
+          'sample': f'{prob["name"]}; {what}; the stepping path is scipy CSR SpMV + numpy, which is single-threaded '
+                    f'({os.cpu_count()} host cores present)'}
     emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': prob['name'], 'note': 'bounded CPU sample of the GPU arm\'s law'},
+        'config': {'workload': prob['name'], 'note': 'bounded CPU sample of the GPU arm\'s law at the size the reference '
+                                                     'can hold (it densifies the incidence matrix)'},
         'cpu_baseline': cb,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))

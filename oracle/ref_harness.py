@@ -1,8 +1,11 @@
-"""Loader for the UNMODIFIED reference (asrvsn/gds at /root/reference) -- TEST INFRASTRUCTURE ONLY.
+"""Loader for the UNMODIFIED reference (asrvsn/gds) -- TEST INFRASTRUCTURE ONLY.
 
-Used only by tests/golden/make_golden.py (run in the build container, where /root/reference
-exists) to generate golden vectors.  Nothing in the product path, the `-m gpu` tests, smoke()
-or bench.py imports this module: /root/reference does not exist on the GPU box.
+The reference is pure Python.  It is imported from /root/reference where that tree is mounted (the build
+container), else from oracle/_ref/gds_reference.zip -- its `gds` package, unmodified, packed by oracle/build_ref.py at
+build() time and imported through zipimport (git-ignored, so it stays out of history, but not gpurun-ignored, so it travels to the GPU box
+like a built .so).  Used by tests/golden/make_golden.py (golden vectors), tests/test_golden_fresh_cpu.py and
+the CPU legs of bench.py (`--impl reference`, `cpu_baseline`: the reference itself timed on the host cores).
+Nothing in the product path (gds_b200/) imports this module.
 
 `import gds` fails here because non-numerical dependencies (cvxpy, shortuuid, hickle, shapely,
 trimesh, matplotlib, bokeh, colorcet, selenium, ujson, tornado ...) are absent and networkx 3
@@ -19,7 +22,22 @@ import types
 import uuid
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ARCHIVE = os.path.join(_HERE, "_ref", "gds_reference.zip")
+
+
+def reference_root():
+    """sys.path entry holding the reference's `gds` package -- the mounted tree, else the archive -- or None"""
+    if os.path.isfile("/root/reference/gds/gds.py"):
+        return "/root/reference"
+    if os.path.isfile(_ARCHIVE):
+        return _ARCHIVE
+    return None
+
+
+REFERENCE_ROOT = reference_root()
 
 _ABSENT = ("cvxpy", "shortuuid", "hickle", "trimesh", "matplotlib", "bokeh", "colorcet",
            "selenium", "ujson", "tornado", "seaborn", "statsmodels", "pyunicorn", "zmq")
@@ -93,9 +111,9 @@ def load_reference():
     global _loaded
     if _loaded is not None:
         return _loaded
-    import os
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError("reference tree not present (only available in the build container)")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference not present: neither /root/reference nor oracle/_ref (python oracle/build_ref.py)")
     import networkx as nx
     if not hasattr(nx, "to_scipy_sparse_matrix"):
         nx.to_scipy_sparse_matrix = nx.to_scipy_sparse_array
@@ -109,7 +127,7 @@ def load_reference():
     sys.modules["shapely.geometry"] = geometry
     import shortuuid  # the mock
     shortuuid.uuid = lambda: uuid.uuid4().hex
-    sys.path.insert(0, REFERENCE_ROOT)
+    sys.path.insert(0, root)
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

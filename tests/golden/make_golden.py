@@ -21,52 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-from oracle.ref_harness import load_reference  # noqa: E402
-from oracle.gds_oracle import RK4, Euler  # noqa: E402  (solver objects only)
+from oracle.ref_api import make_ref_api  # noqa: E402
 import cases  # noqa: E402
 
 warnings.simplefilter('ignore')
-ref = load_reference()
 
 
-class RefAPI:
-    node_gds = staticmethod(ref.node_gds)
-    edge_gds = staticmethod(ref.edge_gds)
-    face_gds = staticmethod(ref.face_gds)
-    combine_bcs = staticmethod(ref.combine_bcs)
-    zero_edge_bc = staticmethod(ref.zero_edge_bc)
-    const_edge_bc = staticmethod(ref.const_edge_bc)
-
-    @staticmethod
-    def evolve(obs, dydt, max_step, order=1, scheme='rk4'):
-        obs.set_evolution(dydt=dydt, order=order, max_step=max_step, integrator=ref.Integrators.implicit_midpoint)
-        cls = RK4 if scheme == 'rk4' else Euler
-        obs.integrator = cls(obs.dydt, obs.t0, obs.y0, np.inf, max_step=max_step)
-        obs._fixed_cls = cls
-
-    @staticmethod
-    def evolve_nil(obs):
-        obs.set_evolution(nil=True)
-
-    @staticmethod
-    def evolve_map(obs, map_fun, dt=1.0):
-        # what fds.py:115-122 would set, with `_y = y0.copy()` in place of the failing `t0.copy()`
-        obs.iter_mode = ref.IterationMode.map
-        obs.map_fun = lambda y: map_fun(obs.t, y)   # step_map passes one argument (fds.py:337)
-        obs.y0 = np.zeros(obs.ndim)
-        obs._dt = dt
-        obs._t = obs.t0
-        obs._n = obs._t
-        obs._y = obs.y0.copy()
-
-    @staticmethod
-    def couple(observables):
-        sysobj = ref.couple(observables)
-        st = sysobj.stepper
-        if st.has_integrator:
-            cls = st.systems[ref.IterationMode.dydt][0]._fixed_cls
-            st.integrator = cls(st.dydt, st.t0, st.dydt_y0, np.inf, max_step=st.dydt_max_step)
-        return sysobj
+RefAPI = make_ref_api()
 
 
 def main(argv):

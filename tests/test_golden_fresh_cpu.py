@@ -1,6 +1,7 @@
-"""The committed golden vectors ARE the outputs of the unmodified reference: where /root/reference is mounted (the build
-container; not the GPU box) a sample of them is regenerated in-process through tests/golden/make_golden.py's adaptor and
-compared with the committed files.  Skipped when the reference is absent."""
+"""The committed golden vectors ARE the outputs of the unmodified reference: where the reference is present
+(/root/reference in the build container; its untouched copy oracle/_ref/ made by build() elsewhere) a sample of them is
+regenerated in-process through tests/golden/make_golden.py's adaptor and compared with the committed files.  Skipped
+when the reference is absent."""
 import importlib.util
 import os
 import sys
@@ -13,19 +14,15 @@ import cases
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, 'golden')
 
-pytestmark = pytest.mark.skipif(not os.path.isdir('/root/reference/gds'), reason='reference not mounted')
+from oracle.ref_harness import reference_root  # noqa: E402
+
+pytestmark = pytest.mark.skipif(reference_root() is None, reason='reference not present (/root/reference or oracle/_ref)')
 
 
 @pytest.fixture(scope='module')
 def ref_api():
-    argv, sys.argv = sys.argv, ['make_golden']
-    try:
-        spec = importlib.util.spec_from_file_location('make_golden', os.path.join(GOLD, 'make_golden.py'))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-    finally:
-        sys.argv = argv
-    return mod.RefAPI
+    from oracle.ref_api import make_ref_api      # the adaptor tests/golden/make_golden.py generates the files with
+    return make_ref_api()
 
 
 def _same(out, path):
