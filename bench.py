@@ -189,7 +189,11 @@ def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):
         V, E, F = p.ndim, u.ndim, len(u.faces)
     # advect 48E + 76V, grad 16E + 8V, Hodge-1 Laplacian 64E + 20V + 32F per RHS
     per_step = 4 * (128 * E + 104 * V + 32 * F) + 136 * E
+    # the law reads accepted state only (fds.py:377-378): its operators are evaluated once per step, the
+    # result k is written once (8E) and read by the four pointwise stages (4 x 8E)
+    hoisted = (128 * E + 104 * V + 32 * F) + 8 * E + 4 * 8 * E + 136 * E
     return dict(stepper=sysobj.stepper, fields=[u], h=h, n_state=E, V=V, E=E, F=F, bytes_per_step=per_step,
+                bytes_per_step_hoisted=hoisted,
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
                 kernel='step level: the law reads accepted state only, so its operators run once per step (5 passes) '
                        'and the 4 stages are pointwise',
@@ -247,7 +251,10 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
         n_own = a.ndim
     V, E = n_own, 3 * n_own
     per_step = 4 * (12 * (V + 2 * E) + 4 * V) + 136 * 2 * V        # Laplacian at every stage
+    # `a.laplacian()` reads the accepted state: one Laplacian per step, written once (8V), read by the four stages
+    hoisted = (12 * (V + 2 * E) + 4 * V) + 8 * V + 4 * 8 * V + 136 * 2 * V
     return dict(stepper=a, fields=[a], h=h, n_state=2 * n_own, V=V, E=E, F=0, bytes_per_step=per_step,
+                bytes_per_step_hoisted=hoisted,
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
                 kernel='step level: 1 lapT pass (accepted-state Laplacian, once per step) + 8 pointwise stage passes',
                 name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{n * world}]) (V={n ** 3 * world})'
@@ -545,6 +552,57 @@ def roofline_of(prob, eng, K, h, ms_step):
                     'graph the kernel stores no weights and moves kernel_bytes_per_launch, see frac_kernel_bytes'}
 
 
+def other_workloads(args, ctx, barrier, local, dist, torch, skip):
+    """The other BASELINE configurations at their full sizes, one after another on the same GPU (N = 1): K steps with the
+    state resident in HBM, CUDA events, clocks sampled -- same protocol as the headline.  frac_algorithmic uses SURVEY.md
+    8d's bytes (operators counted at every stage); laws that read accepted state only are evaluated once per step by the
+    engine, so frac_hoisted counts what such a step really has to move; frac_traffic uses the DRAM bytes of one step
+    from the committed ncu capture (profiles/traffic.json), when there is one."""
+    import gc
+    from adaptors import product_api
+    peak, _ = measured_peak()
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        traffic = {}
+    out = []
+    for name in ('hex_advdiff', 'ns_cavity', 'cml', 'wave3d'):
+        if name == skip:
+            continue
+        builder, size, _ = WORKLOADS[name]
+        t0 = time.perf_counter()
+        try:
+            prob = builder(product_api(), size, native=True)
+            eng = prob['stepper']._ensure_engine()
+            h, K = prob['h'], max(3, min(args.steps, 10))
+            barrier()
+            ctx.timer_start()
+            eng.run(eng.plan_steps(3, h))
+            est = ctx.timer_stop() / 3
+            t_build = time.perf_counter() - t0
+            ms, launches, clocks = time_steps(eng, ctx, K, h, barrier, local, 1, dist, torch, est_ms=est)
+            ms_step = ms / K
+            rec = {'name': prob['name'], 'workload': name, 'size': size, 'steps': K, 'ms_per_step': ms_step,
+                   'value': prob['n_state'] * K / (ms * 1e-3), 'unit': UNIT,
+                   'algorithmic_bytes_per_step': prob['bytes_per_step'],
+                   'frac_algorithmic': prob['bytes_per_step'] / (ms_step * 1e-3) / 1e9 / peak,
+                   'frac_hoisted': (prob['bytes_per_step_hoisted'] / (ms_step * 1e-3) / 1e9 / peak
+                                    if 'bytes_per_step_hoisted' in prob else None),
+                   'kernels_per_step': eng.kernels_per_step, 'gpu_launches': launches, 'build_seconds': t_build,
+                   'clocks': clocks, 'kernel': prob['kernel']}
+            tr = traffic.get(name, {}).get(str(size))
+            rec['traffic_bytes_per_step'] = tr
+            rec['frac_traffic'] = tr / (ms_step * 1e-3) / 1e9 / peak if tr else None
+            out.append(rec)
+            del eng
+            prob.clear()
+        except Exception as exc:          # one workload failing must not cost the headline line
+            out.append({'workload': name, 'error': f'{type(exc).__name__}: {exc}'[:300]})
+        gc.collect()
+    return out
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -638,7 +696,7 @@ def gpu_arm(args):
     # ---- the same lattice with random edge weights: kernel bytes == algorithmic bytes (N=1 only) --------------------
     weighted = None
     if world == 1 and not args.no_weighted and not args.weighted and args.workload == 'heat2d':
-        del eng, st, fields, one_step
+        eng = st = fields = one_step = None
         prob.clear()
         pw = builder(product_api(), size, native=True, weighted=True)
         ew = pw['stepper']._ensure_engine()
@@ -650,6 +708,12 @@ def gpu_arm(args):
                     'kernel_bytes_per_launch': rw['kernel_bytes_per_launch'], 'frac_kernel_bytes': rw['frac_kernel_bytes']}
         prob = pw
     roof['weighted_variant'] = weighted
+
+    others = None
+    if world == 1 and not args.no_workloads:
+        eng = st = fields = one_step = host_in = host_out = None
+        prob.clear()
+        others = other_workloads(args, ctx, barrier, local, dist, torch, skip=args.workload)
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -669,6 +733,8 @@ def gpu_arm(args):
         }
         if multi is not None:
             out['multi_gpu'] = multi
+        if others is not None:
+            out['workloads'] = others
         emit(json.dumps(out))
     if world > 1:
         if getattr(eng, 'p2p', False):
@@ -694,6 +760,7 @@ def main():
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-weighted', action='store_true')
+    ap.add_argument('--no-workloads', action='store_true', help='N = 1: skip the other BASELINE configurations after the headline')
     ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     args = ap.parse_args()
