@@ -40,8 +40,7 @@ extern "C" int gds_ctx_create(int device, gds_ctx** out) {
   GDS_CUDA(cudaEventCreate(&c->ev0));
   GDS_CUDA(cudaEventCreate(&c->ev1));
   GDS_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-  GDS_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  GDS_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (auto& e : c->ev_pool) GDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -59,8 +58,7 @@ extern "C" int gds_ctx_destroy(gds_ctx* c) {
   if (c->flush_buf) cudaFree(c->flush_buf);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
-  cudaEventDestroy(c->ev_fork);
-  cudaEventDestroy(c->ev_join);
+  for (auto& e : c->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->side_stream);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1022,13 +1020,15 @@ static int domain_class(int32_t domain) { return domain == GDS_NODES ? 0 : (doma
 static int n_stages_of(const gds_system* s) { return (s->scheme == GDS_SCHEME_RK4) ? 4 : 1; }
 
 // per-step passes: sub-expressions of the accepted state only, evaluated once before stage 1
-static int enqueue_prestep(gds_system* s, int cur, LaunchTimer* lt) {
+static int enqueue_prestep(gds_system* s, int cur, LaunchTimer* lt, int64_t row0 = 0, int64_t row1 = -1) {
   gds_ctx* c = s->ctx;
   const double* yn = s->Y[cur];
   for (const PassHost& ph : s->passes) {
     if (ph.when != GDS_WHEN_STEP) continue;
     PassParams pp;
     GDS_TRY(resolve_pass(s->g, ph, yn, nullptr, pp));
+    pp.row0 = std::min<int64_t>(row0, pp.n_rows);
+    if (row1 >= 0) pp.n_rows = std::min<int64_t>(row1, pp.n_rows);
     pp.steptab = s->d_steptab; pp.step_counter = s->d_counter; pp.c_stage = 0.0;
     if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
     GDS_TRY(launch_pass(c, pp, ph.domain));
@@ -1147,40 +1147,85 @@ static bool overlapped(const gds_system* s) {
   return s->p2p && !s->peers.empty() && s->owned_rows >= 0 && s->ov_lo_end >= 0 && s->ov_hi_begin >= s->ov_lo_end;
 }
 
-// enqueue every kernel of one step reading Y[cur], writing Y[cur^1].
-// With a peer-to-peer halo and an overlap split (gds_system_p2p_set_overlap) a stage is
-//     main stream:  boundary rows [0, lo) and [hi, owned)  ->  push  ---------.
-//     side stream:  interior rows [lo, hi)  ----------------------------------+->  wait  ->  next stage
-// so the NVLink stores and the flag round trip hide behind the interior rows.  Interior rows neither are sent nor read
-// a ghost row, so a neighbour that runs one exchange ahead can never touch what they read.  Both branches are captured
-// into the one step graph.  Timed stepping (`lt`) keeps one launch per pass and runs the exchange between the event pairs.
-static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
+// One step with the exchange hidden behind the interior rows (peer-to-peer halo + gds_system_p2p_set_overlap).
+// Rows [0, lo) and [hi, owned) -- the BOUNDARY ranges -- hold every row that is sent to, or reads a ghost row from, a
+// neighbour; rows [lo, hi) -- the INTERIOR -- touch owned rows only.  Two branches, both captured into the step graph:
+//
+//   main:  ... wait(k-1) -> boundary(st) -> [tail: Dirichlet rows in the boundary ranges] -> push(k) -> wait(k) -> boundary(st+1) ...
+//   side:  ... interior(st-1) ----------> interior(st) ------------------------------------------------> interior(st+1) ...
+//
+// boundary(st) needs interior(st-1) and interior(st) needs boundary(st-1) (rows next to the seam), but the interior never
+// waits for an exchange: the critical path of a step is its interior kernels back to back, and the NVLink stores, the
+// flag round trip and the skew between ranks run beside them.  A neighbour that is one exchange ahead only stores into
+// ghost rows, which no interior row reads.  Per-step passes (sub-expressions of the accepted state) are split the same
+// way.  The step counter is advanced on the side branch, after both branches have read this step's table row.
+static int enqueue_step_overlapped(gds_system* s, int cur) {
   gds_ctx* c = s->ctx;
-  GDS_TRY(enqueue_prestep(s, cur, lt));
+  cudaStream_t M = c->stream, S = c->side_stream;
+  const int64_t lo = s->ov_lo_end, hi = s->ov_hi_begin;
+  auto mark = [&](cudaStream_t st, cudaEvent_t* out) -> int {   // a point on `st` another branch can wait for
+    cudaEvent_t e = c->ev_pool[c->ev_next];
+    c->ev_next = (c->ev_next + 1) % 16;
+    GDS_CUDA(cudaEventRecord(e, st));
+    *out = e;
+    return 0;
+  };
+  struct OnStream {   // launches go to ctx->stream: point it at a branch for the lifetime of this object
+    gds_ctx* c; cudaStream_t saved;
+    OnStream(gds_ctx* c_, cudaStream_t st) : c(c_), saved(c_->stream) { c->stream = st; }
+    ~OnStream() { c->stream = saved; }
+  };
   const int ns = n_stages_of(s);
-  const bool ov = overlapped(s) && !lt;
+  cudaEvent_t evM, evS;
+  GDS_TRY(mark(M, &evM));
+  GDS_CUDA(cudaStreamWaitEvent(S, evM, 0));               // fork
+  {
+    OnStream on(c, S);
+    GDS_TRY(enqueue_prestep(s, cur, nullptr, lo, hi));
+  }
+  GDS_TRY(enqueue_prestep(s, cur, nullptr, 0, lo));
+  GDS_TRY(enqueue_prestep(s, cur, nullptr, hi, -1));
+  GDS_TRY(mark(M, &evM));
+  GDS_TRY(mark(S, &evS));
   for (int st = 0; st < ns; ++st) {
     const int which = (st < ns - 1) ? 2 + (st & 1) : (cur ^ 1);   // x_next of this stage / the new accepted state
-    if (ov) {
-      cudaStream_t main_stream = c->stream;
-      GDS_CUDA(cudaEventRecord(c->ev_fork, main_stream));
-      GDS_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-      c->stream = c->side_stream;
-      int rc = enqueue_stage(s, cur, st, nullptr, s->ov_lo_end, s->ov_hi_begin);
-      c->stream = main_stream;
-      GDS_TRY(rc);
-      GDS_CUDA(cudaEventRecord(c->ev_join, c->side_stream));
-      GDS_TRY(enqueue_stage(s, cur, st, nullptr, 0, s->ov_lo_end));
-      GDS_TRY(enqueue_stage(s, cur, st, nullptr, s->ov_hi_begin, -1));
-      // the Dirichlet overwrite belongs to the new accepted state and Dirichlet rows may be among the rows sent: the
-      // overwrite of the boundary ranges runs before the push, the rest after the interior rows
-      if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, nullptr, 1));
-      GDS_TRY(enqueue_push(s, which));
-      GDS_CUDA(cudaStreamWaitEvent(main_stream, c->ev_join, 0));
-      if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, nullptr, 0));
-      GDS_TRY(enqueue_wait(s));
-      continue;
+    const bool last = st == ns - 1;
+    GDS_CUDA(cudaStreamWaitEvent(M, evS, 0));             // boundary(st) reads what interior(st-1) wrote
+    GDS_CUDA(cudaStreamWaitEvent(S, evM, 0));             // interior(st) reads what boundary(st-1) wrote
+    GDS_TRY(enqueue_stage(s, cur, st, nullptr, 0, lo));
+    GDS_TRY(enqueue_stage(s, cur, st, nullptr, hi, -1));
+    GDS_TRY(mark(M, &evM));                                // before the push: the side branch never waits for an exchange
+    {
+      OnStream on(c, S);
+      GDS_TRY(enqueue_stage(s, cur, st, nullptr, lo, hi));
     }
+    GDS_TRY(mark(S, &evS));
+    if (last) {
+      // Dirichlet overwrite of the new accepted state: rows in the boundary ranges before the push (they may be among
+      // the rows sent), the others and the step counter on the side branch once main has read this step's table row
+      GDS_TRY(enqueue_tail(s, cur, nullptr, 1));
+      cudaEvent_t evT;
+      GDS_TRY(mark(M, &evT));
+      GDS_CUDA(cudaStreamWaitEvent(S, evT, 0));
+      OnStream on(c, S);
+      GDS_TRY(enqueue_tail(s, cur, nullptr, 0));
+    }
+    GDS_TRY(enqueue_push(s, which));
+    GDS_TRY(enqueue_wait(s));
+  }
+  GDS_TRY(mark(S, &evS));
+  GDS_CUDA(cudaStreamWaitEvent(M, evS, 0));               // join
+  return 0;
+}
+
+// enqueue every kernel of one step reading Y[cur], writing Y[cur^1].  Timed stepping (`lt`) keeps one launch per pass
+// and runs the exchange between the event pairs.
+static int enqueue_step(gds_system* s, int cur, LaunchTimer* lt = nullptr) {
+  if (overlapped(s) && !lt) return enqueue_step_overlapped(s, cur);
+  GDS_TRY(enqueue_prestep(s, cur, lt));
+  const int ns = n_stages_of(s);
+  for (int st = 0; st < ns; ++st) {
+    const int which = (st < ns - 1) ? 2 + (st & 1) : (cur ^ 1);   // x_next of this stage / the new accepted state
     GDS_TRY(enqueue_stage(s, cur, st, lt));
     if (st == ns - 1) GDS_TRY(enqueue_tail(s, cur, lt));
     GDS_TRY(enqueue_push(s, which));

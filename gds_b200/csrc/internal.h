@@ -218,7 +218,8 @@ struct gds_ctx {
   // second stream + fork / join events: the interior rows of a stage run beside the boundary rows and their push
   // (gds_system_p2p_set_overlap); both are captured into the step graph as two branches
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pool[16] = {};   // fork / join points of the two branches (used round-robin while a step is enqueued)
+  int ev_next = 0;
   int64_t kernel_launches = 0;
   int64_t graph_replays = 0;
   void* flush_buf = nullptr;
