@@ -448,7 +448,7 @@ def time_steps(eng, ctx, K, h, barrier, device, world, dist, torch, est_ms=2.0):
     """K steps with the state resident in HBM: CUDA events on the library's stream, max over ranks.  The clock sampler
     (100 ms period) needs load for longer than the timed region, so the same steps first run untimed for about 0.3 s
     and the timed K steps follow without a gap."""
-    n_pre = max(1, min(2000, int(0.3 / max(1e-6, est_ms * 1e-3))))
+    n_pre = 1 if NO_PREROLL[0] else max(1, min(2000, int(0.3 / max(1e-6, est_ms * 1e-3))))
     if world > 1:
         # every rank must enqueue the SAME number of steps: the fused halo exchange pairs them up one by one, and
         # `est_ms` is a rank-local measurement
@@ -591,7 +591,7 @@ def other_workloads(args, ctx, barrier, local, dist, torch, skip):
                                     if 'bytes_per_step_hoisted' in prob else None),
                    'kernels_per_step': eng.kernels_per_step, 'gpu_launches': launches, 'build_seconds': t_build,
                    'clocks': clocks, 'kernel': prob['kernel']}
-            tr = traffic.get(name, {}).get(str(size))
+            tr = traffic.get(name, {}).get('per_step', {}).get(str(size))
             rec['traffic_bytes_per_step'] = tr
             rec['frac_traffic'] = tr / (ms_step * 1e-3) / 1e9 / peak if tr else None
             out.append(rec)
@@ -655,7 +655,7 @@ def gpu_arm(args):
         roof['launch_ms_per_rank'] = [float(x.item()) for x in every]
     try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
-            roof['traffic'] = json.load(fh).get(args.workload, {}).get(str(size))
+            roof['traffic'] = json.load(fh).get(args.workload, {}).get(str(size) + ('_heat_weighted' if args.weighted else ''))
     except Exception:
         pass
 
@@ -745,6 +745,7 @@ def gpu_arm(args):
 
 
 WORKLOAD_NAME = [None]
+NO_PREROLL = [False]     # profiling runs (ncu replays every launch ~40 times): skip the 0.3 s of load for the clock sampler
 SCHEME = ['rk4']
 HALO = ['']
 
@@ -763,7 +764,9 @@ def main():
     ap.add_argument('--no-workloads', action='store_true', help='N = 1: skip the other BASELINE configurations after the headline')
     ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
+    ap.add_argument('--no-preroll', action='store_true', help='profiling runs under ncu: no untimed pre-roll before the timed steps')
     args = ap.parse_args()
+    NO_PREROLL[0] = args.no_preroll
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
