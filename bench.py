@@ -189,14 +189,14 @@ def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):
         V, E, F = p.ndim, u.ndim, len(u.faces)
     # advect 48E + 76V, grad 16E + 8V, Hodge-1 Laplacian 64E + 20V + 32F per RHS
     per_step = 4 * (128 * E + 104 * V + 32 * F) + 136 * E
-    # the law reads accepted state only (fds.py:377-378): its operators are evaluated once per step, the
-    # result k is written once (8E) and read by the four pointwise stages (4 x 8E)
-    hoisted = (128 * E + 104 * V + 32 * F) + 8 * E + 4 * 8 * E + 136 * E
+    # the law reads accepted state only (fds.py:377-378): its operators are evaluated once per step and
+    # the four stage combines happen in registers (collapsed RK4)
+    hoisted = (128 * E + 104 * V + 32 * F) + 16 * E      # + read y_n, write y_{n+1}
     return dict(stepper=sysobj.stepper, fields=[u], h=h, n_state=E, V=V, E=E, F=F, bytes_per_step=per_step,
                 bytes_per_step_hoisted=hoisted,
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
-                kernel='step level: the law reads accepted state only, so its operators run once per step (5 passes) '
-                       'and the 4 stages are pointwise',
+                kernel='step level: the law reads accepted state only, so the step is collapsed -- node aggregates, '
+                       'divergence, curl and the edge law run ONCE per step, the four RK4 stage combines in registers',
                 name=f'Navier-Stokes edge law (advect + grad p + Hodge-1 Laplacian), RK4 h=1e-4, '
                      f'triangular_lattice_graph({n},{n}) (V={V}, E={E}, F={F}), lid + no-slip Dirichlet')
 
@@ -251,12 +251,13 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
         n_own = a.ndim
     V, E = n_own, 3 * n_own
     per_step = 4 * (12 * (V + 2 * E) + 4 * V) + 136 * 2 * V        # Laplacian at every stage
-    # `a.laplacian()` reads the accepted state: one Laplacian per step, written once (8V), read by the four stages
-    hoisted = (12 * (V + 2 * E) + 4 * V) + 8 * V + 4 * 8 * V + 136 * 2 * V
+    # `a.laplacian()` reads the accepted state: one Laplacian per step (collapsed RK4)
+    hoisted = (12 * (V + 2 * E) + 4 * V) + 24 * V + 32 * V      # Laplacian pass: read v_n, write k_v, v_{n+1}; shift pass: read k_v, v_n, x_n, write x_{n+1}
     return dict(stepper=a, fields=[a], h=h, n_state=2 * n_own, V=V, E=E, F=0, bytes_per_step=per_step,
                 bytes_per_step_hoisted=hoisted,
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
-                kernel='step level: 1 lapT pass (accepted-state Laplacian, once per step) + 8 pointwise stage passes',
+                kernel='step level: collapsed RK4 -- one Laplacian pass over the value block (derivative block advanced in '
+                       'its epilogue) + one pointwise pass for the value block',
                 name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{n * world}]) (V={n ** 3 * world})'
                      + (f', {world} slabs with halo exchange' if world > 1 else ''))
 
@@ -532,7 +533,7 @@ def roofline_of(prob, eng, K, h, ms_step):
     cls_ms, cls_n = eng.run_timed(eng.plan_steps(min(K, 64), h))
     dom = prob['dominant_class']
     if dom < 0:      # several kernels per stage: one "launch" = all passes of one stage
-        n_st = 4 if str(eng.scheme).endswith('rk4') else 1
+        n_st = getattr(eng, 'n_stages', 4 if str(eng.scheme).endswith('rk4') else 1)
         launch_ms = float(cls_ms.sum()) / (min(K, 64) * n_st)
         cls_ms = np.array([cls_ms.sum(), 0.0])
         dom = 0
@@ -556,7 +557,7 @@ def other_workloads(args, ctx, barrier, local, dist, torch, skip):
     """The other BASELINE configurations at their full sizes, one after another on the same GPU (N = 1): K steps with the
     state resident in HBM, CUDA events, clocks sampled -- same protocol as the headline.  frac_algorithmic uses SURVEY.md
     8d's bytes (operators counted at every stage); laws that read accepted state only are evaluated once per step by the
-    engine, so frac_hoisted counts what such a step really has to move; frac_traffic uses the DRAM bytes of one step
+    engine (collapsed RK4), so frac_hoisted counts what such a step really has to move; frac_traffic uses the DRAM bytes of one step
     from the committed ncu capture (profiles/traffic.json), when there is one."""
     import gc
     from adaptors import product_api

@@ -1017,7 +1017,7 @@ struct LaunchTimer {
 };
 static int domain_class(int32_t domain) { return domain == GDS_NODES ? 0 : (domain == GDS_EDGES ? 1 : 2); }
 
-static int n_stages_of(const gds_system* s) { return (s->scheme == GDS_SCHEME_RK4) ? 4 : 1; }
+static int n_stages_of(const gds_system* s) { return (s->scheme == GDS_SCHEME_RK4 && !s->collapsed) ? 4 : 1; }
 
 // per-step passes: sub-expressions of the accepted state only, evaluated once before stage 1
 static int enqueue_prestep(gds_system* s, int cur, LaunchTimer* lt, int64_t row0 = 0, int64_t row1 = -1) {
@@ -1039,7 +1039,7 @@ static int enqueue_prestep(gds_system* s, int cur, LaunchTimer* lt, int64_t row0
 
 // vector a stage writes: the next stage state, or the new accepted state after the last stage
 static double* stage_output(gds_system* s, int cur, int st) {
-  return (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : s->Y[cur ^ 1];
+  return (s->scheme == GDS_SCHEME_RK4 && !s->collapsed && st < 3) ? s->XS[st & 1] : s->Y[cur ^ 1];
 }
 
 // every pass of stage `st` over rows [row0, row1) of each pass's domain (row1 < 0: all rows)
@@ -1051,7 +1051,7 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
   static const double c_stage[4] = {0.0, 0.5, 0.5, 1.0};
   static const double acc_w[4] = {1.0, 2.0, 2.0, 1.0};
   const double* stage = (st == 0) ? yn : s->XS[(st - 1) & 1];
-  double* xnext = (s->scheme == GDS_SCHEME_RK4 && st < 3) ? s->XS[st & 1] : nullptr;
+  double* xnext = (s->scheme == GDS_SCHEME_RK4 && !s->collapsed && st < 3) ? s->XS[st & 1] : nullptr;
   for (const PassHost& ph : s->passes) {
     if (ph.when != GDS_WHEN_STAGE) continue;
     PassParams pp;
@@ -1070,7 +1070,20 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
       pp.dmask = ph.dirichlet ? ph.dirichlet->d : nullptr;
       pp.yn = yn + off;
       pp.ynew = ynew + off;
-      if (s->scheme == GDS_SCHEME_RK4) {
+      if (s->scheme == GDS_SCHEME_RK4 && s->collapsed) {
+        // the law reads accepted state only: all four stage derivatives coincide and the whole step is this one pass
+        pp.acc_in = s->ACC + off; pp.acc_out = s->ACC + off;
+        pp.fin = 1.0 / 6.0;
+        pp.stage_mode = GDS_MODE_COLLAPSED;
+        pp.store_k = ph.store_k ? 1 : 0;
+        if (ph.special == 1) {   // order-2 block shift: the row value is the source block's derivative, kept in ACC
+          pp.stage_mode = GDS_MODE_COLLAPSED_SHIFT;
+          pp.aux = yn + ph.sp_src;
+          const double* kv = s->ACC + ph.sp_src;
+          pp.vec[0] = kv;
+          if (pp.use_terms) pp.lap_b = kv;
+        }
+      } else if (s->scheme == GDS_SCHEME_RK4) {
         pp.acc_in = s->ACC + off; pp.acc_out = s->ACC + off;
         pp.xnext = xnext ? xnext + off : nullptr;
         pp.acc_w = acc_w[st]; pp.a_next = a_next[st]; pp.fin = 1.0 / 6.0;
@@ -1281,6 +1294,26 @@ extern "C" int gds_system_finalize(gds_system* s) {
       at += iv.second;
     }
     if (at != s->n_state) GDS_FAIL("RHS passes do not cover the state vector");
+  }
+  if (s->collapsed) {
+    // the shifts of an order-2 field read the derivative of their source block from ACC: its RHS pass must run first
+    // and store it.  Higher orders chain stage values through two shifts and are not collapsed.
+    for (size_t i = 0; i < s->passes.size(); ++i) {
+      PassHost& sh = s->passes[i];
+      if (sh.special != 1) continue;
+      bool found = false;
+      for (size_t j = 0; j < s->passes.size(); ++j) {
+        PassHost& src = s->passes[j];
+        if (src.epilogue != GDS_EPI_RHS || src.special || src.state_offset != sh.sp_src) continue;
+        if (j > i) GDS_FAIL("collapsed stepping: a block shift is ordered before the pass it reads");
+        src.store_k = true;
+        found = true;
+      }
+      if (!found) GDS_FAIL("collapsed stepping supports fields of order <= 2 (a block shift reads another shifted block)");
+    }
+    for (const PassHost& ph : s->passes)
+      for (const gds_vecref& v : ph.vec)
+        if (v.kind == GDS_VEC_STAGE && !ph.special) GDS_FAIL("collapsed stepping: a pass reads the stage state");
   }
   s->cap_steps = GDS_STEP_CAPACITY;
   GDS_CUDA(cudaMalloc((void**)&s->d_steptab, (size_t)s->cap_steps * sizeof(StepRec)));
@@ -1555,6 +1588,15 @@ extern "C" int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t*
   GDS_CUDA(cudaStreamSynchronize(s->ctx->stream));
   if (exchanges) *exchanges = h[0];
   if (error) *error = h[1];
+  return 0;
+}
+
+// RK4 systems whose laws read accepted state only (no stage-state operand, no stage time): one pass per step
+extern "C" int gds_system_set_collapsed(gds_system* s, int32_t on) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("choose collapsed stepping before gds_system_finalize");
+  if (on && s->scheme != GDS_SCHEME_RK4) GDS_FAIL("collapsed stepping is a property of the RK4 scheme");
+  s->collapsed = on != 0;
   return 0;
 }
 

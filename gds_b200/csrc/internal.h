@@ -150,6 +150,9 @@ struct TermForm {
   Chain bchain = {};
 };
 
+#define GDS_MODE_COLLAPSED 5
+#define GDS_MODE_COLLAPSED_SHIFT 6
+
 struct StepRec {  // one row of the per-step table
   double t;       // step start time
   double h;       // step size
@@ -168,7 +171,10 @@ struct PassParams {
   double* out[GDS_MAX_OUT];
   // epilogue
   int32_t epilogue;   // GDS_EPI_*
-  int32_t stage_mode; // 0 first, 1 middle, 2 last (with acc), 3 last (no acc: Euler), 4 map
+  int32_t stage_mode; // 0 first, 1 middle, 2 last (with acc), 3 last (no acc: Euler), 4 map,
+                      // 5 whole RK4 step of a stage-independent law, 6 the same for an order-2 block shift (see GDS_MODE_*)
+  const double* aux;  // mode 6: accepted state of the SOURCE block (v_n), while the row value is its derivative k_v
+  int32_t store_k;    // mode 5: also write the (Dirichlet-masked) derivative to acc_out, for a block shift that needs it
   const uint32_t* dmask;
   const double* yn;
   const double* acc_in;
@@ -264,6 +270,7 @@ struct PassHost {  // a pass as given by the host, operands still symbolic
   // shift / hold pseudo-passes
   int32_t special = 0;  // 0 normal, 1 shift, 2 hold
   int64_t sp_dst = 0, sp_src = 0, sp_n = 0;
+  bool store_k = false; // collapsed stepping: a block shift reads this pass's derivative
 };
 
 struct gds_system {
@@ -271,6 +278,7 @@ struct gds_system {
   gds_graph* g;
   int64_t n_state = 0;
   int32_t scheme = GDS_SCHEME_RK4;
+  bool collapsed = false;             // RK4 of a law that reads accepted state only: one pass per step (gds_system_set_collapsed)
   double* Y[2] = {nullptr, nullptr};  // accepted state ping-pong
   double* XS[2] = {nullptr, nullptr}; // stage state ping-pong
   double* ACC = nullptr;

@@ -286,10 +286,37 @@ __device__ __forceinline__ double f_curl(const GraphDev& g, const double* __rest
 // ---------------------------------------------------------------------------------------------------
 // fused stage epilogue: Dirichlet zeroing of dy/dt (fds.py:303) + Runge-Kutta / Euler / map combine
 // ---------------------------------------------------------------------------------------------------
+// A law that reads accepted state only (`obs.y`, fds.py:377-378 -- SURVEY.md App. B.3) gives the same derivative k at all
+// four RK4 stages, so the step is ONE pass: the four stage combines run here in registers, operation by operation as
+// the four stage passes would (k1 = k2 = k3 = k4 = k), hence bit-identical to them.
+__device__ __forceinline__ double rk4_collapsed(double yn, double k, double fin_h) {
+  double acc = k;                 // stage 1: acc = k1
+  acc = acc + 2.0 * k;            // stage 2: acc += 2 k2
+  acc = acc + 2.0 * k;            // stage 3: acc += 2 k3
+  return yn + fin_h * (acc + k);  // stage 4: y_{n+1} = y_n + (h/6) (acc + k4)
+}
+// ... and a block of an order-2 field advanced by dy/dt = stage value of the next block (fds.py:297-298), whose own
+// derivative k_v is stage-independent: its stage values are v_n, v_n + (h/2) k_v (twice), v_n + h k_v.
+__device__ __forceinline__ double rk4_collapsed_shift(double yn, double vn, double kv, double h, double fin_h) {
+  const double v2 = vn + (0.5 * h) * kv;
+  const double v4 = vn + (1.0 * h) * kv;
+  double acc = vn;
+  acc = acc + 2.0 * v2;
+  acc = acc + 2.0 * v2;
+  return yn + fin_h * (acc + v4);
+}
+
 __device__ __forceinline__ void stage_epilogue(const PassParams& p, int64_t row, double k, double yn, double acc,
                                                uint32_t dbits, double h) {
   if ((dbits >> (row & 31)) & 1u) k = 0.0;  // fds.py:303
   switch (p.stage_mode) {
+    case GDS_MODE_COLLAPSED:
+      if (p.store_k) p.acc_out[row] = k;
+      p.ynew[row] = rk4_collapsed(yn, k, p.fin * h);
+      break;
+    case GDS_MODE_COLLAPSED_SHIFT:
+      p.ynew[row] = rk4_collapsed_shift(yn, __ldg(p.aux + row), k, h, p.fin * h);
+      break;
     case 0:  // first stage
       p.acc_out[row] = k;
       p.xnext[row] = yn + (p.a_next * h) * k;
@@ -600,6 +627,10 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
         break;
       case 2: p.ynew[r] = yn[i] + (p.fin * h) * (ac[i] + k1); break;
       case 3: p.ynew[r] = yn[i] + h * k1; break;
+      case GDS_MODE_COLLAPSED:
+        if (p.store_k) p.acc_out[r] = k1;
+        p.ynew[r] = rk4_collapsed(yn[i], k1, p.fin * h);
+        break;
       default: p.ynew[r] = k1; break;
     }
   }
@@ -611,7 +642,8 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
 // is a template parameter and only FULL groups are handled (the launcher sends the < 128 remaining rows to the generic
 // kernel), which keeps the instruction count per row at about a third of the generic kernel's -- with thousands of
 // resident threads the gather is otherwise bound by instruction issue, not by HBM.
-// MODE 0/1/2: first / middle / last RK4 stage, 3: Euler, 4: map, 5: no stage epilogue (STORE only).
+// MODE 0/1/2: first / middle / last RK4 stage, 3: Euler, 4: map, 5: whole RK4 step of a stage-independent law,
+// 7: no stage epilogue (STORE only).
 // ---------------------------------------------------------------------------------------------------
 #define LAPT_BLOCK 128  // measured best on B200 (128 > 256 threads; register caps and deeper unrolling lose occupancy)
 #define LAPT_GROUP 128
@@ -630,7 +662,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
   const GraphDev& g = p.g;
   const double* __restrict__ v = p.lap_v;
   const int64_t r = group + lane;  // this lane's row in slice i is r + 32 i
-  constexpr bool RHS = MODE != 5;
+  constexpr bool RHS = MODE != 7;
   // slice offsets of the 4 slices: 16-byte aligned (group/32 is a multiple of 4)
   // (computed when every slice has one width: the index loads then depend on nothing)
   uint32_t off[5];
@@ -716,7 +748,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
   }
   if (LAPT_LATE) load_streams();
   double h = 0.0;
-  if (MODE <= 3 && p.steptab) h = p.steptab[*p.step_counter].h;
+  if ((MODE <= 3 || MODE == 5) && p.steptab) h = p.steptab[*p.step_counter].h;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t ri = r + 32 * i;
@@ -736,6 +768,9 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
       p.ynew[ri] = yn[i] + (p.fin * h) * (ac[i] + k1);
     } else if (MODE == 3) {
       p.ynew[ri] = yn[i] + h * k1;
+    } else if (MODE == 5) {
+      if (p.store_k) p.acc_out[ri] = k1;
+      p.ynew[ri] = rk4_collapsed(yn[i], k1, p.fin * h);
     } else {
       p.ynew[ri] = k1;
     }
@@ -745,14 +780,15 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
 template <bool UNITW, bool CHAINED, bool IDX16>
 static void launch_lapT_c(const PassParams& p, int64_t groups, cudaStream_t st) {
   const unsigned blocks = (unsigned)((groups + LAPT_BLOCK / 32 - 1) / (LAPT_BLOCK / 32));
-  const int mode = (p.epilogue == GDS_EPI_RHS) ? p.stage_mode : 5;
+  const int mode = (p.epilogue == GDS_EPI_RHS) ? p.stage_mode : 7;
   switch (mode) {
     case 0: lapT_kernel<UNITW, 0, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
     case 1: lapT_kernel<UNITW, 1, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
     case 2: lapT_kernel<UNITW, 2, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
     case 3: lapT_kernel<UNITW, 3, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
     case 4: lapT_kernel<UNITW, 4, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
-    default: lapT_kernel<UNITW, 5, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    case 5: lapT_kernel<UNITW, 5, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
+    default: lapT_kernel<UNITW, 7, CHAINED, IDX16><<<blocks, LAPT_BLOCK, 0, st>>>(p); break;
   }
 }
 
@@ -999,6 +1035,12 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) l
     case 3:
 #pragma unroll
       for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
+      st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
+      break;
+    case GDS_MODE_COLLAPSED:
+      if (p.store_k) st_quad_v<RUNS>(p.acc_out, r0, p.n_rows, full, k4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o1v[i] = rk4_collapsed(yn[i], k4[i], p.fin * h);
       st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
       break;
     default:

@@ -37,6 +37,17 @@ def step_table(t, t_bound, max_step):
     return np.asarray(ts, dtype=np.float64), np.asarray(hs, dtype=np.float64), t
 
 
+def _reads_stage(e, seen=None):
+    """does the expression DAG contain the stage state (`y` argument of the law) or the stage time?"""
+    seen = set() if seen is None else seen
+    if id(e) in seen:
+        return False
+    seen.add(id(e))
+    if isinstance(e, (Stage, Time)):
+        return True
+    return any(_reads_stage(a, seen) for a in e.args)
+
+
 def overlap_split(send_rows, n_own, max_fraction=0.25):
     """(lo_end, hi_begin), multiples of 128, such that [0, lo_end) and [hi_begin, n_own) hold every row in `send_rows`
     (the owned rows adjacent to a cut: they are sent to, and read ghost rows from, a neighbour) and are as short as
@@ -117,6 +128,15 @@ class StepEngine:
             if root.domain is not None and root.domain != f._domain_code:
                 raise ValueError('evolution law returns a vector over the wrong domain')
             roots.append(root)
+        # A law that reads accepted state only (`obs.y`, operators without an argument: the idiom of
+        # gds/examples/fluid.py:33-34 and wave.py:14 -- SURVEY.md App. B.3) has the same derivative at all four RK4
+        # stages: the step then runs every pass ONCE and combines the stages in registers (bit-identical to the staged
+        # form, gds_system_set_collapsed).  Needs: no stage-state or stage-time leaf anywhere, fields of order <= 2.
+        import os
+        self.collapsed = (self.scheme == Integrators.rk4 and not os.environ.get('GDS_B200_NO_COLLAPSE')
+                          and all(f._order() <= 2 for f in self.fields)
+                          and not any(_reads_stage(r) for r in roots))
+        self.n_stages = 4 if (self.scheme == Integrators.rk4 and not self.collapsed) else 1
         # ... then bind to the lowered operators; the engine keeps them alive for as long as the captured step runs
         self.dev = self.low.dev
         h = L.c_vp()
@@ -124,7 +144,11 @@ class StepEngine:
         self.h = h
         import weakref
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
-        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=True,
+        if self.collapsed:
+            check(lib.gds_system_set_collapsed(self.h, 1))
+        # (sub-expressions of accepted state are hoisted out of the stages into once-per-step passes; a collapsed step
+        # has nothing to hoist them out of)
+        lowering = Lowering(self.ctx, self._resolve_leaf, hoist=not self.collapsed,
                             single_hop=self.part is not None and not hasattr(self.part, 'gid_dom'))
         self.lowering = lowering
         self.passes = []
@@ -487,7 +511,6 @@ class StepEngine:
         self._torch = torch
         self._stream = torch.cuda.Stream(dev)
         check(lib.gds_ctx_set_stream(self.ctx.h, self._stream.cuda_stream))
-        self.n_stages = 4 if self.scheme == Integrators.rk4 else 1
         self.exchanges = 0
         self._exchange(self._state_ptr())
 

@@ -199,6 +199,13 @@ int gds_system_add_hold(gds_system* s, int64_t offset, int64_t n);
 /* Dirichlet overwrite after every step (fds.py:289-290,362): state[idx[i]] = value[i]; dynamic = values come
  * from the table passed to gds_system_step */
 int gds_system_set_dirichlet(gds_system* s, const int64_t* state_idx, const double* values, int64_t n, int32_t dynamic);
+/* RK4 systems whose laws read ACCEPTED state only -- `obs.y` / operators called without an argument, the idiom of
+ * gds/examples/fluid.py:33-34 and wave.py:14; in the reference `obs.y` is integrator.y, which changes at step end only
+ * (fds.py:377-378) -- get the same derivative at all four stages.  With on = 1 (before finalize; every pass must be free
+ * of GDS_VEC_STAGE operands and of PUSH_T, fields of order <= 2) the step runs every pass ONCE and performs the four
+ * stage combines in registers, operation by operation as the staged form: results are bit-identical to on = 0, the
+ * step moves a quarter of the bytes, and a partitioned system exchanges its halo once per step instead of four times. */
+int gds_system_set_collapsed(gds_system* s, int32_t on);
 /* capture the whole step (all passes of all stages + BC overwrite) into a CUDA graph */
 int gds_system_finalize(gds_system* s);
 int gds_system_set_state(gds_system* s, const double* host, int64_t offset, int64_t n);

@@ -5,7 +5,7 @@ pinned against golden vectors of the unmodified reference; like the reference it
 dict entry per row, a Python call per boundary point).  This module restates the SAME formulas over plain arrays -- edge
 list in G.edges() order, weights, faces as a CSR list of node indices, boundary rows as index arrays -- so that the CUDA
 path can be checked against a CPU result at the sizes bench.py runs (BASELINE configs at full size).  Every function
-cites the reference lines it follows; tests/test_oracle_golden.py::test_array_oracle_* pins it against gds_oracle.py
+cites the reference lines it follows; tests/test_array_oracle_cpu.py pins it against gds_oracle.py
 (hence, transitively, against the reference's golden vectors) on small graphs, operator by operator and step by step.
 
 Only tests/ imports this module; the product path never does.
@@ -89,13 +89,16 @@ def edge_laplacian(B, B2, dirichlet_idx=()):
 
 
 def step_fixed(rhs, y0, t0, h, nsteps, dirichlet_idx=(), dirichlet_at=None, scheme='rk4'):
-    """`nsteps` fixed steps of one first-order field following fds.step_dydt / fds.dydt / apply_constraints
-    (gds/fds.py:284-305,359-363): the Dirichlet rows of every stage derivative are zero, and after each step they are
-    overwritten with the boundary values at the new time (`dirichlet_at(t)` -> values; static when it ignores t)."""
+    """`nsteps` fixed steps of one first-order state vector following fds.step_dydt / fds.dydt / apply_constraints
+    (gds/fds.py:284-305,359-363; coupled: 471-507): the Dirichlet rows of every stage derivative are zero, and after each
+    step they are overwritten with the boundary values at the new time (`dirichlet_at(t)` -> values; static when it
+    ignores t).  `rhs(t, y_stage, y_accepted)`: operators the law calls WITHOUT an argument read `obs.y`, which is the
+    solver's accepted state and only changes at the end of a step (fds.py:377-378)."""
     D = np.asarray(dirichlet_idx, dtype=np.intp)
+    it = None
 
     def fun(t, y):
-        d = np.array(rhs(t, y), dtype=float, copy=True)
+        d = np.array(rhs(t, y, it.y), dtype=float, copy=True)
         d[D] = 0.                                                      # fds.py:303-304
         return d
     cls = RK4 if scheme == 'rk4' else Euler

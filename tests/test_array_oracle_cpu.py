@@ -59,5 +59,33 @@ def test_array_stepping_equals_the_object_oracle():
     g = lambda t: np.concatenate([np.sin(t + jj / 4) ** 2, np.zeros(n)])
     y0[D] = g(0.)
     lap = ao.node_laplacian(B, D)
-    got = ao.step_fixed(lambda t, y: lap(y), y0, 0., h, nsteps, D, g)
+    got = ao.step_fixed(lambda t, y, ya: lap(y), y0, 0., h, nsteps, D, g)
     assert rel_l2(got, want) <= 1e-13
+
+
+def test_array_coupled_stepping_keeps_the_accepted_state_semantics():
+    """BASELINE config 2 at small size: `c.advect(u)` (no y argument) reads the ACCEPTED state of both fields at every
+    stage (fds.py:377-378), the Laplacians the stage state -- the array form against the object oracle"""
+    import math
+    m, n, nsteps, h, nu, kappa = 6, 8, 20, 1e-3, 0.1, 0.05
+    want = cases.case_hex_advdiff_c2(__import__('adaptors').oracle_api(), m=m, n=n, nsteps=nsteps, every=nsteps)
+    G = cases.g_hex(m, n)
+    low = go.Lowered(G, need_faces=True)
+    V, eu, ev, w, fptr, fnodes = _arrays(low)
+    E = len(eu)
+    B, B2 = ao.incidence(V, eu, ev, w), ao.curl_matrix(V, eu, ev, w, fptr, fnodes)
+    pos = np.array([G.nodes[v]['pos'] for v in G.nodes()])
+    hh = math.sqrt(3) / 2
+    lo, hi = pos[:, 1].min(), pos[:, 1].max()
+    bnd = (pos[:, 1] < lo + 0.6 * hh) | (pos[:, 1] > hi - 0.6 * hh)
+    D_e = np.nonzero(bnd[eu] & bnd[ev])[0]
+    N_n = np.nonzero(pos[:, 1] > hi - 1e-9)[0]
+    elap, nlap, adv = ao.edge_laplacian(B, B2, D_e), ao.node_laplacian(B, (), N_n, -0.1), ao.node_advect(B)
+    u0 = 0.1 * np.random.default_rng(0).standard_normal(E)
+    c0 = np.random.default_rng(1).random(V)
+    u0[D_e] = 0.
+
+    def rhs(t, y, ya):
+        return np.concatenate([nu * elap(y[:E]), -adv(ya[:E], ya[E:]) + kappa * nlap(y[E:])])
+    got = ao.step_fixed(rhs, np.concatenate([u0, c0]), 0., h, nsteps, D_e, lambda t: np.zeros(D_e.size))
+    assert rel_l2(got[:E], want['y_u'][-1]) <= 1e-13 and rel_l2(got[E:], want['y_c'][-1]) <= 1e-13

@@ -42,7 +42,7 @@ def test_heat_7072_three_steps_against_the_oracle(weighted):
     D = np.concatenate([jj, (n - 1) * n + jj])
     g = lambda t: np.concatenate([np.sin(t + jj / 4) ** 2, np.zeros(n)])
     lap = ao.node_laplacian(B, D)
-    want = ao.step_fixed(lambda t, y: lap(y), y0, 0., h, nsteps, D, g)
+    want = ao.step_fixed(lambda t, y, ya: lap(y), y0, 0., h, nsteps, D, g)
     assert np.all(np.isfinite(got))
     assert rel_l2(got, want) <= TOL
     # the change over the steps, too: a kernel that left the state untouched would pass the line above on a slowly
@@ -75,9 +75,9 @@ def test_hex_2000_advection_diffusion_three_steps_against_the_oracle():
     nlap = ao.node_laplacian(B, (), N_n, -0.1)
     adv = ao.node_advect(B)
 
-    def rhs(t, y):
-        ue, cn = y[:E], y[E:]
-        return np.concatenate([nu * elap(ue), -adv(ue, cn) + kappa * nlap(cn)])
+    def rhs(t, y, ya):
+        # `c.advect(u)` reads the ACCEPTED state of both fields (no y argument: gds.py:166-177 with y = self.y)
+        return np.concatenate([nu * elap(y[:E]), -adv(ya[:E], ya[E:]) + kappa * nlap(y[E:])])
     y0 = np.concatenate([u0, c0])
     want = ao.step_fixed(rhs, y0, 0., h, nsteps, D_e, lambda t: np.zeros(D_e.size))
     assert rel_l2(got_u, want[:E]) <= TOL and rel_l2(got_c, want[E:]) <= TOL

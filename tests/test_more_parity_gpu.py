@@ -69,3 +69,49 @@ def test_navier_stokes_with_pressure_solve_every_step():
     for i in range(b['y_velocity'].shape[0]):
         assert rel_l2(a['y_velocity'][i], b['y_velocity'][i]) <= 1e-9, rel_l2(a['y_velocity'][i], b['y_velocity'][i])
         assert rel_l2(a['y_pressure'][i], b['y_pressure'][i]) <= 1e-8, rel_l2(a['y_pressure'][i], b['y_pressure'][i])
+
+
+COLLAPSIBLE = {
+    # laws that read accepted state only (operators without an argument): the idiom of examples/fluid.py:33-34, wave.py:14
+    'wave_order2': lambda api: cases.case_wave_c5(api, dims=(5, 6, 9), nsteps=12, every=4),
+    'ns_cavity': lambda api: cases.case_ns_cavity_c3(api, m=6, n=10, nsteps=12, every=4),
+    'order2_dirichlet': lambda api: cases.QUIRK_CASES['order2_dirichlet'](api),
+}
+
+
+@pytest.mark.parametrize('cname', list(COLLAPSIBLE))
+def test_collapsed_rk4_is_bit_identical_to_the_staged_form(cname, monkeypatch):
+    """a law without stage-state operands has k1 = k2 = k3 = k4: the engine runs its passes once per step and combines
+    the four stages in registers (gds_system_set_collapsed) -- same operations in the same order as the four stage
+    passes, so the results must agree to the last bit (and with the oracle to 1e-10)"""
+    from gds_b200 import engine as E
+    seen = []
+    build = E.StepEngine._build
+
+    def spy(self):
+        build(self)
+        seen.append((self.collapsed, self.n_stages, self.kernels_per_step))
+    monkeypatch.setattr(E.StepEngine, '_build', spy)
+    fast = COLLAPSIBLE[cname](product_api())
+    assert seen and all(c and n == 1 for c, n, _ in seen), seen
+    k_fast = seen[-1][2]
+    del seen[:]
+    monkeypatch.setenv('GDS_B200_NO_COLLAPSE', '1')
+    slow = COLLAPSIBLE[cname](product_api())
+    assert seen and all((not c) and n == 4 for c, n, _ in seen), seen
+    assert k_fast < seen[-1][2]
+    want = COLLAPSIBLE[cname](oracle_api())
+    for k in want:
+        assert np.array_equal(np.asarray(fast[k]), np.asarray(slow[k])), (cname, k)
+        assert rel_l2(fast[k], want[k]) <= TOL, (cname, k)
+
+
+def test_laws_that_read_the_stage_state_are_not_collapsed():
+    T = __import__('gds_b200').node_gds(cases.g_grid(8, 8))
+    T.set_evolution(dydt=lambda t, y: T.laplacian(y), max_step=1e-2)
+    T.set_initial(y0=lambda x: float(x[0]))
+    assert not T._ensure_engine().collapsed
+    S = __import__('gds_b200').node_gds(cases.g_grid(8, 8))
+    S.set_evolution(dydt=lambda t, y: S.laplacian() * np.cos(t), max_step=1e-2)      # stage time
+    S.set_initial(y0=lambda x: float(x[0]))
+    assert not S._ensure_engine().collapsed
