@@ -85,6 +85,7 @@ _sig('gds_buf_upload', c_vp, c_i64, c_vp, c_i64)
 _sig('gds_buf_download', c_vp, c_i64, c_vp, c_i64)
 _sig('gds_buf_fill', c_vp, c_i64, c_i64, c_f64)
 _sig('gds_buf_devptr', c_vp, P(c_vp), P(c_i64))
+_sig('gds_buf_reduce', c_vp, c_i64, c_i64, c_i32, P(c_f64))
 _sig('gds_mask_create', c_vp, c_i64, c_vp, c_i64, P(c_vp))
 _sig('gds_mask_destroy', c_vp)
 _sig('gds_graph_create', c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, P(c_vp))
@@ -135,7 +136,7 @@ _sig('gds_graph_create_from_host', c_vp, c_vp, c_vp, P(c_vp))
 EXPORTED = [
     'gds_last_error', 'gds_abi_version', 'gds_ctx_create', 'gds_ctx_destroy', 'gds_ctx_set_stream', 'gds_ctx_sync',
     'gds_ctx_timer_start', 'gds_ctx_timer_stop', 'gds_ctx_counters', 'gds_ctx_flush_l2', 'gds_ctx_bandwidth_probe', 'gds_buf_create',
-    'gds_buf_view', 'gds_buf_destroy', 'gds_buf_upload', 'gds_buf_download', 'gds_buf_fill', 'gds_buf_devptr', 'gds_mask_create',
+    'gds_buf_view', 'gds_buf_destroy', 'gds_buf_upload', 'gds_buf_download', 'gds_buf_fill', 'gds_buf_devptr', 'gds_buf_reduce', 'gds_mask_create',
     'gds_mask_destroy', 'gds_graph_create', 'gds_graph_destroy', 'gds_graph_sizes', 'gds_graph_export_csr',
     'gds_graph_device_bytes', 'gds_pass_run', 'gds_pass_kernel_kind', 'gds_cg_solve', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
     'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_set_collapsed', 'gds_system_finalize',

@@ -56,6 +56,7 @@ extern "C" int gds_ctx_destroy(gds_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->reduce_scratch) cudaFree(c->reduce_scratch);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   for (auto& e : c->ev_pool) cudaEventDestroy(e);
@@ -204,6 +205,20 @@ extern "C" int gds_buf_fill(gds_buf* b, int64_t off, int64_t n, double v) {
   GDS_NEED_DEVICE(b->ctx);
   GDS_CUDA(cudaSetDevice(b->ctx->device));
   return launch_fill(b->ctx, b->d + off, n, v);
+}
+
+// scalar reduction of n values of a device vector (kind 0 sum, 1 max, 2 min): only the 8-byte result crosses PCIe
+extern "C" int gds_buf_reduce(gds_buf* b, int64_t off, int64_t n, int32_t kind, double* out) {
+  if (!b || !out || off < 0 || n < 0 || off + n > b->n) GDS_FAIL("range outside buffer");
+  if (kind < 0 || kind > 2) GDS_FAIL("unknown reduction");
+  gds_ctx* c = b->ctx;
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  if (!c->reduce_scratch) GDS_CUDA(cudaMalloc((void**)&c->reduce_scratch, 2048 * sizeof(double)));
+  GDS_TRY(launch_reduce(c, b->d + off, n, kind, c->reduce_scratch));
+  GDS_CUDA(cudaMemcpyAsync(out, c->reduce_scratch + 1184, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GDS_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
 }
 
 extern "C" int gds_buf_devptr(gds_buf* b, void** dev_out, int64_t* n_out) {

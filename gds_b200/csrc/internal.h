@@ -230,6 +230,7 @@ struct gds_ctx {
   int64_t graph_replays = 0;
   void* flush_buf = nullptr;
   int64_t flush_bytes = 0;
+  double* reduce_scratch = nullptr;   // partial results of gds_buf_reduce (fixed grid, fixed tree)
 };
 
 struct gds_buf {
@@ -368,5 +369,6 @@ int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode);
+int launch_reduce(gds_ctx* ctx, const double* x, int64_t n, int kind, double* scratch);
 int launch_probe(gds_ctx* ctx, double* const* bufs, int n_read, int n_write, int64_t n);
 int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int64_t n, int scatter);

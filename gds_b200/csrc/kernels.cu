@@ -1386,6 +1386,49 @@ int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* a
 }
 
 // ---------------------------------------------------------------------------------------------------
+// scalar reductions of a device vector (derived observables: energies, norms, extrema -- gds/types.py:95-105 projections
+// such as `(v.y ** 2).sum()`, examples/lid_driven_cavity.py:95-101): fixed grid, fixed tree => bitwise reproducible.
+// kind 0 sum, 1 max, 2 min.  scratch[0 .. CG_BLOCKS) partial results, scratch[CG_BLOCKS] the result.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double red_op(int kind, double a, double b) {
+  return kind == 0 ? a + b : (kind == 1 ? fmax(a, b) : fmin(a, b));
+}
+__device__ __forceinline__ double red_identity(int kind) {
+  return kind == 0 ? 0.0 : (kind == 1 ? -INFINITY : INFINITY);
+}
+__device__ __forceinline__ void block_reduce_kind(double v, double* out, int kind) {
+  __shared__ double sh[CG_THREADS];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = CG_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = red_op(kind, sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+__global__ void __launch_bounds__(CG_THREADS) reduce_kernel(const double* __restrict__ x, int64_t n, int kind,
+                                                            double* __restrict__ partial) {
+  double acc = red_identity(kind);
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS)
+    acc = red_op(kind, acc, ld_stream_f64(x + i));
+  block_reduce_kind(acc, partial + blockIdx.x, kind);
+}
+__global__ void __launch_bounds__(CG_THREADS) reduce_final_kernel(double* __restrict__ scratch, int kind) {
+  double acc = red_identity(kind);
+  for (int i = threadIdx.x; i < CG_BLOCKS; i += CG_THREADS) acc = red_op(kind, acc, scratch[i]);
+  block_reduce_kind(acc, scratch + CG_BLOCKS, kind);
+}
+
+int launch_reduce(gds_ctx* ctx, const double* x, int64_t n, int kind, double* scratch) {
+  reduce_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(x, n, kind, scratch);
+  GDS_CUDA(cudaGetLastError());
+  reduce_final_kernel<<<1, CG_THREADS, 0, ctx->stream>>>(scratch, kind);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches += 2;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // peer-to-peer halo exchange over NVLink, inside the captured step.
 // push: one block per neighbour announces that this rank's stage is done (ready flag), waits for the neighbour's, stores
 // this rank's boundary values straight into the neighbour's ghost rows (peer-mapped memory), fences, and publishes the

@@ -75,6 +75,12 @@ class Buffer:
         check(lib.gds_buf_download(self.h, int(offset), ptr(out), n))
         return out
 
+    def reduce(self, kind=0, offset=0, n=None) -> float:
+        """sum (0) / max (1) / min (2) of the values, computed on the device"""
+        r = L.c_f64()
+        check(lib.gds_buf_reduce(self.h, int(offset), self.n - offset if n is None else int(n), int(kind), C.byref(r)))
+        return r.value
+
     def fill(self, v, offset=0, n=None):
         check(lib.gds_buf_fill(self.h, int(offset), self.n - offset if n is None else int(n), float(v)))
 

@@ -71,8 +71,9 @@ def overlap_split(send_rows, n_own, max_fraction=0.25):
 class StepEngine:
     """Compiled system of one or more fields advanced together."""
 
-    def __init__(self, fields, scheme, max_step, t0=0.0, ctx: Context = None, record=False):
+    def __init__(self, fields, scheme, max_step, t0=0.0, ctx: Context = None, record=False, allow_collapse=True):
         self.record = bool(record)   # snapshot kernel inside the captured step (System.solve)
+        self.allow_collapse = bool(allow_collapse)
         assert len(fields) >= 1
         self.fields = list(fields)
         self.scheme = scheme
@@ -133,7 +134,7 @@ class StepEngine:
         # stages: the step then runs every pass ONCE and combines the stages in registers (bit-identical to the staged
         # form, gds_system_set_collapsed).  Needs: no stage-state or stage-time leaf anywhere, fields of order <= 2.
         import os
-        self.collapsed = (self.scheme == Integrators.rk4 and not os.environ.get('GDS_B200_NO_COLLAPSE')
+        self.collapsed = (self.scheme == Integrators.rk4 and self.allow_collapse and not os.environ.get('GDS_B200_NO_COLLAPSE')
                           and all(f._order() <= 2 for f in self.fields)
                           and not any(_reads_stage(r) for r in roots))
         self.n_stages = 4 if (self.scheme == Integrators.rk4 and not self.collapsed) else 1
@@ -626,9 +627,31 @@ class StepEngine:
             if ts.size:
                 f._dt = float(hs[-1])
 
-    def apply_map(self, t_new):
+    def run_step_staged(self, t, h, t_after, before_stage):
+        """ONE step enqueued stage by stage, `before_stage(s)` called before the passes of stage s are enqueued (a
+        recurrence map coupled with this system may be applied there, fds.py:505-507)"""
+        if self.part is not None:
+            raise NotImplementedError('stage-by-stage stepping of a distributed system')
+        ts, hs, ta = np.asarray([t], dtype=np.float64), np.asarray([h], dtype=np.float64), np.asarray([t_after], dtype=np.float64)
+        bc = self._bc_table(ta)
+        self._bind_stream()
+        check(lib.gds_system_begin_steps(self.h, 1, ptr(ts), ptr(hs), ptr(bc) if bc is not None else None))
+        for st in range(self.n_stages):
+            before_stage(st)
+            self._bind_stream()
+            check(lib.gds_system_run_stage(self.h, st, 0, -1))
+        check(lib.gds_system_end_step(self.h))
+        self.steps_taken += 1
+        self.version += 1
+        self._read_cache.clear()
+        self.t = float(t_after)
+        for f in self.fields:
+            f._dt = float(h)
+
+    def apply_map(self, t_new, refresh=True):
         """one application of the recurrence map at time t_new (fds.py:332-339)"""
-        self._refresh_externals()
+        if refresh:
+            self._refresh_externals()
         ts, hs = np.asarray([t_new], dtype=np.float64), np.asarray([0.0], dtype=np.float64)
         self._launch(ts, hs, ts)
         self.t = t_new

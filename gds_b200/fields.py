@@ -23,8 +23,9 @@ from ._lib import lib, check
 from .device import Buffer, BufferView
 from .engine import StepEngine
 from .graph import LoweredGraph
-from .trace import (Const, DevVec, EdgeAgg, Expr, Gather, Lowering, MaskZero, Stage, State, Time, TraceError, as_expr,
-                    pass_desc, split_affine, substitute, trace_scope, tracing, unary)
+from .trace import (Binary, Const, DevVec, EdgeAgg, Expr, Gather, Imm, Lowering, MaskZero, PowI, Reduce, Stage, State, Time,
+                    TraceError, Unary, as_expr, pass_desc, split_affine, substitute, trace_scope, tracing, unary,
+                    _fold_binary, _fold_unary)
 from .types import GraphDomain, Integrators, IterationMode, Observable, Steppable
 from .utils import dict_fun, fun_ary
 
@@ -524,6 +525,57 @@ def _run_eager(low, expr):
     return low.from_dev(expr.domain, out.download())
 
 
+def _eval_scalar(e, memo):
+    """value of a scalar expression whose leaves are constants and device reductions of vector expressions"""
+    if isinstance(e, Imm):
+        return e.value
+    if isinstance(e, Reduce):
+        x = e.args[0]
+        low = x.graph
+        n = low.rows(x.domain)
+        if n == 0:
+            return 0.0
+        if low.part is not None:
+            raise TraceError('reductions over a distributed field need a collective')
+        bound = _bind_states(x, memo)
+        if isinstance(bound, DevVec):                        # a bare state vector: reduce it in place
+            return bound.buf.reduce(Reduce.KIND[e.kind], 0, n)
+        tmp = Buffer(low.ctx, n)
+        descs, keep = _lower_into(low, bound, tmp)
+        _run_passes(low, descs)
+        return tmp.reduce(Reduce.KIND[e.kind], 0, n)
+    if isinstance(e, Binary):
+        return _fold_binary(e.op, _eval_scalar(e.args[0], memo), _eval_scalar(e.args[1], memo))
+    if isinstance(e, Unary):
+        return _fold_unary(e.op, _eval_scalar(e.args[0], memo))
+    if isinstance(e, PowI):
+        return _eval_scalar(e.args[0], memo) ** e.n
+    raise TraceError(f'cannot evaluate a scalar {type(e).__name__}')
+
+
+def evaluate_view(view, parent):
+    """value of a derived observable `parent.project(kind, view)` (gds/types.py:95-105).  The view is first run with symbolic
+    field states: if it comes out as an expression over device operators -- `v.curl()`, `(v.y ** 2).sum()`,
+    `np.abs(v.curl()).sum()` (gds/examples/lid_driven_cavity.py:95-101) -- its vector part runs on the device against the
+    state where it lives (no upload) and a reduction returns 8 bytes; anything else (arbitrary numpy code on `v.y`) runs on
+    the host as in the reference."""
+    try:
+        with trace_scope():
+            r = view(parent)
+    except Exception:
+        r = None
+    if isinstance(r, Expr):
+        try:
+            memo = {}
+            if r.domain is None:
+                return _eval_scalar(r, memo)
+            if r.graph.part is None:
+                return _run_eager(r.graph, _bind_states(r, memo))
+        except TraceError:
+            pass
+    return view(parent)
+
+
 def _lower_into(low, expr, out_buf):
     """passes (ctypes descriptors + keep-alives) that evaluate `expr` into the device buffer `out_buf`"""
     def no_leaf(e):
@@ -822,11 +874,10 @@ class coupled_fds(Steppable):
         self.cvxs = [s for s in systems if s.iter_mode is IterationMode.cvx]
         if self.cvxs and not self.cont:
             raise NotImplementedError('lhs= fields are coupled to at least one continuous field')
-        if self.cont and self.maps:
-            raise NotImplementedError('coupling recurrence maps with continuous fields (fds.py:491-503) is not on the device path yet')
         self.has_integrator = len(self.cont) > 0
         self._engine = None
         self._t = 0.
+        self.discrete_t = 0.            # common clock of the discrete systems (fds.py:425)
         members = self.cont or self.maps
         if self.has_integrator:
             kind = self.cont[0].integrator_type
@@ -836,9 +887,10 @@ class coupled_fds(Steppable):
         else:
             self._scheme = 'map'
             self.dydt_max_step = min((s._dt for s in self.maps), default=1.0)
-        for s in members:
+        for s in members + (self.maps if self.cont else []):
             s._drop_engine()
-            s._host_state = np.array(s.y0, dtype=float, copy=True)                  # fds.py:439: state taken at couple() time
+            s._host_state = np.array(s.y0, dtype=float, copy=True)                  # fds.py:426-439: state taken at couple() time
+            s._couple_y0 = s._host_state.copy()                                      # what reset() goes back to (fds.py:509-527)
             s._coupled = self
         self._members = members
         for s in self.cvxs:
@@ -862,13 +914,84 @@ class coupled_fds(Steppable):
             self._t = self._engine.t
             self._engine = None                      # rebuild with the snapshot kernel in the captured step
         if self._engine is None and self._members:
-            self._engine = StepEngine(self._members, self._scheme, self.dydt_max_step, t0=self._t, record=record)
+            # recurrence maps may change between two stages of a step (fds.py:505-507): such a step cannot be collapsed
+            self._engine = StepEngine(self._members, self._scheme, self.dydt_max_step, t0=self._t, record=record,
+                                      allow_collapse=not (self.cont and self.maps))
             for s in self._members:
                 s._engine = self._engine
         return self._engine
 
+    # ---- recurrence maps coupled with continuous fields (fds.py:491-507) ------------------------------------------
+    def _map_clock(self, dt, commit=True):
+        """advance the maps' clocks by dt (fds.py:333-335, step_map); returns the maps that are due.  commit=False: dry run"""
+        due = []
+        for m in self.maps:
+            t = m._t + dt
+            if (t - m._n) >= m._dt:
+                due.append(m)
+                if commit:
+                    m._n = t
+            if commit:
+                m._t = t
+        return due
+
+    def _step_discrete(self, dt, t_now):
+        """fds.py:491-503: every discrete system advances its clock by dt; a map whose clock has run its own `dt` since
+        the last application is applied, at the coupled system's time (`sys.t` is re-bound to it, fds.py:463-467).  All
+        maps read the state the others had BEFORE this call (the reference copies the new states after the loop)."""
+        due = self._map_clock(dt)
+        if due:
+            engines = [m._ensure_engine() for m in due]
+            for e in engines:
+                e._refresh_externals()
+            for m, e in zip(due, engines):
+                e.apply_map(t_now, refresh=False)
+                m._version += 1
+        self.discrete_t += dt
+
+    def _step_interleaved(self, dt):
+        """fds.py:477-489 with the interleave of fds.py:505-507: the shared integrator calls coupled_fds.dydt at every
+        stage, which first steps the discrete systems to the stage time.  Steps during which no map is due replay the
+        captured step; a step in which one is due is enqueued stage by stage with the map applied in between."""
+        from .engine import step_table
+        eng = self._ensure_engine()
+        rk4 = self._scheme is Integrators.rk4
+        ts, hs, t_new = step_table(eng.t, eng.t + dt, eng.max_step)
+        for i in range(ts.size):
+            t, h = float(ts[i]), float(hs[i])
+            t_next = float(ts[i + 1]) if i + 1 < ts.size else t_new
+            for c in self.cvxs:
+                c._solve_lhs(t)
+            stage_t = (t, t + 0.5 * h, t + 0.5 * h, t + h) if rk4 else (t,)      # the solver's RHS evaluation times
+            clock, quiet = self.discrete_t, True
+            saved = [(m._t, m._n) for m in self.maps]
+            for st_t in stage_t:                      # dry run of the clocks: is any map due inside this step?
+                quiet = quiet and not self._map_clock(st_t - clock)
+                clock += st_t - clock
+            for m, (a, b) in zip(self.maps, saved):
+                m._t, m._n = a, b
+            if quiet:
+                for st_t in stage_t:
+                    self._step_discrete(st_t - self.discrete_t, t)
+                eng._refresh_externals()
+                eng.run((np.asarray([t]), np.asarray([h]), np.asarray([t_next]), t_next, eng._bc_table(np.asarray([t_next]))))
+            else:
+                def before(stage):
+                    self._step_discrete(stage_t[stage] - self.discrete_t, t)
+                    eng._refresh_externals()
+                eng.run_step_staged(t, h, t_next, before)
+            if eng.t > self.discrete_t:               # fds.py:482-483
+                self._step_discrete(eng.t - self.discrete_t, eng.t)
+            for f in self.cont:
+                if not f._identity_projection():       # fds.py:488: arbitrary host code, one round trip
+                    full = eng.read(f, full=True)
+                    eng.write(f, np.asarray(f.project_fun(full.copy()), dtype=np.float64))
+        self._t = eng.t
+
     def step(self, dt: float):
-        if self.has_integrator and self.cvxs:
+        if self.has_integrator and self.maps:
+            self._step_interleaved(dt)
+        elif self.has_integrator and self.cvxs:
             # fds.py:505-507 solves the discrete systems before every RHS evaluation; they read accepted state only, so
             # the solves of one internal step coincide: solve once at its start, then advance that step
             from .engine import step_table
@@ -898,7 +1021,25 @@ class coupled_fds(Steppable):
             s._version += 1
 
     def reset(self):
-        raise NotImplementedError
+        """fds.py:509-527: the shared integrator is rebuilt at t0 on the state taken at couple() time; the discrete systems
+        are reset one by one.  (`discrete_t` is left alone there as well.)"""
+        if self._engine is not None:
+            self._engine = None
+            for s in self._members:
+                s._engine = None
+        self.__dict__.pop('_integrator', None)
+        self._t = 0.
+        for s in self.cont:
+            s._host_state = s._couple_y0.copy()
+            s._version += 1
+        for s in self.cvxs + self.maps:
+            s._coupled = None
+            s._engine = None
+            s.reset()                                   # fds.py:248-262
+            s._coupled = self
+            if s.iter_mode is IterationMode.cvx:
+                s._dev_y = Buffer(s._low.ctx, s.ndim, s._low.to_dev(s._domain_code, s._host_state[:s.ndim]))
+                s._dev_y_cache = None
 
     def observables(self):
         return self.cont + self.cvxs + self.maps + self.nils
@@ -986,6 +1127,8 @@ class System:
         members = [st] if isinstance(st, fds) else list(getattr(st, '_members', []))
         if not members or not hasattr(st, '_ensure_engine'):
             return None
+        if isinstance(st, coupled_fds) and (st.cvxs or st.nils or st.maps):
+            return None      # solved / advanced / applied between the captured steps: keep the per-step loop
         if any(m.iter_mode is not IterationMode.dydt or not m._identity_projection() or m._low.part is not None
                for m in members):
             return None

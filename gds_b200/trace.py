@@ -82,6 +82,18 @@ class Expr:
     def copy(self):
         return self
 
+    # ---- scalar reductions (derived observables: `(v.y ** 2).sum()`, gds/examples/lid_driven_cavity.py:95-101) ----------
+    def _reduce(self, kind, axis, out):
+        if self.domain is None or axis not in (None, 0) or out is not None:
+            raise TraceError('only full reductions of a vector expression can be evaluated on the device')
+        return Reduce(kind, self)
+
+    def sum(self, axis=None, dtype=None, out=None, **kw): return self._reduce('sum', axis, out)
+    def max(self, axis=None, out=None, **kw): return self._reduce('max', axis, out)
+    def min(self, axis=None, out=None, **kw): return self._reduce('min', axis, out)
+    def mean(self, axis=None, dtype=None, out=None, **kw): return self._reduce('sum', axis, out) / float(len(self))
+    def dot(self, other): return (self * other).sum()
+
     def __getitem__(self, idx):
         raise TraceError('indexing a traced field expression is not supported in device-captured laws; use the '
                          '`free=` / `normal=` arguments or multiply by a 0/1 vector')
@@ -128,6 +140,14 @@ class Imm(Expr):
 
 class Time(Expr):
     """the `t` argument of the law: stage time t_n + c_s h"""
+
+
+class Reduce(Expr):
+    """scalar: sum / max / min over the rows of a vector expression, evaluated on the device (gds_buf_reduce)"""
+    KIND = {'sum': 0, 'max': 1, 'min': 2}
+
+    def __init__(self, kind, x):
+        self.kind, self.args = kind, (x,)
 
 
 class Stage(Expr):

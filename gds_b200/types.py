@@ -93,7 +93,8 @@ class Observable(ABC):
 
             @property
             def y(self_):
-                return view(parent)
+                from .fields import evaluate_view      # device operators + reductions where the view allows it
+                return evaluate_view(view, parent)
         return Projection()
 
 

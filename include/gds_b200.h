@@ -147,6 +147,10 @@ int gds_buf_upload(gds_buf* b, int64_t offset, const double* host, int64_t n);
 int gds_buf_download(gds_buf* b, int64_t offset, double* host, int64_t n);
 int gds_buf_fill(gds_buf* b, int64_t offset, int64_t n, double value);
 int gds_buf_devptr(gds_buf* b, void** dev_out, int64_t* n_out);
+/* scalar reduction of n values (kind 0 sum, 1 max, 2 min) on the device, fixed grid and tree (bitwise reproducible); only
+ * the 8-byte result is copied back.  Derived observables -- the projections of gds/types.py:95-105 such as the energies
+ * and momenta of gds/examples/lid_driven_cavity.py:95-101 -- evaluate their vector part with gds_pass_run and finish here. */
+int gds_buf_reduce(gds_buf* b, int64_t offset, int64_t n, int32_t kind, double* out);
 
 /* row sets as bitmaps (Dirichlet rows fds.py:303, `free` / `normal` arguments gds.py:296-317) */
 int gds_mask_create(gds_ctx* ctx, int64_t n_rows, const int64_t* rows, int64_t n, gds_mask** out);

@@ -572,7 +572,23 @@ class fds:
         return System(self, {name: self})
 
     def reset(self):
-        raise NotImplementedError
+        """fds.py:248-262: install the law again, then the initial and boundary conditions.  (The reference's dydt branch
+        omits `integrator=` and so falls back to its default adaptive solver; the fixed-step scheme is kept here.)"""
+        assert self.iter_mode != IterationMode.none
+        dirichlet, neumann, project = self.dirichlet_fun, self.neumann_fun, self.project_fun
+        if self.iter_mode is IterationMode.dydt:
+            self.set_evolution(dydt=self.dydt_fun, order=self.order, max_step=self.max_step,
+                               integrator=self.integrator_type, solver_args=self.solver_args)
+        elif self.iter_mode is IterationMode.cvx:
+            self.set_evolution(lhs=self.lhs_fun, refresh_cvx=self.refresh_cvx)
+        elif self.iter_mode is IterationMode.map:
+            self.set_evolution(map_fun=self.map_fun, dt=self._dt)
+        else:
+            self.set_evolution(nil=True)
+        self._set_bcs()
+        self.set_initial(t0=self.t0, y0=self.y0_fun)
+        if self.iter_mode is not IterationMode.nil:
+            self.set_constraints(dirichlet=dirichlet, neumann=neumann, project=project)
 
 
 def make_integrator(kind, fun, t0, y0, max_step, solver_args):
@@ -825,6 +841,17 @@ class coupled_fds:
     def dydt(self, t, y):  # fds.py:505-507
         self.step_discrete(t - self.discrete_t)
         return np.concatenate([s.dydt(t, y[s.view]) for s in self.cont])
+
+    def reset(self):  # fds.py:509-527 (discrete_t is not reset there either)
+        if self.has_integrator:
+            args = {}
+            for s in self.cont:
+                args.update(s.solver_args)
+            self.integrator = make_integrator(self.cont[0].integrator_type, self.dydt, self.t0, self.dydt_y0,
+                                              self.dydt_max_step, args)
+        for s in self.cvxs + self.maps:
+            s.reset()
+            self.discrete_y[id(s)] = s._y.copy()
 
     def observables(self):
         return self.cont + self.cvxs + self.maps

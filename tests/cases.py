@@ -475,7 +475,29 @@ def quirk_accepted_vs_stage(api):
     return out
 
 
+def quirk_map_coupled_continuous(api):
+    """fds.py:491-507: a recurrence map coupled with a continuous field is stepped, before EVERY right-hand-side evaluation
+    of the shared integrator, to that evaluation's stage time; it is applied when its own clock has run `dt` since the last
+    application -- in the middle of an RK4 step if that is where the stage time falls -- reads the ACCEPTED continuous
+    state, and the continuous law sees the new map state from that stage on."""
+    G = g_grid(6, 5)
+    T, m = api.node_gds(G), api.node_gds(G)
+    api.evolve(T, dydt=lambda t, y: T.laplacian(y) + 0.5 * m.y, max_step=1e-2)
+    api.evolve_map(m, map_fun=lambda t, y: 0.9 * y + 0.2 * T.y + 0.01 * t, dt=0.025)
+    T.set_initial(y0=lambda x: math.sin(x[0]) + 0.1 * x[1])
+    m.set_initial(y0=lambda x: 0.05 * x[0] - 0.02 * x[1])
+    T.set_constraints(dirichlet=lambda t, x: math.cos(t) if x[0] == 0 else None)
+    sysobj = api.couple({'T': T, 'm': m})
+    out = {}
+    for i in range(6):
+        sysobj.step(0.02)
+        out[f'T{i}'], out[f'm{i}'] = np.array(T.y, copy=True), np.array(m.y, copy=True)
+    out['t'] = np.array([sysobj.t])
+    return out
+
+
 QUIRK_CASES = {
+    'map_coupled_continuous': quirk_map_coupled_continuous,
     'order2_dirichlet': quirk_order2_dirichlet,
     'map_time_varying_dirichlet': quirk_map_time_varying_dirichlet,
     'euler_coupled_max_steps': quirk_euler_coupled_max_steps,

@@ -67,6 +67,41 @@ def test_point_reads_projections_and_partials():
     assert c.partial(e, x) == pytest.approx(ref_c.grad(x)[ref_u.X[e]], rel=1e-12)   # gds.py:149-150
 
 
+def test_derived_observables_reduce_on_the_device(monkeypatch):
+    """the projections of gds/examples/lid_driven_cavity.py:95-101 -- kinetic energy, momentum, rotational energy, angular
+    momentum: `(v.y ** 2).sum()`, `np.abs(v.y).sum()`, `(v.curl() ** 2).sum()`, `np.abs(v.curl()).sum()` -- evaluated by
+    device passes over the state where it lives plus a device reduction (gds_buf_reduce); only the scalar comes back"""
+    import gds_b200
+    from gds_b200 import device as D
+    G = cases.add_weights(cases.g_tri(5, 7), 4)
+    v, ref_v = gds_b200.edge_gds(G), oracle_api().edge_gds(cases.add_weights(cases.g_tri(5, 7), 4))
+    y0 = np.random.default_rng(8).standard_normal(v.ndim)
+    for f in (v, ref_v):
+        f.set_evolution(dydt=lambda t, y, f=f: 0.05 * f.laplacian(y) - 0.1 * y, max_step=1e-3)
+        f.set_initial(y0=lambda e, f=f: y0[f.X[e]])
+    v.step(4e-3); ref_v.step(4e-3)
+    views = {'kinetic energy': (lambda o: (v.y ** 2).sum(), (ref_v.y ** 2).sum()),
+             'momentum': (lambda o: np.abs(v.y).sum(), np.abs(ref_v.y).sum()),
+             'rotational energy': (lambda o: (v.curl() ** 2).sum(), (ref_v.curl() ** 2).sum()),
+             'angular momentum': (lambda o: np.abs(v.curl()).sum(), np.abs(ref_v.curl()).sum()),
+             'half energy': (lambda o: 0.5 * np.sum(v.y * v.y), 0.5 * np.sum(ref_v.y * ref_v.y)),
+             'peak': (lambda o: np.abs(v.y).max() - v.y.min(), np.abs(ref_v.y).max() - ref_v.y.min()),
+             'mean': (lambda o: v.y.mean(), ref_v.y.mean())}
+    calls, downloads = [], []
+    red, down = D.Buffer.reduce, D.Buffer.download
+    monkeypatch.setattr(D.Buffer, 'reduce', lambda self, *a, **k: (calls.append(1), red(self, *a, **k))[1])
+    monkeypatch.setattr(D.Buffer, 'download', lambda self, *a, **k: (downloads.append(self.n), down(self, *a, **k))[1])
+    for name, (view, want) in views.items():
+        obs = v.project(gds_b200.PointObservable, view)
+        got = obs.y
+        assert isinstance(got, float) and got == pytest.approx(want, rel=1e-10), name
+        assert obs.t == v.t
+    assert len(calls) == 8 and not downloads          # every view ended in a device reduction; no vector was copied back
+    # a view that is arbitrary host code still works (on a copy of the state, as in the reference)
+    norm = v.project(gds_b200.PointObservable, lambda o: float(np.linalg.norm(np.asarray(o.y))))
+    assert norm.y == pytest.approx(float(np.linalg.norm(ref_v.y)), rel=1e-10)
+
+
 def test_native_graph_and_boundary_spec_equal_networkx_and_callables():
     """the same heat problem through nx.Graph + per-point callables and through NativeGraph + vectorised BoundarySpec"""
     import gds_b200

@@ -115,3 +115,28 @@ def test_laws_that_read_the_stage_state_are_not_collapsed():
     S.set_evolution(dydt=lambda t, y: S.laplacian() * np.cos(t), max_step=1e-2)      # stage time
     S.set_initial(y0=lambda x: float(x[0]))
     assert not S._ensure_engine().collapsed
+
+
+def test_coupled_reset_goes_back_to_the_state_taken_at_couple_time():
+    """coupled_fds.reset (fds.py:509-527): the shared solver restarts at t0 from the state concatenated at couple() time,
+    recurrence maps are reset one by one"""
+    def run(api):
+        G = cases.g_grid(6, 5)
+        T, m = api.node_gds(G), api.node_gds(G)
+        api.evolve(T, dydt=lambda t, y: T.laplacian(y) + 0.5 * m.y, max_step=1e-2)
+        api.evolve_map(m, map_fun=lambda t, y: 0.9 * y + 0.2 * T.y, dt=0.025)
+        T.set_initial(y0=lambda x: math.sin(x[0]) + 0.1 * x[1])
+        m.set_initial(y0=lambda x: 0.05 * x[0] - 0.02 * x[1])
+        T.set_constraints(dirichlet=lambda x: 1.0 if x[0] == 0 else None)
+        sysobj = api.couple({'T': T, 'm': m})
+        out = {}
+        for rnd in range(2):
+            for i in range(4):
+                sysobj.step(0.02)
+            out[f'T_{rnd}'], out[f'm_{rnd}'], out[f't_{rnd}'] = np.array(T.y), np.array(m.y), np.array([sysobj.t])
+            sysobj.stepper.reset()
+            out[f'T_reset_{rnd}'], out[f't_reset_{rnd}'] = np.array(T.y), np.array([sysobj.t])
+        return out
+    both(run)
+    a = run(product_api())
+    assert np.array_equal(a['T_reset_0'], a['T_reset_1']) and a['t_reset_0'][0] == 0.
