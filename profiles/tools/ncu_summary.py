@@ -42,10 +42,14 @@ def main():
     for spec in sys.argv[2:]:
         name, workload, size = spec.split(':')
         rep = os.path.join(ROOT, 'gpurun_out', f'{tag}_ncu_{name}.ncu-rep')
-        if not os.path.exists(rep):
+        raw_csv = os.path.join(ROOT, 'gpurun_out', f'{tag}_ncu_{name}_raw.csv')
+        if os.path.exists(raw_csv):
+            raw = open(raw_csv).read()
+        elif os.path.exists(rep):
+            raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        else:
             print('missing', rep)
             continue
-        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         head, units, body = rows[0], rows[1], rows[2:]
         col = {h: i for i, h in enumerate(head)}
