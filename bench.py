@@ -231,7 +231,10 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
     h = 0.1
     if native:
         import gds_b200
-        G = gds_b200.NativeGraph('grid', n, n, n * world)
+        # weak scaling: n x n x (n * world) cut into `world` slabs of n^3; --total: the n^3 grid itself cut into slabs
+        # (strong scaling -- BASELINE config 5 is the 693^3 grid, 10^9 edges, on 8 GPUs)
+        nz = n if TOTAL[0] else n * world
+        G = gds_b200.NativeGraph('grid', n, n, nz)
         if world > 1 and distribute:
             gds_b200.distribute(G, rank, world)
     else:
@@ -241,7 +244,7 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
     api.evolve(a, dydt=lambda t, y: 1.0 * a.laplacian(), order=2, max_step=h)
     if native:
         gid = a.global_ids
-        A, B, C = n * world, n, n
+        A, B, C = nz, n, n
         ia, ib, ic = gid // (B * C), (gid // C) % B, gid % C
         a.set_initial(y0=np.exp(-((ia - (A - 1) / 2) ** 2 + (ib - (B - 1) / 2) ** 2 + (ic - (C - 1) / 2) ** 2) / 200.0))
         n_own = a.ndim if a.partition is None else a.partition.n_own
@@ -258,7 +261,8 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
                 bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
                 kernel='step level: collapsed RK4 -- one Laplacian pass over the value block (derivative block advanced in '
                        'its epilogue) + one pointwise pass for the value block',
-                name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{n * world}]) (V={n ** 3 * world})'
+                name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{nz if native else n}]) '
+                     f'(V={n * n * (nz if native else n)}, E={3 * n * n * (nz if native else n) - n * n - 2 * n * (nz if native else n)})'
                      + (f', {world} slabs with halo exchange' if world > 1 else ''))
 
 
@@ -644,6 +648,10 @@ def gpu_arm(args):
     est = ctx.timer_stop() / W
     ms, launches, clocks = time_steps(eng, ctx, K, h, barrier, local, world, dist, torch, est_ms=est)
     n_total = prob['n_state'] * world
+    if world > 1:       # slabs may differ by a lattice plane: count what the ranks really advance
+        tt = torch.tensor([prob['n_state']], dtype=torch.int64, device='cuda')
+        dist.all_reduce(tt)
+        n_total = int(tt.item())
     value = n_total * K / (ms * 1e-3)
     multi = None
     if world > 1:
@@ -723,7 +731,8 @@ def gpu_arm(args):
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if args.total else 'weak',
+            'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': WORKLOAD_NAME[0], 'scheme': SCHEME[0],
                        'l2': 'inputs exceed L2 (state + operators >> 126 MB)',
@@ -746,6 +755,7 @@ def gpu_arm(args):
 
 
 WORKLOAD_NAME = [None]
+TOTAL = [False]          # --total: --size is the size of the WHOLE problem (strong scaling) instead of the size per rank
 NO_PREROLL = [False]     # profiling runs (ncu replays every launch ~40 times): skip the 0.3 s of load for the clock sampler
 SCHEME = ['rk4']
 HALO = ['']
@@ -765,9 +775,11 @@ def main():
     ap.add_argument('--no-workloads', action='store_true', help='N = 1: skip the other BASELINE configurations after the headline')
     ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
+    ap.add_argument('--total', action='store_true', help='wave3d: --size is the whole grid, cut into --gpus slabs (strong scaling)')
     ap.add_argument('--no-preroll', action='store_true', help='profiling runs under ncu: no untimed pre-roll before the timed steps')
     args = ap.parse_args()
     NO_PREROLL[0] = args.no_preroll
+    TOTAL[0] = args.total
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -1069,6 +1069,7 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
   double* xnext = (s->scheme == GDS_SCHEME_RK4 && !s->collapsed && st < 3) ? s->XS[st & 1] : nullptr;
   for (const PassHost& ph : s->passes) {
     if (ph.when != GDS_WHEN_STAGE) continue;
+    if (ph.fused_away) continue;   // collapsed stepping: this block shift runs inside the RHS pass of its source block
     PassParams pp;
     GDS_TRY(resolve_pass(s->g, ph, yn, stage, pp));
     if (ph.special) pp.n_rows = ph.sp_n;
@@ -1091,6 +1092,7 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
         pp.fin = 1.0 / 6.0;
         pp.stage_mode = GDS_MODE_COLLAPSED;
         pp.store_k = ph.store_k ? 1 : 0;
+        if (ph.fuse_dst >= 0) { pp.yn2 = yn + ph.fuse_dst; pp.ynew2 = ynew + ph.fuse_dst; }
         if (ph.special == 1) {   // order-2 block shift: the row value is the source block's derivative, kept in ACC
           pp.stage_mode = GDS_MODE_COLLAPSED_SHIFT;
           pp.aux = yn + ph.sp_src;
@@ -1321,7 +1323,14 @@ extern "C" int gds_system_finalize(gds_system* s) {
         PassHost& src = s->passes[j];
         if (src.epilogue != GDS_EPI_RHS || src.special || src.state_offset != sh.sp_src) continue;
         if (j > i) GDS_FAIL("collapsed stepping: a block shift is ordered before the pass it reads");
-        src.store_k = true;
+        // same rows on both sides (the blocks of one field): the shift is evaluated in the epilogue of the source's RHS
+        // pass -- no second launch, no derivative written to memory; otherwise the derivative goes through ACC
+        if (src.fuse_dst < 0 && sh.sp_n == domain_rows(s->g, src.domain) && !getenv("GDS_B200_NO_FUSED_SHIFT")) {
+          src.fuse_dst = sh.sp_dst;
+          sh.fused_away = true;
+        } else {
+          src.store_k = true;
+        }
         found = true;
       }
       if (!found) GDS_FAIL("collapsed stepping supports fields of order <= 2 (a block shift reads another shifted block)");

@@ -175,6 +175,8 @@ struct PassParams {
                       // 5 whole RK4 step of a stage-independent law, 6 the same for an order-2 block shift (see GDS_MODE_*)
   const double* aux;  // mode 6: accepted state of the SOURCE block (v_n), while the row value is its derivative k_v
   int32_t store_k;    // mode 5: also write the (Dirichlet-masked) derivative to acc_out, for a block shift that needs it
+  const double* yn2;  // mode 5, order-2 fields: accepted state of the block advanced by dy/dt = stage value of THIS block
+  double* ynew2;      //         ... and where its new value goes: the block shift is fused into this pass (no extra launch)
   const uint32_t* dmask;
   const double* yn;
   const double* acc_in;
@@ -272,6 +274,8 @@ struct PassHost {  // a pass as given by the host, operands still symbolic
   int32_t special = 0;  // 0 normal, 1 shift, 2 hold
   int64_t sp_dst = 0, sp_src = 0, sp_n = 0;
   bool store_k = false; // collapsed stepping: a block shift reads this pass's derivative
+  int64_t fuse_dst = -1;  // collapsed stepping: state offset of the shifted block this RHS pass advances as well
+  bool fused_away = false;  // collapsed stepping: this block shift runs inside the RHS pass of its source block
 };
 
 struct gds_system {

@@ -313,6 +313,7 @@ __device__ __forceinline__ void stage_epilogue(const PassParams& p, int64_t row,
     case GDS_MODE_COLLAPSED:
       if (p.store_k) p.acc_out[row] = k;
       p.ynew[row] = rk4_collapsed(yn, k, p.fin * h);
+      if (p.ynew2) p.ynew2[row] = rk4_collapsed_shift(ld_stream_f64(p.yn2 + row), yn, k, h, p.fin * h);
       break;
     case GDS_MODE_COLLAPSED_SHIFT:
       p.ynew[row] = rk4_collapsed_shift(yn, __ldg(p.aux + row), k, h, p.fin * h);
@@ -630,6 +631,7 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
       case GDS_MODE_COLLAPSED:
         if (p.store_k) p.acc_out[r] = k1;
         p.ynew[r] = rk4_collapsed(yn[i], k1, p.fin * h);
+        if (p.ynew2) p.ynew2[r] = rk4_collapsed_shift(ld_stream_f64(p.yn2 + r), yn[i], k1, h, p.fin * h);
         break;
       default: p.ynew[r] = k1; break;
     }
@@ -771,6 +773,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
     } else if (MODE == 5) {
       if (p.store_k) p.acc_out[ri] = k1;
       p.ynew[ri] = rk4_collapsed(yn[i], k1, p.fin * h);
+      if (p.ynew2) p.ynew2[ri] = rk4_collapsed_shift(ld_stream_f64(p.yn2 + ri), yn[i], k1, h, p.fin * h);
     } else {
       p.ynew[ri] = k1;
     }
@@ -879,8 +882,10 @@ __device__ __forceinline__ void st_quad_v(double* p, int64_t r0, int64_t n_rows,
 // directions, two 128-bit loads for other even offsets -- instead of four 8-byte gathers.  Same operands, same order
 // of additions: results are bit-identical to the scalar gathers.  (ncu on the scalar form: the L1 data pipe, 254
 // wavefronts per 128 rows, was the busiest unit at 67 %; a run costs 8 wavefronts per slot instead of ~40.)
-template <bool UNITW, bool IDX16, bool RUNS>
-__global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) lapq_kernel(const __grid_constant__ PassParams p) {
+// COLL: the collapsed RK4 epilogue (GDS_MODE_COLLAPSED) as its own instantiation, so that the staged kernels keep their
+// register budget (the collapsed form holds the row's own values until the end for the fused order-2 block shift)
+template <bool UNITW, bool IDX16, bool RUNS, bool COLL>
+__global__ void __launch_bounds__(LAPQ_BLOCK, COLL ? 8 : (UNITW ? LAPQ_MINB : LAPQ_MINB_W)) lapq_kernel(const __grid_constant__ PassParams p) {
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
   const bool full = r0 + 3 < p.n_rows;
@@ -1014,6 +1019,28 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) l
   for (int i = 0; i < 4; ++i)
     if ((dbits >> i) & 1u) k4[i] = 0.0;                 // fds.py:303
   double o1v[4], o2v[4];
+  if (COLL) {
+    if (p.store_k) st_quad_v<RUNS>(p.acc_out, r0, p.n_rows, full, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o1v[i] = rk4_collapsed(yn[i], k4[i], p.fin * h);
+    st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
+    if (p.ynew2) {   // order-2 field: the value block, dy/dt = stage value of this (derivative) block, in the same pass
+      double x4[4];
+      if (p.yn2 == v) {   // the Laplacian's own operand (wave equation): already in registers
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x4[i] = c[i];
+      } else if (RUNS) {
+        ld_stream_v4f64(p.yn2 + r0, x4);
+      } else {
+        const double2 a = ld_stream_v2f64(p.yn2 + r0), b = ld_stream_v2f64(p.yn2 + r0 + 2);
+        x4[0] = a.x; x4[1] = a.y; x4[2] = b.x; x4[3] = b.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o2v[i] = rk4_collapsed_shift(x4[i], yn[i], k4[i], h, p.fin * h);
+      st_quad_v<RUNS>(p.ynew2, r0, p.n_rows, full, o2v);
+    }
+    return;
+  }
   switch (mode) {
     case 0:
 #pragma unroll
@@ -1035,12 +1062,6 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, UNITW ? LAPQ_MINB : LAPQ_MINB_W) l
     case 3:
 #pragma unroll
       for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
-      st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
-      break;
-    case GDS_MODE_COLLAPSED:
-      if (p.store_k) st_quad_v<RUNS>(p.acc_out, r0, p.n_rows, full, k4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o1v[i] = rk4_collapsed(yn[i], k4[i], p.fin * h);
       st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
       break;
     default:
@@ -1069,7 +1090,8 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     const bool use_quad = (force ? !strcmp(force, "quad") : true) && p.lap_chain.n == 0 && p.lap_bchain.n == 0 && !p.lap_b2;
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
-      quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew);
+      quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew) &&
+                aligned16(p.yn2) && aligned16(p.ynew2);
     if (quad_ok) {
       int64_t blocks = ((rows + 3) / 4 + LAPQ_BLOCK - 1) / LAPQ_BLOCK;
       // 256-bit accesses and run gathers need 32-byte aligned vectors (the engine lays fields out that way);
@@ -1077,19 +1099,24 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       static const char* runs_env = getenv("GDS_B200_LAPQ_RUNS");
       bool runs = !(runs_env && !strcmp(runs_env, "0")) && aligned32(p.lap_v) && aligned32(p.lap_b) && aligned32(p.lap_store);
       if (runs && p.epilogue == GDS_EPI_RHS)
-        runs = aligned32(p.yn) && aligned32(p.acc_in) && aligned32(p.acc_out) && aligned32(p.xnext) && aligned32(p.ynew);
-      const int variant = (unitw ? 4 : 0) | (p.g.n_nbr16 ? 2 : 0) | (runs ? 1 : 0);
+        runs = aligned32(p.yn) && aligned32(p.acc_in) && aligned32(p.acc_out) && aligned32(p.xnext) && aligned32(p.ynew) &&
+               aligned32(p.yn2) && aligned32(p.ynew2);
+      const bool coll = p.epilogue == GDS_EPI_RHS && p.stage_mode == GDS_MODE_COLLAPSED;
+      const int variant = (coll ? 8 : 0) | (unitw ? 4 : 0) | (p.g.n_nbr16 ? 2 : 0) | (runs ? 1 : 0);
       const unsigned nb = (unsigned)blocks;
+#define LAPQ_CASE(V, A, B, C, D) case V: lapq_kernel<A, B, C, D><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
       switch (variant) {
-        case 7: lapq_kernel<true, true, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 6: lapq_kernel<true, true, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 5: lapq_kernel<true, false, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 4: lapq_kernel<true, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 3: lapq_kernel<false, true, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 2: lapq_kernel<false, true, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        case 1: lapq_kernel<false, false, true><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
-        default: lapq_kernel<false, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        LAPQ_CASE(15, true, true, true, true) LAPQ_CASE(14, true, true, false, true)
+        LAPQ_CASE(13, true, false, true, true) LAPQ_CASE(12, true, false, false, true)
+        LAPQ_CASE(11, false, true, true, true) LAPQ_CASE(10, false, true, false, true)
+        LAPQ_CASE(9, false, false, true, true) LAPQ_CASE(8, false, false, false, true)
+        LAPQ_CASE(7, true, true, true, false) LAPQ_CASE(6, true, true, false, false)
+        LAPQ_CASE(5, true, false, true, false) LAPQ_CASE(4, true, false, false, false)
+        LAPQ_CASE(3, false, true, true, false) LAPQ_CASE(2, false, true, false, false)
+        LAPQ_CASE(1, false, false, true, false)
+        default: lapq_kernel<false, false, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
       }
+#undef LAPQ_CASE
       GDS_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
       return 0;
