@@ -201,28 +201,35 @@ def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):
                      f'triangular_lattice_graph({n},{n}) (V={V}, E={E}, F={F}), lid + no-slip Dirichlet')
 
 
-def cml_problem(api, n, native, world=1, rank=0, weighted=False):
-    """BASELINE config 4: coupled map lattice on random_geometric_graph(n, sqrt(8/(pi n)), seed=42), map mode"""
-    assert world == 1 and not weighted
-    r = math.sqrt(8 / (math.pi * n))
+def cml_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True):
+    """BASELINE config 4: coupled map lattice on random_geometric_graph(n, sqrt(8/(pi n)), seed=42), map mode.  With
+    `world` ranks the graph has n * world nodes (--total: n) and is cut into spatially compact parts along a space-filling
+    curve over the node positions; one halo exchange per map application."""
+    assert not weighted
+    nn = n if (TOTAL[0] or not native) else n * world
+    r = math.sqrt(8 / (math.pi * nn))
     eps = 0.3
     if native:
         import gds_b200
-        G = gds_b200.NativeGraph('random_geometric', n, r, 42)
+        G = gds_b200.NativeGraph('random_geometric', nn, r, 42)
+        if world > 1 and distribute:
+            gds_b200.distribute(G, rank, world, align=32)
     else:
         import cases
         G = cases.g_rgg(n, r, 42)
     x = api.node_gds(G)
     api.evolve_map(x, map_fun=lambda t, y: (1 - 1.7 * y ** 2) + (eps / 8.0) * x.laplacian(1 - 1.7 * y ** 2), dt=1.0)
-    y0 = np.random.default_rng(2).uniform(-1, 1, n)
+    y0 = np.random.default_rng(2).uniform(-1, 1, nn)
     x.set_initial(y0=y0 if native else (lambda v: y0[v]))
-    V = n
-    E = x._low.E if native else G.number_of_edges()
+    part = getattr(x, 'partition', None) if native else None
+    V = nn if part is None else part.n_own
+    E = (x._low.E if part is None else int(x._low.E * V / max(1, x._low.V))) if native else G.number_of_edges()
     per_step = 12 * (V + 2 * E) + 4 * V + 16 * V
     return dict(stepper=x, fields=[x], h=1.0, n_state=V, V=V, E=E, F=0, bytes_per_step=per_step,
                 bytes_per_launch=per_step, kernel_bytes_per_launch=(4 * 2 * E + 8 * 4) * 1.0 + 24 * V,
                 dominant_class=0, kernel='lapT_kernel<unit weights, map> (+ pointwise pass f(y))',
-                name=f'coupled map lattice, random_geometric_graph({n}) (E={E}), map mode')
+                name=f'coupled map lattice, random_geometric_graph({nn}) (E={E if part is None else "~" + str(E * world)}), map mode'
+                     + (f', {world} parts along a space-filling curve, halo exchange per application' if part is not None else ''))
 
 
 def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True):
@@ -497,7 +504,7 @@ def verify_partitioned(eng, builder, args, world, rank, dist, torch):
         every = [torch.zeros_like(st) for _ in range(world)]
         dist.all_gather(every, st)
         out['p2p'] = {'exchanges_per_rank': [int(x[0].item()) for x in every], 'error': max(int(x[1].item()) for x in every)}
-    small = {'heat2d': 512, 'wave3d': 48, 'hex_advdiff': 24}.get(args.workload)
+    small = {'heat2d': 512, 'wave3d': 48, 'hex_advdiff': 24, 'cml': 200_000}.get(args.workload)
     slab_ok = True
     if small is not None and not args.no_slab_check:
         steps = 6

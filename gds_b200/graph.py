@@ -172,7 +172,16 @@ class LoweredGraph:
         elif self.native:
             hg = G.hostgraph(with_faces=False)
             eu, ev = hg.edges()
+            # no locality in the public numbering (random geometric graph): cut along a space-filling curve of the positions
+            i2p = locality_permutation(hg.V, eu, ev, hg.pos()) if hg.has_pos else None
+            if i2p is not None and not os.environ.get('GDS_B200_NO_RENUMBER'):
+                p2i = np.empty(hg.V, dtype=np.int64)
+                p2i[i2p] = np.arange(hg.V, dtype=np.int64)
+                eu, ev = p2i[eu], p2i[ev]
+            else:
+                i2p = None
             part = Partition.from_global(rank, world, hg.V, eu, ev, G.weights, align)
+            part.set_public_ids(i2p)
             lab = hg.labels()[part.global_ids]
             self.nodes = LazyNodeMap(_LabelSource(lab.astype(np.int64), hg.label_dim))
         else:
@@ -182,7 +191,18 @@ class LoweredGraph:
             eu = np.fromiter((gidx[e[0]] for e in G.edges()), dtype=np.int64, count=E)
             ev = np.fromiter((gidx[e[1]] for e in G.edges()), dtype=np.int64, count=E)
             w = np.fromiter((d.get('weight', 1.0) for (_, _, d) in G.edges(data=True)), dtype=np.float64, count=E)
+            i2p = None
+            pos = nx.get_node_attributes(G, 'pos')
+            if len(pos) == len(gnodes) and gnodes and not os.environ.get('GDS_B200_NO_RENUMBER'):
+                P = np.array([pos[v][:2] for v in gnodes], dtype=np.float64).reshape(len(gnodes), -1)
+                if P.shape[1] == 2:
+                    i2p = locality_permutation(len(gnodes), eu, ev, P)
+            if i2p is not None:
+                p2i = np.empty(len(gnodes), dtype=np.int64)
+                p2i[i2p] = np.arange(len(gnodes), dtype=np.int64)
+                eu, ev = p2i[eu], p2i[ev]
             part = Partition.from_global(rank, world, len(gnodes), eu, ev, w, align)
+            part.set_public_ids(i2p)
             self.nodes = {gnodes[int(g)]: i for i, g in enumerate(part.global_ids)}
         self.part = part
         self.V, self.E = part.n_loc, part.E_loc

@@ -1,6 +1,9 @@
 """Graph partitioning for multi-GPU stepping -- no counterpart in the single-process reference.
 
 Nodes are split into contiguous index ranges (slabs of a row-major lattice; `align` keeps cuts on plane boundaries).
+Graphs whose public numbering has no locality (random geometric graphs) are first ordered along a space-filling curve
+over the node positions, so that a contiguous range is a spatially compact part (the coordinate-bisection family of
+partitions; `Partition.set_public_ids`); the public ids never change.
 Rank r lowers its LOCAL graph: owned nodes [lo, hi) first, then the one-hop ghost nodes sorted by global id (hence
 grouped by owner), with every edge that touches an owned node, kept in GLOBAL edge order -- an owned row therefore sums
 its incident edges in the same order as on one GPU and results do not depend on the number of parts.
@@ -24,6 +27,7 @@ def split_bounds(V: int, world: int, align: int = 1) -> np.ndarray:
 
 class Partition:
     """local graph of one rank"""
+    pub = p2i = None      # renumbered cut order <-> public ids (set_public_ids); None: ranges of the public numbering
 
     def __init__(self, rank, world, V_global, bounds, eu_g, ev_g, weights, ghosts=None):
         """eu_g / ev_g: GLOBAL endpoint ids of the local edges (every edge touching [lo, hi)), in global edge order"""
@@ -73,14 +77,27 @@ class Partition:
                              for q in range(world)]}
         self.faces_local = None
 
+    def set_public_ids(self, i2p):
+        """The ranges were cut in a RENUMBERED node order (space-filling curve over the node positions: spatially compact
+        parts for graphs whose public numbering has no locality).  i2p[k] = public id of node k of that order; everything
+        this object hands out (`global_ids`) or takes (`localise`) stays in PUBLIC ids."""
+        if i2p is None:
+            return
+        self.pub = np.ascontiguousarray(i2p, dtype=np.int64)
+        self.p2i = np.empty_like(self.pub)
+        self.p2i[self.pub] = np.arange(self.pub.size, dtype=np.int64)
+
     @property
     def global_ids(self) -> np.ndarray:
-        """global node id of every local row (owned, then ghosts)"""
-        return np.concatenate([np.arange(self.lo, self.hi, dtype=np.int64), self.ghosts])
+        """global (public) node id of every local row (owned, then ghosts)"""
+        ids = np.concatenate([np.arange(self.lo, self.hi, dtype=np.int64), self.ghosts])
+        return ids if self.pub is None else self.pub[ids]
 
     def localise(self, global_idx):
-        """(mask of entries that are local rows, their local indices) for an array of global node ids"""
+        """(mask of entries that are local rows, their local indices) for an array of global (public) node ids"""
         g = np.asarray(global_idx, dtype=np.int64)
+        if self.p2i is not None:
+            g = self.p2i[g]
         own = (g >= self.lo) & (g < self.hi)
         if self.n_ghost:
             pos = np.minimum(np.searchsorted(self.ghosts, g), self.n_ghost - 1)

@@ -293,3 +293,38 @@ def test_deep_partition_is_enough_for_the_edge_self_advection(world, hops):
     # one layer is NOT enough for a rank that owns a cut edge (its far endpoint's star is incomplete); the last rank owns
     # none (an edge belongs to the owner of its tail = lower index) and gets away with it
     assert not all(one_layer_ok) and one_layer_ok[-1]
+
+
+@pytest.mark.parametrize('world', [2, 4, 7])
+def test_graphs_without_index_locality_are_cut_along_a_space_filling_curve(world, monkeypatch):
+    """random geometric graph: node ids are random in space, so index ranges of the PUBLIC numbering would cut almost every
+    edge; the ranges are taken in a space-filling-curve order instead (spatially compact parts), while every id handed
+    out or taken by the partition stays public"""
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    try:
+        n, r = 4000, 0.04
+        hg = NativeGraph('random_geometric', n, r, 42).hostgraph()
+        eu, ev = [a.astype(np.int64) for a in hg.edges()]
+        owner = np.full(n, -1)
+        cut_curve = 0
+        for rank in range(world):
+            G = gds_b200.distribute(NativeGraph('random_geometric', n, r, 42), rank, world, align=32)
+            low = gds_b200.LoweredGraph.of(G)
+            part = low.part
+            gid = part.global_ids
+            assert part.pub is not None and len(set(gid.tolist())) == gid.size
+            owner[gid[:part.n_own]] = rank
+            # local edges = every global edge touching an owned node, in global edge order, public endpoints preserved
+            own = np.zeros(n, dtype=bool); own[gid[:part.n_own]] = True
+            keep = own[eu] | own[ev]
+            assert np.array_equal(gid[low.edge_u], eu[keep]) and np.array_equal(gid[low.edge_v], ev[keep])
+            cut_curve += int(np.sum(own[eu] != own[ev]))
+            sel, loc = part.localise(np.arange(n))
+            assert np.array_equal(gid[loc], np.arange(n)[sel]) and sel.sum() == part.n_loc
+        assert np.all(owner >= 0)
+        cut_curve //= 2
+        cut_index = int(np.sum((eu * world // n) != (ev * world // n)))      # index ranges of the public numbering
+        assert cut_curve < 0.25 * cut_index and cut_curve < 0.2 * eu.size, (cut_curve, cut_index, eu.size)
+    finally:
+        gds_b200.Context._default.clear()
