@@ -95,6 +95,9 @@ def locality_permutation(V, edge_u, edge_v, pos, window=1024):
     if float(np.mean(np.abs(edge_u.astype(np.int64) - edge_v.astype(np.int64)))) <= 0.05 * V:
         return None
     i2p = morton_order(np.asarray(pos, dtype=np.float64))
+    window = int(os.environ.get('GDS_B200_SORT_WINDOW', window))     # A/B knob: 0 = keep the pure curve order
+    if window <= 1:
+        return i2p
     deg = np.bincount(edge_u, minlength=V) + np.bincount(edge_v, minlength=V)
     d = deg[i2p]
     window = min(window, max(32, V // 16))
