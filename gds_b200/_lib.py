@@ -103,6 +103,7 @@ _sig('gds_system_add_shift', c_vp, c_i64, c_i64, c_i64)
 _sig('gds_system_add_hold', c_vp, c_i64, c_i64)
 _sig('gds_system_set_dirichlet', c_vp, c_vp, c_vp, c_i64, c_i32)
 _sig('gds_system_set_collapsed', c_vp, c_i32)
+_sig('gds_system_set_shadow', c_vp, c_i32)
 _sig('gds_system_finalize', c_vp)
 _sig('gds_system_set_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_get_state', c_vp, c_vp, c_i64, c_i64)
@@ -126,6 +127,7 @@ _sig('gds_system_p2p_status', c_vp, P(c_i64), P(c_i64))
 _sig('gds_system_p2p_error', c_vp, P(c_i64))
 _sig('gds_system_p2p_set_overlap', c_vp, c_i64, c_i64)
 _sig('gds_system_info', c_vp, P(c_i64), P(c_i64))
+_sig('gds_system_modes', c_vp, P(c_i32), P(c_i32), P(c_i32))
 _sig('gds_hostgraph_lattice', c_i32, c_i64, c_i64, c_i64, c_f64, c_i32, P(c_vp))
 _sig('gds_hostgraph_from_graph', c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp))
 _sig('gds_hostgraph_sizes', c_vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64), P(c_i32), P(c_i32))
@@ -139,8 +141,8 @@ EXPORTED = [
     'gds_buf_view', 'gds_buf_destroy', 'gds_buf_upload', 'gds_buf_download', 'gds_buf_fill', 'gds_buf_devptr', 'gds_buf_reduce', 'gds_mask_create',
     'gds_mask_destroy', 'gds_graph_create', 'gds_graph_destroy', 'gds_graph_sizes', 'gds_graph_export_csr',
     'gds_graph_device_bytes', 'gds_pass_run', 'gds_pass_kernel_kind', 'gds_cg_solve', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
-    'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_set_collapsed', 'gds_system_finalize',
-    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_timed', 'gds_system_info',
+    'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_set_collapsed', 'gds_system_set_shadow', 'gds_system_finalize',
+    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_timed', 'gds_system_info', 'gds_system_modes',
     'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',
     'gds_halo_create', 'gds_halo_destroy', 'gds_halo_pack', 'gds_halo_unpack',
     'gds_system_ipc_export', 'gds_system_p2p_attach', 'gds_system_p2p_status',

@@ -928,6 +928,7 @@ extern "C" int gds_system_destroy(gds_system* s) {
     if (s->graph[i]) cudaGraphDestroy(s->graph[i]);
     cudaFree(s->Y[i]);
     cudaFree(s->XS[i]);
+    cudaFree(s->Z[i]);
   }
   cudaFree(s->ACC);
   cudaFree(s->d_dir_idx_static); cudaFree(s->d_dir_val_static); cudaFree(s->d_dir_idx_dyn);
@@ -1111,6 +1112,17 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
         pp.stage_mode = 4;
       }
     }
+    if (s->shadow && &ph == &s->passes[(size_t)s->shadow_pass]) {
+      // carried gather operand: gather Z = f(Y) (kept beside the state) instead of evaluating f per gathered neighbour;
+      // the epilogue writes f of the new state next to the new state
+      const int64_t off = ph.state_offset;
+      const bool b_is_v = pp.lap_b == pp.lap_v;
+      pp.shadow_chain = pp.lap_chain;
+      pp.lap_v = s->Z[cur] + off;
+      pp.lap_chain.n = 0;
+      if (b_is_v) { pp.lap_b = s->Z[cur] + off; pp.lap_bchain.n = 0; }
+      pp.shadow_out = s->Z[cur ^ 1] + off;
+    }
     if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
     GDS_TRY(launch_pass(c, pp, ph.domain));
     if (lt) GDS_TRY(lt->end());
@@ -1128,7 +1140,8 @@ static int enqueue_tail(gds_system* s, int cur, LaunchTimer* lt, int phase = -1)
   const bool rec = s->recording && !lt;   // the snapshot reads the step counter after the overwrite: advance it last
   const bool last = phase != 1;
   GDS_TRY(launch_tail(c, ynew, s->d_dir_idx_static, s->d_dir_val_static, s->n_dir_static, s->d_dir_idx_dyn, s->d_bc_tab,
-                      s->n_dir_dyn, s->d_counter, (rec || !last) ? 0 : 1, s->d_dir_phase_static, s->d_dir_phase_dyn, phase));
+                      s->n_dir_dyn, s->d_counter, (rec || !last) ? 0 : 1, s->d_dir_phase_static, s->d_dir_phase_dyn, phase,
+                      s->shadow ? s->Z[cur ^ 1] : nullptr, s->shadow ? &s->passes[(size_t)s->shadow_pass].lap.chain : nullptr));
   if (rec && last) {
     GDS_TRY(launch_record(c, ynew, s->d_traj, s->d_rec, s->d_counter, s->n_state));
     GDS_TRY(launch_advance_counter(c, s->d_counter));
@@ -1339,6 +1352,39 @@ extern "C" int gds_system_finalize(gds_system* s) {
       for (const gds_vecref& v : ph.vec)
         if (v.kind == GDS_VEC_STAGE && !ph.special) GDS_FAIL("collapsed stepping: a pass reads the stage state");
   }
+  if (s->shadow) {
+    // which pass can gather a carried operand: a map whose one Laplacian pass applies a pointwise chain f to its own
+    // stage vector (CML: y <- f(y) + c L f(y)); anything else simply keeps the on-the-fly evaluation
+    s->shadow_pass = -1;
+    int n_rhs = 0;
+    for (size_t i = 0; i < s->passes.size(); ++i) {
+      const PassHost& ph = s->passes[i];
+      if (ph.epilogue != GDS_EPI_RHS || ph.special == 2) continue;
+      ++n_rhs;
+      if (ph.special || !ph.lap.ok || ph.lap.chain.n == 0 || ph.domain != GDS_NODES) continue;
+      const gds_vecref& v = ph.vec[(size_t)ph.lap.v];
+      if (v.kind != GDS_VEC_STAGE || v.offset != ph.state_offset) continue;
+      if (ph.lap.b >= 0 && ph.lap.bchain.n > 0) {   // beta g(b): only b = the same vector with g = f
+        const gds_vecref& b = ph.vec[(size_t)ph.lap.b];
+        bool same = b.kind == v.kind && b.offset == v.offset && ph.lap.bchain.n == ph.lap.chain.n;
+        for (int k = 0; same && k < ph.lap.chain.n; ++k)
+          same = ph.lap.bchain.pre[k] == ph.lap.chain.pre[k] && ph.lap.bchain.m[k] == ph.lap.chain.m[k] &&
+                 ph.lap.bchain.a[k] == ph.lap.chain.a[k];
+        if (!same) continue;
+      }
+      s->shadow_pass = (int)i;
+    }
+    if (s->scheme != GDS_SCHEME_MAP || n_rhs != 1 || s->shadow_pass < 0 || s->p2p) {
+      s->shadow = false;
+    } else {
+      const size_t bytes = (size_t)(s->n_state + 4) * sizeof(double);
+      for (int i = 0; i < 2; ++i) {
+        GDS_CUDA(cudaMalloc((void**)&s->Z[i], bytes));
+        GDS_CUDA(cudaMemsetAsync(s->Z[i], 0, bytes, c->stream));
+        s->device_bytes += (int64_t)bytes;
+      }
+    }
+  }
   s->cap_steps = GDS_STEP_CAPACITY;
   GDS_CUDA(cudaMalloc((void**)&s->d_steptab, (size_t)s->cap_steps * sizeof(StepRec)));
   GDS_CUDA(cudaMemset(s->d_steptab, 0, (size_t)s->cap_steps * sizeof(StepRec)));
@@ -1390,6 +1436,13 @@ extern "C" int gds_system_state_devptr(gds_system* s, void** dev_out) {
 
 static int system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc,
                        const int64_t* rec_slot);
+
+// carried gather operand: Z = f(Y) for the current accepted state.  Done at the start of every stepping call -- between
+// two calls the host may have written the state -- and kept up to date by the kernels that write the state afterwards.
+static int shadow_refresh(gds_system* s) {
+  if (!s->shadow) return 0;
+  return launch_shadow_init(s->ctx, s->Y[s->cur], s->Z[s->cur], s->n_state, s->passes[(size_t)s->shadow_pass].lap.chain);
+}
 
 extern "C" int gds_system_step(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc) {
   return system_step(s, n_steps, t, h, bc, nullptr);
@@ -1451,6 +1504,7 @@ static int system_step(gds_system* s, int64_t n_steps, const double* t, const do
       }
     }
     GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+    if (done == 0) GDS_TRY(shadow_refresh(s));
     for (int64_t i = 0; i < m; ++i) {
       GDS_CUDA(cudaGraphLaunch(s->exec[s->cur], c->stream));
       s->cur ^= 1;
@@ -1480,6 +1534,7 @@ extern "C" int gds_system_step_timed(gds_system* s, int64_t n_steps, const doubl
   if (s->n_dir_dyn > 0)
     GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc, (size_t)n_steps * s->n_dir_dyn * 8, cudaMemcpyHostToDevice, c->stream));
   GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  GDS_TRY(shadow_refresh(s));
   LaunchTimer lt;
   lt.stream = c->stream;
   int rc = 0;
@@ -1519,6 +1574,7 @@ extern "C" int gds_system_begin_steps(gds_system* s, int64_t n_steps, const doub
   if (s->n_dir_dyn > 0)
     GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc, (size_t)n_steps * s->n_dir_dyn * 8, cudaMemcpyHostToDevice, c->stream));
   GDS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+  GDS_TRY(shadow_refresh(s));
   GDS_CUDA(cudaStreamSynchronize(c->stream));  // the tables come from pageable memory the caller may reuse
   return 0;
 }
@@ -1615,6 +1671,14 @@ extern "C" int gds_system_p2p_status(gds_system* s, int64_t* exchanges, int64_t*
   return 0;
 }
 
+// recurrence maps of the form y <- alpha L f(y) + beta f(y) + ... : keep Z = f(Y) beside the state
+extern "C" int gds_system_set_shadow(gds_system* s, int32_t on) {
+  if (!s) GDS_FAIL("null system");
+  if (s->finalized) GDS_FAIL("choose the carried gather operand before gds_system_finalize");
+  s->shadow = on != 0;
+  return 0;
+}
+
 // RK4 systems whose laws read accepted state only (no stage-state operand, no stage time): one pass per step
 extern "C" int gds_system_set_collapsed(gds_system* s, int32_t on) {
   if (!s) GDS_FAIL("null system");
@@ -1680,6 +1744,15 @@ extern "C" int gds_halo_unpack(gds_halo* hl, const void* buf_dev, void* vec_dev)
   if (!hl || !vec_dev || !buf_dev) GDS_FAIL("bad argument");
   GDS_CUDA(cudaSetDevice(hl->ctx->device));
   return launch_halo(hl->ctx, (double*)vec_dev, (double*)buf_dev, hl->d_idx, hl->n, 1);
+}
+
+extern "C" int gds_system_modes(gds_system* s, int32_t* collapsed, int32_t* shadow, int32_t* overlap) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (collapsed) *collapsed = s->collapsed ? 1 : 0;
+  if (shadow) *shadow = s->shadow ? 1 : 0;
+  if (overlap) *overlap = overlapped(s) ? 1 : 0;
+  return 0;
 }
 
 extern "C" int gds_system_info(gds_system* s, int64_t* kps, int64_t* bytes) {

@@ -175,6 +175,10 @@ struct PassParams {
                       // 5 whole RK4 step of a stage-independent law, 6 the same for an order-2 block shift (see GDS_MODE_*)
   const double* aux;  // mode 6: accepted state of the SOURCE block (v_n), while the row value is its derivative k_v
   int32_t store_k;    // mode 5: also write the (Dirichlet-masked) derivative to acc_out, for a block shift that needs it
+  // carried gather operand (gds_system_set_shadow): the pass gathers Z = f(state) kept beside the state instead of
+  // evaluating f for every gathered neighbour; whoever writes the new state writes f of it as well
+  double* shadow_out;
+  Chain shadow_chain;
   const double* yn2;  // mode 5, order-2 fields: accepted state of the block advanced by dy/dt = stage value of THIS block
   double* ynew2;      //         ... and where its new value goes: the block shift is fused into this pass (no extra launch)
   const uint32_t* dmask;
@@ -283,6 +287,9 @@ struct gds_system {
   gds_graph* g;
   int64_t n_state = 0;
   int32_t scheme = GDS_SCHEME_RK4;
+  bool shadow = false;                // carried gather operand Z = f(Y) (gds_system_set_shadow)
+  int shadow_pass = -1;               // index of the pass that gathers it
+  double* Z[2] = {nullptr, nullptr};  // f(Y[i])
   bool collapsed = false;             // RK4 of a law that reads accepted state only: one pass per step (gds_system_set_collapsed)
   double* Y[2] = {nullptr, nullptr};  // accepted state ping-pong
   double* XS[2] = {nullptr, nullptr}; // stage state ping-pong
@@ -369,7 +376,8 @@ int launch_dirichlet(gds_ctx* ctx, double* y, const int64_t* idx, const double* 
 int launch_advance_counter(gds_ctx* ctx, int64_t* counter);
 int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
                 const double* tab, int64_t nd, int64_t* counter, int advance, const uint8_t* sphase = nullptr,
-                const uint8_t* dphase = nullptr, int phase = -1);
+                const uint8_t* dphase = nullptr, int phase = -1, double* z = nullptr, const Chain* zchain = nullptr);
+int launch_shadow_init(gds_ctx* ctx, const double* y, double* z, int64_t n, const Chain& ch);
 int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode);

@@ -633,7 +633,10 @@ __global__ void __launch_bounds__(LAP4_BLOCK) lap4_kernel(const __grid_constant_
         p.ynew[r] = rk4_collapsed(yn[i], k1, p.fin * h);
         if (p.ynew2) p.ynew2[r] = rk4_collapsed_shift(ld_stream_f64(p.yn2 + r), yn[i], k1, h, p.fin * h);
         break;
-      default: p.ynew[r] = k1; break;
+      default:
+        p.ynew[r] = k1;
+        if (p.shadow_out) p.shadow_out[r] = chain_apply(p.shadow_chain, k1);
+        break;
     }
   }
 }
@@ -776,6 +779,7 @@ __global__ void __launch_bounds__(LAPT_BLOCK, LAPT_MINB) lapT_kernel(const __gri
       if (p.ynew2) p.ynew2[ri] = rk4_collapsed_shift(ld_stream_f64(p.yn2 + ri), yn[i], k1, h, p.fin * h);
     } else {
       p.ynew[ri] = k1;
+      if (p.shadow_out) p.shadow_out[ri] = chain_apply(p.shadow_chain, k1);
     }
   }
 }
@@ -884,8 +888,11 @@ __device__ __forceinline__ void st_quad_v(double* p, int64_t r0, int64_t n_rows,
 // wavefronts per 128 rows, was the busiest unit at 67 %; a run costs 8 wavefronts per slot instead of ~40.)
 // COLL: the collapsed RK4 epilogue (GDS_MODE_COLLAPSED) as its own instantiation, so that the staged kernels keep their
 // register budget (the collapsed form holds the row's own values until the end for the fused order-2 block shift)
-template <bool UNITW, bool IDX16, bool RUNS, bool COLL>
-__global__ void __launch_bounds__(LAPQ_BLOCK, COLL ? 8 : (UNITW ? LAPQ_MINB : LAPQ_MINB_W)) lapq_kernel(const __grid_constant__ PassParams p) {
+// EPI 2: recurrence maps with a pointwise chain on the additive vector (beta g(b), own row only) and / or a carried gather
+// operand to write (shadow_out = f(new state)) -- coupled map lattices.
+template <bool UNITW, bool IDX16, bool RUNS, int EPI>
+__global__ void __launch_bounds__(LAPQ_BLOCK, EPI ? 8 : (UNITW ? LAPQ_MINB : LAPQ_MINB_W)) lapq_kernel(const __grid_constant__ PassParams p) {
+  constexpr bool COLL = EPI == 1;
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
   const bool full = r0 + 3 < p.n_rows;
@@ -1007,7 +1014,7 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, COLL ? 8 : (UNITW ? LAPQ_MINB : LA
   for (int i = 0; i < 4; ++i) {
     double l = ((mbits >> i) & 1u) ? 0.0 : s[i];        // Z_mask: Dirichlet rows of L0 (gds.py:116-118)
     double val = p.lap_alpha * l;
-    if (p.lap_b) val += p.lap_beta * bb[i];
+    if (p.lap_b) val += p.lap_beta * (EPI == 2 ? chain_apply(p.lap_bchain, bb[i]) : bb[i]);
     val += p.lap_gamma;
     k4[i] = val;
   }
@@ -1064,8 +1071,13 @@ __global__ void __launch_bounds__(LAPQ_BLOCK, COLL ? 8 : (UNITW ? LAPQ_MINB : LA
       for (int i = 0; i < 4; ++i) o1v[i] = yn[i] + h * k4[i];
       st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, o1v);
       break;
-    default:
+    default:   // map: y <- value; with a carried gather operand (EPI 2) also z <- f(value)
       st_quad_v<RUNS>(p.ynew, r0, p.n_rows, full, k4);
+      if (EPI == 2 && p.shadow_out) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o1v[i] = chain_apply(p.shadow_chain, k4[i]);
+        st_quad_v<RUNS>(p.shadow_out, r0, p.n_rows, full, o1v);
+      }
       break;
   }
 }
@@ -1087,11 +1099,14 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // so the quad kernel takes every plain L0 form; lapT keeps pointwise chains, a second additive vector and
     // operands that are not 16-byte aligned.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
-    const bool use_quad = (force ? !strcmp(force, "quad") : true) && p.lap_chain.n == 0 && p.lap_bchain.n == 0 && !p.lap_b2;
+    // (a chain on the additive vector only in map mode: the EPI 2 instantiation)
+    const bool map_mode = p.epilogue == GDS_EPI_RHS && p.stage_mode == 4;
+    const bool use_quad = (force ? !strcmp(force, "quad") : true) && p.lap_chain.n == 0 &&
+                          (p.lap_bchain.n == 0 || map_mode) && !p.lap_b2 && (!p.shadow_out || map_mode);
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
       quad_ok = aligned16(p.yn) && aligned16(p.acc_in) && aligned16(p.acc_out) && aligned16(p.xnext) && aligned16(p.ynew) &&
-                aligned16(p.yn2) && aligned16(p.ynew2);
+                aligned16(p.yn2) && aligned16(p.ynew2) && aligned16(p.shadow_out);
     if (quad_ok) {
       int64_t blocks = ((rows + 3) / 4 + LAPQ_BLOCK - 1) / LAPQ_BLOCK;
       // 256-bit accesses and run gathers need 32-byte aligned vectors (the engine lays fields out that way);
@@ -1100,22 +1115,22 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       bool runs = !(runs_env && !strcmp(runs_env, "0")) && aligned32(p.lap_v) && aligned32(p.lap_b) && aligned32(p.lap_store);
       if (runs && p.epilogue == GDS_EPI_RHS)
         runs = aligned32(p.yn) && aligned32(p.acc_in) && aligned32(p.acc_out) && aligned32(p.xnext) && aligned32(p.ynew) &&
-               aligned32(p.yn2) && aligned32(p.ynew2);
+               aligned32(p.yn2) && aligned32(p.ynew2) && aligned32(p.shadow_out);
       const bool coll = p.epilogue == GDS_EPI_RHS && p.stage_mode == GDS_MODE_COLLAPSED;
-      const int variant = (coll ? 8 : 0) | (unitw ? 4 : 0) | (p.g.n_nbr16 ? 2 : 0) | (runs ? 1 : 0);
+      const int epi = coll ? 1 : ((map_mode && (p.lap_bchain.n > 0 || p.shadow_out)) ? 2 : 0);
+      const int variant = epi * 8 + ((unitw ? 4 : 0) | (p.g.n_nbr16 ? 2 : 0) | (runs ? 1 : 0));
       const unsigned nb = (unsigned)blocks;
 #define LAPQ_CASE(V, A, B, C, D) case V: lapq_kernel<A, B, C, D><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+#define LAPQ_CASES(E)                                                                                    \
+        LAPQ_CASE(E * 8 + 7, true, true, true, E) LAPQ_CASE(E * 8 + 6, true, true, false, E)             \
+        LAPQ_CASE(E * 8 + 5, true, false, true, E) LAPQ_CASE(E * 8 + 4, true, false, false, E)           \
+        LAPQ_CASE(E * 8 + 3, false, true, true, E) LAPQ_CASE(E * 8 + 2, false, true, false, E)           \
+        LAPQ_CASE(E * 8 + 1, false, false, true, E) LAPQ_CASE(E * 8 + 0, false, false, false, E)
       switch (variant) {
-        LAPQ_CASE(15, true, true, true, true) LAPQ_CASE(14, true, true, false, true)
-        LAPQ_CASE(13, true, false, true, true) LAPQ_CASE(12, true, false, false, true)
-        LAPQ_CASE(11, false, true, true, true) LAPQ_CASE(10, false, true, false, true)
-        LAPQ_CASE(9, false, false, true, true) LAPQ_CASE(8, false, false, false, true)
-        LAPQ_CASE(7, true, true, true, false) LAPQ_CASE(6, true, true, false, false)
-        LAPQ_CASE(5, true, false, true, false) LAPQ_CASE(4, true, false, false, false)
-        LAPQ_CASE(3, false, true, true, false) LAPQ_CASE(2, false, true, false, false)
-        LAPQ_CASE(1, false, false, true, false)
-        default: lapq_kernel<false, false, false, false><<<nb, LAPQ_BLOCK, 0, ctx->stream>>>(p); break;
+        LAPQ_CASES(0) LAPQ_CASES(1) LAPQ_CASES(2)
+        default: GDS_FAIL("internal: no such quad kernel variant");
       }
+#undef LAPQ_CASES
 #undef LAPQ_CASE
       GDS_CUDA(cudaGetLastError());
       ctx->kernel_launches++;
@@ -1203,14 +1218,22 @@ __global__ void __launch_bounds__(256) tail_kernel(double* __restrict__ y, const
                                                    const int64_t* __restrict__ didx, const double* __restrict__ tab,
                                                    int64_t nd, int64_t* counter, int advance,
                                                    const uint8_t* __restrict__ sphase, const uint8_t* __restrict__ dphase,
-                                                   int phase) {
+                                                   int phase, double* __restrict__ z, const Chain zchain) {
   const int64_t step = counter[0];
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   // phase >= 0: only the entries of that phase (overlap split: boundary ranges first, the rest after the interior rows)
+  // z: the carried gather operand f(y) follows the overwritten rows
   if (i < ns) {
-    if (phase < 0 || !sphase || sphase[i] == phase) y[sidx[i]] = sval[i];
+    if (phase < 0 || !sphase || sphase[i] == phase) {
+      y[sidx[i]] = sval[i];
+      if (z) z[sidx[i]] = chain_apply(zchain, sval[i]);
+    }
   } else if (i < ns + nd) {
-    if (phase < 0 || !dphase || dphase[i - ns] == phase) y[didx[i - ns]] = tab[step * nd + (i - ns)];
+    if (phase < 0 || !dphase || dphase[i - ns] == phase) {
+      const double v = tab[step * nd + (i - ns)];
+      y[didx[i - ns]] = v;
+      if (z) z[didx[i - ns]] = chain_apply(zchain, v);
+    }
   }
   if (!advance) return;
   __syncthreads();
@@ -1223,10 +1246,29 @@ __global__ void __launch_bounds__(256) tail_kernel(double* __restrict__ y, const
 
 int launch_tail(gds_ctx* ctx, double* y, const int64_t* sidx, const double* sval, int64_t ns, const int64_t* didx,
                 const double* tab, int64_t nd, int64_t* counter, int advance, const uint8_t* sphase,
-                const uint8_t* dphase, int phase) {
+                const uint8_t* dphase, int phase, double* z, const Chain* zchain) {
   if (ns + nd <= 0 && !advance) return 0;
   const unsigned blocks = (unsigned)std::max<int64_t>(1, (ns + nd + 255) / 256);
-  tail_kernel<<<blocks, 256, 0, ctx->stream>>>(y, sidx, sval, ns, didx, tab, nd, counter, advance, sphase, dphase, phase);
+  Chain zc = {};
+  if (z && zchain) zc = *zchain;
+  tail_kernel<<<blocks, 256, 0, ctx->stream>>>(y, sidx, sval, ns, didx, tab, nd, counter, advance, sphase, dphase, phase,
+                                               z, zc);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+// carried gather operand: z = f(y) over the whole state (at the start of every stepping call: the host may have written y)
+__global__ void __launch_bounds__(256) shadow_init_kernel(const double* __restrict__ y, double* __restrict__ z, int64_t n,
+                                                          const Chain ch) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    z[i] = chain_apply(ch, ld_stream_f64(y + i));
+}
+
+int launch_shadow_init(gds_ctx* ctx, const double* y, double* z, int64_t n, const Chain& ch) {
+  if (n <= 0) return 0;
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 16);
+  shadow_init_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(y, z, n, ch);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;

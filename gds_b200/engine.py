@@ -147,6 +147,9 @@ class StepEngine:
         self._fin = weakref.finalize(self, lib.gds_system_destroy, h)
         if self.collapsed:
             check(lib.gds_system_set_collapsed(self.h, 1))
+        if self.scheme == 'map' and self.part is None and not os.environ.get('GDS_B200_NO_SHADOW'):
+            # y <- ... L f(y) ...: keep f(y) beside the state instead of evaluating f for every gathered neighbour
+            check(lib.gds_system_set_shadow(self.h, 1))
         # (sub-expressions of accepted state are hoisted out of the stages into once-per-step passes; a collapsed step
         # has nothing to hoist them out of)
         lowering = Lowering(self.ctx, self._resolve_leaf, hoist=not self.collapsed,
@@ -201,6 +204,9 @@ class StepEngine:
         kps, nbytes = L.c_i64(), L.c_i64()
         check(lib.gds_system_info(self.h, C.byref(kps), C.byref(nbytes)))
         self.kernels_per_step = kps.value
+        m = [L.c_i32(), L.c_i32(), L.c_i32()]
+        check(lib.gds_system_modes(self.h, *[C.byref(x) for x in m]))
+        self.modes = {'collapsed': bool(m[0].value), 'shadow': bool(m[1].value), 'overlap': bool(m[2].value)}
         self.device_bytes = nbytes.value + lowering.temp_bytes
         self.push_state()
         if self.part is not None:

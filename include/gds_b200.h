@@ -210,6 +210,14 @@ int gds_system_set_dirichlet(gds_system* s, const int64_t* state_idx, const doub
  * stage combines in registers, operation by operation as the staged form: results are bit-identical to on = 0, the
  * step moves a quarter of the bytes, and a partitioned system exchanges its halo once per step instead of four times. */
 int gds_system_set_collapsed(gds_system* s, int32_t on);
+/* Carried gather operand.  A recurrence map y <- alpha L0 f(y) + beta f(y) + ... (coupled map lattices: f(y) = 1 - a y^2;
+ * a pointwise chain f applied to the map's own stage vector inside GDS_OP_N_LAP) evaluates f for the row and for EVERY
+ * gathered neighbour.  With on = 1 (before finalize; honoured for map systems with one such pass on an undistributed
+ * graph, ignored otherwise) the system keeps Z = f(Y) beside the state: the pass gathers Z, and every kernel that writes
+ * the new state -- the pass's epilogue, the Dirichlet overwrite -- writes f of it as well; Z is rebuilt from Y at the start
+ * of every stepping call (the host may have written the state in between).  f is evaluated once per row by the same
+ * code, so results are bit-identical. */
+int gds_system_set_shadow(gds_system* s, int32_t on);
 /* capture the whole step (all passes of all stages + BC overwrite) into a CUDA graph */
 int gds_system_finalize(gds_system* s);
 int gds_system_set_state(gds_system* s, const double* host, int64_t offset, int64_t n);
@@ -278,6 +286,8 @@ int gds_system_p2p_error(gds_system* s, int64_t* error);
 int gds_system_p2p_set_overlap(gds_system* s, int64_t lo_end, int64_t hi_begin);
 /* algorithmic facts for the roofline: kernels per step and device bytes held */
 int gds_system_info(gds_system* s, int64_t* kernels_per_step, int64_t* device_bytes);
+/* which of the optional forms the finalized system really runs in: collapsed RK4, carried gather operand, overlapped exchange */
+int gds_system_modes(gds_system* s, int32_t* collapsed, int32_t* shadow, int32_t* overlap);
 
 /* ---- native host graphs for sizes where an nx.Graph is impossible: generators that reproduce
  *      networkx's node order, G.edges() order/orientation and adjacency order bit-exactly, plus the planar face walk

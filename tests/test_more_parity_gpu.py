@@ -140,3 +140,44 @@ def test_coupled_reset_goes_back_to_the_state_taken_at_couple_time():
     both(run)
     a = run(product_api())
     assert np.array_equal(a['T_reset_0'], a['T_reset_1']) and a['t_reset_0'][0] == 0.
+
+
+def _cml_with_dirichlet(api):
+    """coupled map lattice y <- f(y) + (eps/8) L f(y), f(y) = 1 - 1.7 y^2, with a time-varying Dirichlet row set and a host
+    write in the middle (the carried operand f(y) must follow both)"""
+    G = cases.g_rgg(700, 0.08, 5)
+    x = api.node_gds(G)
+    api.evolve_map(x, map_fun=lambda t, y: (1 - 1.7 * y ** 2) + (0.3 / 8.0) * x.laplacian(1 - 1.7 * y ** 2), dt=1.0)
+    y0 = np.random.default_rng(2).uniform(-1, 1, 700)
+    x.set_initial(y0=lambda v: y0[v])
+    x.set_constraints(dirichlet=lambda t, v: 0.5 * math.sin(0.7 * t) if v % 13 == 0 else None)
+    out = {}
+    for i in range(6):
+        x.step(1.0)
+        out[f'y{i}'] = np.array(x.y, copy=True)
+    return out
+
+
+def test_carried_gather_operand_is_bit_identical_to_on_the_fly_evaluation(monkeypatch):
+    """maps of the form y <- ... L f(y) ...: the engine keeps Z = f(Y) beside the state (gds_system_set_shadow) and gathers
+    that, instead of evaluating f for every gathered neighbour -- same f, evaluated once per row: identical bits"""
+    from gds_b200 import engine as E
+    seen = []
+    build = E.StepEngine._build
+
+    def spy(self):
+        build(self)
+        seen.append(self.modes['shadow'])
+    monkeypatch.setattr(E.StepEngine, '_build', spy)
+    fast = _cml_with_dirichlet(product_api())
+    fast2 = cases.case_cml_c4(product_api(), n=3000, iters=8, every=4)
+    assert seen == [True, True], seen
+    monkeypatch.setenv('GDS_B200_NO_SHADOW', '1')
+    slow = _cml_with_dirichlet(product_api())
+    slow2 = cases.case_cml_c4(product_api(), n=3000, iters=8, every=4)
+    assert seen[2:] == [False, False], seen
+    want = _cml_with_dirichlet(oracle_api())
+    for k in want:
+        assert np.array_equal(fast[k], slow[k]), k
+        assert rel_l2(fast[k], want[k]) <= TOL, k
+    assert np.array_equal(fast2['y_x'], slow2['y_x'])
