@@ -806,6 +806,40 @@ extern "C" int gds_pass_run(gds_ctx* c, gds_graph* g, const gds_pass_desc* pass,
   return launch_pass(c, pp, ph.domain);
 }
 
+// Matrix operands (operators applied to `np.eye(n)`, examples/fluid.py:350; blocks of tangent vectors for advect_jvp): the
+// pass list is validated, matched and resolved ONCE, then enqueued for every column with the operands that hold one
+// column per `stride` advanced accordingly -- one call, one upload and one download for the whole matrix.
+extern "C" int gds_passes_run_cols(gds_ctx* c, gds_graph* g, int32_t n_pass, const gds_pass_desc* passes, double t,
+                                   int64_t ncols, int32_t n_strided, gds_buf* const* strided, const int64_t* stride) {
+  if (!c || !g || n_pass < 0 || (n_pass > 0 && !passes) || ncols < 0 || n_strided < 0) GDS_FAIL("bad argument");
+  std::vector<PassHost> ph((size_t)n_pass);
+  for (int i = 0; i < n_pass; ++i) {
+    GDS_TRY(copy_pass(&passes[i], ph[(size_t)i]));
+    if (ph[(size_t)i].epilogue != GDS_EPI_NONE) GDS_FAIL("eager passes take GDS_EPI_NONE");
+  }
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  auto stride_of = [&](const gds_buf* b) -> int64_t {
+    for (int k = 0; k < n_strided; ++k) if (strided[k] == b) return stride[k];
+    return 0;
+  };
+  for (int k = 0; k < n_strided; ++k)
+    if (!strided[k] || stride[k] < 0 || stride[k] * ncols > strided[k]->n) GDS_FAIL("column stride outside its buffer");
+  for (auto& p : ph) if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(p);
+  for (int64_t col = 0; col < ncols; ++col) {
+    for (auto& p : ph) {
+      PassHost q = p;     // operands of this column
+      for (auto& v : q.vec) if (v.kind == GDS_VEC_BUF && v.buf) v.offset += col * stride_of(v.buf);
+      for (size_t j = 0; j < q.out.size(); ++j) q.out_offset[j] += col * stride_of(q.out[j]);
+      PassParams pp;
+      GDS_TRY(resolve_pass(g, q, nullptr, nullptr, pp));
+      pp.t_fixed = t;
+      GDS_TRY(launch_pass(c, pp, q.domain));
+    }
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // conjugate gradients with the operator given as a pass
 // ---------------------------------------------------------------------------------------------------

@@ -469,10 +469,8 @@ class gds(fds, GraphObservable):
             return build(*[as_expr(o, d, self._low) for o, d in zip(operands, domains)])
         arrs = [np.asarray(o, dtype=float) for o in operands]
         if any(a.ndim == 2 for a in arrs):
-            # matrix right-hand side (e.g. laplacian(np.eye(n)), examples/fluid.py:350): column by column
-            ncol = next(a.shape[1] for a in arrs if a.ndim == 2)
-            cols = [self._apply(build, *[a[:, j] if a.ndim == 2 else a for a in arrs], domains=domains) for j in range(ncol)]
-            return np.stack(cols, axis=1)
+            # matrix right-hand side (e.g. laplacian(np.eye(n)), examples/fluid.py:350)
+            return _run_eager_cols(self._low, build, arrs, domains)
         for a, d in zip(arrs, domains):
             if a.shape != (self._low.rows(d),):
                 raise ValueError(f'operand of shape {a.shape} where a vector of length {self._low.rows(d)} is expected')
@@ -574,6 +572,47 @@ def evaluate_view(view, parent):
         except TraceError:
             pass
     return view(parent)
+
+
+def _run_eager_cols(low, build, arrs, domains):
+    """operator on matrix operands, all columns in one device call: one lowering, one upload of every matrix (column
+    after column), the pass list enqueued per column with strided operands (gds_passes_run_cols), one download"""
+    import ctypes as C
+    ctx = low.ctx
+    ncol = next(a.shape[1] for a in arrs if a.ndim == 2)
+    leaves, strided = [], []
+    for a, d in zip(arrs, domains):
+        n = low.rows(d)
+        if a.ndim == 2:
+            if a.shape != (n, ncol):
+                raise ValueError(f'operand of shape {a.shape} where a matrix of shape {(n, ncol)} is expected')
+            cols = np.ascontiguousarray(low.to_dev(d, a).T)          # [ncol, n]: one contiguous column after the other
+            buf = Buffer(ctx, ncol * n, cols)
+            strided.append((buf, n))
+            leaves.append(DevVec(buf, d, low))
+        else:
+            if a.shape != (n,):
+                raise ValueError(f'operand of shape {a.shape} where a vector of length {n} is expected')
+            leaves.append(Const(a, d, low))
+    expr = build(*leaves)
+    n_out = low.rows(expr.domain)
+    if n_out == 0 or ncol == 0:
+        return np.zeros((n_out, ncol))
+    out = Buffer(ctx, ncol * n_out)
+    strided.append((out, n_out))
+
+    def no_leaf(e):
+        raise TraceError('field state used outside an evolution law')
+    lowering = Lowering(ctx, no_leaf, hoist=False)
+    lowering.store_pass(expr, out)
+    # intermediate vectors are rewritten for every column: they stay unstrided
+    descs = [pass_desc(p) for p in lowering.passes]
+    arr = (L.PassDesc * len(descs))(*[d for d, _ in descs])
+    bufs = (L.c_vp * len(strided))(*[b.h for b, _ in strided])
+    strides = (C.c_int64 * len(strided))(*[int(s) for _, s in strided])
+    check(lib.gds_passes_run_cols(ctx.h, low.dev.h, len(descs), arr, 0.0, ncol, len(strided), bufs, strides))
+    res = out.download().reshape(ncol, n_out).T
+    return np.ascontiguousarray(low.from_dev(expr.domain, res))
 
 
 def _lower_into(low, expr, out_buf):

@@ -177,6 +177,12 @@ int gds_graph_device_bytes(gds_graph* g, int64_t* bytes);
 /* ---- eager operator application: `op(y)` on host arrays (gds.py:152-345, the `y is not None` path).
  *      Runs ONE pass (epilogue must be GDS_EPI_NONE) at time t. -------------------------------------------- */
 int gds_pass_run(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* pass, double t);
+/* the same for MATRIX operands (an operator applied to np.eye(n), gds/examples/fluid.py:350; a block of tangent vectors):
+ * `passes` is a short list evaluated in order (intermediate vectors, then the result) for each of `ncols` columns; every
+ * operand / output whose buffer is listed in `strided` holds one column per `stride[k]` values and is advanced by that
+ * much from column to column, the others are shared.  Validated and resolved once; one call for the whole matrix. */
+int gds_passes_run_cols(gds_ctx* ctx, gds_graph* g, int32_t n_pass, const gds_pass_desc* passes, double t, int64_t ncols,
+                        int32_t n_strided, gds_buf* const* strided, const int64_t* stride);
 /* which kernel family would run this pass: 0 row-program interpreter, 1 Laplacian kernels, 2 term-list kernel
  * (validates the program; no device needed) */
 int gds_pass_kernel_kind(const gds_pass_desc* pass, int32_t* kind_out);
