@@ -1150,11 +1150,10 @@ static int enqueue_stage(gds_system* s, int cur, int st, LaunchTimer* lt, int64_
       // carried gather operand: gather Z = f(Y) (kept beside the state) instead of evaluating f per gathered neighbour;
       // the epilogue writes f of the new state next to the new state
       const int64_t off = ph.state_offset;
-      const bool b_is_v = pp.lap_b == pp.lap_v;
       pp.shadow_chain = pp.lap_chain;
       pp.lap_v = s->Z[cur] + off;
       pp.lap_chain.n = 0;
-      if (b_is_v) { pp.lap_b = s->Z[cur] + off; pp.lap_bchain.n = 0; }
+      if (s->shadow_b_same) { pp.lap_b = s->Z[cur] + off; pp.lap_bchain.n = 0; }
       pp.shadow_out = s->Z[cur ^ 1] + off;
     }
     if (lt) GDS_TRY(lt->begin(domain_class(ph.domain)));
@@ -1398,13 +1397,16 @@ extern "C" int gds_system_finalize(gds_system* s) {
       if (ph.special || !ph.lap.ok || ph.lap.chain.n == 0 || ph.domain != GDS_NODES) continue;
       const gds_vecref& v = ph.vec[(size_t)ph.lap.v];
       if (v.kind != GDS_VEC_STAGE || v.offset != ph.state_offset) continue;
-      if (ph.lap.b >= 0 && ph.lap.bchain.n > 0) {   // beta g(b): only b = the same vector with g = f
+      // beta g(b) on the row's own value: read from Z as well when b is the same vector with g = f, otherwise left as it
+      // is (one evaluation per row)
+      s->shadow_b_same = false;
+      if (ph.lap.b >= 0) {
         const gds_vecref& b = ph.vec[(size_t)ph.lap.b];
         bool same = b.kind == v.kind && b.offset == v.offset && ph.lap.bchain.n == ph.lap.chain.n;
         for (int k = 0; same && k < ph.lap.chain.n; ++k)
           same = ph.lap.bchain.pre[k] == ph.lap.chain.pre[k] && ph.lap.bchain.m[k] == ph.lap.chain.m[k] &&
                  ph.lap.bchain.a[k] == ph.lap.chain.a[k];
-        if (!same) continue;
+        s->shadow_b_same = same;
       }
       s->shadow_pass = (int)i;
     }

@@ -289,6 +289,7 @@ struct gds_system {
   int32_t scheme = GDS_SCHEME_RK4;
   bool shadow = false;                // carried gather operand Z = f(Y) (gds_system_set_shadow)
   int shadow_pass = -1;               // index of the pass that gathers it
+  bool shadow_b_same = false;         // its additive term beta g(b) is beta f(same vector): read from Z too
   double* Z[2] = {nullptr, nullptr};  // f(Y[i])
   bool collapsed = false;             // RK4 of a law that reads accepted state only: one pass per step (gds_system_set_collapsed)
   double* Y[2] = {nullptr, nullptr};  // accepted state ping-pong
