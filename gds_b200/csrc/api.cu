@@ -395,6 +395,7 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
     std::vector<uint32_t> soff;
     std::vector<int32_t> packed;
     pack(E, h.ef_ptr, h.ef_face, h.ef_sign, soff, packed);
+    for (size_t i = 0; i + 1 < soff.size(); ++i) d.ef_maxw = std::max<int32_t>(d.ef_maxw, (int32_t)(soff[i + 1] - soff[i]));
     GDS_TRY(upload(g, soff, &d.ef_soff));
     GDS_TRY(upload(g, packed, &d.ef_face));
     pack(F, h.f_ptr, h.f_edge, h.f_sign, soff, packed);

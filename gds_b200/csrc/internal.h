@@ -88,6 +88,7 @@ struct GraphDev {
   // edge -> faces, sliced-ELL over edges: (face << 1) | (1 if B2[f,e] < 0), padding = -1
   const uint32_t* ef_soff;
   const int32_t* ef_face;
+  int32_t ef_maxw;        // widest slice of the edge -> face table (2 on planar graphs)
   // face -> edges, sliced-ELL over faces: (edge << 1) | (1 if B2[f,e] < 0), padding = -1
   const uint32_t* fe_soff;
   const int32_t* fe_edge;

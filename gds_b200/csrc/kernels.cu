@@ -546,6 +546,128 @@ __global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ Pa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// term lists over EDGE rows, phased.  terms_kernel evaluates its terms one after another, each one a dependent chain
+// (endpoints -> gathers; slice offset -> face indices -> gathers): with the 4 terms of the Navier-Stokes edge law a thread
+// sits through ~8 memory round trips in sequence and the kernel runs at a third of the DRAM bandwidth although it moves
+// the minimum number of bytes (ncu, profiles/r2_ncu_full_ns_cavity.csv).  Here the loads of ALL terms are issued level by
+// level -- (0) everything addressed by the row itself: endpoints, weights, the row's own values, the slice of the
+// edge -> face table; (1) everything addressed through those: endpoint gathers, upwind aggregates, face indices;
+// (2) face gathers -- and only then consumed, in term order and with the arithmetic of e_gradt / e_curlt / e_advfin,
+// so the result is bit-identical to terms_kernel.  Up to ET_MAX terms, edges with at most 2 faces (every planar graph).
+// ---------------------------------------------------------------------------------------------------
+#define ET_MAX 4
+template <bool UNITW>
+__global__ void __launch_bounds__(BLOCK) edge_terms_kernel(const __grid_constant__ PassParams p) {
+  const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (row >= p.n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const GraphDev& g = p.g;
+  // ---- level 0 ---------------------------------------------------------------------------------------------------
+  const int32_t u = ld_stream_i32(g.e_u + row), v = ld_stream_i32(g.e_v + row);
+  double e_yn = 0.0, e_acc = 0.0;
+  uint32_t e_dbits = 0u;
+  if (p.epilogue == GDS_EPI_RHS) {
+    if (p.stage_mode != 4) e_yn = ld_stream_f64(p.yn + row);
+    if (p.stage_mode == 1 || p.stage_mode == 2) e_acc = ld_plain_f64(p.acc_in + row);
+    if (p.dmask) e_dbits = __ldg(p.dmask + (row >> 5));
+  }
+  double bval = 0.0, b2val = 0.0;
+  if (p.lap_b) bval = ld_stream_f64(p.lap_b + row);
+  if (p.lap_b2) b2val = ld_stream_f64(p.lap_b2 + row);
+  double omega = 1.0, we = 1.0;
+  bool any_curlt = false, any_adv = false;
+#pragma unroll
+  for (int k = 0; k < ET_MAX; ++k)
+    if (k < p.n_terms) {
+      any_curlt |= p.term[k].op == GDS_OP_E_CURLT;
+      any_adv |= p.term[k].op == GDS_OP_E_ADVFIN;
+    }
+  if (!UNITW) {
+    omega = ld_stream_f64(g.e_omega + row);
+    if (any_adv) we = ld_stream_f64(g.e_w + row);
+  }
+  uint32_t o0 = 0u, fw = 0u;
+  if (any_curlt) {
+    o0 = __ldg(g.ef_soff + (row >> 5));
+    fw = __ldg(g.ef_soff + (row >> 5) + 1) - o0;
+  }
+  uint32_t mb[ET_MAX];
+  double own[ET_MAX];      // E_ADVFIN: the row's own value of its operand
+#pragma unroll
+  for (int k = 0; k < ET_MAX; ++k) {
+    mb[k] = 0u; own[k] = 0.0;
+    if (k < p.n_terms) {
+      if (p.term[k].m0) mb[k] = __ldg(p.term[k].m0 + (row >> 5));
+      if (p.term[k].m1) mb[k] |= __ldg(p.term[k].m1 + (row >> 5));
+      if (p.term[k].op == GDS_OP_E_ADVFIN) own[k] = ld_gather(p.term[k].a + row);
+    }
+  }
+  // ---- level 1 ---------------------------------------------------------------------------------------------------
+  int32_t pk0 = -1, pk1 = -1;
+  if (any_curlt) {
+    const int64_t base = (int64_t)o0 * GDS_SLICE + lane;
+    if (fw > 0u) pk0 = ld_stream_i32(g.ef_face + base);
+    if (fw > 1u) pk1 = ld_stream_i32(g.ef_face + base + GDS_SLICE);
+  }
+  double r0[ET_MAX], r1[ET_MAX], r2[ET_MAX], r3[ET_MAX];
+#pragma unroll
+  for (int k = 0; k < ET_MAX; ++k) {
+    r0[k] = r1[k] = r2[k] = r3[k] = 0.0;
+    if (k < p.n_terms) {
+      const double* a = p.term[k].a;
+      if (p.term[k].op == GDS_OP_E_GRADT) {
+        r0[k] = ld_gather(a + v);
+        r1[k] = ld_gather(a + u);
+      } else if (p.term[k].op == GDS_OP_E_ADVFIN) {
+        const double s = sgn(own[k]);
+        const int32_t t = (s > 0.0) ? u : v, h = (s > 0.0) ? v : u;
+        const double2 at = __ldg(reinterpret_cast<const double2*>(p.term[k].b) + 2 * (int64_t)t);
+        const double2 ah = __ldg(reinterpret_cast<const double2*>(p.term[k].b) + 2 * (int64_t)h + 1);
+        r0[k] = at.x; r1[k] = at.y; r2[k] = ah.x; r3[k] = ah.y;
+      }
+    }
+  }
+  // ---- level 2 ---------------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < ET_MAX; ++k)
+    if (k < p.n_terms && p.term[k].op == GDS_OP_E_CURLT) {
+      const double* c = p.term[k].a;
+      r0[k] = ld_gather(c + ((pk0 >= 0) ? (pk0 >> 1) : 0));
+      r1[k] = ld_gather(c + ((pk1 >= 0) ? (pk1 >> 1) : 0));
+    }
+  // ---- the terms, in order ------------------------------------------------------------------------------------------
+  double val = p.lap_gamma;
+  if (p.lap_b) val += p.lap_beta * chain_apply(p.lap_bchain, bval);
+  if (p.lap_b2) val += p.lap_beta2 * b2val;
+#pragma unroll
+  for (int k = 0; k < ET_MAX; ++k)
+    if (k < p.n_terms) {
+      double gv;
+      if (p.term[k].op == GDS_OP_E_GRADT) {
+        const double d = r0[k] - r1[k];                               // e_gradt
+        gv = UNITW ? d : omega * d;
+      } else if (p.term[k].op == GDS_OP_E_CURLT) {                    // e_curlt, width <= 2
+        double acc = 0.0;
+        acc += (pk0 >= 0) ? ((pk0 & 1) ? -r0[k] : r0[k]) : 0.0;
+        if (fw > 1u) acc += (pk1 >= 0) ? ((pk1 & 1) ? -r1[k] : r1[k]) : 0.0;
+        gv = UNITW ? acc : omega * acc;
+      } else {                                                         // e_advfin
+        const double ye = own[k], s = sgn(ye);
+        const double s1 = we * (r0[k] - r2[k]), s2 = we * (r1[k] - r3[k]);
+        gv = (s == 0.0) ? 0.0 : -(ye * s1 + s * s2);
+      }
+      if ((mb[k] >> (row & 31)) & 1u) gv = 0.0;
+      val += p.term[k].coef * gv;
+    }
+  if (p.lap_store) p.lap_store[row] = val;
+  if (p.epilogue == GDS_EPI_RHS) {
+    double h = 0.0;
+    if (p.steptab) h = p.steptab[*p.step_counter].h;
+    stage_epilogue(p, row, val, e_yn, e_acc, e_dbits, h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the specialised node-Laplacian kernel: 4 rows per thread, one per slice of a 4-slice group, so that every warp
 // access -- indices, weights, state, accumulator, and the gather of a lattice neighbour -- is one contiguous run
 // ---------------------------------------------------------------------------------------------------
@@ -1158,7 +1280,12 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
       if (unitw) terms_kernel<GDS_NODES, true><<<grid, block, 0, ctx->stream>>>(p);
       else terms_kernel<GDS_NODES, false><<<grid, block, 0, ctx->stream>>>(p);
     } else if (domain == GDS_EDGES) {
-      if (unitw) terms_kernel<GDS_EDGES, true><<<grid, block, 0, ctx->stream>>>(p);
+      // level-by-level loads when the list fits the phased kernel (<= 4 terms, every edge on <= 2 faces)
+      const char* no_phased = getenv("GDS_B200_NO_PHASED");   // A/B and bit-identity tests; read at enqueue / capture time
+      if (!no_phased && p.n_terms > 0 && p.n_terms <= ET_MAX && p.g.ef_maxw <= 2) {
+        if (unitw) edge_terms_kernel<true><<<grid, block, 0, ctx->stream>>>(p);
+        else edge_terms_kernel<false><<<grid, block, 0, ctx->stream>>>(p);
+      } else if (unitw) terms_kernel<GDS_EDGES, true><<<grid, block, 0, ctx->stream>>>(p);
       else terms_kernel<GDS_EDGES, false><<<grid, block, 0, ctx->stream>>>(p);
     } else if (domain == GDS_FACES) {
       if (unitw) terms_kernel<GDS_FACES, true><<<grid, block, 0, ctx->stream>>>(p);

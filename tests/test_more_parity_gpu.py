@@ -181,3 +181,25 @@ def test_carried_gather_operand_is_bit_identical_to_on_the_fly_evaluation(monkey
         assert np.array_equal(fast[k], slow[k]), k
         assert rel_l2(fast[k], want[k]) <= TOL, k
     assert np.array_equal(fast2['y_x'], slow2['y_x'])
+
+
+def test_phased_edge_term_kernel_is_bit_identical_to_the_term_by_term_kernel(monkeypatch):
+    """edge_terms_kernel issues the loads of all terms level by level before consuming them; same arithmetic per term,
+    same order of accumulation as terms_kernel: identical bits (Navier-Stokes edge law: advect + grad p + Hodge Laplacian;
+    Hodge Laplacian with Dirichlet rows; on unit-weight and weighted graphs)"""
+    import gds_b200
+
+    def run():
+        out = dict(cases.case_ns_cavity_c3(product_api(), m=7, n=10, nsteps=6, every=3))
+        out.update({'hx_' + k: v for k, v in cases.case_hex_advdiff_c2(product_api(), m=6, n=8, nsteps=6, every=3).items()})
+        G = cases.add_weights(cases.g_tri(5, 7), 12)
+        u = gds_b200.edge_gds(G)
+        y = np.random.default_rng(5).standard_normal(u.ndim)
+        y[::7] = 0.0
+        out['w_lap'], out['w_adv'], out['w_dd'] = u.laplacian(y), u.advect(y), u.dd_(y)
+        return out
+    fast = run()
+    monkeypatch.setenv('GDS_B200_NO_PHASED', '1')
+    slow = run()
+    for k in fast:
+        assert np.array_equal(np.asarray(fast[k]), np.asarray(slow[k])), k
