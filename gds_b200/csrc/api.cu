@@ -35,11 +35,15 @@ extern "C" int gds_ctx_create(int device, gds_ctx** out) {
   GDS_CUDA(cudaSetDevice(device));
   gds_ctx* c = new gds_ctx();
   c->device = device;
-  GDS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  // the context's stream carries the boundary rows / push / wait branch of an overlapped step and gets the higher
+  // priority; the side stream carries the interior rows, whose grid would otherwise keep small late kernels waiting
+  int prio_lo = 0, prio_hi = 0;
+  GDS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GDS_CUDA(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_hi));
   c->stream = c->own_stream;
   GDS_CUDA(cudaEventCreate(&c->ev0));
   GDS_CUDA(cudaEventCreate(&c->ev1));
-  GDS_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  GDS_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_lo));
   for (auto& e : c->ev_pool) GDS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = c;
   return 0;
@@ -971,7 +975,7 @@ extern "C" int gds_system_destroy(gds_system* s) {
   cudaFree(s->d_dir_phase_static); cudaFree(s->d_dir_phase_dyn);
   for (auto& pr : s->peers)
     for (void* m : pr.mapped) if (m) cudaIpcCloseMemHandle(m);
-  cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst);
+  cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst); cudaFree(s->d_p2p_done);
   if (s->h_p2p_err) cudaFreeHost(s->h_p2p_err);
   cudaFree(s->d_rec); cudaFree(s->d_traj);
   delete s;
@@ -1199,6 +1203,10 @@ static int enqueue_push(gds_system* s, int which) {
   // node-only partitions stop their RHS passes at the owned rows, so nothing but the owners' pushes ever writes a ghost
   // row and no handshake is needed (it costs a second cross-GPU round trip per exchange: 0.32 vs 0.05 ms per RK4 step)
   pu.handshake = s->owned_rows < 0 ? 1 : 0;
+  pu.done = s->d_p2p_done;
+  int64_t longest = 1;
+  for (const gds_system::Peer& pr : s->peers) longest = std::max<int64_t>(longest, pr.send1 - pr.send0);
+  pu.blocks_per_peer = (int32_t)std::min<int64_t>(64, std::max<int64_t>(1, (longest + 256 * 8 - 1) / (256 * 8)));
   for (size_t q = 0; q < s->peers.size(); ++q) {
     const gds_system::Peer& pr = s->peers[q];
     pu.dst[q] = (double*)pr.mapped[which];
@@ -1686,6 +1694,8 @@ extern "C" int gds_system_p2p_attach(gds_system* s, int32_t my_rank, int32_t n_p
   const int64_t n = n_peers ? send_ptr[n_peers] : 0;
   GDS_CUDA(cudaMalloc((void**)&s->d_p2p_src, (size_t)std::max<int64_t>(n, 1) * 8));
   GDS_CUDA(cudaMalloc((void**)&s->d_p2p_dst, (size_t)std::max<int64_t>(n, 1) * 8));
+  GDS_CUDA(cudaMalloc((void**)&s->d_p2p_done, GDS_MAX_PEERS * sizeof(unsigned int)));
+  GDS_CUDA(cudaMemset(s->d_p2p_done, 0, GDS_MAX_PEERS * sizeof(unsigned int)));
   if (n) {
     GDS_CUDA(cudaMemcpy(s->d_p2p_src, src_idx, (size_t)n * 8, cudaMemcpyHostToDevice));
     GDS_CUDA(cudaMemcpy(s->d_p2p_dst, dst_idx, (size_t)n * 8, cudaMemcpyHostToDevice));

@@ -334,6 +334,7 @@ struct gds_system {
   int64_t* d_p2p_epoch = nullptr; // [2]: exchanges sent so far; error flag of the wait kernel
   int64_t* d_p2p_src = nullptr;
   int64_t* d_p2p_dst = nullptr;
+  unsigned int* d_p2p_done = nullptr;   // per-neighbour block counters of the push kernel
   // the error flag again in pinned, device-mapped host memory: the host polls it without synchronising the stream
   int64_t* h_p2p_err = nullptr;   // host address
   int64_t* d_p2p_err_host = nullptr;  // the same word as seen from the device
@@ -358,6 +359,8 @@ struct PushParams {
   const int64_t* src_idx;
   const int64_t* dst_idx;
   int64_t* epoch;
+  unsigned int* done;                // [GDS_MAX_PEERS] blocks that have finished their stores (self-resetting)
+  int32_t blocks_per_peer;
 };
 struct WaitParams {
   int32_t n_peers;

@@ -24,15 +24,20 @@
 
 #define BLOCK 256
 
-// streaming (read-once) loads: bypass L1 allocation so L1 stays available for the gathered vectors
+// streaming (read-once) loads: bypass L1 allocation so L1 stays available for the gathered vectors.
+// The scalar forms are plain (non-volatile) asm: read-only data, so the compiler may issue the index loads of several
+// unrolled slots ahead of the gathers that depend on them (GDS_LD_VOLATILE=volatile restores program order for A/B runs).
+#ifndef GDS_LD_VOLATILE
+#define GDS_LD_VOLATILE
+#endif
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
   int32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm GDS_LD_VOLATILE("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double ld_stream_f64(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm GDS_LD_VOLATILE("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double ld_gather(const double* p) { return __ldg(p); }
@@ -115,22 +120,40 @@ __device__ __forceinline__ double n_lap(const GraphDev& g, const double* __restr
   return acc;
 }
 
+// The slot loops below run in chunks of GCH slots: all index loads of a chunk are issued, then all gathers that depend on
+// them, then the values are consumed in slot order -- two memory round trips per chunk instead of two per slot, and the
+// same order of additions as the plain loop (bit-identical).  Slots past the slice width are skipped (warp-uniform).
+#ifndef GCH
+#define GCH 4
+#endif
+
 // (B1 y)[row] = sum_e sigma*omega_e*y_e ; MODE 0: plain, 1: relu(+), 2: relu(-)    (gds.py:280,285,290)
 template <int MODE, bool UNITW>
 __device__ __forceinline__ double n_bdot(const GraphDev& g, const double* __restrict__ y, int64_t row, int lane) {
   SliceRange s = slice_of(g.n_soff, row, lane);
   double acc = 0.0;
   const int32_t* ed = g.n_edge + s.base;
-#pragma unroll 4
-  for (uint32_t j = 0; j < s.width; ++j) {
-    int32_t pk = ld_stream_i32(ed + (int64_t)j * GDS_SLICE);
-    bool valid = pk >= 0;
-    int32_t e = valid ? (pk >> 1) : 0;
-    double sg = (pk & 1) ? 1.0 : -1.0;
-    double term = UNITW ? sg * ld_gather(y + e) : sg * (__ldg(g.e_omega + e) * ld_gather(y + e));
-    if (MODE == 1) term = fmax(term, 0.0);
-    if (MODE == 2) term = fmax(-term, 0.0);
-    acc += valid ? term : 0.0;
+  for (uint32_t j0 = 0; j0 < s.width; j0 += GCH) {
+    int32_t pk[GCH];
+    double yv[GCH], om[GCH];
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) pk[jj] = (j0 + jj < s.width) ? ld_stream_i32(ed + (int64_t)(j0 + jj) * GDS_SLICE) : -1;
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) {
+      const int32_t e = (pk[jj] >= 0) ? (pk[jj] >> 1) : 0;
+      yv[jj] = ld_gather(y + e);
+      om[jj] = UNITW ? 1.0 : __ldg(g.e_omega + e);
+    }
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj)
+      if (j0 + jj < s.width) {
+        const bool valid = pk[jj] >= 0;
+        const double sg = (pk[jj] & 1) ? 1.0 : -1.0;
+        double term = UNITW ? sg * yv[jj] : sg * (om[jj] * yv[jj]);
+        if (MODE == 1) term = fmax(term, 0.0);
+        if (MODE == 2) term = fmax(-term, 0.0);
+        acc += valid ? term : 0.0;
+      }
   }
   return acc;
 }
@@ -143,23 +166,34 @@ __device__ __forceinline__ double n_advect(const GraphDev& g, const double* __re
   SliceRange s = slice_of(g.n_soff, row, lane);
   const double yc = ld_gather(y + row);
   double acc = 0.0;
-#pragma unroll 2
-  for (uint32_t j = 0; j < s.width; ++j) {
-    int64_t slot = s.base + (int64_t)j * GDS_SLICE;
-    int32_t pk = ld_stream_i32(g.n_edge + slot);
-    int32_t nb = ld_stream_i32(g.n_nbr + slot);
-    double wj = UNITW ? ((pk >= 0) ? 1.0 : 0.0) : ld_stream_f64(g.n_w + slot);  // 0 on padding
-    int32_t e = (pk >= 0) ? (pk >> 1) : 0;
-    double sg = (pk & 1) ? 1.0 : -1.0;
-    double ve = ld_gather(v + e);
-    double dir = sg * sgn(ve);
-    double yn = ld_gather(y + nb);
-    if (LIE) {
-      acc += (dir > 0.0) ? wj * ve * sg * (yc - yn) : 0.0;
-    } else {
-      double src = (dir < 0.0) ? yc : yn;
-      acc -= sg * wj * ve * src;
+  for (uint32_t j0 = 0; j0 < s.width; j0 += GCH) {
+    int32_t pk[GCH], nb[GCH];
+    double wj[GCH], ve[GCH], yn[GCH];
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) {
+      const bool on = j0 + jj < s.width;
+      const int64_t slot = s.base + (int64_t)(j0 + jj) * GDS_SLICE;
+      pk[jj] = on ? ld_stream_i32(g.n_edge + slot) : -1;
+      nb[jj] = on ? ld_stream_i32(g.n_nbr + slot) : (int32_t)row;
+      wj[jj] = UNITW ? ((pk[jj] >= 0) ? 1.0 : 0.0) : (on ? ld_stream_f64(g.n_w + slot) : 0.0);  // 0 on padding
     }
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) {
+      ve[jj] = ld_gather(v + ((pk[jj] >= 0) ? (pk[jj] >> 1) : 0));
+      yn[jj] = ld_gather(y + nb[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj)
+      if (j0 + jj < s.width) {
+        const double sg = (pk[jj] & 1) ? 1.0 : -1.0;
+        const double dir = sg * sgn(ve[jj]);
+        if (LIE) {
+          acc += (dir > 0.0) ? wj[jj] * ve[jj] * sg * (yc - yn[jj]) : 0.0;
+        } else {
+          const double src = (dir < 0.0) ? yc : yn[jj];
+          acc -= sg * wj[jj] * ve[jj] * src;
+        }
+      }
   }
   return acc;
 }
@@ -170,20 +204,30 @@ template <bool UNITW>
 __device__ __forceinline__ double4 n_eagg(const GraphDev& g, const double* __restrict__ y, int64_t row, int lane) {
   SliceRange s = slice_of(g.n_soff, row, lane);
   double p1 = 0, p2 = 0, q1 = 0, q2 = 0;
-#pragma unroll 2
-  for (uint32_t j = 0; j < s.width; ++j) {
-    int64_t slot = s.base + (int64_t)j * GDS_SLICE;
-    int32_t pk = ld_stream_i32(g.n_edge + slot);
-    double wj = UNITW ? ((pk >= 0) ? 1.0 : 0.0) : ld_stream_f64(g.n_w + slot);
-    int32_t e = (pk >= 0) ? (pk >> 1) : 0;
-    double sg = (pk & 1) ? 1.0 : -1.0;
-    double ye = ld_gather(y + e);
-    double dir = sg * sgn(ye);
-    double a1 = wj * fabs(ye), a2 = wj * ye * ye;
-    p1 += (dir > 0.0) ? a1 : 0.0;
-    p2 += (dir > 0.0) ? a2 : 0.0;
-    q1 += (dir < 0.0) ? a1 : 0.0;
-    q2 += (dir < 0.0) ? a2 : 0.0;
+  for (uint32_t j0 = 0; j0 < s.width; j0 += GCH) {
+    int32_t pk[GCH];
+    double wj[GCH], yv[GCH];
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) {
+      const bool on = j0 + jj < s.width;
+      const int64_t slot = s.base + (int64_t)(j0 + jj) * GDS_SLICE;
+      pk[jj] = on ? ld_stream_i32(g.n_edge + slot) : -1;
+      wj[jj] = UNITW ? ((pk[jj] >= 0) ? 1.0 : 0.0) : (on ? ld_stream_f64(g.n_w + slot) : 0.0);
+    }
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) yv[jj] = ld_gather(y + ((pk[jj] >= 0) ? (pk[jj] >> 1) : 0));
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj)
+      if (j0 + jj < s.width) {
+        const double sg = (pk[jj] & 1) ? 1.0 : -1.0;
+        const double ye = yv[jj];
+        const double dir = sg * sgn(ye);
+        const double a1 = wj[jj] * fabs(ye), a2 = wj[jj] * ye * ye;
+        p1 += (dir > 0.0) ? a1 : 0.0;
+        p2 += (dir > 0.0) ? a2 : 0.0;
+        q1 += (dir < 0.0) ? a1 : 0.0;
+        q2 += (dir < 0.0) ? a2 : 0.0;
+      }
   }
   double d = __ldg(g.n_dinv + row);
   return make_double4(d * p1, d * p2, d * q1, d * q2);
@@ -272,13 +316,25 @@ template <bool UNITW>
 __device__ __forceinline__ double f_curl(const GraphDev& g, const double* __restrict__ y, int64_t row, int lane) {
   SliceRange s = slice_of(g.fe_soff, row, lane);
   double acc = 0.0;
-#pragma unroll 2
-  for (uint32_t j = 0; j < s.width; ++j) {
-    int32_t pk = ld_stream_i32(g.fe_edge + s.base + (int64_t)j * GDS_SLICE);
-    bool valid = pk >= 0;
-    int32_t e = valid ? (pk >> 1) : 0;
-    double term = UNITW ? ld_gather(y + e) : __ldg(g.e_omega + e) * ld_gather(y + e);
-    acc += valid ? ((pk & 1) ? -term : term) : 0.0;
+  for (uint32_t j0 = 0; j0 < s.width; j0 += GCH) {
+    int32_t pk[GCH];
+    double yv[GCH], om[GCH];
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj)
+      pk[jj] = (j0 + jj < s.width) ? ld_stream_i32(g.fe_edge + s.base + (int64_t)(j0 + jj) * GDS_SLICE) : -1;
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj) {
+      const int32_t e = (pk[jj] >= 0) ? (pk[jj] >> 1) : 0;
+      yv[jj] = ld_gather(y + e);
+      om[jj] = UNITW ? 1.0 : __ldg(g.e_omega + e);
+    }
+#pragma unroll
+    for (int jj = 0; jj < GCH; ++jj)
+      if (j0 + jj < s.width) {
+        const bool valid = pk[jj] >= 0;
+        const double term = UNITW ? yv[jj] : om[jj] * yv[jj];
+        acc += valid ? ((pk[jj] & 1) ? -term : term) : 0.0;
+      }
   }
   return acc;
 }
@@ -1626,9 +1682,8 @@ int launch_reduce(gds_ctx* ctx, const double* x, int64_t n, int kind, double* sc
 
 // ---------------------------------------------------------------------------------------------------
 // peer-to-peer halo exchange over NVLink, inside the captured step.
-// push: one block per neighbour announces that this rank's stage is done (ready flag), waits for the neighbour's, stores
-// this rank's boundary values straight into the neighbour's ghost rows (peer-mapped memory), fences, and publishes the
-// exchange number in the neighbour's arrival flag.
+// push: stores this rank's boundary values straight into the neighbours' ghost rows (peer-mapped memory), fences, and
+// publishes the exchange number in each neighbour's arrival flag (deep partitions: after a ready-flag handshake).
 // wait: right after the push, one thread per neighbour polls the local flag slot until the neighbour's values of the
 // same exchange have arrived; only then may the next stage gather from the ghost rows.
 // ---------------------------------------------------------------------------------------------------
@@ -1642,34 +1697,46 @@ __device__ __forceinline__ void p2p_raise(int64_t* err, int64_t* err_host, int64
   __threadfence_system();
 }
 
-__global__ void __launch_bounds__(1024) push_kernel(const __grid_constant__ PushParams p) {
-  const int q = blockIdx.x;
+// Handshake before writing (deep partitions, whose passes also run over ghost rows): the neighbour's own stage kernel may
+// still be storing (meaningless) values into its ghost rows, so every rank first announces "my stage of this exchange is
+// done" (ready flag, slot 64 + rank) to its neighbours and waits for theirs; the push proper follows in stream order.
+__global__ void ready_kernel(const __grid_constant__ PushParams p) {
+  const int q = threadIdx.x;
+  if (q >= p.n_peers) return;
+  const int64_t e = *p.epoch + 1;
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q] + 64), "l"(e) : "memory");
+  if (*reinterpret_cast<volatile int64_t*>(p.err) != 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  int64_t seen;
+  do {
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.ready[q]) : "memory");
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > p.timeout_ns) { p2p_raise(p.err, p.err_host, 101 + q); break; }
+  } while (seen < e);
+}
+
+// grid = (blocks per neighbour, neighbours), SMALL blocks: the push runs beside the interior rows of the stage, whose grid
+// keeps every SM full -- a 256-thread block fits into the room one retiring block leaves, a 1024-thread block would wait
+// for the interior grid to drain.  The last block of a neighbour to finish publishes the exchange number.
+#define PUSH_THREADS 256
+__global__ void __launch_bounds__(PUSH_THREADS) push_kernel(const __grid_constant__ PushParams p) {
+  const int q = blockIdx.y;
   const double* __restrict__ src = p.src;
   double* dst = p.dst[q];
-  // Handshake before writing (deep partitions, whose passes also run over ghost rows): the neighbour's own stage kernel
-  // may still be storing (meaningless) values into its ghost rows, so it first announces "my stage of this exchange is
-  // done" (ready flag, slot 64 + rank), and the push waits for it.
-  if (p.handshake && threadIdx.x == 0) {
-    const int64_t e = *p.epoch + 1;
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q] + 64), "l"(e) : "memory");
-    if (*reinterpret_cast<volatile int64_t*>(p.err) == 0) {
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      int64_t seen;
-      do {
-        asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(p.ready[q]) : "memory");
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > p.timeout_ns) { p2p_raise(p.err, p.err_host, 101 + q); break; }
-      } while (seen < e);
-    }
-  }
-  __syncthreads();
-  for (int64_t i = p.s0[q] + threadIdx.x; i < p.s1[q]; i += 1024) dst[p.dst_idx[i]] = src[p.src_idx[i]];
+  const int64_t stride = (int64_t)gridDim.x * PUSH_THREADS;
+  for (int64_t i = p.s0[q] + (int64_t)blockIdx.x * PUSH_THREADS + threadIdx.x; i < p.s1[q]; i += stride)
+    dst[p.dst_idx[i]] = src[p.src_idx[i]];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int64_t e = *p.epoch + 1;          // number of this exchange; the counter is advanced by the wait that follows
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q]), "l"(e) : "memory");
+    const unsigned int t = atomicAdd(p.done + q, 1u);
+    if (t == gridDim.x - 1) {
+      p.done[q] = 0u;
+      __threadfence_system();
+      const int64_t e = *p.epoch + 1;        // number of this exchange; the counter is advanced by the wait that follows
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.flag[q]), "l"(e) : "memory");
+    }
   }
 }
 
@@ -1694,7 +1761,12 @@ __global__ void wait_kernel(const __grid_constant__ WaitParams p) {
 
 int launch_push(gds_ctx* ctx, const PushParams& p) {
   if (p.n_peers <= 0) return 0;
-  push_kernel<<<p.n_peers, 1024, 0, ctx->stream>>>(p);
+  if (p.handshake) {
+    ready_kernel<<<1, 32, 0, ctx->stream>>>(p);
+    GDS_CUDA(cudaGetLastError());
+    ctx->kernel_launches++;
+  }
+  push_kernel<<<dim3((unsigned)p.blocks_per_peer, (unsigned)p.n_peers), PUSH_THREADS, 0, ctx->stream>>>(p);
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;
   return 0;
