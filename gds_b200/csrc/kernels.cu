@@ -545,6 +545,24 @@ __global__ void __launch_bounds__(BLOCK) pass_kernel(const __grid_constant__ Pas
 }
 
 // ---------------------------------------------------------------------------------------------------
+// the upwind aggregates of the edge self-advection (pass 1 of gds.py:326-345, and their tangent for the Jacobian-vector
+// product) as their own kernel: a one-instruction row program does not need the interpreter's stack and locals (64
+// registers, 44 % occupancy there)
+// ---------------------------------------------------------------------------------------------------
+template <bool UNITW, bool TANGENT>
+__global__ void __launch_bounds__(BLOCK) eagg_kernel(const __grid_constant__ PassParams p) {
+  const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (row >= p.n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t ins = p.code[0];
+  const uint32_t a = (ins >> 8) & 0xffu, b = (ins >> 16) & 0xffu;
+  const double4 q = TANGENT ? n_eaggt<UNITW>(p.g, p.vec[a], p.vec[ins >> 24], row, lane) : n_eagg<UNITW>(p.g, p.vec[a], row, lane);
+  double2* dst = reinterpret_cast<double2*>(p.out[b]) + 2 * row;
+  dst[0] = make_double2(q.x, q.y);
+  dst[1] = make_double2(q.z, q.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // linear combinations of masked one-hop operators (TermForm): the terms are evaluated one after another and
 // accumulated -- no stack machine, one warp-uniform switch per term
 // ---------------------------------------------------------------------------------------------------
@@ -1353,7 +1371,12 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     ctx->kernel_launches++;
     return 0;
   }
-  if (domain == GDS_NODES) {
+  if (domain == GDS_NODES && p.n_code == 1 && p.epilogue == GDS_EPI_NONE &&
+      ((p.code[0] & 0xffu) == GDS_OP_N_EAGG || (p.code[0] & 0xffu) == GDS_OP_N_EAGGT)) {
+    const bool tangent = (p.code[0] & 0xffu) == GDS_OP_N_EAGGT;
+    if (unitw) { if (tangent) eagg_kernel<true, true><<<grid, block, 0, ctx->stream>>>(p); else eagg_kernel<true, false><<<grid, block, 0, ctx->stream>>>(p); }
+    else { if (tangent) eagg_kernel<false, true><<<grid, block, 0, ctx->stream>>>(p); else eagg_kernel<false, false><<<grid, block, 0, ctx->stream>>>(p); }
+  } else if (domain == GDS_NODES) {
     if (unitw) pass_kernel<GDS_NODES, true><<<grid, block, 0, ctx->stream>>>(p);
     else pass_kernel<GDS_NODES, false><<<grid, block, 0, ctx->stream>>>(p);
   } else if (domain == GDS_EDGES) {
