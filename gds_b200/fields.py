@@ -503,6 +503,32 @@ def _bind_states(expr, memo):
     return c
 
 
+def _state_fields(*exprs):
+    """fields whose accepted state the expressions read"""
+    seen, out = set(), []
+
+    def walk(e):
+        if e is None or id(e) in seen:
+            return
+        seen.add(id(e))
+        if isinstance(e, State) and not any(e.field is f for f in out):
+            out.append(e.field)
+        for a in e.args:
+            walk(a)
+    for e in exprs:
+        walk(e)
+    return out
+
+
+def _state_address(f):
+    """device address the state of field f is read from (None: still on the host, uploaded per use)"""
+    if f._engine is not None:
+        return f._engine._state_ptr().value + 8 * f._engine.offsets[id(f)]
+    if f._dev_y is not None:
+        return id(f._dev_y)
+    return None
+
+
 def _run_eager(low, expr):
     """lower one expression to passes, run them on the device, download the result"""
     ctx = low.ctx
@@ -648,41 +674,55 @@ def _solve_lhs(self, t):
         self._lhs_cache['split'] = (const, lin)
     const, lin = self._lhs_cache['split']
     D = self.dirichlet_indices
-    g = np.zeros(n)
-    g[D] = self.dirichlet_values
-    gvec = Const(g, dom, low)
     work = self._lhs_cache.setdefault('work', tuple(Buffer(ctx, n) for _ in range(6)))
     x, b, r, p, ap, out = work
-    memo = {}
-    rhs = substitute(lin, self, gvec) if const is None else const + substitute(lin, self, gvec)
-    rhs = _bind_states(MaskZero(unary('NEG', rhs), D), memo)
-    d_rhs, k1 = _lower_into(low, rhs, b)
-    _run_passes_at(low, d_rhs, t)
-    op = _bind_states(MaskZero(substitute(lin, self, DevVec(p, dom, low)), D), memo)
-    d_op, k2 = _lower_into(low, op, ap)
-    if len(d_op) != 1:
-        raise NotImplementedError('lhs=: the part linear in y must be a one-hop operator (a Laplacian form)')
-    kind = C.c_int32()
-    check(lib.gds_pass_kernel_kind(C.byref(d_op[0][0]), C.byref(kind)))
+    if self._dev_y is None:
+        self._dev_y = Buffer(ctx, n)
+    # The lowered pass lists are kept between solves.  They bind the other fields' state where it lives, and an engine's
+    # accepted state alternates between two buffers, so a plan is keyed by the addresses it was bound to; a field whose
+    # state is still on the host (re-uploaded per solve) or time-varying boundary values rule the cache out.
+    fields = self._lhs_cache.setdefault('fields', _state_fields(const, lin))
+    key = tuple(_state_address(f) for f in fields) + (id(self._dev_y),)
+    plans = self._lhs_cache.setdefault('plans', {})
+    plan = plans.get(key) if (not self.dynamic_dirichlet and None not in key) else None
+    if plan is None:
+        g = np.zeros(n)
+        g[D] = self.dirichlet_values
+        gvec = Const(g, dom, low)
+        memo = {}
+        rhs = substitute(lin, self, gvec) if const is None else const + substitute(lin, self, gvec)
+        rhs = _bind_states(MaskZero(unary('NEG', rhs), D), memo)
+        plan = {'rhs': _lower_into(low, rhs, b)}
+        op = _bind_states(MaskZero(substitute(lin, self, DevVec(p, dom, low)), D), memo)
+        plan['op'] = _lower_into(low, op, ap)
+        if len(plan['op'][0]) != 1:
+            raise NotImplementedError('lhs=: the part linear in y must be a one-hop operator (a Laplacian form)')
+        opn = _bind_states(MaskZero(unary('NEG', substitute(lin, self, DevVec(p, dom, low))), D), memo)
+        plan['op_neg'] = _lower_into(low, opn, ap)
+        plan['neg_b'] = _lower_into(low, unary('NEG', DevVec(b, dom, low)), r)
+        plan['copy_b'] = _lower_into(low, DevVec(r, dom, low) + 0.0, b)
+        plan['out'] = _lower_into(low, DevVec(x, dom, low) + gvec, self._dev_y)
+        plan['negative'] = False
+        if not self.dynamic_dirichlet and None not in key:
+            if len(plans) >= 4:
+                plans.clear()
+            plans[key] = plan
+    _run_passes_at(low, plan['rhs'][0], t)
     iters, relres = C.c_int32(), C.c_double()
     max_iter = max(1000, 20 * int(np.sqrt(n)) + 200)
     for attempt in range(2):
+        d_op = plan['op_neg' if plan['negative'] else 'op'][0]
+        if plan['negative']:
+            _run_passes_at(low, plan['neg_b'][0], t)
+            _run_passes_at(low, plan['copy_b'][0], t)
         check(lib.gds_cg_solve(ctx.h, low.dev.h, C.byref(d_op[0][0]), x.h, b.h, r.h, p.h, ap.h, n, 1e-13, max_iter, 25,
                                C.byref(iters), C.byref(relres)))
-        if attempt == 0 and iters.value <= 25 and relres.value > 0.5:
+        if attempt == 0 and not plan['negative'] and iters.value <= 25 and relres.value > 0.5:
             # p.Ap was not positive: the linear part is negative definite -- solve (-lin) p = -b instead
-            op = _bind_states(MaskZero(unary('NEG', substitute(lin, self, DevVec(p, dom, low))), D), memo)
-            d_op, k2 = _lower_into(low, op, ap)
-            d_neg, k3 = _lower_into(low, unary('NEG', DevVec(b, dom, low)), r)
-            _run_passes_at(low, d_neg, t)
-            d_cp, k4 = _lower_into(low, DevVec(r, dom, low) + 0.0, b)
-            _run_passes_at(low, d_cp, t)
+            plan['negative'] = True
             continue
         break
-    if self._dev_y is None:
-        self._dev_y = Buffer(ctx, n)
-    d_out, k5 = _lower_into(low, DevVec(x, dom, low) + gvec, self._dev_y)
-    _run_passes_at(low, d_out, t)
+    _run_passes_at(low, plan['out'][0], t)
     self._dev_y_cache = None
     self.last_solve = {'iterations': iters.value, 'relative_residual': relres.value}
     self._version += 1
