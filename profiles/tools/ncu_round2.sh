@@ -10,7 +10,7 @@ B="python bench.py --steps 3 --warmup 3 --no-cpu --no-weighted --no-workloads --
 cap() {   # name, kernels per step, extra env, bench args...
   name=$1; kps=$2; envs=$3; shift 3
   if env $envs $B "$@" > gpurun_out/${tag}_plain_${name}.json 2> gpurun_out/${tag}_plain_${name}.err; then
-    env $envs $NCU -s $((kps * 4)) -c $kps -o gpurun_out/${tag}_ncu_${name} $B "$@" > gpurun_out/${tag}_ncu_${name}.log 2>&1
+    env $envs $NCU -s $((kps * 2)) -c $kps -o gpurun_out/${tag}_ncu_${name} $B "$@" > gpurun_out/${tag}_ncu_${name}.log 2>&1
     echo "$name: captured (rc=$?)"
     # gpurun brings back at most 64 MiB: keep the raw metric table of every capture, the report itself only when asked
     ncu -i gpurun_out/${tag}_ncu_${name}.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_${name}_raw.csv 2>/dev/null
@@ -21,10 +21,12 @@ cap() {   # name, kernels per step, extra env, bench args...
 }
 KEEP_REPORTS=${KEEP_REPORTS:-"cml ns_cavity"}
 [ -n "$WITH_HEAT_UNIT" ] && cap heat_unit 5 A=1 --workload heat2d
-cap heat_weighted 5 A=1 --workload heat2d --weighted
-cap hex_advdiff 27 A=1 --workload hex_advdiff
+# (launches captured: two steps' worth, so that the capture holds one complete step whatever it starts with)
+cap heat_weighted 10 A=1 --workload heat2d --weighted
+cap hex_advdiff 52 A=1 --workload hex_advdiff
 cap ns_cavity 10 A=1 --workload ns_cavity
-cap wave3d 10 A=1 --workload wave3d
-cap cml 2 A=1 --workload cml
-cap cml_norenumber 2 GDS_B200_NO_RENUMBER=1 --workload cml
+cap wave3d 4 A=1 --workload wave3d
+cap cml 4 A=1 --workload cml
+cap cml_norenumber 4 GDS_B200_NO_RENUMBER=1 --workload cml
+cap cml_noshadow 4 GDS_B200_NO_SHADOW=1 --workload cml
 ls -la gpurun_out/${tag}_ncu_*; du -sh gpurun_out
