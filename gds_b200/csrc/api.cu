@@ -351,6 +351,26 @@ extern "C" int gds_graph_create(gds_ctx* c, int64_t V, int64_t E, const int32_t*
       int64_t width = soff[(x >> 5) + 1] - soff[x >> 5];
       for (int64_t j = 0; j < width; ++j) nbr[base + j * GDS_SLICE] = 0;
     }
+    {  // how do the quads (4 consecutive rows) of this graph gather?  sampled over the slices
+      const int64_t n_slices = (V + GDS_SLICE - 1) / GDS_SLICE;
+      const int64_t step = std::max<int64_t>(1, n_slices / 4096);
+      int64_t runs_good = 0, runs_odd = 0, total = 0;
+      for (int64_t sl = 0; sl < n_slices; sl += step) {
+        const int64_t width = soff[sl + 1] - soff[sl];
+        for (int64_t j = 0; j < width; ++j)
+          for (int64_t q4 = 0; q4 < GDS_SLICE; q4 += 4) {
+            const int64_t row = sl * GDS_SLICE + q4;
+            if (row + 3 >= V) continue;
+            const int64_t slot = (int64_t)soff[sl] * GDS_SLICE + j * GDS_SLICE + q4;
+            const int64_t k0 = nbr[slot];
+            ++total;
+            if (nbr[slot + 1] != k0 + 1 || nbr[slot + 2] != k0 + 2 || nbr[slot + 3] != k0 + 3) continue;
+            const int64_t dlt = k0 - row;
+            if ((dlt & 3) == 0 || dlt == 1 || dlt == -1) ++runs_good; else ++runs_odd;
+          }
+      }
+      d.n_quad_odd = (total > 0 && runs_odd * 4 > total && runs_odd > runs_good) ? 1 : 0;
+    }
     GDS_TRY(upload(g, soff, &d.n_soff));
     GDS_TRY(upload(g, nbr, &d.n_nbr));
     {  // 16-bit relative neighbour indices.  A difference that does not fit (the ghost rows of a partition sit behind

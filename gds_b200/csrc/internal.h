@@ -77,6 +77,10 @@ struct GraphDev {
                           // graphs): half the index bytes for the quad Laplacian kernel.  -32768 = escape: the difference
                           // does not fit, read n_nbr.  Null when more than 1 slot in 64 would escape
   int32_t n_uniw;         // > 0: every slice of the node ELL has this width (slice s starts at slot s * n_uniw * 32)
+  int32_t n_quad_odd;     // 1: most quads of the node ELL gather RUNS at offsets that are neither multiples of 4 nor +-1
+                          // (a lattice whose row / plane length is odd: 693^3).  The quad kernel then falls back to four
+                          // scalar gathers per slot, each touching 8 lines per warp; lapT (lane = row) reads the same run
+                          // as one contiguous 256-byte access and is the faster kernel (measured 0.39 vs 0.51 ms)
   const int32_t* n_edge;  // (edge << 1) | (1 if this node is the head v of the edge), padding = -1
   const double* n_w;      // w_e, padding = 0
   const double* n_dinv;   // [V]

@@ -1297,7 +1297,7 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
     // (a chain on the additive vector only in map mode: the EPI 2 instantiation)
     const bool map_mode = p.epilogue == GDS_EPI_RHS && p.stage_mode == 4;
-    const bool use_quad = (force ? !strcmp(force, "quad") : true) && p.lap_chain.n == 0 &&
+    const bool use_quad = (force ? !strcmp(force, "quad") : !p.g.n_quad_odd) && p.lap_chain.n == 0 &&
                           (p.lap_bchain.n == 0 || map_mode) && !p.lap_b2 && (!p.shadow_out || map_mode);
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
