@@ -1289,15 +1289,19 @@ int launch_pass(gds_ctx* ctx, const PassParams& p, int32_t domain) {
     // full 128-row groups in lapT, the remainder (< 128 rows) in the generic kernel
     if (rows / 32 > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
     PassParams q = p;
-    // measured on B200, same box, heat RK4 on a 7072^2 grid, ms per launch (profiles/README.md):
-    //   unit weights: quad 0.361 (scalar-gather form with early stream loads, 64 registers: 0.50), lapT 0.56
+    // measured on B200, same box, ms per launch (profiles/README.md):
+    //   heat RK4 on a 7072^2 grid, unit weights: quad 0.361 (scalar-gather form with early stream loads: 0.50), lapT 0.56;
     //   random weights: quad 0.606, lapT 0.674 (early stream loads, 96 registers: 0.787)
-    // so the quad kernel takes every plain L0 form; lapT keeps pointwise chains, a second additive vector and
-    // operands that are not 16-byte aligned.  GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
+    //   wave equation on a 400^3 grid (no 16-bit indices: the plane stride does not fit): quad 0.729, lapT 0.605;
+    //   693^3 (odd strides: the quad's runs are unaligned, four scalar gathers per slot): quad 0.51, lapT 0.39
+    //   CML on the 10^7-node RGG (carried operand): quad 0.241, lapT 0.239
+    // so the quad kernel takes the plain L0 forms of graphs that have 16-bit relative indices (2-D lattices, where one
+    // 64-bit load brings the four indices of a slot) and whose runs are aligned; lapT takes everything else: other graphs,
+    // pointwise chains, a second additive vector, operands that are not 16-byte aligned.
+    // GDS_B200_LAP_KERNEL=quad|lapT forces one for A/B runs.
     static const char* force = getenv("GDS_B200_LAP_KERNEL");
-    // (a chain on the additive vector only in map mode: the EPI 2 instantiation)
     const bool map_mode = p.epilogue == GDS_EPI_RHS && p.stage_mode == 4;
-    const bool use_quad = (force ? !strcmp(force, "quad") : !p.g.n_quad_odd) && p.lap_chain.n == 0 &&
+    const bool use_quad = (force ? !strcmp(force, "quad") : (p.g.n_nbr16 != nullptr && !p.g.n_quad_odd)) && p.lap_chain.n == 0 &&
                           (p.lap_bchain.n == 0 || map_mode) && !p.lap_b2 && (!p.shadow_out || map_mode);
     bool quad_ok = use_quad && aligned16(p.lap_v) && aligned16(p.lap_b) && aligned16(p.lap_store) && (p.row0 % 4 == 0);
     if (quad_ok && p.epilogue == GDS_EPI_RHS)
