@@ -136,8 +136,12 @@ def hex_advdiff_problem(api, n, native, world=1, rank=0, weighted=False, distrib
         V, E, F = c.ndim, u.ndim, len(u.faces)
     # edge law 64E + 20V + 44F, node law 72E + 28V per RHS; RK4 vectors 136 B per state component
     per_step = 4 * ((64 * E + 20 * V + 44 * F) + (72 * E + 28 * V)) + 136 * (E + V)
+    # what the kernels' own layout moves (unit weights: no weight streams; int32 indices, 3 / 6 / 2 slots per node / face /
+    # edge): per stage node divergence + face curl + edge RHS + node RHS with their RK vectors, once per step the advection term
+    own = 4 * (104 * V + 80 * E + 40 * F) + (40 * V + 8 * E)
     return dict(stepper=sysobj.stepper, fields=[u, c], h=h, n_state=E + V, V=V, E=E, F=F, bytes_per_step=per_step,
-                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
+                kernel_bytes_per_step=own,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=own / 4.0, dominant_class=-1,
                 kernel='all passes of one RK stage (terms_kernel: node divergence, face curl, edge RHS; lapT_kernel: '
                        'node RHS)',
                 name=f'edge diffusion + node advection-diffusion, RK4 h=1e-3, hexagonal_lattice_graph({n},{n * world}) '
@@ -192,9 +196,11 @@ def ns_cavity_problem(api, n, native, world=1, rank=0, weighted=False):
     # the law reads accepted state only (fds.py:377-378): its operators are evaluated once per step and
     # the four stage combines happen in registers (collapsed RK4)
     hoisted = (128 * E + 104 * V + 32 * F) + 16 * E      # + read y_n, write y_{n+1}
+    # the kernels' own layout, collapsed step: aggregates, divergence, curl, edge law (unit weights, int32 indices)
+    own = 144 * V + 64 * E + 28 * F
     return dict(stepper=sysobj.stepper, fields=[u], h=h, n_state=E, V=V, E=E, F=F, bytes_per_step=per_step,
-                bytes_per_step_hoisted=hoisted,
-                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
+                bytes_per_step_hoisted=hoisted, kernel_bytes_per_step=own,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=own, dominant_class=-1,
                 kernel='step level: the law reads accepted state only, so the step is collapsed -- node aggregates, '
                        'divergence, curl and the edge law run ONCE per step, the four RK4 stage combines in registers',
                 name=f'Navier-Stokes edge law (advect + grad p + Hodge-1 Laplacian), RK4 h=1e-4, '
@@ -226,6 +232,7 @@ def cml_problem(api, n, native, world=1, rank=0, weighted=False, distribute=True
     E = (x._low.E if part is None else int(x._low.E * V / max(1, x._low.V))) if native else G.number_of_edges()
     per_step = 12 * (V + 2 * E) + 4 * V + 16 * V
     return dict(stepper=x, fields=[x], h=1.0, n_state=V, V=V, E=E, F=0, bytes_per_step=per_step,
+                kernel_bytes_per_step=4 * 2 * E + 24 * V,      # int32 indices, gather of f(y) once, y and f(y) written
                 bytes_per_launch=per_step, kernel_bytes_per_launch=(4 * 2 * E + 8 * 4) * 1.0 + 24 * V,
                 dominant_class=0, kernel='lapT_kernel<unit weights, map> (+ pointwise pass f(y))',
                 name=f'coupled map lattice, random_geometric_graph({nn}) (E={E if part is None else "~" + str(E * world)}), map mode'
@@ -263,11 +270,12 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
     per_step = 4 * (12 * (V + 2 * E) + 4 * V) + 136 * 2 * V        # Laplacian at every stage
     # `a.laplacian()` reads the accepted state: one Laplacian per step (collapsed RK4)
     hoisted = (12 * (V + 2 * E) + 4 * V) + 24 * V + 32 * V      # Laplacian pass: read v_n, write k_v, v_{n+1}; shift pass: read k_v, v_n, x_n, write x_{n+1}
+    own = (4 * 6 + 32) * V        # one pass per step: 6 int32 indices, read x and v_n, write x_{n+1} and v_{n+1}
     return dict(stepper=a, fields=[a], h=h, n_state=2 * n_own, V=V, E=E, F=0, bytes_per_step=per_step,
-                bytes_per_step_hoisted=hoisted,
-                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=per_step / 4.0, dominant_class=-1,
-                kernel='step level: collapsed RK4 -- one Laplacian pass over the value block (derivative block advanced in '
-                       'its epilogue) + one pointwise pass for the value block',
+                bytes_per_step_hoisted=hoisted, kernel_bytes_per_step=own,
+                bytes_per_launch=per_step / 4.0, kernel_bytes_per_launch=own, dominant_class=-1,
+                kernel='step level: collapsed RK4 -- ONE Laplacian pass per step that advances the derivative block and, in '
+                       'the same epilogue, the value block',
                 name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{nz if native else n}]) '
                      f'(V={n * n * (nz if native else n)}, E={3 * n * n * (nz if native else n) - n * n - 2 * n * (nz if native else n)})'
                      + (f', {world} slabs with halo exchange' if world > 1 else ''))
@@ -567,9 +575,11 @@ def roofline_of(prob, eng, K, h, ms_step):
 def other_workloads(args, ctx, barrier, local, dist, torch, skip):
     """The other BASELINE configurations at their full sizes, one after another on the same GPU (N = 1): K steps with the
     state resident in HBM, CUDA events, clocks sampled -- same protocol as the headline.  frac_algorithmic uses SURVEY.md
-    8d's bytes (operators counted at every stage); laws that read accepted state only are evaluated once per step by the
-    engine (collapsed RK4), so frac_hoisted counts what such a step really has to move; frac_traffic uses the DRAM bytes of one step
-    from the committed ncu capture (profiles/traffic.json), when there is one."""
+    8d's bytes (operators counted at every stage, general weighted CSR) and may exceed 1; laws that read accepted state only
+    are evaluated once per step by the engine (collapsed RK4): frac_hoisted counts SURVEY's bytes with the operators once;
+    frac_kernel_bytes counts what the kernels' own layout has to move (unit weights: no weight streams) -- the honest
+    bandwidth fraction by design; frac_traffic uses the DRAM bytes of one step from the committed ncu capture
+    (profiles/traffic.json), when there is one."""
     import gc
     from adaptors import product_api
     peak, _ = measured_peak()
@@ -601,6 +611,9 @@ def other_workloads(args, ctx, barrier, local, dist, torch, skip):
                    'frac_algorithmic': prob['bytes_per_step'] / (ms_step * 1e-3) / 1e9 / peak,
                    'frac_hoisted': (prob['bytes_per_step_hoisted'] / (ms_step * 1e-3) / 1e9 / peak
                                     if 'bytes_per_step_hoisted' in prob else None),
+                   'kernel_bytes_per_step': prob.get('kernel_bytes_per_step'),
+                   'frac_kernel_bytes': (prob['kernel_bytes_per_step'] / (ms_step * 1e-3) / 1e9 / peak
+                                         if prob.get('kernel_bytes_per_step') else None),
                    'kernels_per_step': eng.kernels_per_step, 'gpu_launches': launches, 'build_seconds': t_build,
                    'clocks': clocks, 'kernel': prob['kernel']}
             tr = traffic.get(name, {}).get('per_step', {}).get(str(size))
