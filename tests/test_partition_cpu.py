@@ -328,3 +328,43 @@ def test_graphs_without_index_locality_are_cut_along_a_space_filling_curve(world
         assert cut_curve < 0.25 * cut_index and cut_curve < 0.2 * eu.size, (cut_curve, cut_index, eu.size)
     finally:
         gds_b200.Context._default.clear()
+
+
+def test_overlap_split_covers_every_boundary_row():
+    """engine.overlap_split: the two row ranges [0, lo) and [hi, n_own) hold every row adjacent to a cut, are multiples of
+    128, as short as possible, and the split is refused when there is nothing to hide an exchange behind"""
+    from gds_b200.engine import overlap_split
+    n = 7072
+    both = np.concatenate([np.arange(n), np.arange(n * n - n, n * n)])
+    assert overlap_split(both, n * n) == (7168, n * n - 7168)            # one lattice row per side, rounded to 128
+    assert overlap_split(np.arange(n), n * n) == (7168, n * n)             # first rank of a chain: nothing at the top
+    assert overlap_split(np.arange(n * n - n, n * n), n * n) == (0, n * n - 7168)
+    assert overlap_split(np.arange(0, n * n, 50), n * n) is None           # boundary rows everywhere (unordered graph)
+    assert overlap_split(np.zeros(0, dtype=np.int64), n * n) is None
+    assert overlap_split(np.arange(10), 500) is None                        # too small to bother
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n_own = int(rng.integers(2000, 100000))
+        k = int(rng.integers(1, 40))
+        rows = np.unique(np.concatenate([rng.integers(0, 300, k), rng.integers(n_own - 300, n_own, k)]))
+        lo, hi = overlap_split(rows, n_own)
+        assert lo % 128 == 0 and hi % 128 == 0 and 0 <= lo <= hi <= n_own
+        assert np.all((rows < lo) | (rows >= hi))
+
+
+def test_stage_independent_laws_are_recognised():
+    """engine._reads_stage: a law is collapsible when its expression contains neither the stage vector nor the stage time"""
+    from gds_b200.engine import _reads_stage
+    from gds_b200.trace import Gather, Stage, State, Time, as_expr
+
+    class F:   # stand-in for a field
+        _domain_code, _low = 0, None
+    f = F()
+    lap_acc = Gather.__new__(Gather)
+    lap_acc.args, lap_acc.domain, lap_acc.graph = (State(f),), 0, None
+    lap_stage = Gather.__new__(Gather)
+    lap_stage.args, lap_stage.domain, lap_stage.graph = (Stage(f),), 0, None
+    assert not _reads_stage(2.0 * lap_acc + State(f))
+    assert _reads_stage(2.0 * lap_stage)
+    assert _reads_stage(lap_acc * Time())
+    assert _reads_stage(lap_acc + 0.1 * Stage(f))
