@@ -159,11 +159,20 @@ class LoweredGraph:
                     self._set_perm(locality_permutation(V, self.edge_u, self.edge_v, P))
 
     # -- one rank's part of a distributed graph -------------------------------------------------------------
-    def _init_distributed(self, G, rank, world, align, hops=1):
-        from .partition import Partition
+    def _init_distributed(self, G, rank, world, align, hops=1, blocks=None):
+        from .partition import BlockPartition, Partition
         if hops > 1:
             return self._init_distributed_deep(G, rank, world, align, hops)
-        if self.native and G.kind in ('grid_2d', 'grid') and G.weights is None:
+        if blocks is not None:
+            A, B, C = (G.dims[0], G.dims[1], 1) if G.kind == 'grid_2d' else (G.dims[2], G.dims[1], G.dims[0])
+            part = BlockPartition(rank, blocks, A, B, C)
+            gids = part.global_ids
+            if G.kind == 'grid_2d':
+                lab = np.stack([gids // B, gids % B], axis=1)
+            else:
+                lab = np.stack([gids // (B * C), (gids // C) % B, gids % C], axis=1)
+            self.nodes = LazyNodeMap(_LabelSource(lab.astype(np.int64), lab.shape[1]))
+        elif self.native and G.kind in ('grid_2d', 'grid') and G.weights is None:
             A, B, C = (G.dims[0], G.dims[1], 1) if G.kind == 'grid_2d' else (G.dims[2], G.dims[1], G.dims[0])
             part = Partition.grid_slab(rank, world, A, B, C)      # closed form: only this slab is ever generated
             gids = part.global_ids
@@ -458,7 +467,7 @@ class _LabelSource:
         return self._labels
 
 
-def distribute(G, rank=None, world=None, align=1, hops=1):
+def distribute(G, rank=None, world=None, align=1, hops=1, blocks=None):
     """Mark graph G (nx.Graph or NativeGraph) as partitioned over `world` ranks; fields built on it afterwards hold
     this rank's rows and exchange boundary values every stage.  Defaults come from the torch.distributed / torchrun
     environment.  hops = 1: node fields with one-hop laws (owned nodes, then one layer of ghosts).  hops > 1: `hops`
@@ -467,7 +476,13 @@ def distribute(G, rank=None, world=None, align=1, hops=1):
     import os
     rank = int(os.environ.get('RANK', '0')) if rank is None else int(rank)
     world = int(os.environ.get('WORLD_SIZE', '1')) if world is None else int(world)
-    G.__dict__['_gds_b200_distribute'] = (rank, world, int(align), int(hops))
+    if blocks is not None:
+        # block decomposition of a native grid: (pa, pb, pc) blocks along the axes of node labels (a, b, c)
+        blocks = tuple(int(x) for x in blocks) + (1,) * (3 - len(blocks))
+        assert int(np.prod(blocks)) == world, 'the blocks must multiply to the number of ranks'
+        assert isinstance(G, NativeGraph) and G.kind in ('grid_2d', 'grid') and G.weights is None and hops == 1, \
+            'block decomposition is available for unweighted native grids'
+    G.__dict__['_gds_b200_distribute'] = (rank, world, int(align), int(hops)) + ((blocks,) if blocks is not None else ())
     G.__dict__.pop('_gds_b200_lowered', None)
     return G
 

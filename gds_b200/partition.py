@@ -150,6 +150,122 @@ class Partition:
         return Partition(rank, world, V, bounds, u, v, None, ghosts=ghosts)
 
 
+class BlockPartition(Partition):
+    """One rank's BLOCK of a row-major grid (2 x 2 x 2 blocks of the 3-D grid instead of slabs -- three faces
+    of ~n^2/4 ghost rows per rank instead of two of n^2).  Node (a, b, c) has global id a*B*C + b*C + c and G.edges()
+    yields, per node, its +a, +b, +c neighbour (Appendix C), as in `Partition.grid_slab`; only this block and its face
+    layers are generated.
+
+    Local rows: [owned rows next to another block (they are sent, and only they read ghost values) | the other owned rows |
+    ghost rows], each group in global id order -- so the rows that take part in the exchange form a prefix and the engine
+    can run them first and hide the exchange behind the rest (engine.overlap_split).  Every owned row still lists its edges
+    in GLOBAL edge order: same summation order, same bits as on one GPU."""
+
+    def __init__(self, rank, blocks, A, B, C=1):
+        pa, pb, pc = (int(x) for x in blocks)
+        world = pa * pb * pc
+        assert 0 <= rank < world and pa <= A and pb <= B and pc <= C
+        self.rank, self.world, self.V_global = int(rank), world, A * B * C
+        self.blocks, self.dims = (pa, pb, pc), (A, B, C)
+        cuts = [np.array([n * k // p for k in range(p + 1)], dtype=np.int64) for n, p in ((A, pa), (B, pb), (C, pc))]
+        self.cuts = cuts
+        r = (rank // (pb * pc), (rank // pc) % pb, rank % pc)
+        lo = [int(cuts[d][r[d]]) for d in range(3)]
+        hi = [int(cuts[d][r[d] + 1]) for d in range(3)]
+        stride = np.array([B * C, C, 1], dtype=np.int64)
+        dims = (A, B, C)
+
+        def box(l, h):
+            a, b, c = np.meshgrid(np.arange(l[0], h[0]), np.arange(l[1], h[1]), np.arange(l[2], h[2]), indexing='ij')
+            return np.stack([a.ravel(), b.ravel(), c.ravel()], axis=1).astype(np.int64)
+        own = box(lo, hi)                                                   # lexicographic = global id order
+        own_gid = own @ stride
+        # owned rows with a neighbour in another block
+        edge_of_block = np.zeros(own.shape[0], dtype=bool)
+        ghosts = []
+        for d in range(3):
+            if lo[d] > 0:
+                edge_of_block |= own[:, d] == lo[d]
+                l, h = list(lo), list(hi)
+                l[d], h[d] = lo[d] - 1, lo[d]
+                ghosts.append(box(l, h))
+            if hi[d] < dims[d]:
+                edge_of_block |= own[:, d] == hi[d] - 1
+                l, h = list(lo), list(hi)
+                l[d], h[d] = hi[d], hi[d] + 1
+                ghosts.append(box(l, h))
+        gh = np.concatenate(ghosts) if ghosts else np.zeros((0, 3), dtype=np.int64)
+        gh_gid = gh @ stride
+        order = np.argsort(gh_gid)
+        gh, gh_gid = gh[order], gh_gid[order]
+        self.n_own, self.n_ghost = int(own_gid.size), int(gh_gid.size)
+        self.n_loc = self.n_own + self.n_ghost
+        self.n_boundary = int(edge_of_block.sum())
+        self.own_gid = np.concatenate([own_gid[edge_of_block], own_gid[~edge_of_block]])
+        self.ghosts = gh_gid
+        self.lo, self.hi = 0, 0        # no contiguous global range
+        self._sorted_ids = np.concatenate([self.own_gid, self.ghosts])
+        self._sort_perm = np.argsort(self._sorted_ids, kind='stable')
+        self._sorted_ids = self._sorted_ids[self._sort_perm]
+        # edges touching an owned node: out-edges of owned nodes, and the edge a lower ghost sends into the block
+        tails = np.concatenate([own, gh])
+        tails_owned = np.concatenate([np.ones(self.n_own, dtype=bool), np.zeros(self.n_ghost, dtype=bool)])
+        eu, ev, key = [], [], []
+        for d in range(3):
+            head = tails.copy()
+            head[:, d] += 1
+            ok = head[:, d] < dims[d]
+            inside = np.all((head >= np.array(lo)) & (head < np.array(hi)), axis=1)
+            keep = ok & (tails_owned | inside)                            # at least one endpoint is owned
+            u, v = tails[keep] @ stride, head[keep] @ stride
+            eu.append(u); ev.append(v); key.append(u * 3 + d)               # global edge order: by tail, then direction
+        eu, ev, key = np.concatenate(eu), np.concatenate(ev), np.concatenate(key)
+        o = np.argsort(key, kind='stable')
+        eu, ev = eu[o], ev[o]
+        self.edge_u, self.edge_v = self._to_local(eu).astype(np.int32), self._to_local(ev).astype(np.int32)
+        self.weights = None
+        self.E_loc = int(eu.size)
+        # halo lists: ghost rows by owner; owned rows each neighbour needs -- both in global id order
+        def owner_of(coords):
+            idx = [np.searchsorted(cuts[d], coords[:, d], side='right') - 1 for d in range(3)]
+            return idx[0] * (pb * pc) + idx[1] * pc + idx[2]
+        gh_owner = owner_of(gh)
+        u_own, v_own = self.edge_u < self.n_own, self.edge_v < self.n_own
+        cut = u_own != v_own
+        cut_owned_local = np.where(u_own[cut], self.edge_u[cut], self.edge_v[cut]).astype(np.int64)
+        cut_ghost_local = np.where(u_own[cut], self.edge_v[cut], self.edge_u[cut]).astype(np.int64) - self.n_own
+        cut_owner = gh_owner[cut_ghost_local]
+        self.send_rows, recv = [], []
+        for q in range(world):
+            rows = np.unique(cut_owned_local[cut_owner == q]) if q != rank else np.zeros(0, dtype=np.int64)
+            rows = rows[np.argsort(self.own_gid[rows], kind='stable')]     # the receiver lists them by global id
+            self.send_rows.append(rows.astype(np.int64))
+            recv.append((self.n_own + np.nonzero(gh_owner == q)[0]).astype(np.int64) if q != rank else np.zeros(0, dtype=np.int64))
+        self.send_counts = np.array([x.size for x in self.send_rows], dtype=np.int64)
+        self.recv_counts = np.array([x.size for x in recv], dtype=np.int64)
+        self.peers = [q for q in range(world) if q != rank and (self.send_counts[q] or self.recv_counts[q])]
+        self.hops = 1
+        self.send_dom, self.recv_dom = {0: self.send_rows}, {0: recv}
+        self.faces_local = None
+
+    def _to_local(self, gids):
+        pos = np.searchsorted(self._sorted_ids, gids)
+        assert np.all(self._sorted_ids[np.minimum(pos, self._sorted_ids.size - 1)] == gids), 'node outside this block and its halo'
+        return self._sort_perm[pos]
+
+    @property
+    def global_ids(self) -> np.ndarray:
+        return np.concatenate([self.own_gid, self.ghosts])
+
+    def localise(self, global_idx):
+        g = np.asarray(global_idx, dtype=np.int64)
+        if self._sorted_ids.size == 0:
+            return np.zeros(g.shape, dtype=bool), np.zeros(0, dtype=np.int64)
+        pos = np.minimum(np.searchsorted(self._sorted_ids, g), self._sorted_ids.size - 1)
+        sel = self._sorted_ids[pos] == g
+        return sel, self._sort_perm[pos][sel]
+
+
 def _reach(V, eu, ev, lo, hi, hops):
     """node levels: 0 for [lo, hi), k for nodes first reached after k hops, -1 beyond `hops`"""
     level = np.full(V, -1, dtype=np.int64)

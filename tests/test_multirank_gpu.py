@@ -144,3 +144,63 @@ def test_unmatched_exchange_raises_instead_of_returning_stale_ghosts():
     assert 'timed out waiting for rank 1' in ret[0], ret[0]
     assert 'timed out' in ret['again'], ret['again']
     assert ret[1] == 'ok'
+
+
+def _native_grid_problem(dist_args=None):
+    """heat (stage-state Laplacian, time-varying Dirichlet plane) and wave (order 2, accepted-state Laplacian: collapsed)
+    on a native 3-D grid; returns {name: (global ids of the owned rows, their values)}"""
+    import gds_b200
+    out = {}
+    dims = (10, 12, 14)                       # grid_graph(dim=[10, 12, 14]): labels (a, b, c) with a < 14, b < 12, c < 10
+    A, B, C = dims[2], dims[1], dims[0]
+    for name in ('heat', 'wave'):
+        G = gds_b200.NativeGraph('grid', *dims)
+        if dist_args is not None:
+            gds_b200.distribute(G, *dist_args[0], **dist_args[1])
+        T = gds_b200.node_gds(G)
+        gid = np.asarray(T.global_ids)
+        a, b, c = gid // (B * C), (gid // C) % B, gid % C
+        if name == 'heat':
+            T.set_evolution(dydt=lambda t, y: 0.4 * T.laplacian(y), max_step=2e-2, integrator=gds_b200.Integrators.rk4)
+            T.set_initial(y0=np.sin(0.3 * a) + 0.1 * b - 0.05 * c)
+            plane = np.arange(B * C)             # a == 0
+            T.set_constraints(dirichlet=gds_b200.BoundarySpec(plane, fun=lambda t: np.cos(t) * np.ones(plane.size)))
+        else:
+            T.set_evolution(dydt=lambda t, y: 0.5 * T.laplacian(), order=2, max_step=5e-2, integrator=gds_b200.Integrators.rk4)
+            T.set_initial(y0=np.exp(-((a - 6.5) ** 2 + (b - 5.5) ** 2 + (c - 4.5) ** 2) / 8.0))
+        for _ in range(4):
+            T.step(0.1)
+        own = np.asarray(T.owned_mask)
+        out[name] = (gid[own], np.asarray(T.y)[own], T._ensure_engine().overlap, bool(T._ensure_engine().p2p))
+    return out
+
+
+def _block_worker(rank, world, port, blocks, transport, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), GDS_B200_DEVICE='0', GDS_B200_HALO=transport)
+    torch.cuda.set_device(0)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ret[rank] = _native_grid_problem(((rank, world), dict(blocks=blocks)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('blocks,transport', [((2, 2, 1), 'p2p'), ((2, 1, 2), 'host'), ((2, 2, 2), 'p2p')])
+def test_block_decomposition_matches_undistributed(blocks, transport):
+    """blocks of a 3-D grid (BlockPartition: up to 6 face neighbours, boundary rows first) against the one-GPU run, bit for
+    bit; the peer-to-peer transport hides the exchange behind the interior rows here too"""
+    import torch.multiprocessing as mp
+    world = int(np.prod(blocks))
+    port = 29500 + (os.getpid() + 31 * world + (5 if transport == 'p2p' else 0)) % 1500
+    ret = mp.Manager().dict()
+    mp.spawn(_block_worker, args=(world, port, blocks, transport, ret), nprocs=world, join=True)
+    single = _native_grid_problem()
+    for name, (gid1, y1, _, _) in single.items():
+        got = np.full_like(y1, np.nan)
+        for r in range(world):
+            gid, y, overlap, p2p = ret[r][name]
+            got[gid] = y
+            assert p2p == (transport == 'p2p')
+        assert np.array_equal(got, y1[np.argsort(gid1)][...] if False else y1), name

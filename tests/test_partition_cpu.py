@@ -368,3 +368,38 @@ def test_stage_independent_laws_are_recognised():
     assert _reads_stage(2.0 * lap_stage)
     assert _reads_stage(lap_acc * Time())
     assert _reads_stage(lap_acc + 0.1 * Stage(f))
+
+
+@pytest.mark.parametrize('kind,dims,abc,blocks', [('grid', (5, 6, 7), (7, 6, 5), (2, 2, 2)), ('grid', (4, 9, 6), (6, 9, 4), (3, 2, 1)),
+                                                   ('grid_2d', (9, 8), (9, 8, 1), (2, 3, 1)), ('grid', (3, 3, 8), (8, 3, 3), (4, 1, 1))])
+def test_block_partition_of_a_grid(kind, dims, abc, blocks):
+    """BlockPartition: every node owned once; local edges = every global edge touching an owned node, in global edge order
+    with public endpoints preserved; halo lists symmetric and in the same order on both sides; the rows that take part
+    in the exchange form a prefix of the local numbering"""
+    from gds_b200.partition import BlockPartition
+    V, eu, ev = global_edges(kind, *dims)
+    A, B, C = abc
+    world = int(np.prod(blocks))
+    parts = [BlockPartition(r, blocks, A, B, C) for r in range(world)]
+    owner = np.full(V, -1)
+    for r, p in enumerate(parts):
+        gid = p.global_ids
+        assert np.all(owner[gid[:p.n_own]] == -1)
+        owner[gid[:p.n_own]] = r
+    assert np.all(owner >= 0)
+    for r, p in enumerate(parts):
+        gid = p.global_ids
+        own = owner == r
+        keep = own[eu] | own[ev]
+        assert np.array_equal(gid[p.edge_u], eu[keep]) and np.array_equal(gid[p.edge_v], ev[keep])
+        assert np.all(owner[gid[p.n_own:]] != r)
+        # rows with a cut edge are exactly the first n_boundary rows
+        cut_rows = np.unique(np.concatenate([p.edge_u[(p.edge_v >= p.n_own)], p.edge_v[(p.edge_u >= p.n_own)]]))
+        assert np.array_equal(cut_rows, np.arange(p.n_boundary))
+        for q in p.peers:
+            sent = gid[p.send_rows[q]]
+            got = parts[q].global_ids[parts[q].recv_dom[0][r]]
+            assert np.array_equal(sent, got) and sent.size > 0
+        sel, loc = p.localise(np.arange(V))
+        assert np.array_equal(gid[loc], np.arange(V)[sel]) and sel.sum() == p.n_loc
+        assert len(p.peers) <= 6
