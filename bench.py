@@ -250,7 +250,8 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
         nz = n if TOTAL[0] else n * world
         G = gds_b200.NativeGraph('grid', n, n, nz)
         if world > 1 and distribute:
-            gds_b200.distribute(G, rank, world)
+            # slabs along the first label axis by default; --blocks pa,pb,pc: blocks (2 x 2 x 2 for config 5)
+            gds_b200.distribute(G, rank, world, blocks=BLOCKS[0])
     else:
         import cases
         G = cases.g_grid3((n, n, n))
@@ -278,7 +279,8 @@ def wave3d_problem(api, n, native, world=1, rank=0, weighted=False, distribute=T
                        'the same epilogue, the value block',
                 name=f'wave equation order 2, RK4 h=0.1, grid_graph([{n},{n},{nz if native else n}]) '
                      f'(V={n * n * (nz if native else n)}, E={3 * n * n * (nz if native else n) - n * n - 2 * n * (nz if native else n)})'
-                     + (f', {world} slabs with halo exchange' if world > 1 else ''))
+                     + (f', {world} ' + ('blocks ' + 'x'.join(map(str, BLOCKS[0])) if BLOCKS[0] else 'slabs') + ' with halo exchange'
+                        if world > 1 else ''))
 
 
 # name -> (builder, default GPU size per rank, CPU sample size)
@@ -775,6 +777,7 @@ def gpu_arm(args):
 
 
 WORKLOAD_NAME = [None]
+BLOCKS = [None]          # --blocks pa,pb,pc: block decomposition of the 3-D grid instead of slabs
 TOTAL = [False]          # --total: --size is the size of the WHOLE problem (strong scaling) instead of the size per rank
 NO_PREROLL = [False]     # profiling runs (ncu replays every launch ~40 times): skip the 0.3 s of load for the clock sampler
 SCHEME = ['rk4']
@@ -796,10 +799,12 @@ def main():
     ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     ap.add_argument('--total', action='store_true', help='wave3d: --size is the whole grid, cut into --gpus slabs (strong scaling)')
+    ap.add_argument('--blocks', default='', help='wave3d at N > 1: pa,pb,pc blocks along the label axes instead of slabs')
     ap.add_argument('--no-preroll', action='store_true', help='profiling runs under ncu: no untimed pre-roll before the timed steps')
     args = ap.parse_args()
     NO_PREROLL[0] = args.no_preroll
     TOTAL[0] = args.total
+    BLOCKS[0] = tuple(int(x) for x in args.blocks.split(',')) if args.blocks else None
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
