@@ -9,7 +9,9 @@ Default workload: the heat law of BASELINE config 1 (`dydt = T.laplacian(y)`, st
 the 10^8-edge lattice `grid_2d_graph(7072, 7072)` the north-star roofline target is stated on.
 `value` times K steps with the state resident in HBM (CUDA events on the library's stream, max over ranks);
 `e2e` times the same steps through the public API with HOST state buffers: every step uploads the state from pinned
-host memory, advances one step and reads the result back.  Inputs (>= 400 MB state + operators) exceed the 126 MB L2.
+host memory, advances one step and reads the result back -- at N = 1 for an ensemble of independent host states through
+`step_ensemble` (uploads, steps and read-backs of consecutive members overlapped; `e2e.serial` keeps the one-at-a-time
+figure).  Inputs (>= 400 MB state + operators) exceed the 126 MB L2.
 """
 import argparse
 import json
@@ -723,6 +725,47 @@ def gpu_arm(args):
         e2e_s = float(tt.item())
     e2e = {'value': n_total * Ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * sum(sizes), 'd2h_bytes_per_step': 8 * sum(sizes),
            'steps': Ke, 'note': 'per step: pinned-host state upload, one public step() call, state read-back; wall clock'}
+    if world == 1 and all(fl._order() == 1 for fl in fields) and hasattr(st, 'step_ensemble') and eng.scheme != 'map':
+        # The same per-step work -- a host state goes up, one step, the new state comes back -- for an ENSEMBLE of
+        # independent host-resident states through the public step_ensemble call: uploads, steps and read-backs of
+        # consecutive members overlap (both PCIe directions busy at once).  Two distinct input states alternate; every
+        # member's 8 * n bytes cross PCIe in each direction inside the timed region.
+        try:
+            serial = dict(e2e)
+            in2 = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
+            out2 = [torch.empty(s_, dtype=torch.float64).pin_memory().numpy() for s_ in sizes]
+            for a, b in zip(in2, host_out):
+                a[:] = b                      # a second, different state (one step later)
+            from gds_b200.fields import fds as _fds
+            single = isinstance(st, _fds)
+            wrap = (lambda grp: grp[0]) if single else (lambda grp: grp)
+            ring_in, ring_out = [host_in, in2], [host_out, out2]
+            t_start = eng.t
+            st.step_ensemble(h, [wrap(ring_in[i & 1]) for i in range(2)], [wrap(ring_out[i & 1]) for i in range(2)])
+            eng.t = t_start                   # members share the start time: rewind the clock for the next call
+            barrier()
+            t0 = time.perf_counter()
+            st.step_ensemble(h, [wrap(ring_in[i & 1]) for i in range(Ke)], [wrap(ring_out[i & 1]) for i in range(Ke)])
+            ens_s = time.perf_counter() - t0
+            eng.t = t_start
+            ok = True                         # against the serial call on the same inputs at the same time, bit for bit
+            chk = [np.empty(s_, dtype=np.float64) for s_ in sizes]
+            for b in range(2):
+                one_step(ring_in[b], chk)
+                eng.t = t_start
+                ok = ok and all(np.array_equal(x, y) for x, y in zip(chk, ring_out[b]))
+            e2e = {'value': n_total * Ke / ens_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * sum(sizes),
+                   'd2h_bytes_per_step': 8 * sum(sizes), 'steps': Ke,
+                   'note': 'public step_ensemble call over an ensemble of independent pinned-host states: per member the '
+                           'state goes up, one step runs, the new state comes back; uploads, steps and read-backs of '
+                           'consecutive members overlap on three streams; wall clock around the call (it synchronises)',
+                   'check': 'bit-identical to the serial call' if ok else 'MISMATCH against the serial call',
+                   'serial': {'value': serial['value'], 'note': serial['note']}}
+            if not ok:
+                e2e = dict(serial, ensemble_error='results differ from the serial call')
+            in2 = out2 = ring_in = ring_out = chk = None
+        except Exception as exc:               # keep the serial figure rather than lose the line
+            e2e['ensemble_error'] = f'{type(exc).__name__}: {exc}'[:200]
 
     # ---- the same lattice with random edge weights: kernel bytes == algorithmic bytes (N=1 only) --------------------
     weighted = None

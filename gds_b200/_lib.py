@@ -110,6 +110,7 @@ _sig('gds_system_set_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_get_state', c_vp, c_vp, c_i64, c_i64)
 _sig('gds_system_state_devptr', c_vp, P(c_vp))
 _sig('gds_system_step', c_vp, c_i64, c_vp, c_vp, c_vp)
+_sig('gds_system_step_ensemble', c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp)
 _sig('gds_system_enable_recording', c_vp)
 _sig('gds_system_set_trajectory', c_vp, c_vp)
 _sig('gds_system_step_record', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp)
@@ -143,7 +144,7 @@ EXPORTED = [
     'gds_mask_destroy', 'gds_graph_create', 'gds_graph_destroy', 'gds_graph_sizes', 'gds_graph_export_csr',
     'gds_graph_device_bytes', 'gds_pass_run', 'gds_passes_run_cols', 'gds_pass_kernel_kind', 'gds_cg_solve', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
     'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_set_collapsed', 'gds_system_set_shadow', 'gds_system_finalize',
-    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_timed', 'gds_system_info', 'gds_system_modes',
+    'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_ensemble', 'gds_system_step_timed', 'gds_system_info', 'gds_system_modes',
     'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',
     'gds_halo_create', 'gds_halo_destroy', 'gds_halo_pack', 'gds_halo_unpack',
     'gds_system_ipc_export', 'gds_system_p2p_attach', 'gds_system_p2p_status',

@@ -884,30 +884,42 @@ extern "C" int gds_cg_solve(gds_ctx* c, gds_graph* g, const gds_pass_desc* apply
   GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
   double* S = nullptr;
   double* partial = nullptr;
-  GDS_CUDA(cudaMalloc((void**)&S, 8 * sizeof(double)));
-  if (cudaMalloc((void**)&partial, 2048 * sizeof(double)) != cudaSuccess) { cudaFree(S); GDS_FAIL("out of device memory"); }
+  GDS_CUDA(cudaMalloc((void**)&S, 16 * sizeof(double)));
+  if (cudaMalloc((void**)&partial, 4096 * sizeof(double)) != cudaSuccess) { cudaFree(S); GDS_FAIL("out of device memory"); }
   int rc = 0, it = 0;
-  double h[7] = {0, 0, 0, 0, 0, 0, 0};
+  double h[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool fused = !getenv("GDS_B200_CG_UNFUSED");   // 4 launches per iteration instead of 6 (same arithmetic, same bits)
   auto fetch = [&]() -> int {
-    GDS_CUDA(cudaMemcpyAsync(h, S, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GDS_CUDA(cudaMemcpyAsync(h, S, 10 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GDS_CUDA(cudaStreamSynchronize(c->stream));
+    if (fused && it > 0) {   // the last direction update left its scalars in the shadow slots
+      h[0] = h[7];
+      if (h[8] != 0.0 || h[9] != 0.0) h[6] = 1.0;
+    }
     return 0;
   };
   // x = 0, r = b, p = b, rr = bb = b.b
   rc = cudaMemsetAsync(x->d, 0, (size_t)n * 8, c->stream) != cudaSuccess;
   rc = rc || cudaMemcpyAsync(r->d, b->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
   rc = rc || cudaMemcpyAsync(p->d, b->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
-  rc = rc || cudaMemsetAsync(S, 0, 8 * sizeof(double), c->stream) != cudaSuccess;
+  rc = rc || cudaMemsetAsync(S, 0, 16 * sizeof(double), c->stream) != cudaSuccess;
   if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, r->d, r->d, n, S, partial, 0);
   if (!rc) rc = launch_cg(c, 1, nullptr, nullptr, nullptr, nullptr, n, S, partial, 2);
   if (!rc) rc = fetch();
   const double bb = h[4], target = rtol * rtol * bb;
   double best = bb;
   if (!rc) rc = cudaMemcpyAsync(S + 5, &target, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess;
+  if (!rc) rc = cudaMemcpyAsync(S + 7, &bb, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess;   // shadow of r.r
   if (!rc) rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
   while (!rc && it < max_iter && h[0] > target && bb > 0.0 && h[6] == 0.0) {
     int m = std::min<int>(check_every, max_iter - it);
-    for (int k = 0; k < m && !rc; ++k) {
+    for (int k = 0; k < m && !rc && fused; ++k) {
+      rc = launch_pass(c, pp, ph.domain);                                                   // ap = A p
+      if (!rc) rc = launch_cg(c, 4, nullptr, nullptr, p->d, ap->d, n, S, partial, 0);       // p.Ap partial sums (+ commit)
+      if (!rc) rc = launch_cg(c, 5, x->d, r->d, p->d, ap->d, n, S, partial, 0);             // alpha; x, r; r.r partial sums
+      if (!rc) rc = launch_cg(c, 6, nullptr, r->d, p->d, nullptr, n, S, partial, 0);        // beta; p = r + beta p
+    }
+    for (int k = 0; k < m && !rc && !fused; ++k) {
       rc = launch_pass(c, pp, ph.domain);                                                   // ap = A p
       if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, p->d, ap->d, n, S, partial, 0);       // p.Ap
       if (!rc) rc = launch_cg(c, 1, nullptr, nullptr, nullptr, nullptr, n, S, partial, 0);  // alpha
@@ -998,6 +1010,15 @@ extern "C" int gds_system_destroy(gds_system* s) {
   cudaFree(s->d_flags); cudaFree(s->d_p2p_epoch); cudaFree(s->d_p2p_src); cudaFree(s->d_p2p_dst); cudaFree(s->d_p2p_done);
   if (s->h_p2p_err) cudaFreeHost(s->h_p2p_err);
   cudaFree(s->d_rec); cudaFree(s->d_traj);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(s->ens_in[i]); cudaFree(s->ens_out[i]);
+    if (s->ens_in_ready[i]) cudaEventDestroy(s->ens_in_ready[i]);
+    if (s->ens_in_free[i]) cudaEventDestroy(s->ens_in_free[i]);
+    if (s->ens_out_ready[i]) cudaEventDestroy(s->ens_out_ready[i]);
+    if (s->ens_out_free[i]) cudaEventDestroy(s->ens_out_free[i]);
+  }
+  if (s->ens_h2d) cudaStreamDestroy(s->ens_h2d);
+  if (s->ens_d2h) cudaStreamDestroy(s->ens_d2h);
   delete s;
   return 0;
 }
@@ -1578,6 +1599,90 @@ static int system_step(gds_system* s, int64_t n_steps, const double* t, const do
     }
     done += m;
   }
+  return 0;
+}
+
+// ---- ensemble stepping with host buffers (include/gds_b200.h): member m + 1 is uploaded and member m - 1 downloaded
+//      while member m steps.  Three streams: H2D into IN[b], the context's stream (IN[b] -> Y, the captured steps,
+//      Y -> OUT[b]), D2H out of OUT[b]; b = m & 1.  Events order the reuse of the two staging pairs.
+static int ensemble_setup(gds_system* s) {
+  if (s->ens_h2d) return 0;
+  for (int i = 0; i < 2; ++i) {
+    GDS_CUDA(cudaMalloc((void**)&s->ens_in[i], (size_t)s->n_state * 8));
+    GDS_CUDA(cudaMalloc((void**)&s->ens_out[i], (size_t)s->n_state * 8));
+    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_ready[i], cudaEventDisableTiming));
+    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_free[i], cudaEventDisableTiming));
+    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_ready[i], cudaEventDisableTiming));
+    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_free[i], cudaEventDisableTiming));
+  }
+  s->device_bytes += 4 * s->n_state * 8;
+  GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_d2h, cudaStreamNonBlocking));
+  GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_h2d, cudaStreamNonBlocking));
+  return 0;
+}
+
+extern "C" int gds_system_step_ensemble(gds_system* s, int64_t n_members, int32_t n_seg, const int64_t* seg_off,
+                                        const int64_t* seg_n, const double* const* host_in, double* const* host_out,
+                                        int64_t n_steps, const double* t, const double* h, const double* bc) {
+  if (!s) GDS_FAIL("null system");
+  if (!s->finalized) GDS_FAIL("system not finalized");
+  if (s->p2p || s->owned_rows >= 0) GDS_FAIL("ensemble stepping is not available on a rank of a partitioned system");
+  if (n_members < 0 || n_seg <= 0 || !seg_off || !seg_n || !host_in || !host_out) GDS_FAIL("bad argument");
+  if (n_steps <= 0 || n_steps > s->cap_steps) GDS_FAIL("ensemble stepping takes 1 .. cap_steps steps per member");
+  if (s->n_dir_dyn > 0 && !bc) GDS_FAIL("dynamic Dirichlet values missing");
+  for (int k = 0; k < n_seg; ++k)
+    if (seg_off[k] < 0 || seg_n[k] < 0 || seg_off[k] + seg_n[k] > s->n_state) GDS_FAIL("segment outside the state vector");
+  for (int64_t i = 0; i < n_members * n_seg; ++i)
+    if (!host_in[i] || !host_out[i]) GDS_FAIL("null host buffer");
+  if (n_members == 0) return 0;
+  gds_ctx* c = s->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  GDS_TRY(ensemble_setup(s));
+  // the step tables are the same for every member: uploaded once
+  std::vector<StepRec> tab((size_t)n_steps);
+  for (int64_t i = 0; i < n_steps; ++i) { tab[i].t = t[i]; tab[i].h = h[i]; }
+  GDS_CUDA(cudaMemcpyAsync(s->d_steptab, tab.data(), (size_t)n_steps * sizeof(StepRec), cudaMemcpyHostToDevice, c->stream));
+  if (s->n_dir_dyn > 0)
+    GDS_CUDA(cudaMemcpyAsync(s->d_bc_tab, bc, (size_t)n_steps * s->n_dir_dyn * 8, cudaMemcpyHostToDevice, c->stream));
+  if (s->recording) GDS_CUDA(cudaMemsetAsync(s->d_rec, 0xff, (size_t)n_steps * 8, c->stream));
+  // rows of the state outside the segments keep what the system holds now, for every member
+  const size_t state_bytes = (size_t)s->n_state * 8;
+  for (int b = 0; b < 2 && b < n_members; ++b) {
+    GDS_CUDA(cudaMemcpyAsync(s->ens_in[b], s->Y[s->cur], state_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    GDS_CUDA(cudaEventRecord(s->ens_in_free[b], c->stream));
+    GDS_CUDA(cudaEventRecord(s->ens_out_free[b], c->stream));
+  }
+  int rc = 0;
+  auto fail = [&](cudaError_t e) { if (e != cudaSuccess && !rc) { gds_set_error(std::string("CUDA: ") + cudaGetErrorString(e)); rc = 1; } };
+  for (int64_t m = 0; m < n_members && !rc; ++m) {
+    const int b = (int)(m & 1);
+    fail(cudaStreamWaitEvent(s->ens_h2d, s->ens_in_free[b], 0));
+    for (int k = 0; k < n_seg; ++k)
+      fail(cudaMemcpyAsync(s->ens_in[b] + seg_off[k], host_in[m * n_seg + k], (size_t)seg_n[k] * 8, cudaMemcpyHostToDevice, s->ens_h2d));
+    fail(cudaEventRecord(s->ens_in_ready[b], s->ens_h2d));
+    fail(cudaStreamWaitEvent(c->stream, s->ens_in_ready[b], 0));
+    fail(cudaMemcpyAsync(s->Y[s->cur], s->ens_in[b], state_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    fail(cudaEventRecord(s->ens_in_free[b], c->stream));
+    fail(cudaMemsetAsync(s->d_counter, 0, sizeof(int64_t), c->stream));
+    if (!rc) rc = shadow_refresh(s);
+    for (int64_t i = 0; i < n_steps && !rc; ++i) {
+      fail(cudaGraphLaunch(s->exec[s->cur], c->stream));
+      s->cur ^= 1;
+      c->graph_replays++;
+      c->kernel_launches += s->kernels_per_step;
+    }
+    fail(cudaStreamWaitEvent(c->stream, s->ens_out_free[b], 0));
+    fail(cudaMemcpyAsync(s->ens_out[b], s->Y[s->cur], state_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    fail(cudaEventRecord(s->ens_out_ready[b], c->stream));
+    fail(cudaStreamWaitEvent(s->ens_d2h, s->ens_out_ready[b], 0));
+    for (int k = 0; k < n_seg; ++k)
+      fail(cudaMemcpyAsync(host_out[m * n_seg + k], s->ens_out[b] + seg_off[k], (size_t)seg_n[k] * 8, cudaMemcpyDeviceToHost, s->ens_d2h));
+    fail(cudaEventRecord(s->ens_out_free[b], s->ens_d2h));
+  }
+  cudaError_t e0 = cudaStreamSynchronize(s->ens_h2d), e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(s->ens_d2h);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
+    GDS_FAIL(std::string("ensemble stepping failed: ") + cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
   return 0;
 }
 

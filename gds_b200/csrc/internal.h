@@ -346,6 +346,11 @@ struct gds_system {
   // overlap: rows [0, ov_lo_end) and [ov_hi_begin, owned_rows) hold every row that is sent to / reads from a neighbour;
   // they run first, their push follows at once, the interior rows run on a second stream meanwhile (-1: no overlap)
   int64_t ov_lo_end = -1, ov_hi_begin = -1;
+  // ensemble stepping with host buffers (gds_system_step_ensemble): double-buffered staging, one stream per PCIe direction
+  double* ens_in[2] = {nullptr, nullptr};
+  double* ens_out[2] = {nullptr, nullptr};
+  cudaStream_t ens_h2d = nullptr, ens_d2h = nullptr;
+  cudaEvent_t ens_in_ready[2] = {}, ens_in_free[2] = {}, ens_out_ready[2] = {}, ens_out_free[2] = {};
 };
 
 #define GDS_MAX_PEERS 8

@@ -1651,13 +1651,89 @@ __global__ void __launch_bounds__(CG_THREADS) cg_direction_kernel(double* __rest
     p[i] = r[i] + beta * p[i];
 }
 
+// total of the per-block partial sums, computed by EVERY block for itself in the fixed order cg_final_kernel uses (thread t
+// adds partial[t], partial[t + 256], ...; then the block tree): the same bits in every block, no extra launch
+__device__ __forceinline__ double cg_total(const double* __restrict__ partial) {
+  __shared__ double sh[CG_THREADS];
+  __shared__ double total;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < CG_BLOCKS; i += CG_THREADS) acc += partial[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = CG_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total = sh[0];
+  __syncthreads();
+  const double v = total;
+  __syncthreads();     // `sh` is reused by the reduction that follows in the same kernel
+  return v;
+}
+
+// Fused iteration (4 launches: A p, p.Ap partials, this, the direction update).  Scalars written by one block while the
+// others still read them go to shadow slots and are committed by a LATER kernel: S[7] = new r.r (committed to S[0]),
+// S[8] / S[9] = "finished" raised by the update / by the direction kernel (committed to S[6]).
+// p.Ap partial sums; block 0 first commits the scalars the previous direction update left in the shadow slots
+__global__ void __launch_bounds__(CG_THREADS) cg_dot_commit_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                                   int64_t n, double* __restrict__ partial, double* S) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    S[0] = S[7];
+    if (S[8] != 0.0 || S[9] != 0.0) S[6] = 1.0;
+  }
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS)
+    acc += a[i] * b[i];
+  block_reduce_store(acc, partial + blockIdx.x);
+}
+
+// alpha = r.r / p.Ap from the partial sums;  x += alpha p;  r -= alpha Ap;  partial sums of the new r.r into partial2
+__global__ void __launch_bounds__(CG_THREADS) cg_update_fused_kernel(double* __restrict__ x, double* __restrict__ r,
+                                                                     const double* __restrict__ p, const double* __restrict__ ap,
+                                                                     int64_t n, double* S, const double* __restrict__ partial,
+                                                                     double* __restrict__ partial2) {
+  const double v = cg_total(partial);                       // p.Ap
+  const bool live = S[6] == 0.0 && v > 0.0 && isfinite(v);  // S[6], S[0] are not written in this kernel
+  const double alpha = live ? S[0] / v : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    S[1] = v; S[2] = alpha;
+    if (!live) S[8] = 1.0;
+  }
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    acc += ri * ri;
+  }
+  block_reduce_store(acc, partial2 + blockIdx.x);
+}
+
+// beta = r.r_new / r.r_old from the partial sums;  p = r + beta p
+__global__ void __launch_bounds__(CG_THREADS) cg_direction_fused_kernel(double* __restrict__ p, const double* __restrict__ r,
+                                                                        int64_t n, double* S, const double* __restrict__ partial2) {
+  const double v = cg_total(partial2);                      // new r.r
+  const bool stopped = S[6] != 0.0 || S[8] != 0.0;          // S[8] was last written by the kernel before this one
+  const double beta = (!stopped && S[0] != 0.0) ? v / S[0] : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    S[3] = beta; S[7] = v;
+    if (!(v > S[5])) S[9] = 1.0;                            // read by nobody in this kernel
+  }
+  for (int64_t i = (int64_t)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (int64_t)CG_BLOCKS * CG_THREADS)
+    p[i] = r[i] + beta * p[i];
+}
+
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode) {
   switch (what) {
     case 0: cg_dot_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, ap, n, partial); break;      // any two vectors
     case 1: cg_final_kernel<<<1, CG_THREADS, 0, ctx->stream>>>(partial, S, mode); break;
     case 2: cg_update_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(x, r, p, ap, n, S, partial); break;
-    default: cg_direction_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, r, n, S); break;
+    case 3: cg_direction_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, r, n, S); break;
+    // fused iteration: `partial` holds 2 x 2048 slots (p.Ap sums, then r.r sums)
+    case 4: cg_dot_commit_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, ap, n, partial, S); break;
+    case 5: cg_update_fused_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(x, r, p, ap, n, S, partial, partial + 2048); break;
+    default: cg_direction_fused_kernel<<<CG_BLOCKS, CG_THREADS, 0, ctx->stream>>>(p, r, n, S, partial + 2048); break;
   }
   GDS_CUDA(cudaGetLastError());
   ctx->kernel_launches++;

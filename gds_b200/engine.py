@@ -357,6 +357,50 @@ class StepEngine:
         for f in self.fields:
             f._dt = float(hs[-1])
 
+    def step_ensemble(self, members_in, members_out, dt):
+        """advance every member of an ensemble of HOST-resident states from t to t + dt: the loop
+        `set_initial(y0=member); step(dt); read y` of the reference (fds.py:137-162,264-290) as one call.  members_in /
+        members_out: per member, one float64 array per field of the system (its state blocks, public row order; pinned
+        memory lets the uploads, the steps and the read-backs of consecutive members overlap).  Bit-identical to
+        write / run / read_into member by member.  Afterwards the engine holds the last member's state at t + dt."""
+        import ctypes
+        if self.part is not None:
+            raise NotImplementedError('ensemble stepping on a partitioned engine (ghost rows need an exchange per upload)')
+        if self.scheme == 'map' or any(not f._identity_projection() for f in self.fields):
+            raise NotImplementedError('ensemble stepping covers continuous laws without a user projection')
+        if len(members_in) != len(members_out):
+            raise ValueError('one output per input member')
+        nf = len(self.fields)
+        for f in self.fields:
+            if f._domain_code == L.NODES and f._low.i2p is not None:
+                raise NotImplementedError('ensemble stepping of an internally renumbered field')
+        for grp in list(members_in) + list(members_out):
+            if len(grp) != nf:
+                raise ValueError('one array per field of the system')
+            for f, a in zip(self.fields, grp):
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+                        and a.size == f.ndim * f._order()):
+                    raise ValueError('ensemble buffers are contiguous float64 arrays of ndim * order values per field')
+        ts, hs, t_after, t_new, bc = self.plan(dt)
+        M = len(members_in)
+        if ts.size == 0 or M == 0:
+            return
+        self._refresh_externals()
+        self._bind_stream()
+        off = np.array([self.offsets[id(f)] for f in self.fields], dtype=np.int64)
+        cnt = np.array([f.ndim * f._order() for f in self.fields], dtype=np.int64)
+        PA = ctypes.c_void_p * (M * nf)
+        pin = PA(*[a.ctypes.data for grp in members_in for a in grp])
+        pout = PA(*[a.ctypes.data for grp in members_out for a in grp])
+        check(lib.gds_system_step_ensemble(self.h, M, nf, ptr(off), ptr(cnt), pin, pout, ts.size, ptr(ts), ptr(hs),
+                                           ptr(bc) if bc is not None else None))
+        self.steps_taken += int(ts.size) * M
+        self.version += 1
+        self._read_cache.clear()
+        self.t = t_new
+        for f in self.fields:
+            f._dt = float(hs[-1])
+
     # ---- one rank of a partitioned system (SURVEY.md 8e) ------------------------------------------------------
     def _halo_blocks(self):
         """(offset, domain) of every state block that has ghost rows"""

@@ -294,6 +294,19 @@ class fds(Observable, Steppable):
             self._t += dt
         self._version += 1
 
+    def step_ensemble(self, dt: float, states_in, states_out):
+        """Extension (no reference counterpart; it replaces the user's loop `set_initial(y0=m); step(dt); m_new = y` over
+        the members of an ensemble, fds.py:137-162,264-290): advance every HOST-resident state in `states_in` (one
+        float64 array of ndim * order values per member, pinned memory for full overlap) from t to t + dt and leave the
+        results in `states_out`.  Uploads, device steps and read-backs of consecutive members overlap; results are
+        bit-identical to the loop.  The field itself ends up holding the last member's state at t + dt."""
+        if self._coupled is not None:
+            raise Exception('this field is advanced by its coupled system; step that instead')
+        if self.iter_mode is not IterationMode.dydt:
+            raise NotImplementedError('ensemble stepping covers continuous (dydt=) laws')
+        self._ensure_engine().step_ensemble([[a] for a in states_in], [[a] for a in states_out], dt)
+        self._version += 1
+
     def reset(self):
         """back to the initial conditions (fds.py:248-262)"""
         self._drop_engine(pull=False)
@@ -1099,6 +1112,19 @@ class coupled_fds(Steppable):
         for s in self._members:
             s._version += 1
 
+    def step_ensemble(self, dt: float, states_in, states_out):
+        """fds.step_ensemble for a coupled system of continuous fields: every member is a list with one array per
+        continuous field, in the order of couple()'s arguments"""
+        if not self.has_integrator or self.maps or self.cvxs:
+            raise NotImplementedError('ensemble stepping covers coupled continuous (dydt=) laws')
+        eng = self._ensure_engine()
+        eng.step_ensemble([list(m) for m in states_in], [list(m) for m in states_out], dt)
+        self._t = eng.t
+        for s in self.nils:
+            s._t += dt
+        for s in self._members:
+            s._version += 1
+
     def reset(self):
         """fds.py:509-527: the shared integrator is rebuilt at t0 on the state taken at couple() time; the discrete systems
         are reset one by one.  (`discrete_t` is left alone there as well.)"""
@@ -1142,6 +1168,11 @@ class System:
 
     def step(self, dt: float):
         self._stepper.step(dt)
+
+    def step_ensemble(self, dt: float, states_in, states_out):
+        """fds.step_ensemble / coupled_fds.step_ensemble of the system's stepper (extension: an ensemble of HOST-resident
+        states advanced by dt with uploads, device steps and read-backs overlapped)"""
+        self._stepper.step_ensemble(dt, states_in, states_out)
 
     def reset(self):
         self._stepper.reset()

@@ -246,6 +246,19 @@ int gds_system_set_trajectory(gds_system* s, gds_buf* traj);
 int gds_system_step_record(gds_system* s, int64_t n_steps, const double* t, const double* h, const double* bc_values,
                            const int64_t* rec_slot);
 
+/* ---- ensemble stepping with HOST buffers: the caller's loop `for every member: set_initial(y0=member); step(dt);
+ *      read y` (gds/fds.py:137-162,264-290 once per member) as ONE call.  Every member is a whole state held in host
+ *      memory, given as n_seg segments (offset, length) of the state vector; member m is uploaded, advanced by the SAME
+ *      n_steps table rows (t, h, bc_values as in gds_system_step) and its new state downloaded to host_out.  Uploads,
+ *      steps and downloads of consecutive members run on three streams with double-buffered device staging, so the two
+ *      PCIe directions and the kernels overlap (pinned host memory needed for that; pageable memory works, serially).
+ *      host_in / host_out: [n_members x n_seg] pointers.  Synchronises.  Afterwards the system holds the last member's
+ *      new state.  Results are bit-identical to set_state / step / get_state member by member.  Not for a rank of a
+ *      partitioned system (ghost rows would need an exchange per upload). ---- */
+int gds_system_step_ensemble(gds_system* s, int64_t n_members, int32_t n_seg, const int64_t* seg_offset,
+                             const int64_t* seg_n, const double* const* host_in, double* const* host_out,
+                             int64_t n_steps, const double* t, const double* h, const double* bc_values);
+
 /* ---- stage-granular stepping, for one rank of a system partitioned over several GPUs: the host runs the halo
  *      exchange between the stages, so the step is enqueued stage by stage instead of replayed as one graph.
  *      begin_steps uploads the per-step tables; then per step: run_stage(0..n_stages-1) [exchange the vector returned by

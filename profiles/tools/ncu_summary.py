@@ -59,8 +59,8 @@ def main():
         tails = [i for i, nm in enumerate(names) if nm.startswith('tail_kernel')]
         if len(tails) >= 2:
             body = body[tails[-2] + 1:tails[-1] + 1]
-        elif len(tails) == 1 and tails[0] == len(body) - 1:
-            pass
+        elif len(tails) == 1:     # the capture starts on a step boundary: the kernels up to and including the tail
+            body = body[:tails[0] + 1]
         out_rows, total, total_us = [], 0.0, 0.0
         for r in body:
             rec = {}
@@ -81,7 +81,7 @@ def main():
             w.writerows(out_rows)
         print(f'{name}: {len(out_rows)} kernels, DRAM bytes per step {total:.4g}, sum of kernel times {total_us:.1f} us '
               f'(cold, serialised) -> {os.path.relpath(dst, ROOT)}')
-        key = size if not name.endswith(('weighted', 'norenumber')) else f'{size}_{name}'
+        key = size if not name.endswith(('weighted', 'norenumber', 'noshadow')) else f'{size}_{name}'
         traffic.setdefault(workload, {}).setdefault('per_step', {})[key] = total
         # the dominant kernel (largest share of the step's time): mean DRAM bytes per launch, what roofline.traffic reports
         by_name = {}

@@ -291,3 +291,97 @@ def test_solver_object_facade_steps_like_step():
     y[3] += 1.0
     it.y = y                                              # assignment reaches the device state
     assert b.y[3] == pytest.approx(y[3])
+
+
+def _ensemble_problem(kind):
+    """(stepper, fields in engine order, dt) of a fresh small problem"""
+    import gds_b200
+    api = product_api()
+    if kind == 'heat':                      # time-varying Dirichlet values, 3 internal steps per call
+        T = heat(api, n=40)
+        return T, [T], 0.006
+    if kind == 'wave':                      # order 2, collapsed RK4
+        a = api.node_gds(cases.g_grid3((9, 10, 11)))
+        api.evolve(a, dydt=lambda t, y: a.laplacian(), order=2, max_step=0.1)
+        a.set_initial(y0=lambda x: math.exp(-sum((xi - 4.0) ** 2 for xi in x) / 4.0))
+        return a, [a], 0.1
+    G = cases.g_hex(7, 9)                   # two coupled fields on different domains
+    u, c = api.edge_gds(G), api.node_gds(G)
+    api.evolve(u, dydt=lambda t, y: 0.1 * u.laplacian(y), max_step=1e-3)
+    api.evolve(c, dydt=lambda t, y: -c.advect(u) + 0.05 * c.laplacian(y), max_step=1e-3)
+    u.set_initial(y0=lambda e: 0.)
+    c.set_initial(y0=lambda x: 0.)
+    u.set_constraints(dirichlet=api.zero_edge_bc(cases.boundary_edges_hex_top_bottom(G)))
+    sysobj = gds_b200.couple({'u': u, 'c': c})
+    return sysobj, [u, c], 2e-3
+
+
+@pytest.mark.parametrize('kind', ['heat', 'wave', 'hex_coupled'])
+def test_ensemble_stepping_equals_the_member_loop_bit_for_bit(kind):
+    """step_ensemble (uploads, steps and read-backs of consecutive members overlapped on three streams) against
+    write / step / read of one member at a time on a fresh system, two consecutive calls"""
+    import torch
+    rng = np.random.default_rng(11)
+    M = 5
+    st, fields, dt = _ensemble_problem(kind)
+    sizes = [f.ndim * f._order() for f in fields]
+    members = [[rng.standard_normal(n) for n in sizes] for _ in range(M)]
+
+    def pinned(a):
+        t = torch.empty(a.size, dtype=torch.float64).pin_memory().numpy()
+        t[:] = a
+        return t
+    ins = [[pinned(a) for a in m] for m in members]
+    mid = [[pinned(np.zeros_like(a)) for a in m] for m in members]
+    outs = [[pinned(np.zeros_like(a)) for a in m] for m in members]
+    single = len(fields) == 1 and not hasattr(st, 'stepper')
+    if single:
+        st.step_ensemble(dt, [m[0] for m in ins], [m[0] for m in mid])
+        st.step_ensemble(dt, [m[0] for m in mid], [m[0] for m in outs])
+    else:
+        st.step_ensemble(dt, ins, mid)
+        st.step_ensemble(dt, mid, outs)
+    assert fields[0].t == pytest.approx(2 * dt)
+    for k in range(M):
+        ref, rf, _ = _ensemble_problem(kind)
+        eng = (ref.stepper if hasattr(ref, 'stepper') else ref)._ensure_engine()
+        for f, a in zip(rf, members[k]):
+            eng.write(f, a)
+        ref.step(dt)
+        for f, got in zip(rf, mid[k]):
+            assert np.array_equal(eng.read(f, full=True), got), (kind, k, 'first call')
+        ref.step(dt)
+        for f, got in zip(rf, outs[k]):
+            assert np.array_equal(eng.read(f, full=True), got), (kind, k, 'second call')
+    # the system is left holding the last member's state
+    eng = (st.stepper if hasattr(st, 'stepper') else st)._ensure_engine()
+    for f, got in zip(fields, outs[-1]):
+        assert np.array_equal(eng.read(f, full=True), got)
+
+
+def test_ensemble_stepping_rejects_what_it_cannot_overlap():
+    T = heat(product_api())
+    with pytest.raises(ValueError):
+        T.step_ensemble(0.002, [np.zeros(T.ndim)], [np.zeros(T.ndim + 1)])
+    with pytest.raises(ValueError):
+        T.step_ensemble(0.002, [np.zeros(T.ndim, dtype=np.float32)], [np.zeros(T.ndim)])
+    # pageable buffers work (the copies serialise)
+    a, b = np.linspace(0, 1, T.ndim), np.zeros(T.ndim)
+    T.step_ensemble(0.002, [a], [b])
+    assert np.array_equal(np.asarray(T.y), b)
+
+
+def test_fused_cg_iteration_equals_the_six_launch_form_bit_for_bit(monkeypatch):
+    """gds_cg_solve runs an iteration in 4 launches (every block totals the partial sums itself, scalars committed through
+    shadow slots); GDS_B200_CG_UNFUSED=1 keeps the 6-launch form: same iterates, same iteration count, same bits"""
+    import gds_b200
+    for make in (lambda: cases.add_weights(cases.g_tri(9, 12), 4), lambda: cases.g_hex(7, 9)):
+        u = gds_b200.edge_gds(make())
+        y = np.random.default_rng(8).standard_normal(u.ndim)
+        monkeypatch.delenv('GDS_B200_CG_UNFUSED', raising=False)
+        z1, i1 = u.leray_project(y, return_info=True)
+        i1 = dict(i1)
+        monkeypatch.setenv('GDS_B200_CG_UNFUSED', '1')
+        z2, i2 = u.leray_project(y, return_info=True)
+        assert np.array_equal(z1, z2)
+        assert i1 == dict(i2) and i1['iterations'] > 0
