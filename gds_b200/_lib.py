@@ -97,6 +97,14 @@ _sig('gds_pass_run', c_vp, c_vp, P(PassDesc), c_f64)
 _sig('gds_passes_run_cols', c_vp, c_vp, c_i32, P(PassDesc), c_f64, c_i64, c_i32, P(c_vp), P(c_i64))
 _sig('gds_pass_kernel_kind', P(PassDesc), P(c_i32))
 _sig('gds_cg_solve', c_vp, c_vp, P(PassDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_i32, c_i32, P(c_i32), P(c_f64))
+_sig('gds_mg_aggregate', c_i64, c_vp, c_vp, c_vp, c_f64, c_vp, P(c_i64))
+_sig('gds_mg_create', c_vp, P(c_vp))
+_sig('gds_mg_destroy', c_vp)
+_sig('gds_mg_add_level', c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp)
+_sig('gds_mg_set_sweeps', c_vp, c_i32, c_i32)
+_sig('gds_mg_info', c_vp, P(c_i32), P(c_i64), P(c_i64))
+_sig('gds_mg_apply', c_vp, c_vp, c_vp)
+_sig('gds_pcg_solve', c_vp, c_vp, P(PassDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f64, c_i32, c_i32, P(c_i32), P(c_f64))
 _sig('gds_system_create', c_vp, c_vp, c_i64, c_i32, P(c_vp))
 _sig('gds_system_destroy', c_vp)
 _sig('gds_system_add_pass', c_vp, P(PassDesc))
@@ -142,7 +150,7 @@ EXPORTED = [
     'gds_ctx_timer_start', 'gds_ctx_timer_stop', 'gds_ctx_counters', 'gds_ctx_flush_l2', 'gds_ctx_bandwidth_probe', 'gds_buf_create',
     'gds_buf_view', 'gds_buf_destroy', 'gds_buf_upload', 'gds_buf_download', 'gds_buf_fill', 'gds_buf_devptr', 'gds_buf_reduce', 'gds_mask_create',
     'gds_mask_destroy', 'gds_graph_create', 'gds_graph_destroy', 'gds_graph_sizes', 'gds_graph_export_csr',
-    'gds_graph_device_bytes', 'gds_pass_run', 'gds_passes_run_cols', 'gds_pass_kernel_kind', 'gds_cg_solve', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
+    'gds_graph_device_bytes', 'gds_pass_run', 'gds_passes_run_cols', 'gds_pass_kernel_kind', 'gds_cg_solve', 'gds_mg_aggregate', 'gds_mg_create', 'gds_mg_destroy', 'gds_mg_add_level', 'gds_mg_set_sweeps', 'gds_mg_info', 'gds_mg_apply', 'gds_pcg_solve', 'gds_system_create', 'gds_system_destroy', 'gds_system_add_pass',
     'gds_system_add_shift', 'gds_system_add_hold', 'gds_system_set_dirichlet', 'gds_system_set_collapsed', 'gds_system_set_shadow', 'gds_system_finalize',
     'gds_system_set_state', 'gds_system_get_state', 'gds_system_state_devptr', 'gds_system_step', 'gds_system_step_ensemble', 'gds_system_step_timed', 'gds_system_info', 'gds_system_modes',
     'gds_system_begin_steps', 'gds_system_run_stage', 'gds_system_stage_output', 'gds_system_end_step',

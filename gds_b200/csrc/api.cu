@@ -945,6 +945,253 @@ extern "C" int gds_cg_solve(gds_ctx* c, gds_graph* g, const gds_pass_desc* apply
 }
 
 // ---------------------------------------------------------------------------------------------------
+// multigrid preconditioner (include/gds_b200.h: gds_mg_*, gds_pcg_solve)
+// ---------------------------------------------------------------------------------------------------
+struct MgCsr {
+  int64_t rows = 0, nnz = 0;
+  int32_t* rowptr = nullptr;
+  int32_t* col = nullptr;
+  double* val = nullptr;
+  int tpr = 1;          // threads that share a row
+};
+struct MgLevel {
+  int64_t n = 0, n_coarse = 0;
+  MgCsr A, P, R;        // coarsest level: A holds the dense pseudo-inverse, P and R are empty
+  double* w = nullptr;  // omega / diag(A)
+  double* xa = nullptr; // iterate (ping)
+  double* xb = nullptr; // iterate (pong); the level's result when it is not written straight into the caller's buffer
+  double* b = nullptr;  // right-hand side (levels > 0: the restricted residual)
+  double* r = nullptr;  // residual
+};
+struct gds_mg {
+  gds_ctx* ctx = nullptr;
+  std::vector<MgLevel> lev;
+  int pre = 1, post = 1;
+  int64_t device_bytes = 0;
+  bool closed = false;  // the coarsest level has been added
+};
+
+static void mg_free_csr(MgCsr& m) { cudaFree(m.rowptr); cudaFree(m.col); cudaFree(m.val); m = MgCsr(); }
+
+static int mg_upload_csr(gds_mg* mg, int64_t rows, int64_t cols, const int64_t* rowptr, const int32_t* col, const double* val,
+                         MgCsr& out) {
+  if (!rowptr || rowptr[0] != 0) GDS_FAIL("CSR row pointers start at 0");
+  const int64_t nnz = rowptr[rows];
+  if (nnz < 0 || nnz >= (int64_t(1) << 31) - 64) GDS_FAIL("CSR matrix too large for 32-bit positions");
+  if (nnz > 0 && (!col || !val)) GDS_FAIL("CSR columns / values missing");
+  std::vector<int32_t> rp((size_t)rows + 1);
+  for (int64_t i = 0; i <= rows; ++i) {
+    if (i > 0 && rowptr[i] < rowptr[i - 1]) GDS_FAIL("CSR row pointers must not decrease");
+    rp[(size_t)i] = (int32_t)rowptr[i];
+  }
+  for (int64_t k = 0; k < nnz; ++k)
+    if (col[k] < 0 || col[k] >= cols) GDS_FAIL("CSR column index out of range");
+  out.rows = rows; out.nnz = nnz;
+  const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
+  int tpr = 1;
+  while (tpr < 32 && (double)tpr * 2.0 < avg) tpr *= 2;     // about half the mean row length, a power of two
+  out.tpr = tpr;
+  GDS_CUDA(cudaMalloc((void**)&out.rowptr, (size_t)(rows + 1) * sizeof(int32_t)));
+  GDS_CUDA(cudaMalloc((void**)&out.col, (size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+  GDS_CUDA(cudaMalloc((void**)&out.val, (size_t)std::max<int64_t>(nnz, 1) * sizeof(double)));
+  GDS_CUDA(cudaMemcpy(out.rowptr, rp.data(), (size_t)(rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (nnz > 0) {
+    GDS_CUDA(cudaMemcpy(out.col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    GDS_CUDA(cudaMemcpy(out.val, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  mg->device_bytes += (rows + 1) * 4 + nnz * 12;
+  return 0;
+}
+
+extern "C" int gds_mg_create(gds_ctx* c, gds_mg** out) {
+  if (!c || !out) GDS_FAIL("bad argument");
+  GDS_NEED_DEVICE(c);
+  gds_mg* mg = new gds_mg();
+  mg->ctx = c;
+  *out = mg;
+  return 0;
+}
+
+extern "C" int gds_mg_destroy(gds_mg* mg) {
+  if (!mg) return 0;
+  cudaSetDevice(mg->ctx->device);
+  cudaStreamSynchronize(mg->ctx->stream);
+  for (auto& l : mg->lev) {
+    mg_free_csr(l.A); mg_free_csr(l.P); mg_free_csr(l.R);
+    cudaFree(l.w); cudaFree(l.xa); cudaFree(l.xb); cudaFree(l.b); cudaFree(l.r);
+  }
+  delete mg;
+  return 0;
+}
+
+extern "C" int gds_mg_add_level(gds_mg* mg, int64_t n, const int64_t* a_rowptr, const int32_t* a_col, const double* a_val,
+                                const double* jacobi_w, int64_t n_coarse, const int64_t* p_rowptr, const int32_t* p_col,
+                                const double* p_val, const int64_t* r_rowptr, const int32_t* r_col, const double* r_val) {
+  if (!mg || n <= 0 || n_coarse < 0) GDS_FAIL("bad argument");
+  if (mg->closed) GDS_FAIL("the coarsest level has already been added");
+  if (!mg->lev.empty() && mg->lev.back().n_coarse != n) GDS_FAIL("level size differs from the previous level's coarse size");
+  if (n_coarse > 0 && (!jacobi_w || !p_rowptr || !r_rowptr)) GDS_FAIL("a level with a coarser one needs weights, P and R");
+  gds_ctx* c = mg->ctx;
+  GDS_CUDA(cudaSetDevice(c->device));
+  mg->lev.emplace_back();
+  MgLevel& l = mg->lev.back();
+  l.n = n; l.n_coarse = n_coarse;
+  GDS_TRY(mg_upload_csr(mg, n, n, a_rowptr, a_col, a_val, l.A));
+  const size_t vb = (size_t)(n + 4) * sizeof(double);
+  if (n_coarse > 0) {
+    GDS_TRY(mg_upload_csr(mg, n, n_coarse, p_rowptr, p_col, p_val, l.P));
+    GDS_TRY(mg_upload_csr(mg, n_coarse, n, r_rowptr, r_col, r_val, l.R));
+    GDS_CUDA(cudaMalloc((void**)&l.w, vb));
+    GDS_CUDA(cudaMemcpy(l.w, jacobi_w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    GDS_CUDA(cudaMalloc((void**)&l.xa, vb));
+    GDS_CUDA(cudaMalloc((void**)&l.r, vb));
+    mg->device_bytes += 3 * (int64_t)vb;
+  } else {
+    mg->closed = true;
+  }
+  GDS_CUDA(cudaMalloc((void**)&l.xb, vb));
+  mg->device_bytes += (int64_t)vb;
+  if (mg->lev.size() > 1) {       // level 0 takes its right-hand side from the caller
+    GDS_CUDA(cudaMalloc((void**)&l.b, vb));
+    mg->device_bytes += (int64_t)vb;
+  }
+  return 0;
+}
+
+extern "C" int gds_mg_set_sweeps(gds_mg* mg, int32_t pre, int32_t post) {
+  if (!mg || pre < 1 || post < 1 || pre > 8 || post > 8) GDS_FAIL("1 .. 8 sweeps before and after the coarse correction");
+  mg->pre = pre; mg->post = post;
+  return 0;
+}
+
+extern "C" int gds_mg_info(gds_mg* mg, int32_t* n_levels, int64_t* device_bytes, int64_t* launches_per_cycle) {
+  if (!mg) GDS_FAIL("null hierarchy");
+  if (n_levels) *n_levels = (int32_t)mg->lev.size();
+  if (device_bytes) *device_bytes = mg->device_bytes;
+  if (launches_per_cycle) *launches_per_cycle = mg->lev.empty() ? 0 : (int64_t)(mg->lev.size() - 1) * (mg->pre + mg->post + 3) + 1;
+  return 0;
+}
+
+static int mg_spmv(gds_ctx* c, const MgCsr& m, const double* x, const double* u, const double* v, const double* w,
+                   double* out, int mode) {
+  return launch_mg_spmv(c, m.tpr, m.rows, m.rowptr, m.col, m.val, x, u, v, w, out, mode);
+}
+
+// one V-cycle from a zero guess on level `li`: out = M_l^-1 b.  Sweeps alternate between the level's two iterate buffers;
+// the LAST post-sweep writes `out`, so nothing is copied.
+static int mg_cycle(gds_mg* mg, size_t li, const double* b, double* out) {
+  gds_ctx* c = mg->ctx;
+  MgLevel& l = mg->lev[li];
+  if (l.n_coarse == 0) return mg_spmv(c, l.A, b, nullptr, nullptr, nullptr, out, 0);     // dense pseudo-inverse
+  // `out` may be this level's xb (the parent reads the result there): start on the buffer that leaves the iterate in xa
+  // before the last sweep, whatever the number of sweeps
+  const int flips = (mg->pre - 1) + (mg->post - 1);
+  double* cur = (flips % 2 == 0) ? l.xa : l.xb;
+  double* other = (cur == l.xa) ? l.xb : l.xa;
+  GDS_TRY(launch_mg_scale(c, l.n, l.w, b, cur));                                          // sweep 1 from x = 0
+  for (int k = 1; k < mg->pre; ++k) {
+    GDS_TRY(mg_spmv(c, l.A, cur, b, cur, l.w, other, 3));
+    std::swap(cur, other);
+  }
+  GDS_TRY(mg_spmv(c, l.A, cur, b, nullptr, nullptr, l.r, 1));                             // r = b - A x
+  MgLevel& n = mg->lev[li + 1];
+  GDS_TRY(mg_spmv(c, l.R, l.r, nullptr, nullptr, nullptr, n.b, 0));                       // b_c = R r
+  GDS_TRY(mg_cycle(mg, li + 1, n.b, n.xb));
+  GDS_TRY(mg_spmv(c, l.P, n.xb, cur, nullptr, nullptr, cur, 2));                          // x += P x_c
+  for (int k = 0; k < mg->post; ++k) {
+    double* dst = (k == mg->post - 1) ? out : other;
+    GDS_TRY(mg_spmv(c, l.A, cur, b, cur, l.w, dst, 3));
+    other = cur;
+    cur = dst;
+  }
+  return 0;
+}
+
+static int mg_check(gds_mg* mg, int64_t n) {
+  if (!mg || mg->lev.empty() || !mg->closed) GDS_FAIL("the hierarchy is not complete (add levels down to the coarsest one)");
+  if (mg->lev[0].n != n) GDS_FAIL("vector length differs from the finest level");
+  return 0;
+}
+
+extern "C" int gds_mg_apply(gds_mg* mg, gds_buf* r, gds_buf* z) {
+  if (!mg || !r || !z) GDS_FAIL("bad argument");
+  GDS_TRY(mg_check(mg, mg->lev.empty() ? -1 : mg->lev[0].n));
+  if (r->n < mg->lev[0].n || z->n < mg->lev[0].n || r->d == z->d) GDS_FAIL("need two distinct vectors of the finest level's size");
+  GDS_CUDA(cudaSetDevice(mg->ctx->device));
+  return mg_cycle(mg, 0, r->d, z->d);
+}
+
+extern "C" int gds_pcg_solve(gds_ctx* c, gds_graph* g, const gds_pass_desc* apply, gds_mg* mg, gds_buf* x, gds_buf* b,
+                             gds_buf* r, gds_buf* p, gds_buf* ap, gds_buf* z, int64_t n, double rtol, int32_t max_iter,
+                             int32_t check_every, int32_t* iters_out, double* relres_out) {
+  if (!c || !g || !apply || !mg || !x || !b || !r || !p || !ap || !z) GDS_FAIL("bad argument");
+  if (n < 0 || x->n < n || b->n < n || r->n < n || p->n < n || ap->n < n || z->n < n) GDS_FAIL("vector shorter than n");
+  if (max_iter < 0 || check_every < 1 || !(rtol >= 0.0)) GDS_FAIL("bad iteration parameters");
+  if (mg->ctx != c) GDS_FAIL("the hierarchy belongs to another context");
+  GDS_TRY(mg_check(mg, n));
+  PassHost ph;
+  GDS_TRY(copy_pass(apply, ph));
+  if (ph.epilogue != GDS_EPI_NONE) GDS_FAIL("the operator pass takes GDS_EPI_NONE");
+  GDS_NEED_DEVICE(c);
+  GDS_CUDA(cudaSetDevice(c->device));
+  if (!getenv("GDS_B200_NO_FASTPATH")) match_forms(ph);
+  PassParams pp;
+  GDS_TRY(resolve_pass(g, ph, nullptr, nullptr, pp));
+  double* S = nullptr;
+  double* partial = nullptr;
+  GDS_CUDA(cudaMalloc((void**)&S, 16 * sizeof(double)));
+  if (cudaMalloc((void**)&partial, 2048 * sizeof(double)) != cudaSuccess) { cudaFree(S); GDS_FAIL("out of device memory"); }
+  int rc = 0, it = 0;
+  double h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto fetch = [&]() -> int {
+    GDS_CUDA(cudaMemcpyAsync(h, S, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GDS_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  // x = 0, r = b, z = M^-1 r, p = z, |r|^2 = |b|^2, r.z
+  rc = cudaMemsetAsync(x->d, 0, (size_t)n * 8, c->stream) != cudaSuccess;
+  rc = rc || cudaMemcpyAsync(r->d, b->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
+  rc = rc || cudaMemsetAsync(S, 0, 16 * sizeof(double), c->stream) != cudaSuccess;
+  if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, r->d, r->d, n, S, partial, 0);
+  if (!rc) rc = launch_pcg_final(c, partial, S, 3);
+  if (!rc) rc = mg_cycle(mg, 0, r->d, z->d);
+  if (!rc) rc = cudaMemcpyAsync(p->d, z->d, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess;
+  if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, r->d, z->d, n, S, partial, 0);
+  if (!rc) rc = launch_pcg_final(c, partial, S, 4);
+  if (!rc) rc = fetch();
+  const double bb = h[4], target = rtol * rtol * bb;
+  double best = bb;
+  if (!rc) rc = cudaMemcpyAsync(S + 5, &target, sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess;
+  if (!rc) rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
+  while (!rc && it < max_iter && h[7] > target && bb > 0.0 && h[6] == 0.0) {
+    int m = std::min<int>(check_every, max_iter - it);
+    for (int k = 0; k < m && !rc; ++k) {
+      rc = launch_pass(c, pp, ph.domain);                                                     // ap = A p
+      if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, p->d, ap->d, n, S, partial, 0);         // p.Ap
+      if (!rc) rc = launch_pcg_final(c, partial, S, 0);                                       // alpha = r.z / p.Ap
+      if (!rc) rc = launch_cg(c, 2, x->d, r->d, p->d, ap->d, n, S, partial, 0);               // x, r, partial |r|^2
+      if (!rc) rc = launch_pcg_final(c, partial, S, 1);                                       // |r|^2, finished?
+      if (!rc) rc = mg_cycle(mg, 0, r->d, z->d);                                              // z = M^-1 r
+      if (!rc) rc = launch_cg(c, 0, nullptr, nullptr, r->d, z->d, n, S, partial, 0);          // r.z
+      if (!rc) rc = launch_pcg_final(c, partial, S, 2);                                       // beta
+      if (!rc) rc = launch_cg(c, 3, nullptr, z->d, p->d, nullptr, n, S, partial, 0);          // p = z + beta p
+    }
+    it += m;
+    if (!rc) rc = fetch();
+    if (!rc) {
+      if (!(h[7] == h[7]) || h[7] > 1e4 * best) break;
+      best = std::min(best, h[7]);
+    }
+  }
+  cudaFree(S);
+  cudaFree(partial);
+  if (rc) { if (rc == 1) GDS_FAIL("CUDA failure inside the preconditioned CG loop"); return rc; }
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = (bb > 0.0) ? std::sqrt(h[7] / bb) : 0.0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // systems
 // ---------------------------------------------------------------------------------------------------
 #define GDS_FLAGS_BYTES (2u << 20)

@@ -396,5 +396,9 @@ int launch_fill(gds_ctx* ctx, double* p, int64_t n, double v);
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode);
 int launch_reduce(gds_ctx* ctx, const double* x, int64_t n, int kind, double* scratch);
+int launch_mg_spmv(gds_ctx* ctx, int tpr, int64_t n, const int32_t* rowptr, const int32_t* col, const double* val,
+                   const double* x, const double* u, const double* v, const double* w, double* out, int mode);
+int launch_mg_scale(gds_ctx* ctx, int64_t n, const double* w, const double* b, double* out);
+int launch_pcg_final(gds_ctx* ctx, const double* partial, double* S, int mode);
 int launch_probe(gds_ctx* ctx, double* const* bufs, int n_read, int n_write, int64_t n);
 int launch_halo(gds_ctx* ctx, double* vec, double* buf, const int64_t* idx, int64_t n, int scatter);

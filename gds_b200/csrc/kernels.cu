@@ -1723,6 +1723,111 @@ __global__ void __launch_bounds__(CG_THREADS) cg_direction_fused_kernel(double* 
     p[i] = r[i] + beta * p[i];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// multigrid preconditioner (gds_mg_*): every operator of the hierarchy -- level matrices, prolongations, restrictions, the
+// dense pseudo-inverse of the coarsest level -- is a CSR matrix applied by ONE kernel family.  TPR threads share a row
+// (lane-strided partial sums, then a fixed shuffle tree: bitwise reproducible); what happens to the row sum is the mode:
+//   0: out = A x            (restriction, coarsest solve)        1: out = u - A x              (residual)
+//   2: out = u + A x        (prolongation, in place: u == out)   3: out = v + w .* (u - A x)   (damped Jacobi sweep)
+// ---------------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256) mg_spmv_kernel(int64_t n, const int32_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                      const double* __restrict__ x, const double* u, const double* v,
+                                                      const double* __restrict__ w, double* out, int mode) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = t / TPR;
+  const int lane = (int)(t % TPR);
+  double acc = 0.0;
+  if (row < n) {
+    const int32_t k1 = rowptr[row + 1];
+    for (int32_t k = rowptr[row] + lane; k < k1; k += TPR) acc += val[k] * x[col[k]];
+  }
+#pragma unroll
+  for (int off = TPR / 2; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off, TPR);
+  if (row < n && lane == 0) {
+    double r;
+    if (mode == 0) r = acc;
+    else if (mode == 1) r = u[row] - acc;
+    else if (mode == 2) r = u[row] + acc;
+    else r = v[row] + w[row] * (u[row] - acc);
+    out[row] = r;
+  }
+}
+
+// out = w .* b  (the first damped Jacobi sweep from a zero guess)
+__global__ void __launch_bounds__(256) mg_scale_kernel(int64_t n, const double* __restrict__ w, const double* __restrict__ b,
+                                                       double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = w[i] * b[i];
+}
+
+int launch_mg_spmv(gds_ctx* ctx, int tpr, int64_t n, const int32_t* rowptr, const int32_t* col, const double* val,
+                   const double* x, const double* u, const double* v, const double* w, double* out, int mode) {
+  if (n <= 0) return 0;
+  const int64_t blocks = (n * tpr + 255) / 256;
+  if (blocks > 0x7fffffffLL) GDS_FAIL("too many rows for one launch");
+  switch (tpr) {
+    case 1: mg_spmv_kernel<1><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    case 2: mg_spmv_kernel<2><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    case 4: mg_spmv_kernel<4><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    case 8: mg_spmv_kernel<8><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    case 16: mg_spmv_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    case 32: mg_spmv_kernel<32><<<(unsigned)blocks, 256, 0, ctx->stream>>>(n, rowptr, col, val, x, u, v, w, out, mode); break;
+    default: GDS_FAIL("threads per row must be a power of two up to 32");
+  }
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+int launch_mg_scale(gds_ctx* ctx, int64_t n, const double* w, const double* b, double* out) {
+  if (n <= 0) return 0;
+  mg_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, w, b, out);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
+// scalars of the preconditioned iteration (one block): S[0] = r.z, S[1] = p.Ap, S[2] = alpha, S[3] = beta, S[4] = |b|^2,
+// S[5] = target for |r|^2, S[6] = finished, S[7] = |r|^2
+//   mode 0: p.Ap -> alpha      mode 1: |r|^2 (finished when at the target)      mode 2: r.z -> beta
+//   mode 3 (start): |r|^2 = |b|^2      mode 4 (start): r.z
+__global__ void __launch_bounds__(CG_THREADS) pcg_final_kernel(const double* __restrict__ partial, double* __restrict__ S,
+                                                               int mode) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < CG_BLOCKS; i += CG_THREADS) acc += partial[i];
+  __shared__ double total;
+  block_reduce_store(acc, &total);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double v = total;
+    if (mode == 0) {
+      S[1] = v;
+      const bool live = S[6] == 0.0 && v > 0.0 && isfinite(v);
+      if (!live) S[6] = 1.0;
+      S[2] = live ? S[0] / v : 0.0;
+    } else if (mode == 1) {
+      S[7] = v;
+      if (!(v > S[5])) S[6] = 1.0;
+    } else if (mode == 2) {
+      S[3] = (S[6] == 0.0 && S[0] != 0.0) ? v / S[0] : 0.0;
+      S[0] = v;
+    } else if (mode == 3) {
+      S[7] = v; S[4] = v;
+    } else {
+      S[0] = v;
+    }
+  }
+}
+
+int launch_pcg_final(gds_ctx* ctx, const double* partial, double* S, int mode) {
+  pcg_final_kernel<<<1, CG_THREADS, 0, ctx->stream>>>(partial, S, mode);
+  GDS_CUDA(cudaGetLastError());
+  ctx->kernel_launches++;
+  return 0;
+}
+
 int launch_cg(gds_ctx* ctx, int what, double* x, double* r, double* p, double* ap, int64_t n, double* S, double* partial,
               int mode) {
   switch (what) {

@@ -100,3 +100,64 @@ int lower_graph_host(int64_t V, int64_t E, const int32_t* eu, const int32_t* ev,
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Aggregation for the multigrid preconditioner of the pressure / Leray solves (include/gds_b200.h, gds_mg_*).
+// Input: a symmetric matrix in CSR (a masked graph Laplacian or a Galerkin coarse operator).  j is a STRONG neighbour of i
+// when |a_ij| >= theta * max_{k != i} |a_ik| (i != j, a_ij != 0; 0 <= theta <= 1, so the largest off-diagonal entry of a
+// row is always strong whatever the row's degree).  Three sweeps in index order, so the result is a pure
+// function of the matrix:  (1) a node whose strong neighbours are all free founds an aggregate with them;  (2) a node left
+// over joins the aggregate of its most strongly connected aggregated neighbour (as it stood after sweep 1);  (3) what is
+// still free founds aggregates with its free strong neighbours.  Rows without a strong neighbour (Dirichlet rows kept as
+// identity rows, isolated nodes) stay outside: agg = -1, they have no coarse representation.
+extern "C" int gds_mg_aggregate(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, double theta,
+                                int32_t* agg, int64_t* n_agg) {
+  if (n < 0 || !rowptr || (n > 0 && (!col || !val)) || !agg || !n_agg || !(theta >= 0.0 && theta <= 1.0)) GDS_FAIL("bad argument");
+  if (n >= (int64_t(1) << 31) - 64) GDS_FAIL("too many rows for int32 aggregate ids");
+  std::vector<double> rowmax((size_t)n, 0.0);     // largest off-diagonal magnitude of every row
+  for (int64_t i = 0; i < n; ++i) {
+    if (rowptr[i + 1] < rowptr[i]) GDS_FAIL("row pointers must not decrease");
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      if (col[k] < 0 || col[k] >= n) GDS_FAIL("column index out of range");
+      if (col[k] != i) rowmax[(size_t)i] = std::max(rowmax[(size_t)i], std::fabs(val[k]));
+    }
+  }
+  auto strong = [&](int64_t i, int64_t k) {
+    if (col[k] == i || val[k] == 0.0) return false;
+    return std::fabs(val[k]) >= theta * rowmax[(size_t)i];
+  };
+  std::fill(agg, agg + n, (int32_t)-1);
+  std::vector<uint8_t> has_strong((size_t)n, 0);
+  int32_t na = 0;
+  for (int64_t i = 0; i < n; ++i) {                       // sweep 1
+    bool any = false, all_free = agg[i] < 0;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (strong(i, k)) { any = true; if (agg[col[k]] >= 0) all_free = false; }
+    has_strong[(size_t)i] = any;
+    if (!any || !all_free) continue;
+    agg[i] = na;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (strong(i, k)) agg[col[k]] = na;
+    ++na;
+  }
+  {                                                         // sweep 2 (reads the result of sweep 1 only)
+    std::vector<int32_t> joined((size_t)n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+      if (agg[i] >= 0 || !has_strong[(size_t)i]) continue;
+      double best = -1.0;
+      for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        if (strong(i, k) && agg[col[k]] >= 0 && std::fabs(val[k]) > best) { best = std::fabs(val[k]); joined[(size_t)i] = agg[col[k]]; }
+    }
+    for (int64_t i = 0; i < n; ++i)
+      if (joined[(size_t)i] >= 0) agg[i] = joined[(size_t)i];
+  }
+  for (int64_t i = 0; i < n; ++i) {                       // sweep 3
+    if (agg[i] >= 0 || !has_strong[(size_t)i]) continue;
+    agg[i] = na;
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (strong(i, k) && agg[col[k]] < 0) agg[col[k]] = na;
+    ++na;
+  }
+  *n_agg = na;
+  return 0;
+}

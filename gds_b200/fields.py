@@ -16,6 +16,8 @@ on the device by conjugate gradients.  Out of scope (raise NotImplementedError):
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -670,6 +672,28 @@ def _run_passes(low, descs):
         check(lib.gds_pass_run(low.ctx.h, dev.h, C.byref(d), 0.0))
 
 
+def _use_multigrid(low, dom, n):
+    """node-domain solves on one device are preconditioned with a smoothed-aggregation V-cycle (gds_b200/multigrid.py) from
+    4096 rows up; GDS_B200_MG=1 forces it (tests on small graphs), GDS_B200_MG=0 keeps plain conjugate gradients"""
+    mode = os.environ.get('GDS_B200_MG', 'auto')
+    if dom != L.NODES or low.part is not None or mode == '0':
+        return False
+    return mode == '1' or n >= 4096
+
+
+def _cg(low, d_op, x, b, r, p, ap, n, rtol, max_iter, mg=None, z=None):
+    """gds_cg_solve, or gds_pcg_solve when a hierarchy is given -> (iterations, relative residual)"""
+    import ctypes as C
+    iters, relres = C.c_int32(), C.c_double()
+    if mg is None:
+        check(lib.gds_cg_solve(low.ctx.h, low.dev.h, C.byref(d_op), x.h, b.h, r.h, p.h, ap.h, n, float(rtol), int(max_iter), 25,
+                               C.byref(iters), C.byref(relres)))
+    else:
+        check(lib.gds_pcg_solve(low.ctx.h, low.dev.h, C.byref(d_op), mg.h, x.h, b.h, r.h, p.h, ap.h, z.h, n, float(rtol),
+                                int(max_iter), 4, C.byref(iters), C.byref(relres)))
+    return iters.value, relres.value
+
+
 def _solve_lhs(self, t):
     """`lhs(t, y) = 0` for an lhs affine in y (module docstring of set_evolution): trace once, split into constant and
     linear part, then per call  b = -Z_D(const + lin(g)),  lin(p) = b by conjugate gradients,  y = p + g  (g = Dirichlet
@@ -721,23 +745,30 @@ def _solve_lhs(self, t):
                 plans.clear()
             plans[key] = plan
     _run_passes_at(low, plan['rhs'][0], t)
-    iters, relres = C.c_int32(), C.c_double()
     max_iter = max(1000, 20 * int(np.sqrt(n)) + 200)
+    mg = zbuf = None
+    if _use_multigrid(low, dom, n):
+        # V-cycle of the Dirichlet-masked graph Laplacian as preconditioner: built once per (graph, Dirichlet set); conjugate
+        # gradients do not see a positive scaling of the preconditioner, so it serves c * Z_D(L0 .) for every c
+        from .multigrid import Multigrid
+        mg = Multigrid.for_graph(low, D)
+        if 'z' not in self._lhs_cache:
+            self._lhs_cache['z'] = Buffer(ctx, n)
+        zbuf = self._lhs_cache['z']
     for attempt in range(2):
         d_op = plan['op_neg' if plan['negative'] else 'op'][0]
         if plan['negative']:
             _run_passes_at(low, plan['neg_b'][0], t)
             _run_passes_at(low, plan['copy_b'][0], t)
-        check(lib.gds_cg_solve(ctx.h, low.dev.h, C.byref(d_op[0][0]), x.h, b.h, r.h, p.h, ap.h, n, 1e-13, max_iter, 25,
-                               C.byref(iters), C.byref(relres)))
-        if attempt == 0 and not plan['negative'] and iters.value <= 25 and relres.value > 0.5:
+        iters, relres = _cg(low, d_op[0][0], x, b, r, p, ap, n, 1e-13, max_iter, mg, zbuf)
+        if attempt == 0 and not plan['negative'] and iters <= 25 and relres > 0.5:
             # p.Ap was not positive: the linear part is negative definite -- solve (-lin) p = -b instead
             plan['negative'] = True
             continue
         break
     _run_passes_at(low, plan['out'][0], t)
     self._dev_y_cache = None
-    self.last_solve = {'iterations': iters.value, 'relative_residual': relres.value}
+    self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None}
     self._version += 1
     if not self._identity_projection():
         y = np.asarray(self.project_fun(np.array(self.y, copy=True)), dtype=float)   # fds.py:364-366
@@ -919,14 +950,16 @@ class edge_gds(gds):
         b.upload(bh)
         d_op, k2 = _lower_into(low, unary('NEG', Gather('N_LAP', low, DevVec(p, L.NODES, low))), ap)  # B1 B1^T p = -L0 p
         assert len(d_op) == 1
-        iters, relres = C.c_int32(), C.c_double()
         max_iter = int(max_iter) if max_iter is not None else max(1000, 20 * int(np.sqrt(V)) + 200)
-        check(lib.gds_cg_solve(ctx.h, low.dev.h, C.byref(d_op[0][0]), x.h, b.h, r.h, p.h, ap.h, V, float(rtol),
-                               max_iter, 25, C.byref(iters), C.byref(relres)))
+        mg = zbuf = None
+        if _use_multigrid(low, L.NODES, V):
+            from .multigrid import Multigrid
+            mg, zbuf = Multigrid.for_graph(low), Buffer(ctx, V)
+        iters, relres = _cg(low, d_op[0][0], x, b, r, p, ap, V, rtol, max_iter, mg, zbuf)
         d_out, k3 = _lower_into(low, DevVec(yb, L.EDGES, low) - Gather('E_GRADT', low, DevVec(x, L.NODES, low)), out)
         _run_passes(low, d_out)
         res = out.download()
-        self.last_solve = {'iterations': iters.value, 'relative_residual': relres.value}
+        self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None}
         return (res, self.last_solve) if return_info else res
 
 

@@ -196,6 +196,33 @@ int gds_cg_solve(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* apply, gds_buf
                  gds_buf* ap, int64_t n, double rtol, int32_t max_iter, int32_t check_every, int32_t* iters_out,
                  double* relres_out);
 
+/* ---- multigrid preconditioner for those solves.  The reference solves its pressure problem with a general convex solver
+ *      per step (gds/fds.py:97-113,317-328 via examples/fluid.py:24-38) and builds the Leray projector from a dense
+ *      pseudo-inverse (gds/gds.py:249); plain conjugate gradients need O(sqrt(V)) x 10 iterations on a lattice.  Here the
+ *      host builds a smoothed-aggregation hierarchy of the masked graph Laplacian once per (graph, Dirichlet set)
+ *      (gds_b200/multigrid.py; gds_mg_aggregate is its aggregation sweep, host-only) and hands every level over as CSR
+ *      matrices: the level matrix A_l with its damped-Jacobi weights w_l = omega / diag(A_l), the prolongation P_l
+ *      (n_l x n_{l+1}) and the restriction R_l = P_l^T.  The last level (n_coarse = 0) passes the dense pseudo-inverse of
+ *      its matrix as `a_*` and no weights.  One application is a symmetric V-cycle (pre / post damped-Jacobi sweeps), so it
+ *      is a valid preconditioner for conjugate gradients; gds_pcg_solve is gds_cg_solve with z = M^-1 r.  The operator
+ *      `apply` stays the caller's pass (the V-cycle uses its own level-0 matrix), so the solution satisfies the caller's
+ *      system to `rtol` whatever the quality of the hierarchy. ---- */
+typedef struct gds_mg gds_mg;
+int gds_mg_aggregate(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, double theta,
+                     int32_t* agg_out /* n: aggregate of every row, -1 = none */, int64_t* n_agg_out);
+int gds_mg_create(gds_ctx* ctx, gds_mg** out);
+int gds_mg_destroy(gds_mg* mg);
+int gds_mg_add_level(gds_mg* mg, int64_t n, const int64_t* a_rowptr, const int32_t* a_col, const double* a_val,
+                     const double* jacobi_w, int64_t n_coarse,
+                     const int64_t* p_rowptr, const int32_t* p_col, const double* p_val,
+                     const int64_t* r_rowptr, const int32_t* r_col, const double* r_val);
+int gds_mg_set_sweeps(gds_mg* mg, int32_t pre, int32_t post);      /* default 1, 1; equal counts keep the cycle symmetric */
+int gds_mg_info(gds_mg* mg, int32_t* n_levels, int64_t* device_bytes, int64_t* launches_per_cycle);
+int gds_mg_apply(gds_mg* mg, gds_buf* r, gds_buf* z);              /* z = M^-1 r: one V-cycle (asynchronous) */
+int gds_pcg_solve(gds_ctx* ctx, gds_graph* g, const gds_pass_desc* apply, gds_mg* mg, gds_buf* x, gds_buf* b, gds_buf* r,
+                  gds_buf* p, gds_buf* ap, gds_buf* z, int64_t n, double rtol, int32_t max_iter, int32_t check_every,
+                  int32_t* iters_out, double* relres_out);
+
 /* ---- the stepping core: replaces fds.step / step_dydt / dydt / step_map / apply_constraints and
  *      coupled_fds.step_continuous / dydt (gds/fds.py:264-305,332-369,471-507) plus the solver object
  *      (gds/ode/midpoint.py:10-32).  One system = one concatenated state vector (fds.py:439,456-460). -------- */
