@@ -629,7 +629,70 @@ def other_workloads(args, ctx, barrier, local, dist, torch, skip):
         except Exception as exc:          # one workload failing must not cost the headline line
             out.append({'workload': name, 'error': f'{type(exc).__name__}: {exc}'[:300]})
         gc.collect()
+    if skip != 'ns_cavity' and not args.no_pressure:
+        try:
+            out.append(pressure_workload(ctx, WORKLOADS['ns_cavity'][1], max(3, min(args.steps, 5))))
+        except Exception as exc:
+            out.append({'workload': 'ns_pressure', 'error': f'{type(exc).__name__}: {exc}'[:300]})
+        gc.collect()
     return out
+
+
+def pressure_workload(ctx, n, steps):
+    """BASELINE config 3 with the pressure SOLVED every step (examples/fluid.py:14-38 `navier_stokes`, lid-driven cavity of
+    examples/lid_driven_cavity.py:56-67: pressure reference at one node): the `lhs=` pressure field is a preconditioned
+    conjugate-gradient solve on the device (gds_pcg_solve, smoothed-aggregation V-cycle) before every internal step
+    (fds.py:505-507), the velocity law the collapsed RK4 step of ns_cavity.  Wall clock around the public step() calls --
+    every solve reads its residual back, so the calls are synchronous."""
+    import gds_b200
+    from adaptors import product_api
+    api = product_api()
+    h, rho, visc, min_step = 1e-4, 0.1, 200.0, 1e-3
+    t0 = time.perf_counter()
+    G = gds_b200.NativeGraph('triangular', n, n)
+    p, u = api.node_gds(G), api.edge_gds(G)
+    hg = G.hostgraph(with_faces=True)
+    pos, (eu, ev) = hg.pos(), hg.edges()
+
+    def pressure_f(t, y):
+        dt = max(min_step, u.dt)
+        lhs = u.div(u.y / dt - u.advect() + u.laplacian() * visc / rho)
+        lhs -= p.laplacian(y) / rho
+        return lhs
+    api.evolve_lhs(p, pressure_f)
+    api.evolve(u, dydt=lambda t, y: -u.advect() - p.grad() / rho + u.laplacian() * visc / rho, max_step=h)
+    u.set_initial(y0=0.05 * np.random.default_rng(4).standard_normal(u.ndim))
+    x0, x1, y0_, y1 = pos[:, 0].min(), pos[:, 0].max(), pos[:, 1].min(), pos[:, 1].max()
+    lid = _edges_inside(eu, ev, pos[:, 1] > y1 - 1e-9)
+    walls = np.unique(np.concatenate([_edges_inside(eu, ev, pos[:, 1] < y0_ + 1e-9),
+                                      _edges_inside(eu, ev, pos[:, 0] < x0 + 0.51),
+                                      _edges_inside(eu, ev, pos[:, 0] > x1 - 0.51)]))
+    lid = np.setdiff1d(lid, walls)
+    u.set_constraints(dirichlet=gds_b200.BoundarySpec(np.concatenate([walls, lid]),
+                                                      values=np.concatenate([np.zeros(walls.size), np.full(lid.size, 10.0)])))
+    p.set_constraints(dirichlet=gds_b200.BoundarySpec(np.array([0]), values=0.0))      # pressure reference
+    sysobj = api.couple({'u': u, 'p': p})
+    sysobj.step(h)                                   # builds the hierarchy, the pass lists and the captured step
+    ctx.sync()
+    t_build = time.perf_counter() - t0
+    sysobj.step(h)
+    ctx.sync()
+    its, solve_s = [], []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sysobj.step(h)
+        its.append(p.last_solve['iterations'])
+        solve_s.append(p.last_solve['solve_seconds'])
+    ctx.sync()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    from gds_b200.multigrid import Multigrid
+    info = Multigrid.for_graph(p._low, p.dirichlet_indices).info()
+    return {'name': f'Navier-Stokes with the pressure solved every step (lhs= field, multigrid-preconditioned CG) + velocity '
+                    f'RK4 h=1e-4, triangular_lattice_graph({n},{n}) (V={hg.V}, E={hg.E}, F={hg.F}), lid-driven cavity',
+            'workload': 'ns_pressure', 'size': n, 'steps': steps, 'ms_per_step': ms, 'value': hg.E * steps / (ms * steps * 1e-3),
+            'unit': UNIT, 'solve_iterations': its, 'solve_ms': [1e3 * x for x in solve_s],
+            'relative_residual': p.last_solve['relative_residual'], 'hierarchy': info, 'build_seconds': t_build,
+            'timing': 'wall clock around the public step() calls (each solve synchronises)'}
 
 
 def gpu_arm(args):
@@ -745,7 +808,8 @@ def gpu_arm(args):
             eng.t = t_start                   # members share the start time: rewind the clock for the next call
             barrier()
             t0 = time.perf_counter()
-            st.step_ensemble(h, [wrap(ring_in[i & 1]) for i in range(Ke)], [wrap(ring_out[i & 1]) for i in range(Ke)])
+            Km = max(3, min(K, 20))           # members = timed steps (the pipeline fills once per call)
+            st.step_ensemble(h, [wrap(ring_in[i & 1]) for i in range(Km)], [wrap(ring_out[i & 1]) for i in range(Km)])
             ens_s = time.perf_counter() - t0
             eng.t = t_start
             ok = True                         # against the serial call on the same inputs at the same time, bit for bit
@@ -754,8 +818,8 @@ def gpu_arm(args):
                 one_step(ring_in[b], chk)
                 eng.t = t_start
                 ok = ok and all(np.array_equal(x, y) for x, y in zip(chk, ring_out[b]))
-            e2e = {'value': n_total * Ke / ens_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * sum(sizes),
-                   'd2h_bytes_per_step': 8 * sum(sizes), 'steps': Ke,
+            e2e = {'value': n_total * Km / ens_s, 'unit': UNIT, 'h2d_bytes_per_step': 8 * sum(sizes),
+                   'd2h_bytes_per_step': 8 * sum(sizes), 'steps': Km,
                    'note': 'public step_ensemble call over an ensemble of independent pinned-host states: per member the '
                            'state goes up, one step runs, the new state comes back; uploads, steps and read-backs of '
                            'consecutive members overlap on three streams; wall clock around the call (it synchronises)',
@@ -839,6 +903,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-weighted', action='store_true')
     ap.add_argument('--no-workloads', action='store_true', help='N = 1: skip the other BASELINE configurations after the headline')
+    ap.add_argument('--no-pressure', action='store_true', help='N = 1: skip the Navier-Stokes workload with the per-step pressure solve')
     ap.add_argument('--no-slab-check', action='store_true', help='N > 1: skip the small partitioned-vs-one-GPU comparison')
     ap.add_argument('--weighted', action='store_true', help='heat2d: random edge weights on the main problem (kernel A/B runs)')
     ap.add_argument('--total', action='store_true', help='wave3d: --size is the whole grid, cut into --gpus slabs (strong scaling)')

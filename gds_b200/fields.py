@@ -684,13 +684,16 @@ def _use_multigrid(low, dom, n):
 def _cg(low, d_op, x, b, r, p, ap, n, rtol, max_iter, mg=None, z=None):
     """gds_cg_solve, or gds_pcg_solve when a hierarchy is given -> (iterations, relative residual)"""
     import ctypes as C
+    import time
     iters, relres = C.c_int32(), C.c_double()
+    t0 = time.perf_counter()
     if mg is None:
         check(lib.gds_cg_solve(low.ctx.h, low.dev.h, C.byref(d_op), x.h, b.h, r.h, p.h, ap.h, n, float(rtol), int(max_iter), 25,
                                C.byref(iters), C.byref(relres)))
     else:
         check(lib.gds_pcg_solve(low.ctx.h, low.dev.h, C.byref(d_op), mg.h, x.h, b.h, r.h, p.h, ap.h, z.h, n, float(rtol),
                                 int(max_iter), 4, C.byref(iters), C.byref(relres)))
+    _cg.last_seconds = time.perf_counter() - t0       # the call returns after its last residual read-back
     return iters.value, relres.value
 
 
@@ -768,7 +771,8 @@ def _solve_lhs(self, t):
         break
     _run_passes_at(low, plan['out'][0], t)
     self._dev_y_cache = None
-    self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None}
+    self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None,
+                       'solve_seconds': _cg.last_seconds}
     self._version += 1
     if not self._identity_projection():
         y = np.asarray(self.project_fun(np.array(self.y, copy=True)), dtype=float)   # fds.py:364-366
@@ -959,7 +963,8 @@ class edge_gds(gds):
         d_out, k3 = _lower_into(low, DevVec(yb, L.EDGES, low) - Gather('E_GRADT', low, DevVec(x, L.NODES, low)), out)
         _run_passes(low, d_out)
         res = out.download()
-        self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None}
+        self.last_solve = {'iterations': iters, 'relative_residual': relres, 'preconditioner': 'multigrid' if mg else None,
+                       'solve_seconds': _cg.last_seconds}
         return (res, self.last_solve) if return_info else res
 
 
