@@ -566,8 +566,15 @@ __global__ void __launch_bounds__(BLOCK) eagg_kernel(const __grid_constant__ Pas
 // linear combinations of masked one-hop operators (TermForm): the terms are evaluated one after another and
 // accumulated -- no stack machine, one warp-uniform switch per term
 // ---------------------------------------------------------------------------------------------------
+#ifndef TK_MINB
+#define TK_MINB 5     // resident blocks per SM the term-list kernel is compiled for: 48 registers instead of 56, a few spilled
+#endif                // words, 5 x 256 threads per SM -- measured on B200 (profiles/README.md 2.3): config 2 1.66 -> 1.24 ms, config 3
+                      // 0.84 -> 0.63 ms with ET_MINB = 5 as well (6: 1.25 / 0.66).  A/B: -DTK_MINB=..
+#ifndef TK_MINB_F
+#define TK_MINB_F 8         // face rows: 32 registers (config 3: 0.639 -> 0.606 ms; 6: 0.625)
+#endif
 template <int DOMAIN, bool UNITW>
-__global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(BLOCK, DOMAIN == GDS_FACES ? TK_MINB_F : TK_MINB) terms_kernel(const __grid_constant__ PassParams p) {
   const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (row >= p.n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -630,8 +637,11 @@ __global__ void __launch_bounds__(BLOCK) terms_kernel(const __grid_constant__ Pa
 // so the result is bit-identical to terms_kernel.  Up to ET_MAX terms, edges with at most 2 faces (every planar graph).
 // ---------------------------------------------------------------------------------------------------
 #define ET_MAX 4
+#ifndef ET_MINB
+#define ET_MINB 5     // resident blocks per SM the phased edge kernel is compiled for (48 registers; see TK_MINB)
+#endif
 template <bool UNITW>
-__global__ void __launch_bounds__(BLOCK) edge_terms_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(BLOCK, ET_MINB) edge_terms_kernel(const __grid_constant__ PassParams p) {
   const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (row >= p.n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -1086,8 +1096,11 @@ __device__ __forceinline__ void st_quad_v(double* p, int64_t r0, int64_t n_rows,
 // register budget (the collapsed form holds the row's own values until the end for the fused order-2 block shift)
 // EPI 2: recurrence maps with a pointwise chain on the additive vector (beta g(b), own row only) and / or a carried gather
 // operand to write (shadow_out = f(new state)) -- coupled map lattices.
+#ifndef LAPQ_MINB_EPI    // EPI 2 (coupled map lattice, gather served by L1 / L2: latency-bound): 12 blocks x 128 threads, 40
+#define LAPQ_MINB_EPI 12 // registers, a few spilled words -- measured 0.112 -> 0.096 ms per application at n = 4e6 (10: 0.098)
+#endif
 template <bool UNITW, bool IDX16, bool RUNS, int EPI>
-__global__ void __launch_bounds__(LAPQ_BLOCK, EPI ? 8 : (UNITW ? LAPQ_MINB : LAPQ_MINB_W)) lapq_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(LAPQ_BLOCK, EPI == 2 ? LAPQ_MINB_EPI : (EPI ? 8 : (UNITW ? LAPQ_MINB : LAPQ_MINB_W))) lapq_kernel(const __grid_constant__ PassParams p) {
   constexpr bool COLL = EPI == 1;
   const int64_t r0 = p.row0 + ((int64_t)blockIdx.x * LAPQ_BLOCK + threadIdx.x) * 4;
   if (r0 >= p.n_rows) return;
