@@ -384,4 +384,4 @@ def test_fused_cg_iteration_equals_the_six_launch_form_bit_for_bit(monkeypatch):
         monkeypatch.setenv('GDS_B200_CG_UNFUSED', '1')
         z2, i2 = u.leray_project(y, return_info=True)
         assert np.array_equal(z1, z2)
-        assert i1 == dict(i2) and i1['iterations'] > 0
+        assert all(i1[k] == i2[k] for k in ('iterations', 'relative_residual', 'preconditioner')) and i1['iterations'] > 0
