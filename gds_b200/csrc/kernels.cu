@@ -566,15 +566,21 @@ __global__ void __launch_bounds__(BLOCK) eagg_kernel(const __grid_constant__ Pas
 // linear combinations of masked one-hop operators (TermForm): the terms are evaluated one after another and
 // accumulated -- no stack machine, one warp-uniform switch per term
 // ---------------------------------------------------------------------------------------------------
-#ifndef TK_MINB
-#define TK_MINB 5     // resident blocks per SM the term-list kernel is compiled for: 48 registers instead of 56, a few spilled
-#endif                // words, 5 x 256 threads per SM -- measured on B200 (profiles/README.md 2.3): config 2 1.66 -> 1.24 ms, config 3
-                      // 0.84 -> 0.63 ms with ET_MINB = 5 as well (6: 1.25 / 0.66).  A/B: -DTK_MINB=..
-#ifndef TK_MINB_F
-#define TK_MINB_F 8         // face rows: 32 registers (config 3: 0.639 -> 0.606 ms; 6: 0.625)
+// Resident blocks per SM the term-list kernels are compiled for (a register cap).  Same-box A/B on B200 (profiles/README.md
+// 2.3, profiles/r2/ab/): with 5 blocks (48 registers, ~100 bytes spilled) config 2 at hex 1500^2 ran 1.66 -> 1.24 ms and
+// config 3 at tri 3000^2 0.84 -> 0.63 ms -- but at the BASELINE sizes (hex 2000^2, tri 4000^2), where the passes are closer
+// to the DRAM limit than to the latency limit, the same builds measured 2.12 -> 2.06 ms and 1.00 -> 1.05 ms: no gain, so the
+// default stays uncapped.  -DTK_MINB=5 -DET_MINB=5 -DTK_MINB_F=8 rebuilds the capped form for smaller graphs.
+#if defined(TK_MINB) && !defined(TK_MINB_F)
+#define TK_MINB_F TK_MINB   // face rows
+#endif
+#ifdef TK_MINB
+#define TK_BOUNDS __launch_bounds__(BLOCK, DOMAIN == GDS_FACES ? TK_MINB_F : TK_MINB)
+#else
+#define TK_BOUNDS __launch_bounds__(BLOCK)     // the compiler's own choice: 56 / 40 registers (nodes / faces)
 #endif
 template <int DOMAIN, bool UNITW>
-__global__ void __launch_bounds__(BLOCK, DOMAIN == GDS_FACES ? TK_MINB_F : TK_MINB) terms_kernel(const __grid_constant__ PassParams p) {
+__global__ void TK_BOUNDS terms_kernel(const __grid_constant__ PassParams p) {
   const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (row >= p.n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -637,11 +643,13 @@ __global__ void __launch_bounds__(BLOCK, DOMAIN == GDS_FACES ? TK_MINB_F : TK_MI
 // so the result is bit-identical to terms_kernel.  Up to ET_MAX terms, edges with at most 2 faces (every planar graph).
 // ---------------------------------------------------------------------------------------------------
 #define ET_MAX 4
-#ifndef ET_MINB
-#define ET_MINB 5     // resident blocks per SM the phased edge kernel is compiled for (48 registers; see TK_MINB)
+#ifdef ET_MINB           // see TK_MINB
+#define ET_BOUNDS __launch_bounds__(BLOCK, ET_MINB)
+#else
+#define ET_BOUNDS __launch_bounds__(BLOCK)     // 64 registers
 #endif
 template <bool UNITW>
-__global__ void __launch_bounds__(BLOCK, ET_MINB) edge_terms_kernel(const __grid_constant__ PassParams p) {
+__global__ void ET_BOUNDS edge_terms_kernel(const __grid_constant__ PassParams p) {
   const int64_t row = p.row0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (row >= p.n_rows) return;
   const int lane = threadIdx.x & 31;
