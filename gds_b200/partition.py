@@ -338,9 +338,10 @@ class DeepPartition(Partition):
         self.send_dom = {d: [np.zeros(0, dtype=np.int64) for _ in range(world)] for d in gid}
         e_g2l = np.full(eu.size, -1, dtype=np.int64); e_g2l[self.edge_gid] = np.arange(self.E_loc)
         f_g2l = np.full(F, -1, dtype=np.int64); f_g2l[self.face_gid] = np.arange(self.F_loc)
-        for q in range(world):
-            if q == rank:
-                continue
+        # Reach is symmetric (undirected graph, same number of hops): a row of mine can only lie inside rank q's layers if
+        # a node of q lies inside mine -- so the only ranks that receive from this one are the owners of its ghost nodes,
+        # not all `world - 1` others (their layers are not walked at all).
+        for q in np.unique(node_owner[ghosts]).tolist():
             _, inn_q, e_q, f_q = local_sets(q)
             self.send_dom[0][q] = g2l[np.nonzero(inn_q & (node_owner == rank))[0]]
             self.send_dom[1][q] = e_g2l[np.nonzero(e_q & (edge_owner == rank))[0]]

@@ -199,8 +199,9 @@ def _hodge1(V, eu, ev, faces, y):
     return -(B1.T @ (B1 @ y)) - (B2.T @ (B2 @ y))
 
 
-@pytest.mark.parametrize('kind,dims,hops', [('hexagonal', (5, 6), 4), ('triangular', (6, 8), 2)])
-@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('kind,dims,hops,world', [('hexagonal', (5, 6), 4, 2), ('hexagonal', (5, 6), 4, 3), ('triangular', (6, 8), 2, 2),
+                                                  ('triangular', (6, 8), 2, 3),
+                                                  ('hexagonal', (6, 30), 3, 7), ('triangular', (8, 40), 2, 6)])   # most ranks are not neighbours
 def test_deep_partition_recomputes_two_hop_operators_on_the_ghost_layers(kind, dims, hops, world):
     """edge fields on a partitioned graph: with enough ghost layers the Hodge-1 Laplacian of the OWNED edges needs no
     exchange of intermediates -- every rank evaluates it on its local graph after one exchange of the edge values"""
@@ -214,6 +215,8 @@ def test_deep_partition_recomputes_two_hop_operators_on_the_ghost_layers(kind, d
     want = _hodge1(V, eu, ev, faces, y)
     bounds = split_bounds(V, world)
     parts = [DeepPartition(r, world, V, eu, ev, None, bounds, hops, fp, fn) for r in range(world)]
+    if world > 3:
+        assert any(len(p.peers) < world - 1 for p in parts)
     # ownership partitions every domain, halo lists are symmetric
     for d, n in ((0, V), (1, E), (3, len(faces))):
         owned = np.concatenate([p.gid_dom[d][p.owned_dom[d]] for p in parts])
