@@ -21,9 +21,13 @@ Deliberate positions on reference quirks:
   * map mode follows gds/fds.py:332-339 with the two fixes needed to make it reachable
     (`_y = y0.copy()` for fds.py:122, documented `(t, y)` signature for fds.py:337).
   * `set_initial(y0=ndarray)` is accepted (fds.py:151-152 recurses in the reference).
-  * `lhs=` (cvx mode, fds.py:97-113,309-328): the reference hands `sum_squares(lhs(t, y))` to CVXPY, which is not
-    installed here, so this mode is PARITY UNPINNED against the reference: for an `lhs` affine in y the restatement
-    takes the least-squares solution with the Dirichlet values imposed (minimum norm over the free unknowns).
+  * `lhs=` (cvx mode, fds.py:97-113,309-328): the reference hands `sum_squares(lhs(t, y))` to CVXPY; for an `lhs` affine
+    in y the restatement takes the least-squares solution with the Dirichlet values imposed (minimum norm over the free
+    unknowns).  CVXPY is not installed here.  PARITY PINNED TO THE REFERENCE'S OWN CVX CODE PATH, run unmodified with
+    oracle/cvx_shim.py standing in for `cvxpy` (affine expressions of the variable; the programme is minimised exactly by
+    dense least squares): tests/golden/lhs_*.npz, <= 1e-12.  What that pins is everything the reference contributes --
+    how the objective is assembled from its operators, the Dirichlet constraint, the solves before every RHS evaluation of
+    a coupled system, the state bookkeeping; what it cannot pin is CVXPY's own numerical solve (OSQP / ECOS tolerance).
 """
 from __future__ import annotations
 

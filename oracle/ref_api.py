@@ -35,6 +35,11 @@ def make_ref_api():
         @staticmethod
         def evolve_nil(obs):
             obs.set_evolution(nil=True)
+
+        @staticmethod
+        def evolve_lhs(obs, lhs):
+            # the reference's own cvx path (fds.py:97-113); its `cvxpy` is oracle/cvx_shim.py where CVXPY is absent
+            obs.set_evolution(lhs=lhs)
     
         @staticmethod
         def evolve_map(obs, map_fun, dt=1.0):

@@ -7,13 +7,15 @@ like a built .so).  Used by tests/golden/make_golden.py (golden vectors), tests/
 the CPU legs of bench.py (`--impl reference`, `cpu_baseline`: the reference itself timed on the host cores).
 Nothing in the product path (gds_b200/) imports this module.
 
-`import gds` fails here because non-numerical dependencies (cvxpy, shortuuid, hickle, shapely,
+`import gds` fails here because non-numerical dependencies (shortuuid, hickle, shapely,
 trimesh, matplotlib, bokeh, colorcet, selenium, ujson, tornado ...) are absent and networkx 3
 removed `to_scipy_sparse_matrix` (used at gds/utils/graph/common.py:6).  We install import-time
 stand-ins for those modules; the numerical path (gds/gds.py, gds/fds.py) then runs unmodified on
 numpy/scipy/networkx.  `shapely` gets a real point-in-closed-polygon stand-in because
 embedded_faces() (gds/utils/graph/generators.py:498-506) uses Polygon.intersects(Point) to pick
-the outer face; a truthy mock would silently delete face 0.
+the outer face; a truthy mock would silently delete face 0.  `cvxpy` (absent as well) gets oracle/cvx_shim.py: the
+affine-expression subset the reference's `lhs=` path touches, with the quadratic programme solved exactly by dense least
+squares -- so that path of the reference runs too (see that module's header for what this does and does not pin).
 """
 import importlib.abc
 import importlib.machinery
@@ -39,7 +41,7 @@ def reference_root():
 
 REFERENCE_ROOT = reference_root()
 
-_ABSENT = ("cvxpy", "shortuuid", "hickle", "trimesh", "matplotlib", "bokeh", "colorcet",
+_ABSENT = ("shortuuid", "hickle", "trimesh", "matplotlib", "bokeh", "colorcet",
            "selenium", "ujson", "tornado", "seaborn", "statsmodels", "pyunicorn", "zmq")
 
 
@@ -125,6 +127,11 @@ def load_reference():
     shapely, geometry = _make_shapely()
     sys.modules["shapely"] = shapely
     sys.modules["shapely.geometry"] = geometry
+    try:            # CVXPY itself where it exists; else the least-squares stand-in (oracle/cvx_shim.py) for the lhs= path
+        import cvxpy  # noqa: F401
+    except ImportError:
+        from . import cvx_shim
+        sys.modules["cvxpy"] = cvx_shim
     import shortuuid  # the mock
     shortuuid.uuid = lambda: uuid.uuid4().hex
     sys.path.insert(0, root)

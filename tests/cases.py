@@ -299,7 +299,7 @@ def case_ns_pressure(api, m=5, n=8, nsteps=12, every=6, rho=1.0, visc=0.05, h=1e
     """Navier-Stokes with the pressure solved every step (examples/fluid.py:14-38 `navier_stokes`): the pressure field
     is defined by `lhs=` -- divergence of the provisional velocity minus the pressure Laplacian, set to zero -- with a
     pressure drop between an inlet and an outlet node; the velocity law reads `pressure.grad()`.  NOT in the golden
-    set: the reference solves `lhs=` with CVXPY, which is not installed here (parity unpinned).  h equals the law's
+    set of round 1; pinned since (tests/golden/lhs_ns_pressure.npz: the reference's cvx path with oracle/cvx_shim.py as its CVXPY).  h equals the law's
     min_step so that `max(min_step, velocity.dt)` does not depend on the reference's `dt` bookkeeping (App. B.7)."""
     G = g_tri(m, n)
     pressure, velocity = api.node_gds(G), api.edge_gds(G)
@@ -363,6 +363,64 @@ TRAJ_CASES = {
     'ns_cavity_c3': case_ns_cavity_c3,
     'wave_c5': case_wave_c5,
     'cml_c4': case_cml_c4,
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# `lhs=` fields (gds/fds.py:97-113,196-202,307-328).  Golden vectors in tests/golden/lhs_*.npz come from the UNMODIFIED
+# reference with oracle/cvx_shim.py standing in for CVXPY (absent here): the reference assembles the programme, the
+# stand-in solves it exactly.
+# ------------------------------------------------------------------------------------------------
+def case_poisson_lhs(api, m=6, n=7, nsteps=3):
+    """a single `lhs=` field stepped on its own (fds.step -> step_cvx): weighted Poisson problem L0 y = f with
+    time-varying Dirichlet values on two rows of the grid"""
+    G = add_weights(g_grid(m, n), 21)
+    p = api.node_gds(G)
+    f = np.random.default_rng(22).standard_normal(p.ndim)
+    api.evolve_lhs(p, lambda t, y: p.laplacian(y) - f)
+    p.set_constraints(dirichlet=lambda t, x: (1.0 + t) * x[1] if x[0] == 0 else (-0.5 if x[0] == m - 1 else None))
+    ys, ts = [], []
+    for _ in range(nsteps):
+        p.step(0.25)
+        ys.append(np.array(p.y, dtype=float, copy=True))
+        ts.append(float(p.t))
+    return {'y_p': np.array(ys), 't': np.array(ts)}
+
+
+def case_stokes_hex_lhs(api, m=4, n=5, nsteps=8, every=4, rho=0.7, visc=0.3, h=1e-3):
+    """Stokes flow (examples/fluid.py:40-41: navier_stokes with the advection switched off) on a WEIGHTED hexagonal
+    lattice, inlet and outlet made of several nodes with a time-varying pressure drop, no-slip edges top and bottom"""
+    G = add_weights(g_hex(m, n), 23)
+    pressure, velocity = api.node_gds(G), api.edge_gds(G)
+    pos = nx.get_node_attributes(G, 'pos')
+    xs = [q[0] for q in pos.values()]
+    x0, x1 = min(xs), max(xs)
+    inlet = [x for x in pressure.X if pos[x][0] < x0 + 1e-9]
+    outlet = [x for x in pressure.X if pos[x][0] > x1 - 1e-9]
+    v_free = np.array([pressure.X[x] for x in inlet + outlet], dtype=np.intp)
+    min_step = 1e-3
+
+    def pressure_f(t, y):
+        dt = max(min_step, velocity.dt)
+        lhs = velocity.div(velocity.y / dt + velocity.laplacian() * visc / rho)
+        lhs[v_free] = 0.
+        lhs -= pressure.laplacian(y) / rho
+        return lhs
+    api.evolve_lhs(pressure, pressure_f)
+    api.evolve(velocity, dydt=lambda t, y: -pressure.grad() / rho + velocity.laplacian() * visc / rho, max_step=h)
+    u0 = 0.05 * np.random.default_rng(24).standard_normal(velocity.ndim)
+    velocity.set_initial(y0=lambda e: u0[velocity.X[e]])
+    velocity.set_constraints(dirichlet=api.zero_edge_bc(boundary_edges_hex_top_bottom(G)))
+    ins, outs = set(inlet), set(outlet)
+    pressure.set_constraints(dirichlet=lambda t, x: (1.0 + 40.0 * t) if x in ins else (-1.0 if x in outs else None))
+    sysobj = api.couple({'velocity': velocity, 'pressure': pressure})
+    return _snap(sysobj, {'velocity': velocity, 'pressure': pressure}, h, nsteps, every)
+
+
+LHS_CASES = {
+    'ns_pressure': lambda api: case_ns_pressure(api),
+    'poisson': case_poisson_lhs,
+    'stokes_hex_w': case_stokes_hex_lhs,
 }
 
 

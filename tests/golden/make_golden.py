@@ -8,7 +8,9 @@ created with `Integrators.implicit_midpoint` and its `integrator` attribute is t
 solver object that follows the same protocol (gds/ode/midpoint.py:10-32) -- before set_initial/set_constraints,
 which write into `integrator.y`.  Map mode is unreachable through the reference's
 `set_evolution` (fds.py:122 raises), so the adaptor sets the attributes that branch would have set and lets the
-reference's own `step_map` (fds.py:332-339) run.
+reference's own `step_map` (fds.py:332-339) run.  `lhs=` fields (lhs_*.npz) run the reference's cvx path with
+oracle/cvx_shim.py installed as `cvxpy` (CVXPY is absent): the reference assembles the programme, the stand-in solves it
+exactly by dense least squares.
 """
 import os
 import sys
@@ -71,6 +73,13 @@ def main(argv):
         out = fn(RefAPI)
         np.savez_compressed(os.path.join(HERE, key + '.npz'), **{k: np.asarray(v) for k, v in out.items()})
         print('wrote', key, {k: np.shape(v) for k, v in out.items()})
+    for cname, fn in cases.LHS_CASES.items():
+        key = f'lhs_{cname}'
+        if want and key not in want:
+            continue
+        out = fn(RefAPI)      # the reference's cvx path with oracle/cvx_shim.py as its `cvxpy` (exact least squares)
+        np.savez_compressed(os.path.join(HERE, key + '.npz'), **out)
+        print('wrote', key, {k: v.shape for k, v in out.items()})
     for cname, fn in cases.TRAJ_CASES.items():
         key = f'traj_{cname}'
         if want and key not in want:

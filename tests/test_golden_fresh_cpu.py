@@ -51,6 +51,42 @@ def test_trajectory_golden_is_fresh(ref_api):
     _same(cases.TRAJ_CASES['heat_c1_euler_small'](ref_api), os.path.join(GOLD, 'traj_heat_c1_euler_small.npz'))
 
 
+@pytest.mark.parametrize('cname', ['poisson', 'stokes_hex_w'])
+def test_lhs_golden_is_fresh(ref_api, cname):
+    """the reference's cvx path (fds.py:97-113,307-328) with oracle/cvx_shim.py as its `cvxpy`"""
+    gold = np.load(os.path.join(GOLD, f'lhs_{cname}.npz'))
+    out = cases.LHS_CASES[cname](ref_api)
+    assert set(out) == set(gold.files)
+    for k in gold.files:       # a dense least-squares solve sits inside: LAPACK rounding, not last-bit identity
+        assert np.allclose(np.asarray(out[k]), gold[k], rtol=1e-10, atol=1e-13), k
+
+
+def test_cvx_stand_in_solves_the_constrained_least_squares_problem_exactly():
+    """oracle/cvx_shim.py on its own: argmin |A y - f|^2 subject to y[idx] == v equals the KKT solution"""
+    from oracle import cvx_shim as cp
+    rng = np.random.default_rng(3)
+    A, f = rng.standard_normal((9, 6)), rng.standard_normal(9)
+    idx, v = np.array([1, 4]), np.array([0.3, -1.2])
+    y = cp.Variable(6)
+    par = cp.Parameter(2)
+    par.value = v
+    expr = A @ y - f
+    expr2 = f - A @ y                                  # ndarray on the left
+    assert np.allclose(expr2.M, -expr.M) and np.allclose(expr2.c, -expr.c)
+    prob = cp.Problem(cp.Minimize(cp.sum_squares(expr)), [y[idx] == par])
+    prob.solve(warm_start=True)
+    assert prob.status == 'optimal'
+    free = np.setdiff1d(np.arange(6), idx)
+    want = np.zeros(6); want[idx] = v
+    want[free] = np.linalg.solve(A[:, free].T @ A[:, free], A[:, free].T @ (f - A[:, idx] @ v))
+    assert np.allclose(y.value, want, rtol=1e-12, atol=1e-13)
+    # in-place arithmetic with an ndarray on the left turns the name into an expression (examples/fluid.py:28-30)
+    lhs = np.ones(9)
+    lhs[2] = 0.
+    lhs -= (A @ y) / 2.0
+    assert isinstance(lhs, cp.Affine) and np.allclose(lhs.M, -A / 2.0) and lhs.c[2] == 0. and lhs.c[0] == 1.
+
+
 def test_jacobian_and_ragged_golden_are_fresh(ref_api):
     _same(cases.jacobian_outputs(ref_api, 'hex_3x4'), os.path.join(GOLD, 'jac_hex_3x4.npz'))
     _same(cases.run_ops(ref_api, cases.RAGGED['star_70_weighted']()), os.path.join(GOLD, 'ragged_star_70_weighted.npz'))

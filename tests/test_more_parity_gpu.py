@@ -63,12 +63,29 @@ def test_linearised_advection_perturbation_equation(gname):
 
 def test_navier_stokes_with_pressure_solve_every_step():
     """`lhs=` pressure field coupled to the velocity law (examples/fluid.py:14-38): device CG against the oracle's dense
-    least squares.  Parity against the reference itself is unpinned for this mode (CVXPY is not installed here)."""
+    least squares (the golden vectors of the reference's own cvx path are compared in the next test)."""
     a, b = cases.case_ns_pressure(product_api()), cases.case_ns_pressure(oracle_api())
     assert np.allclose(a['t'], b['t'], rtol=0, atol=1e-12)
     for i in range(b['y_velocity'].shape[0]):
         assert rel_l2(a['y_velocity'][i], b['y_velocity'][i]) <= 1e-9, rel_l2(a['y_velocity'][i], b['y_velocity'][i])
         assert rel_l2(a['y_pressure'][i], b['y_pressure'][i]) <= 1e-8, rel_l2(a['y_pressure'][i], b['y_pressure'][i])
+
+
+@pytest.mark.parametrize('cname', list(cases.LHS_CASES))
+def test_lhs_fields_match_the_reference_golden_vectors(cname):
+    """the device solve of `lhs=` fields against golden vectors of the UNMODIFIED reference's cvx path (its CVXPY replaced
+    by the exact least-squares stand-in oracle/cvx_shim.py, tests/golden/make_golden.py): the coupled Navier-Stokes case of
+    the test above, a Poisson field stepped on its own with time-varying Dirichlet values, Stokes flow on a weighted
+    hexagonal lattice with a time-varying pressure drop"""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', f'lhs_{cname}.npz'))
+    out = cases.LHS_CASES[cname](product_api())
+    assert np.allclose(out['t'], gold['t'], rtol=0, atol=1e-12)
+    for k in gold.files:
+        if k == 't':
+            continue
+        tol = 2e-8 if 'pressure' in k or k == 'y_p' else 2e-9
+        for i in range(gold[k].shape[0]):
+            assert rel_l2(out[k][i], gold[k][i]) <= tol, (cname, k, i, rel_l2(out[k][i], gold[k][i]))
 
 
 COLLAPSIBLE = {

@@ -95,3 +95,23 @@ def test_trajectories_match_reference(cname):
         for i in range(gold[k].shape[0]):
             err = rel_l2(out[k][i], gold[k][i])
             assert err <= TOL, (cname, k, i, err)
+
+
+@pytest.mark.parametrize('cname', list(cases.LHS_CASES))
+def test_lhs_fields_match_the_reference_cvx_path(cname):
+    """`set_evolution(lhs=...)` (fds.py:97-113,196-202,307-328; the pressure field of examples/fluid.py:14-38), alone and
+    coupled to a velocity field, static and time-varying Dirichlet values: golden vectors from the UNMODIFIED reference
+    running its own cvx path, with oracle/cvx_shim.py standing in for the absent CVXPY (the reference assembles the
+    programme -- objective from its operators, Dirichlet constraint, solves before every RHS evaluation of the coupled
+    system -- and the stand-in minimises it exactly)"""
+    gold = np.load(os.path.join(GOLD, f'lhs_{cname}.npz'))
+    out = cases.LHS_CASES[cname](oracle_api())
+    assert set(out) == set(gold.files)
+    assert np.allclose(out['t'], gold['t'], rtol=0, atol=1e-12)
+    for k in gold.files:
+        if k == 't':
+            continue
+        assert np.all(np.isfinite(gold[k])) and np.linalg.norm(gold[k]) > 0
+        for i in range(gold[k].shape[0]):
+            err = rel_l2(out[k][i], gold[k][i])
+            assert err <= TOL, (cname, k, i, err)
