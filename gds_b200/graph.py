@@ -106,6 +106,24 @@ def locality_permutation(V, edge_u, edge_v, pos, window=1024):
     return i2p[order]
 
 
+def connectivity_order(V, edge_u, edge_v):
+    """Ordering for CUTTING a graph that has neither index locality nor node positions into contiguous ranges: reverse
+    Cuthill-McKee over the adjacency structure (breadth-first levels, so an index range is a band of a few levels and the
+    cut between two ranges is a level boundary).  Returns i2p (position in the order -> public id) or None when the public
+    numbering is already local.  Used by `distribute` only (SURVEY.md 8e: partitioners for graphs that are not lattices);
+    graphs with positions take the space-filling curve of `locality_permutation`."""
+    E = len(edge_u)
+    if V < 64 or E == 0:
+        return None
+    u, v = np.asarray(edge_u, dtype=np.int64), np.asarray(edge_v, dtype=np.int64)
+    if float(np.mean(np.abs(u - v))) <= 0.05 * V:
+        return None
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    A = sp.coo_matrix((np.ones(2 * E, dtype=np.int8), (np.concatenate([u, v]), np.concatenate([v, u]))), shape=(V, V)).tocsr()
+    return np.ascontiguousarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int64)
+
+
 class LoweredGraph:
     """Index maps + device operators of one graph, shared by every field built on it.  Use `LoweredGraph.of(G)`.
 
@@ -209,6 +227,8 @@ class LoweredGraph:
                 P = np.array([pos[v][:2] for v in gnodes], dtype=np.float64).reshape(len(gnodes), -1)
                 if P.shape[1] == 2:
                     i2p = locality_permutation(len(gnodes), eu, ev, P)
+            elif not os.environ.get('GDS_B200_NO_RENUMBER'):
+                i2p = connectivity_order(len(gnodes), eu, ev)       # no positions: cut along breadth-first levels
             if i2p is not None:
                 p2i = np.empty(len(gnodes), dtype=np.int64)
                 p2i[i2p] = np.arange(len(gnodes), dtype=np.int64)

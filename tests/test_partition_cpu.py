@@ -333,6 +333,45 @@ def test_graphs_without_index_locality_are_cut_along_a_space_filling_curve(world
         gds_b200.Context._default.clear()
 
 
+@pytest.mark.parametrize('world', [2, 5])
+def test_graphs_without_positions_are_cut_along_breadth_first_levels(world, monkeypatch):
+    """a lattice whose nodes were relabelled at random and that carries no positions: index ranges of the public numbering
+    cut almost every edge; the ranges are taken in reverse Cuthill-McKee order instead, ids stay public"""
+    import networkx as nx
+    monkeypatch.setenv('GDS_B200_DEVICE', '-1')
+    gds_b200.Context._default.clear()
+    try:
+        H = nx.grid_2d_graph(40, 50)
+        perm = np.random.default_rng(6).permutation(H.number_of_nodes())
+        G0 = nx.relabel_nodes(H, {v: int(perm[i]) for i, v in enumerate(H.nodes())})
+        def make():
+            G = nx.Graph()
+            G.add_nodes_from(sorted(G0.nodes()))          # public id = label: no locality at all
+            G.add_edges_from(G0.edges())
+            G.faces = []
+            return G
+        n = H.number_of_nodes()
+        ref = make()
+        eu = np.array([a for a, b in ref.edges()]); ev = np.array([b for a, b in ref.edges()])
+        owner, cut = np.full(n, -1), 0
+        for rank in range(world):
+            low = gds_b200.LoweredGraph.of(gds_b200.distribute(make(), rank, world))
+            part = low.part
+            gid = part.global_ids
+            assert part.pub is not None and len(set(gid.tolist())) == gid.size
+            owner[gid[:part.n_own]] = rank
+            own = np.zeros(n, dtype=bool); own[gid[:part.n_own]] = True
+            keep = own[eu] | own[ev]
+            assert np.array_equal(gid[low.edge_u], eu[keep]) and np.array_equal(gid[low.edge_v], ev[keep])
+            cut += int(np.sum(own[eu] != own[ev]))
+        assert np.all(owner >= 0)
+        cut //= 2
+        cut_index = int(np.sum((eu * world // n) != (ev * world // n)))
+        assert cut < 0.2 * cut_index and cut < 0.12 * eu.size, (cut, cut_index, eu.size)
+    finally:
+        gds_b200.Context._default.clear()
+
+
 def test_overlap_split_covers_every_boundary_row():
     """engine.overlap_split: the two row ranges [0, lo) and [hi, n_own) hold every row adjacent to a cut, are multiples of
     128, as short as possible, and the split is refused when there is nothing to hide an exchange behind"""
