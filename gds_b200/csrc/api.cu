@@ -1854,17 +1854,17 @@ static int system_step(gds_system* s, int64_t n_steps, const double* t, const do
 //      Y -> OUT[b]), D2H out of OUT[b]; b = m & 1.  Events order the reuse of the two staging pairs.
 static int ensemble_setup(gds_system* s) {
   if (s->ens_h2d) return 0;
+  // every resource is created once: a call that failed half-way (out of memory) is resumed, not repeated, by the next one
   for (int i = 0; i < 2; ++i) {
-    GDS_CUDA(cudaMalloc((void**)&s->ens_in[i], (size_t)s->n_state * 8));
-    GDS_CUDA(cudaMalloc((void**)&s->ens_out[i], (size_t)s->n_state * 8));
-    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_ready[i], cudaEventDisableTiming));
-    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_free[i], cudaEventDisableTiming));
-    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_ready[i], cudaEventDisableTiming));
-    GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_free[i], cudaEventDisableTiming));
+    if (!s->ens_in[i]) { GDS_CUDA(cudaMalloc((void**)&s->ens_in[i], (size_t)s->n_state * 8)); s->device_bytes += s->n_state * 8; }
+    if (!s->ens_out[i]) { GDS_CUDA(cudaMalloc((void**)&s->ens_out[i], (size_t)s->n_state * 8)); s->device_bytes += s->n_state * 8; }
+    if (!s->ens_in_ready[i]) GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_ready[i], cudaEventDisableTiming));
+    if (!s->ens_in_free[i]) GDS_CUDA(cudaEventCreateWithFlags(&s->ens_in_free[i], cudaEventDisableTiming));
+    if (!s->ens_out_ready[i]) GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_ready[i], cudaEventDisableTiming));
+    if (!s->ens_out_free[i]) GDS_CUDA(cudaEventCreateWithFlags(&s->ens_out_free[i], cudaEventDisableTiming));
   }
-  s->device_bytes += 4 * s->n_state * 8;
-  GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_d2h, cudaStreamNonBlocking));
-  GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_h2d, cudaStreamNonBlocking));
+  if (!s->ens_d2h) GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_d2h, cudaStreamNonBlocking));
+  GDS_CUDA(cudaStreamCreateWithFlags(&s->ens_h2d, cudaStreamNonBlocking));      // last: its presence marks the set complete
   return 0;
 }
 
