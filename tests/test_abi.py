@@ -63,3 +63,16 @@ def test_python_constants_equal_the_header():
     from gds_b200.trace import Lowering
     chain = {k[len('GDS_CHAIN_'):]: v for k, v in enums.items() if k.startswith('GDS_CHAIN_')}
     assert chain == Lowering.CHAIN
+
+
+def test_new_device_entry_points_fail_loudly_without_a_device():
+    """the multigrid hierarchy and the preconditioned solve have no CPU fallback: a host-only context refuses them"""
+    ctx = gds_b200.Context(-1)
+    h = L.c_vp()
+    assert L.lib.gds_mg_create(ctx.h, ctypes.byref(h)) != 0
+    assert b'host-only' in L.lib.gds_last_error()
+    assert L.lib.gds_mg_create(None, ctypes.byref(h)) != 0
+    assert L.lib.gds_mg_apply(None, None, None) != 0
+    assert L.lib.gds_pcg_solve(ctx.h, None, None, None, None, None, None, None, None, None, 0, 1e-8, 10, 1, None, None) != 0
+    assert L.lib.gds_system_step_ensemble(None, 1, 1, None, None, None, None, 1, None, None, None) != 0
+    assert b'null system' in L.lib.gds_last_error()
