@@ -1,7 +1,6 @@
 """Host side of the multigrid preconditioner (gds_b200/multigrid.py): the native aggregation sweep, the smoothed-aggregation
 hierarchy of the masked graph Laplacian and the V-cycle as a conjugate-gradient preconditioner -- all on the CPU (the numpy
 V-cycle here is the model the device V-cycle is compared with in tests/test_multigrid_gpu.py)."""
-import networkx as nx
 import numpy as np
 import pytest
 import scipy.sparse as sp
