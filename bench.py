@@ -402,7 +402,7 @@ def _replica_worker(workload, size, kind, steps, barrier, q):
         os.dup2(devnull, 1)                      # the reference prints ("Faces: n") on stdout
         prob, _ = cpu_run(workload, size, steps=1, warmup=1, kind=kind)
         st, h = prob['stepper'], prob['h']
-        barrier.wait(timeout=300)
+        barrier.wait(timeout=90)
         t0 = time.perf_counter()
         for _ in range(steps):
             st.step(h)
@@ -435,10 +435,10 @@ def cpu_all_cores(workload, size, kind, steps):
     procs = [ctx.Process(target=_replica_worker, args=(workload, size, kind, steps, barrier, q)) for _ in range(n)]
     for pr in procs:
         pr.start()
-    res = []
+    res, deadline = [], time.perf_counter() + 120.0        # a bounded extra: never more than two minutes of the run
     try:
         for _ in procs:
-            res.append(q.get(timeout=600))
+            res.append(q.get(timeout=max(1.0, deadline - time.perf_counter())))
     except Exception:
         pass
     for pr in procs:
